@@ -1,0 +1,217 @@
+"""Pins the CPU oracle (oracle/*.c) before anything is checked against it.
+
+  - reader: bit-exact against the reference's own lsbench_matrix_read, via the
+    sha256 fixtures in tests/golden/reader.json (made from oracle/_ref) and,
+    when oracle/_ref is present, live.
+  - operator: the upper-triangle-mirrored matrix CHOLMOD sees
+    (src/cholmod-impl.h:5-21) against an independent scipy construction.
+  - direct solve and PCG: against tests/golden/direct.npz (scipy SuperLU) and
+    the analytic I1 answer.
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import orc
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+READER = json.load(open(os.path.join(GOLD, "reader.json")))
+DIRECT = np.load(os.path.join(GOLD, "direct.npz"))
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("name", orc.TOY + orc.NEK)
+def test_reader_matches_reference_fixture(name):
+    A = orc.matrix_read(orc.matrix_path(name))
+    g = READER[name]
+    assert (A.nrows, A.nnz, A.base) == (g["n"], g["nnz"], g["base"])
+    assert sha(A.offs) == g["offs"]
+    assert sha(A.cols) == g["cols"]
+    assert sha(A.vals) == g["vals"]
+
+
+@pytest.mark.parametrize("name", orc.TOY + ["tj7a_A_18", "xn3b_A_18"])
+def test_reader_matches_reference_live(name):
+    p = orc.matrix_path(name)
+    R = orc.ref_matrix_read(p)
+    if R is None:
+        pytest.skip("oracle/_ref not built (no reference tree on this box)")
+    A = orc.matrix_read(p)
+    assert (A.nrows, A.base) == (R.nrows, R.base)
+    assert np.array_equal(A.offs, R.offs) and np.array_equal(A.cols, R.cols)
+    assert A.vals.tobytes() == R.vals.tobytes()
+
+
+def _write(tmp_path, text, name="m.txt"):
+    p = tmp_path / name
+    p.write_text(text)
+    return str(p)
+
+
+def test_reader_semantics(tmp_path):
+    # unsorted input, a duplicate to be summed, an absent row (row 2) that is
+    # compressed away, base kept on the columns: src/lsbench-csr.c:54-86
+    p = _write(tmp_path, "6 1\n3 1 5.0\n1 2 1.5\n1 1 2.0\n1 2 0.25\n4 4 7\n3 3 -1e0\n")
+    A = orc.matrix_read(p)
+    assert A.nrows == 3 and A.base == 1
+    assert A.offs.tolist() == [0, 2, 4, 5]
+    assert A.cols.tolist() == [1, 2, 1, 3, 4]
+    assert A.vals.tolist() == [2.0, 1.75, 5.0, -1.0, 7.0]
+    R = orc.ref_matrix_read(p)
+    if R is not None:
+        assert R.offs.tolist() == A.offs.tolist() and R.vals.tolist() == A.vals.tolist()
+
+
+@pytest.mark.parametrize("text", [
+    "",                      # no header
+    "0 1\n",                 # nnz == 0          (:42)
+    "2 2\n1 1 1\n2 2 1\n",   # base > 1          (:40)
+    "2 1\n1 1 1\n",          # short file        (:50-52)
+    "1 1\n1 1 1",            # last record lacks '\n' (:51)
+    "1 1 \n1 1 1\n",         # header not newline-terminated (:38)
+])
+def test_reader_rejects(tmp_path, text):
+    assert orc.matrix_read(_write(tmp_path, text)) is None
+
+
+def test_reader_missing_file():
+    assert orc.matrix_read("/nonexistent/file.txt") is None
+
+
+def test_base_equivalence():
+    A0 = orc.matrix_read(orc.matrix_path("A0_02x02"))
+    A1 = orc.matrix_read(orc.matrix_path("A1_02x02"))
+    M0, M1 = orc.op_full(A0), orc.op_full(A1)
+    assert np.array_equal(M0.cols, M1.cols) and np.array_equal(M0.vals, M1.vals)
+    assert M0.scipy().toarray().tolist() == [[1, 1], [1, -1]]
+
+
+@pytest.mark.parametrize("name", ["I1_05x05"] + orc.NEK)
+def test_operator_upper_mirror(name):
+    import scipy.sparse as sp
+    A = orc.matrix_read(orc.matrix_path(name))
+    M = orc.op_upper_mirror(A)
+    g = READER[name]
+    assert M.nnz == g["op_nnz"] and sha(M.vals) == g["op_vals"] and sha(M.cols) == g["op_cols"]
+    F = orc.op_full(A).scipy()
+    U = sp.triu(F, 0)
+    S = (U + sp.triu(F, 1).T).tocsr()
+    S.sort_indices()
+    assert np.array_equal(S.indices, M.cols.astype(S.indices.dtype))
+    assert np.array_equal(S.data, M.vals)
+    for i in range(M.n):  # ascending columns in every row
+        c = M.cols[M.offs[i]:M.offs[i + 1]].astype(np.int64)
+        assert np.all(np.diff(c) > 0)
+
+
+def test_operator_ignores_lower_triangle(tmp_path):
+    # value-asymmetric input: only a_12 = 3 may survive, a_21 = 9 is ignored
+    A = orc.matrix_read(_write(tmp_path, "4 1\n1 1 4\n1 2 3\n2 1 9\n2 2 5\n"))
+    M = orc.op_upper_mirror(A)
+    assert M.scipy().toarray().tolist() == [[4, 3], [3, 5]]
+    # pattern-asymmetric input: a_12 present, a_21 absent -> mirror is inserted
+    A = orc.matrix_read(_write(tmp_path, "3 0\n0 0 4\n0 1 3\n1 1 5\n", "n.txt"))
+    assert orc.op_upper_mirror(A).scipy().toarray().tolist() == [[4, 3], [3, 5]]
+
+
+def test_i1_known_answer():
+    A = orc.matrix_read(orc.matrix_path("I1_05x05"))
+    M = orc.op_upper_mirror(A)
+    b = orc.rhs(M.n)
+    want = np.array([0, 1 / 2, 2 / 3, 3 / 4, 4 / 5])
+    assert b.tolist() == [0, 1, 2, 3, 4]
+    np.testing.assert_allclose(orc.Ldlt(M).solve(b), want, rtol=1e-15)
+    x, it, rel, rc = orc.pcg(M, b)
+    assert (it, rc) == (1, 0) and rel == 0.0
+    np.testing.assert_allclose(x, want, rtol=1e-15)
+    np.testing.assert_allclose(DIRECT["I1_05x05"], want, rtol=1e-15)
+
+
+@pytest.mark.parametrize("name", orc.NEK)
+def test_direct_and_pcg_against_superlu(name):
+    A = orc.matrix_read(orc.matrix_path(name))
+    M = orc.op_upper_mirror(A)
+    b = orc.rhs(M.n)
+    xg = DIRECT[name]
+    F = orc.Ldlt(M, 1)
+    assert F.spd
+    x = F.solve(b)
+    assert np.linalg.norm(x - xg) / np.linalg.norm(xg) < 1e-10
+    assert orc.true_relres(M, b, x) < 1e-10
+    if name in ("tj7a_A_18", "xn3b_A_18"):
+        xn = orc.Ldlt(M, 0).solve(b)  # natural ordering: same answer
+        assert np.linalg.norm(xn - xg) / np.linalg.norm(xg) < 1e-10
+    xp, it, rel, rc = orc.pcg(M, b, tol=1e-10)
+    assert rc == 0 and rel <= 1e-10 and 200 < it < 400
+    assert orc.true_relres(M, b, xp) <= 1.05e-10
+    assert np.linalg.norm(xp - xg) / np.linalg.norm(xg) < 1e-8  # the parity bar
+
+
+def test_full_operator_is_a_different_problem():
+    # solving the as-stored (value-asymmetric) matrix moves x by ~1e-7,
+    # i.e. outside the 1e-8 bar -- the reason the operator must be the mirror.
+    A = orc.matrix_read(orc.matrix_path("tj7a_A_18"))
+    xf, *_ = orc.pcg(orc.op_full(A), orc.rhs(A.nrows))
+    xg = DIRECT["tj7a_A_18"]
+    assert np.linalg.norm(xf - xg) / np.linalg.norm(xg) > 1e-8
+
+
+def test_spmv_and_abs_scale():
+    M = orc.gen_poisson27(6)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(M.n)
+    y, ya = orc.spmv(M, x, want_abs=True)
+    S = M.scipy()
+    np.testing.assert_allclose(y, S @ x, rtol=0, atol=1e-13 * ya.max())
+    np.testing.assert_allclose(ya, abs(S) @ abs(x), rtol=1e-14)
+
+
+@pytest.mark.parametrize("N", [5, 12])
+def test_poisson_generators(N):
+    import scipy.sparse as sp
+    I = sp.identity(N)
+    T = sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(N, N))
+    L7 = sp.kron(sp.kron(I, I), T) + sp.kron(sp.kron(I, T), I) + sp.kron(sp.kron(T, I), I)
+    B = sp.diags([1.0, 1.0, 1.0], [-1, 0, 1], shape=(N, N))
+    L27 = 27.0 * sp.identity(N ** 3) - sp.kron(sp.kron(B, B), B)
+    M7, M27 = orc.gen_poisson7(N), orc.gen_poisson27(N)
+    assert abs(M7.scipy() - L7).max() == 0 and M7.nnz == 7 * N ** 3 - 6 * N * N
+    assert abs(M27.scipy() - L27).max() == 0 and M27.nnz == (3 * N - 2) ** 3
+    lo, hi = N * N, 3 * N * N  # a z-slab row block, global column ids
+    Mb = orc.gen_poisson27(N, lo, hi)
+    assert np.array_equal(Mb.cols, M27.cols[M27.offs[lo]:M27.offs[hi]])
+
+
+def test_powerlaw_generator():
+    n = 20000
+    P = orc.gen_powerlaw(n, 3)
+    rl = P.rowlens()
+    assert rl.min() >= 3 and rl.max() <= n // 4 and 8 < rl.mean() < 25
+    assert np.array_equal(rl, [orc.lib().orc_powerlaw_rowlen(n, 3, i) for i in range(n)])
+    for i in range(n):
+        c = P.cols[P.offs[i]:P.offs[i + 1]].astype(np.int64)
+        assert np.all(np.diff(c) > 0) and c[0] >= 0 and c[-1] < n
+    assert -1 <= P.vals.min() and P.vals.max() < 1
+    Pb = orc.gen_powerlaw(n, 3, 5000, 7000)  # row block == slice of the whole
+    s, e = int(P.offs[5000]), int(P.offs[7000])
+    assert np.array_equal(Pb.cols, P.cols[s:e]) and np.array_equal(Pb.vals, P.vals[s:e])
+    assert not np.array_equal(orc.gen_powerlaw(n, 4).rowlens(), rl)  # seed matters
+    t = orc.powerlaw_table()
+    assert t[3] == 2 ** 53 and np.all(np.diff(t[3:].astype(np.float64)) <= 0)
+
+
+def test_pcg_iteration_counts_poisson():
+    # SURVEY 6 planning numbers: 7-pt N=32 -> 125 its, 27-pt N=32 -> 73 its
+    for gen, want in ((orc.gen_poisson7, 125), (orc.gen_poisson27, 73)):
+        M = gen(32)
+        x, it, rel, rc = orc.pcg(M, orc.rhs(M.n))
+        assert rc == 0 and abs(it - want) <= 1
+        xo, ito, relo, rco = orc.pcg(M, orc.rhs(M.n), omp=True)
+        assert rco == 0 and abs(ito - it) <= 1
+        assert np.linalg.norm(xo - x) / np.linalg.norm(x) < 1e-9
