@@ -1,0 +1,189 @@
+/*
+ * b200.h -- C ABI of the B200-native sparse solver layer (libb200.so).
+ *
+ * This is the thin layer `src/b200.c` (the lsbench `--solver b200` backend,
+ * see INTEGRATION.md) calls; it is also what tests/ and bench.py bind with
+ * ctypes.  Plain pointers and sizes only; every function returns 0 on success
+ * and a B200_E* code otherwise, with a message in b200_last_error().  There is
+ * no CPU fallback: on a machine without a usable CUDA device the calls fail.
+ *
+ * Which reference interface each entry point replaces (paths relative to the
+ * lsbench tree):
+ *
+ *   b200_ctx_create / _destroy     X_init / X_finalize file-scope handles,
+ *                                  src/cusparse.c:33-36,138-162
+ *   b200_mat_from_csr              backend csr_init: host `struct csr`
+ *                                  (src/lsbench-impl.h:22-26) -> backend
+ *                                  layout + H2D, src/cusparse.c:47-125; with
+ *                                  B200_MAT_SYM_UPPER the operator is the one
+ *                                  CHOLMOD factorises, src/cholmod-impl.h:5-21
+ *   b200_mat_destroy               csr_finalize, src/cusparse.c:127-136
+ *   b200_pcg_solve                 the solve inside the X_bench timed loop,
+ *                                  src/cusparse.c:189-197 /
+ *                                  src/cholmod-impl.h:58-63 /
+ *                                  src/ginkgo.cpp:91-99 (x reset per trial)
+ *   b200_spmv*                     no reference counterpart
+ *   b200_mat_generate              no reference counterpart: BASELINE.json
+ *                                  configs 3-5 cannot go through the text
+ *                                  reader (src/lsbench-csr.c:35,54)
+ */
+#ifndef B200_H_
+#define B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_ABI_VERSION 1
+
+enum {
+  B200_OK = 0,
+  B200_EINVAL = 1,   /* bad argument */
+  B200_ECUDA = 2,    /* CUDA runtime / driver error */
+  B200_ENOMEM = 3,
+  B200_ENCCL = 4,    /* NCCL missing or failed */
+  B200_ENOTSPD = 5,  /* PCG breakdown: p.Ap <= 0 or NaN */
+  B200_ERANGE = 6    /* index width exceeded */
+};
+
+typedef struct b200_ctx b200_ctx;
+typedef struct b200_mat b200_mat;
+
+const char *b200_last_error(void);
+int b200_abi_version(void);
+/* Number of CUDA devices visible; fails (B200_ECUDA) without a driver. */
+int b200_device_count(int *count);
+
+/* ---- context: one per rank, one GPU per rank ---------------------------- */
+int b200_ctx_create(int device, b200_ctx **ctx);
+/* Row-block distributed context.  nccl_id is B200_NCCL_ID_BYTES bytes from
+ * b200_nccl_unique_id() on rank 0, handed to every rank by the caller
+ * (torch.distributed broadcast, or shared memory in a threaded host). */
+#define B200_NCCL_ID_BYTES 128
+int b200_nccl_unique_id(void *id_out);
+int b200_ctx_create_dist(int device, int rank, int nranks, const void *nccl_id,
+                         b200_ctx **ctx);
+int b200_ctx_destroy(b200_ctx *ctx);
+/* Launch on a caller-owned cudaStream_t (e.g. torch's current stream) so the
+ * caller's CUDA events bracket the kernels.  NULL = the context's own. */
+int b200_ctx_set_stream(b200_ctx *ctx, void *cuda_stream);
+int b200_ctx_sync(b200_ctx *ctx);
+int b200_ctx_rank(const b200_ctx *ctx, int *rank, int *nranks);
+
+/* Device memory owned by the library (so a C host needs no CUDA headers). */
+int b200_malloc(b200_ctx *ctx, size_t bytes, void **dptr);
+int b200_free(b200_ctx *ctx, void *dptr);
+int b200_memcpy_h2d(b200_ctx *ctx, void *dst, const void *src, size_t bytes);
+int b200_memcpy_d2h(b200_ctx *ctx, void *dst, const void *src, size_t bytes);
+int b200_memset(b200_ctx *ctx, void *dst, int byte, size_t bytes);
+/* Pinned host memory for the end-to-end path. */
+int b200_host_alloc(size_t bytes, void **hptr);
+int b200_host_free(void *hptr);
+
+/* ---- matrix -------------------------------------------------------------- */
+enum {
+  B200_MAT_SYM_UPPER = 1u << 0, /* solve the upper triangle mirrored */
+  B200_MAT_FORCE_VECTOR = 1u << 1, /* kernel sweep: no SELL bin */
+  B200_MAT_FORCE_SELL = 1u << 2,   /* kernel sweep: everything in SELL */
+  B200_MAT_NO_SORT = 1u << 3       /* SELL without the length-sort window */
+};
+
+/* Host CSR exactly as lsbench_matrix_read leaves it: offs 0-based, cols
+ * carrying `base` (src/lsbench-csr.c:79-86).  The matrix is global; in a
+ * distributed context each rank keeps its row block [n*rank/P, n*(rank+1)/P)
+ * rounded to 32 rows. */
+int b200_mat_from_csr(b200_ctx *ctx, uint32_t nrows, uint32_t base,
+                      const uint32_t *offs, const uint32_t *cols,
+                      const double *vals, uint32_t flags, b200_mat **M);
+
+enum { B200_GEN_POISSON7 = 1, B200_GEN_POISSON27 = 2, B200_GEN_POWERLAW = 3 };
+/* Synthetic operator generated on the device, only this rank's rows.
+ * size = N (grid edge) for the Poisson kinds, n (rows) for powerlaw. */
+int b200_mat_generate(b200_ctx *ctx, int kind, uint64_t size, uint64_t seed,
+                      uint32_t flags, b200_mat **M);
+int b200_mat_destroy(b200_mat *M);
+
+#define B200_HIST_BINS 24
+typedef struct {
+  uint64_t n_global;      /* rows of the whole operator */
+  uint64_t row_begin;     /* first global row owned by this rank */
+  uint64_t n_local;       /* rows owned */
+  uint64_t n_halo;        /* remote x entries this rank reads */
+  uint64_t nnz;           /* stored entries of the local rows (after mirror) */
+  uint64_t nnz_padded;    /* entries in the device streams incl. padding */
+  uint64_t sell_rows, sell_slices, sell_sigma, sell_max_width;
+  uint64_t vec_rows, vec_nnz;      /* warp-per-row bin */
+  uint64_t long_rows, long_nnz;    /* block-per-row bin */
+  uint64_t interior_begin, interior_end; /* local rows with no halo column */
+  uint64_t hist[B200_HIST_BINS];  /* rows with 2^(b-1) < len <= 2^b; hist[0]: len 0..1 */
+  uint64_t max_row_len;
+  uint32_t pattern_symmetric;     /* SYM_UPPER: mirror slots all existed */
+  uint32_t sell_perm;             /* 1 if SELL rows are permuted */
+  uint64_t device_bytes;
+} b200_mat_info;
+int b200_mat_get_info(const b200_mat *M, b200_mat_info *info);
+
+/* Reads the local rows back as plain CSR in ORIGINAL row order with local
+ * column ids (halo columns >= n_local), padding removed: what the device
+ * layout represents.  Pass NULL arrays to query sizes. */
+int b200_mat_export(const b200_mat *M, uint64_t *offs, uint32_t *cols,
+                    double *vals);
+/* Global column id of halo slot j (j < n_halo). */
+int b200_mat_halo_cols(const b200_mat *M, uint64_t *gcols);
+int b200_mat_inv_diag(const b200_mat *M, double *h_dinv);
+
+/* ---- SpMV ------------------------------------------------------------------ */
+/* y = A x on the local rows.  d_x holds the n_local owned entries; the halo is
+ * exchanged inside.  d_y: n_local.  Device pointers. */
+int b200_spmv(b200_mat *M, const double *d_x, double *d_y);
+/* Host buffers: H2D x, SpMV, D2H y. */
+int b200_spmv_host(b200_mat *M, const double *h_x, double *h_y);
+/* Times `reps` back-to-back launches with CUDA events on the launch stream
+ * and returns the mean milliseconds per SpMV (all bins, halo included). */
+int b200_spmv_time(b200_mat *M, const double *d_x, double *d_y, int reps,
+                   float *ms_per_spmv);
+
+/* ---- Jacobi-preconditioned CG --------------------------------------------- */
+typedef struct {
+  double tol;        /* stop when ||r||_2 <= tol * ||b||_2 (recurrence r) */
+  int32_t maxit;
+  int32_t check_every; /* iterations queued between host looks; 0 = default */
+  uint32_t flags;
+} b200_pcg_opts;
+enum {
+  B200_PCG_TIME_KERNELS = 1u << 0, /* per-class CUDA-event timing */
+  B200_PCG_NO_GRAPH = 1u << 1,
+  B200_PCG_NO_SMALL = 1u << 2      /* never take the on-chip small-matrix path */
+};
+
+typedef struct {
+  int32_t iters;
+  int32_t status;      /* 0 converged, 1 maxit, 2 breakdown (not SPD / NaN) */
+  double relres;       /* recurrence ||r|| / ||b|| at exit */
+  double true_relres;  /* ||b - A x|| / ||b|| recomputed with one SpMV */
+  double bnorm;
+  float solve_ms;      /* CUDA events around the whole solve */
+  float spmv_ms, update_ms, pupdate_ms; /* B200_PCG_TIME_KERNELS only */
+  int32_t kernel_launches;
+  int32_t path;        /* 0 = streaming kernels, 1 = on-chip small-matrix */
+} b200_pcg_result;
+
+/* x: in x0, out solution (n_local).  b: n_local.  Device pointers. */
+int b200_pcg_solve(b200_mat *M, const double *d_b, double *d_x,
+                   const b200_pcg_opts *opts, b200_pcg_result *res);
+/* Host buffers: H2D b and x0, solve, D2H x -- the X_bench call shape. */
+int b200_pcg_solve_host(b200_mat *M, const double *h_b, double *h_x,
+                        const b200_pcg_opts *opts, b200_pcg_result *res);
+
+/* ---- bytes the roofline is quoted on --------------------------- */
+/* 12*nnz + 4*(n+1) + 16*n  and  12*nnz + 4*(n+1) + 104*n, local rows. */
+int b200_mat_algorithmic_bytes(const b200_mat *M, uint64_t *spmv_bytes,
+                               uint64_t *pcg_iter_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

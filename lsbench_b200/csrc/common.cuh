@@ -1,0 +1,230 @@
+// common.cuh -- internal types and device helpers of libb200.so (sm_100a).
+#pragma once
+#include "b200.h"
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#define B200_SM_COUNT_FALLBACK 148
+#define B2_SLICE 32  // SELL slice height = one warp, one row per lane
+
+void b200_set_error(const char *fmt, ...);
+
+#define CU_TRY(expr)                                                           \
+  do {                                                                         \
+    cudaError_t e_ = (expr);                                                   \
+    if (e_ != cudaSuccess) {                                                   \
+      b200_set_error("%s:%d cuda error: %s (%s)", __FILE__, __LINE__,          \
+                     cudaGetErrorString(e_), #expr);                           \
+      return e_ == cudaErrorMemoryAllocation ? B200_ENOMEM : B200_ECUDA;       \
+    }                                                                          \
+  } while (0)
+
+#define B_TRY(expr)                                                            \
+  do {                                                                         \
+    int r_ = (expr);                                                           \
+    if (r_ != B200_OK)                                                         \
+      return r_;                                                               \
+  } while (0)
+
+#define B_FAIL(code, ...)                                                      \
+  do {                                                                         \
+    b200_set_error(__VA_ARGS__);                                               \
+    return (code);                                                             \
+  } while (0)
+
+// ---- NCCL, bound at run time (dist.cu) ------------------------------------
+struct NcclApi;
+
+struct b200_ctx {
+  int device = 0;
+  int sm_count = B200_SM_COUNT_FALLBACK;
+  int rank = 0, nranks = 1;
+  cudaStream_t own_stream = nullptr;   // created by the context
+  cudaStream_t stream = nullptr;       // where kernels go (own or caller's)
+  cudaStream_t comm_stream = nullptr;  // halo exchange, overlapped with interior
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_halo = nullptr,
+              ev_ready = nullptr;
+  void *nccl_comm = nullptr;
+  const NcclApi *nccl = nullptr;
+  int *h_flag = nullptr;  // pinned: PCG progress word read by the host
+};
+
+// Plain CSR on the device: the intermediate every input goes through.
+struct PlainCsr {
+  uint64_t n = 0;      // rows held
+  uint64_t nnz = 0;
+  uint64_t *offs = nullptr;  // n+1
+  uint32_t *cols = nullptr;
+  double *vals = nullptr;
+};
+
+struct HaloPlan {
+  // receive side: halo slots are sorted by global column, grouped by owner
+  uint64_t n_halo = 0;
+  uint64_t *d_gcols = nullptr;           // n_halo global ids
+  int n_peers = 0;                       // ranks we exchange with
+  int *peer = nullptr;                   // host arrays, n_peers long
+  uint64_t *recv_off = nullptr;          // n_peers+1, into the halo section
+  uint64_t *send_off = nullptr;          // n_peers+1, into send buffer
+  uint32_t *d_send_idx = nullptr;        // local row ids to pack
+  double *d_send_buf = nullptr;
+  uint64_t n_send = 0;
+};
+
+struct SpmvPlan {
+  uint32_t b0, e0, b1, e1;  // SELL slice ranges of the phase
+  int g_sell, g_vec, g_long;
+};
+
+// Device-resident scalars of one PCG solve.  red[] holds the values that are
+// all-reduced across ranks: {rz, rr} for iteration parity 0 at [0..1], parity
+// 1 at [2..3], and the start-up triple {rz, rr, bb} at [4..6].
+struct PcgState {
+  double pq;
+  double red[7];
+  double bb, thr2, tol;
+  double true_rr;
+  int iter, done, status, maxit;
+  unsigned ticket[4];
+};
+
+struct b200_mat {
+  b200_ctx *ctx = nullptr;
+  uint64_t n_global = 0, row_begin = 0, n_local = 0, nnz = 0;
+  uint32_t flags = 0;
+  // --- SELL-32 bin: slice s holds rows perm[32s .. 32s+31], column-major ----
+  uint32_t sell_rows = 0, sell_slices = 0, sell_sigma = 1, sell_max_width = 0;
+  uint32_t *sell_off = nullptr;   // sell_slices+1, in units of 32 entries
+  uint32_t *sell_cols = nullptr;
+  double *sell_vals = nullptr;
+  uint32_t *sell_perm = nullptr;  // nullptr == identity (row = 32 s + lane)
+  uint64_t sell_entries = 0;      // padded
+  // --- warp-per-row and block-per-row bins: row-major, rows padded to 4 ----
+  uint32_t vec_rows = 0, long_rows = 0;
+  uint32_t *vec_row_ids = nullptr, *long_row_ids = nullptr;
+  uint64_t *vec_off = nullptr, *long_off = nullptr;  // rows+1 each
+  uint32_t *vl_cols = nullptr;
+  double *vl_vals = nullptr;
+  uint64_t vl_entries = 0, vec_nnz = 0, long_nnz = 0;
+  // --- common -----------------------------------------------------------------
+  double *dinv = nullptr;        // n_local
+  uint32_t *row_len = nullptr;   // n_local, true lengths (export / checks)
+  uint64_t hist[B200_HIST_BINS] = {0};
+  uint64_t max_row_len = 0;
+  uint32_t pattern_symmetric = 1;
+  uint64_t interior_begin = 0, interior_end = 0;
+  HaloPlan halo;
+  uint64_t device_bytes = 0;
+  // --- solver workspace (lazily allocated) ----------------------------------
+  double *w_r = nullptr, *w_p = nullptr, *w_q = nullptr;  // p has halo room
+  double *w_x = nullptr;          // iterate (graph-stable pointer)
+  int grid_ew = 0;                // element-wise kernels
+  unsigned partial_stride = 0;
+  double *x_ext = nullptr;        // spmv staging: n_local + n_halo
+  double *partials = nullptr;     // per-CTA partial sums, 4 lanes of them
+  PcgState *state = nullptr;
+  SpmvPlan plan[3];              // phase 0 all, 1 interior, 2 boundary
+  bool plan_ready = false;
+  void *small = nullptr;          // on-chip small-matrix plan (small.cu)
+  void *graph_exec = nullptr;     // cudaGraphExec_t of one iteration chunk
+  int graph_chunk = 0;
+  void *graph_stream = nullptr;
+};
+
+// ---- helpers implemented across the .cu files --------------------------------
+int dev_alloc(b200_mat *M, void **p, size_t bytes);  // tracks device_bytes
+int plain_free(PlainCsr *A);
+int build_layout(b200_ctx *ctx, PlainCsr *A, uint64_t n_global,
+                 uint64_t row_begin, uint32_t flags, b200_mat **out);
+int partition_and_renumber(b200_ctx *ctx, PlainCsr *A, uint64_t n_global,
+                           uint64_t row_begin, b200_mat *M);
+int halo_setup(b200_mat *M);
+int halo_exchange_begin(b200_mat *M, double *d_x_ext);  // on comm stream
+int halo_exchange_wait(b200_mat *M);
+void halo_free(b200_mat *M);
+int ensure_workspace(b200_mat *M);
+int launch_spmv(b200_mat *M, const double *x_ext, double *y, bool fuse_dot,
+                int phase /*0 all, 1 interior, 2 boundary*/);
+int allreduce_sum(b200_ctx *ctx, double *d_vals, int count);
+int small_try_build(b200_mat *M);
+void small_free(b200_mat *M);
+int small_solve(b200_mat *M, const double *d_b, double *d_x,
+                const b200_pcg_opts *o, b200_pcg_result *res);
+
+// ---- device-side helpers -----------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ double warp_sum(double v) {
+  // fixed butterfly: the same tree for every run
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of one value per thread, fixed order: warp trees, then the
+// warp results in ascending warp order by warp 0.  Result valid in thread 0.
+template <int NWARPS>
+__device__ __forceinline__ double block_sum(double v, double *smem /*NWARPS*/) {
+  v = warp_sum(v);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0)
+    smem[w] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (w == 0) {
+    t = lane < NWARPS ? smem[lane] : 0.0;
+    t = warp_sum(t);
+  }
+  __syncthreads();
+  return t;
+}
+
+// Grid-wide deterministic sum of NV values per CTA.  Each CTA stores its
+// block sums to partials[v * stride + slot]; the CTA drawing the last ticket
+// adds the `total` partials of every lane in a fixed order (strided per
+// thread, then the block tree) and writes out[v].  The order depends only on
+// `total`, i.e. on the launch geometry -- never on scheduling.
+template <int NV, int NWARPS>
+__device__ __forceinline__ void grid_sum_finish(const double (&block_val)[NV],
+                                                double *partials,
+                                                unsigned stride, unsigned slot,
+                                                unsigned total, unsigned *ticket,
+                                                double *out, double *smem) {
+  __shared__ bool is_last;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int v = 0; v < NV; v++)
+      partials[v * stride + slot] = block_val[v];
+    __threadfence();
+    unsigned t = atomicAdd(ticket, 1u);
+    is_last = (t == total - 1);
+  }
+  __syncthreads();
+  if (!is_last)
+    return;
+  __threadfence();
+#pragma unroll
+  for (int v = 0; v < NV; v++) {
+    double acc = 0.0;
+    for (unsigned i = threadIdx.x; i < total; i += blockDim.x)
+      acc += __ldcg(partials + v * stride + i);
+    acc = block_sum<NWARPS>(acc, smem);
+    if (threadIdx.x == 0)
+      out[v] = acc;
+  }
+  if (threadIdx.x == 0)
+    *ticket = 0;
+}
+
+// streaming (read-once) loads: keep them out of L1, evict-first in L2
+__device__ __forceinline__ double ld_stream(const double *p) {
+  return __ldcs(p);
+}
+__device__ __forceinline__ uint32_t ld_stream(const uint32_t *p) {
+  return __ldcs(p);
+}
+#endif

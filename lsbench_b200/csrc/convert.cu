@@ -1,0 +1,759 @@
+// convert.cu -- north_star piece (1): host CSR (src/lsbench-impl.h:22-26, as
+// built by src/lsbench-csr.c:79-86) -> device layout.
+//
+// Stands where a reference backend's csr_init stands (src/cusparse.c:47-125):
+// index conversion, base handling (:59,:63) and H2D, but instead of handing
+// the arrays to a library it rewrites them for the SpMV kernels:
+//
+//   SELL-32 bin   rows with len <= B2_SELL_MAX.  32 rows form a slice; a slice is
+//                 stored column-major (entry k of lane l at off*32 + 32k + l),
+//                 so every warp load of cols / vals is one aligned 128 B /
+//                 256 B segment and each lane accumulates its own row left to
+//                 right.  Slices are padded to their longest row; a sort of
+//                 the rows by length inside windows of B2_SELL_SIGMA rows keeps
+//                 that padding small on irregular matrices and is skipped
+//                 (identity permutation) when the natural order already pads
+//                 less than 3 %.
+//   vector bin    B2_SELL_MAX < len < B2_LONG_MIN: row-major, each row padded to a
+//                 multiple of 4 entries and 32 B aligned for 128-bit loads,
+//                 one warp per row.
+//   long bin      len >= B2_LONG_MIN: same storage, one CTA per row.
+//
+// With B200_MAT_SYM_UPPER the operator is first replaced by the one CHOLMOD
+// factorises (src/cholmod-impl.h:5-21): entries with col >= row, mirrored.
+#include "common.cuh"
+#include <cub/cub.cuh>
+
+#define B2_SELL_MAX 256u
+#define B2_LONG_MIN 8192u
+#define B2_SELL_SIGMA 1024u
+#define T256 256
+
+static inline unsigned nblk(uint64_t n, unsigned t = T256) {
+  return (unsigned)((n + t - 1) / t);
+}
+
+// ---------------------------------------------------------------------------
+// scans (CUB is used for the set-up prefix sums only, never on the solve path)
+template <typename T>
+static int exclusive_scan(cudaStream_t s, const T *in, T *out, uint64_t n) {
+  void *tmp = nullptr;
+  size_t bytes = 0;
+  CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, n, s));
+  CU_TRY(cudaMalloc(&tmp, bytes ? bytes : 8));
+  CU_TRY(cub::DeviceScan::ExclusiveSum(tmp, bytes, in, out, n, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  CU_TRY(cudaFree(tmp));
+  return B200_OK;
+}
+
+int plain_free(PlainCsr *A) {
+  if (A->offs) cudaFree(A->offs);
+  if (A->cols) cudaFree(A->cols);
+  if (A->vals) cudaFree(A->vals);
+  *A = PlainCsr();
+  return B200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// upload
+__global__ void k_widen_offs(const uint32_t *in, uint64_t *out, uint64_t n) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n)
+    out[i] = in[i];
+}
+__global__ void k_rebase_cols(uint32_t *cols, uint64_t nnz, uint32_t base) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < nnz)
+    cols[i] -= base;  // src/cholmod-impl.h:16, src/amgx.c:41
+}
+
+static int upload_csr(b200_ctx *c, uint32_t nrows, uint32_t base,
+                      const uint32_t *offs, const uint32_t *cols,
+                      const double *vals, PlainCsr *A) {
+  uint64_t nnz = offs[nrows];  // src/cusparse.c:55
+  A->n = nrows, A->nnz = nnz;
+  uint32_t *tmp = nullptr;
+  CU_TRY(cudaMalloc(&tmp, (nrows + 1ull) * 4));
+  CU_TRY(cudaMalloc(&A->offs, (nrows + 1ull) * 8));
+  CU_TRY(cudaMalloc(&A->cols, (nnz ? nnz : 1) * 4));
+  CU_TRY(cudaMalloc(&A->vals, (nnz ? nnz : 1) * 8));
+  cudaStream_t s = c->stream;
+  CU_TRY(cudaMemcpyAsync(tmp, offs, (nrows + 1ull) * 4, cudaMemcpyHostToDevice, s));
+  CU_TRY(cudaMemcpyAsync(A->cols, cols, nnz * 4, cudaMemcpyHostToDevice, s));
+  CU_TRY(cudaMemcpyAsync(A->vals, vals, nnz * 8, cudaMemcpyHostToDevice, s));
+  k_widen_offs<<<nblk(nrows + 1ull), T256, 0, s>>>(tmp, A->offs, nrows + 1ull);
+  if (base && nnz)
+    k_rebase_cols<<<nblk(nnz), T256, 0, s>>>(A->cols, nnz, base);
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaStreamSynchronize(s));
+  CU_TRY(cudaFree(tmp));
+  return B200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// upper-triangle mirror (src/cholmod-impl.h:11-17 + triplet_to_sparse :21)
+__global__ void k_sym_count(uint64_t n, const uint64_t *offs,
+                            const uint32_t *cols, uint32_t *n_upper,
+                            uint32_t *n_mirror) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  uint32_t u = 0;
+  for (uint64_t k = offs[i]; k < offs[i + 1]; k++) {
+    uint64_t j = cols[k];
+    if (j >= i) {
+      u++;
+      if (j > i && j < n)
+        atomicAdd(&n_mirror[j], 1u);  // integer count: order-independent
+    }
+  }
+  n_upper[i] = u;
+}
+
+__global__ void k_add_u32_to_u64(const uint32_t *a, const uint32_t *b,
+                                 uint64_t *out, uint64_t n) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n)
+    out[i] = (uint64_t)a[i] + b[i];
+  if (i == n)
+    out[i] = 0;
+}
+
+__global__ void k_sym_fill(uint64_t n, const uint64_t *offs,
+                           const uint32_t *cols, const double *vals,
+                           const uint64_t *noffs, const uint32_t *n_mirror,
+                           uint32_t *cursor, uint32_t *ncols, double *nvals) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  uint64_t up = noffs[i] + n_mirror[i];
+  for (uint64_t k = offs[i]; k < offs[i + 1]; k++) {
+    uint64_t j = cols[k];
+    if (j < i)
+      continue;  // lower-triangle file values are never used
+    double v = vals[k];
+    ncols[up] = (uint32_t)j, nvals[up] = v, up++;
+    if (j > i && j < n) {
+      uint64_t slot = noffs[j] + atomicAdd(&cursor[j], 1u);
+      ncols[slot] = (uint32_t)i, nvals[slot] = v;
+    }
+  }
+}
+
+// The mirrored part of each row was filled in arrival order; put it in
+// ascending column order so the result does not depend on scheduling.
+__global__ void k_sym_sort(uint64_t n, const uint64_t *noffs,
+                           const uint32_t *n_mirror, uint32_t *ncols,
+                           double *nvals) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  uint64_t s = noffs[i];
+  uint32_t m = n_mirror[i];
+  for (uint32_t a = 1; a < m; a++) {
+    uint32_t c = ncols[s + a];
+    double v = nvals[s + a];
+    uint32_t b = a;
+    while (b > 0 && ncols[s + b - 1] > c) {
+      ncols[s + b] = ncols[s + b - 1], nvals[s + b] = nvals[s + b - 1];
+      b--;
+    }
+    ncols[s + b] = c, nvals[s + b] = v;
+  }
+}
+
+__global__ void k_cols_differ(const uint32_t *a, const uint32_t *b, uint64_t n,
+                              uint32_t *flag) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n && a[i] != b[i])
+    *flag = 1;
+}
+
+static int sym_upper(b200_ctx *c, PlainCsr *A, uint32_t *pattern_symmetric) {
+  cudaStream_t s = c->stream;
+  uint64_t n = A->n;
+  uint32_t *n_upper, *n_mirror, *cursor, *flag;
+  uint64_t *len64, *noffs;
+  CU_TRY(cudaMalloc(&n_upper, (n + 1) * 4));
+  CU_TRY(cudaMalloc(&n_mirror, (n + 1) * 4));
+  CU_TRY(cudaMalloc(&cursor, (n + 1) * 4));
+  CU_TRY(cudaMalloc(&flag, 4));
+  CU_TRY(cudaMalloc(&len64, (n + 1) * 8));
+  CU_TRY(cudaMalloc(&noffs, (n + 1) * 8));
+  CU_TRY(cudaMemsetAsync(n_mirror, 0, (n + 1) * 4, s));
+  CU_TRY(cudaMemsetAsync(cursor, 0, (n + 1) * 4, s));
+  CU_TRY(cudaMemsetAsync(flag, 0, 4, s));
+  k_sym_count<<<nblk(n), T256, 0, s>>>(n, A->offs, A->cols, n_upper, n_mirror);
+  k_add_u32_to_u64<<<nblk(n + 1), T256, 0, s>>>(n_upper, n_mirror, len64, n);
+  B_TRY(exclusive_scan<uint64_t>(s, len64, noffs, n + 1));
+  uint64_t nnz = 0;
+  CU_TRY(cudaMemcpy(&nnz, noffs + n, 8, cudaMemcpyDeviceToHost));
+  uint32_t *ncols;
+  double *nvals;
+  CU_TRY(cudaMalloc(&ncols, (nnz ? nnz : 1) * 4));
+  CU_TRY(cudaMalloc(&nvals, (nnz ? nnz : 1) * 8));
+  k_sym_fill<<<nblk(n), T256, 0, s>>>(n, A->offs, A->cols, A->vals, noffs,
+                                      n_mirror, cursor, ncols, nvals);
+  k_sym_sort<<<nblk(n), T256, 0, s>>>(n, noffs, n_mirror, ncols, nvals);
+  uint32_t differ = 1;
+  if (nnz == A->nnz) {
+    k_cols_differ<<<nblk(nnz ? nnz : 1), T256, 0, s>>>(A->cols, ncols, nnz, flag);
+    CU_TRY(cudaMemcpyAsync(&differ, flag, 4, cudaMemcpyDeviceToHost, s));
+  }
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaStreamSynchronize(s));
+  *pattern_symmetric = !differ;
+  cudaFree(A->offs), cudaFree(A->cols), cudaFree(A->vals);
+  A->offs = noffs, A->cols = ncols, A->vals = nvals, A->nnz = nnz;
+  cudaFree(n_upper), cudaFree(n_mirror), cudaFree(cursor), cudaFree(flag);
+  cudaFree(len64);
+  return B200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// layout planning
+__global__ void k_row_len(uint64_t n, const uint64_t *offs, uint32_t *len,
+                          unsigned long long *hist, unsigned long long *maxlen) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  uint64_t l = offs[i + 1] - offs[i];
+  len[i] = (uint32_t)l;
+  int b = l <= 1 ? 0 : 64 - __clzll((unsigned long long)(l - 1));
+  if (b >= B200_HIST_BINS)
+    b = B200_HIST_BINS - 1;
+  atomicAdd(&hist[b], 1ull);
+  atomicMax(maxlen, (unsigned long long)l);
+}
+
+// bin: 0 SELL, 1 vector, 2 long
+__device__ __forceinline__ int bin_of(uint32_t len, uint32_t sell_max,
+                                      uint32_t long_min) {
+  return len <= sell_max ? 0 : (len < long_min ? 1 : 2);
+}
+
+__global__ void k_bin_flags(uint64_t n, const uint32_t *len, uint32_t sell_max,
+                            uint32_t long_min, uint32_t *f0, uint32_t *f1,
+                            uint32_t *f2) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i > n)
+    return;
+  int b = i < n ? bin_of(len[i], sell_max, long_min) : -1;
+  f0[i] = b == 0, f1[i] = b == 1, f2[i] = b == 2;
+}
+
+__global__ void k_scatter_ids(uint64_t n, const uint32_t *len,
+                              uint32_t sell_max, uint32_t long_min,
+                              const uint32_t *p0, const uint32_t *p1,
+                              const uint32_t *p2, uint32_t *l0, uint32_t *l1,
+                              uint32_t *l2) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  int b = bin_of(len[i], sell_max, long_min);
+  if (b == 0)
+    l0[p0[i]] = (uint32_t)i;
+  else if (b == 1)
+    l1[p1[i]] = (uint32_t)i;
+  else
+    l2[p2[i]] = (uint32_t)i;
+}
+
+__global__ void k_iota_u32(uint32_t *p, uint64_t n) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n)
+    p[i] = (uint32_t)i;
+}
+
+__global__ void k_fill_u32(uint32_t *p, uint64_t n, uint32_t v) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n)
+    p[i] = v;
+}
+
+// Sort the SELL row list by decreasing length inside windows of B2_SELL_SIGMA
+// entries; ties keep the original order (the key carries the position).
+__global__ void __launch_bounds__(256) k_window_sort(uint32_t *list,
+                                                     uint64_t padded,
+                                                     const uint32_t *len) {
+  typedef cub::BlockRadixSort<uint32_t, 256, 4, uint32_t> Sort;
+  __shared__ typename Sort::TempStorage tmp;
+  uint64_t base = (uint64_t)blockIdx.x * B2_SELL_SIGMA;
+  uint32_t key[4], val[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    uint32_t idx = threadIdx.x * 4 + j;
+    uint32_t row = base + idx < padded ? list[base + idx] : 0xffffffffu;
+    uint32_t l = row == 0xffffffffu ? 0u : len[row];
+    key[j] = ((B2_SELL_MAX - l) << 10) | idx;  // B2_SELL_MAX - l in [0, 256]
+    val[j] = row;
+  }
+  Sort(tmp).Sort(key, val, 0, 20);
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    uint32_t idx = threadIdx.x * 4 + j;
+    if (base + idx < padded)
+      list[base + idx] = val[j];
+  }
+}
+
+// one warp per slice: width = longest row in the slice
+__global__ void k_slice_width(uint32_t nslices, const uint32_t *list,
+                              uint64_t n, const uint32_t *len, uint32_t *width,
+                              unsigned long long *entries_true) {
+  uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (s >= nslices)
+    return;
+  uint64_t pos = (uint64_t)s * B2_SLICE + lane;
+  uint32_t row = list ? list[pos] : (pos < n ? (uint32_t)pos : 0xffffffffu);
+  uint32_t l = row == 0xffffffffu ? 0u : len[row];
+  uint32_t w = l, t = l;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    w = max(w, __shfl_xor_sync(0xffffffffu, w, o));
+    t += __shfl_xor_sync(0xffffffffu, t, o);
+  }
+  if (lane == 0) {
+    width[s] = w;
+    atomicAdd(entries_true, (unsigned long long)t);
+  }
+  if (s == nslices - 1 && lane == 0)
+    width[nslices] = 0;
+}
+
+__global__ void k_sell_fill(uint32_t nslices, const uint32_t *list, uint64_t n,
+                            const uint32_t *len, const uint32_t *sell_off,
+                            const uint64_t *offs, const uint32_t *cols,
+                            const double *vals, uint32_t *scols, double *svals) {
+  uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (s >= nslices)
+    return;
+  uint64_t pos = (uint64_t)s * B2_SLICE + lane;
+  uint32_t row = list ? list[pos] : (pos < n ? (uint32_t)pos : 0xffffffffu);
+  uint32_t l = 0;
+  uint64_t src = 0;
+  if (row != 0xffffffffu)
+    l = len[row], src = offs[row];
+  uint32_t o = sell_off[s], w = sell_off[s + 1] - o;
+  uint64_t dst = (uint64_t)o * B2_SLICE + lane;
+  // padding multiplies x[own row] (always a valid local index) by zero
+  uint32_t padcol = row == 0xffffffffu ? 0u : row;
+  for (uint32_t k = 0; k < w; k++, dst += B2_SLICE) {
+    bool live = k < l;
+    scols[dst] = live ? cols[src + k] : padcol;
+    svals[dst] = live ? vals[src + k] : 0.0;
+  }
+}
+
+__global__ void k_pad4_len(uint32_t nrows, const uint32_t *ids,
+                           const uint32_t *len, uint64_t *out,
+                           unsigned long long *true_nnz) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nrows) {
+    out[i] = (len[ids[i]] + 3u) & ~3ull;
+    atomicAdd(true_nnz, (unsigned long long)len[ids[i]]);
+  }
+  if (i == nrows)
+    out[i] = 0;
+}
+
+__global__ void k_add_const_u64(uint64_t *p, uint64_t n, uint64_t v) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n)
+    p[i] += v;
+}
+
+// one warp per row of the vector / long bins
+__global__ void k_vl_fill(uint32_t nrows, const uint32_t *ids,
+                          const uint32_t *len, const uint64_t *voff,
+                          const uint64_t *offs, const uint32_t *cols,
+                          const double *vals, uint32_t *vcols, double *vvals) {
+  uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= nrows)
+    return;
+  uint32_t row = ids[r], l = len[row];
+  uint64_t src = offs[row], dst = voff[r], cap = voff[r + 1] - dst;
+  for (uint64_t k = lane; k < cap; k += 32) {
+    bool live = k < l;
+    vcols[dst + k] = live ? cols[src + k] : row;
+    vvals[dst + k] = live ? vals[src + k] : 0.0;
+  }
+}
+
+__global__ void k_inv_diag(uint64_t n, const uint64_t *offs,
+                           const uint32_t *cols, const double *vals,
+                           double *dinv) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  double d = 0.0;
+  for (uint64_t k = offs[i]; k < offs[i + 1]; k++)
+    if (cols[k] == i)
+      d = vals[k];
+  dinv[i] = d != 0.0 ? 1.0 / d : 1.0;
+}
+
+int build_layout(b200_ctx *c, PlainCsr *A, uint64_t n_global,
+                 uint64_t row_begin, uint32_t flags, b200_mat **out) {
+  // NOTE: *out may already carry halo / partition fields; create if null.
+  b200_mat *M = *out ? *out : new b200_mat();
+  *out = M;
+  cudaStream_t s = c->stream;
+  uint64_t n = A->n;
+  M->ctx = c, M->n_global = n_global, M->row_begin = row_begin;
+  M->n_local = n, M->nnz = A->nnz, M->flags = flags;
+  if (n >= 0xffffffffull)
+    B_FAIL(B200_ERANGE, "b200: %llu local rows exceed 32-bit row ids",
+           (unsigned long long)n);
+
+  // ---- row lengths, histogram ------------------------------------------------
+  B_TRY(dev_alloc(M, (void **)&M->row_len, (n + 1) * 4));
+  unsigned long long *d_hist;
+  CU_TRY(cudaMalloc(&d_hist, (B200_HIST_BINS + 2) * 8));
+  CU_TRY(cudaMemsetAsync(d_hist, 0, (B200_HIST_BINS + 2) * 8, s));
+  if (n)
+    k_row_len<<<nblk(n), T256, 0, s>>>(n, A->offs, M->row_len, d_hist,
+                                       d_hist + B200_HIST_BINS);
+  unsigned long long h_hist[B200_HIST_BINS + 2];
+  CU_TRY(cudaMemcpyAsync(h_hist, d_hist, sizeof h_hist, cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  for (int b = 0; b < B200_HIST_BINS; b++)
+    M->hist[b] = h_hist[b];
+  M->max_row_len = h_hist[B200_HIST_BINS];
+
+  // ---- kernel selection by row-length histogram -----------------------------
+  uint32_t sell_max = B2_SELL_MAX, long_min = B2_LONG_MIN;
+  if (flags & B200_MAT_FORCE_VECTOR)
+    sell_max = 0, long_min = 0xffffffffu;  // every row: one warp
+  if (flags & B200_MAT_FORCE_SELL) {
+    if (M->max_row_len > B2_SELL_MAX)
+      B_FAIL(B200_EINVAL, "FORCE_SELL: longest row %llu > %u",
+             (unsigned long long)M->max_row_len, B2_SELL_MAX);
+    long_min = 0xffffffffu;
+  }
+
+  uint32_t *f[3], *p[3], *ids[3] = {nullptr, nullptr, nullptr};
+  uint32_t cnt[3] = {0, 0, 0};
+  bool all_sell = M->max_row_len <= sell_max;
+  if (all_sell) {
+    cnt[0] = (uint32_t)n;
+  } else {
+    for (int b = 0; b < 3; b++) {
+      CU_TRY(cudaMalloc(&f[b], (n + 1) * 4));
+      CU_TRY(cudaMalloc(&p[b], (n + 1) * 4));
+    }
+    k_bin_flags<<<nblk(n + 1), T256, 0, s>>>(n, M->row_len, sell_max, long_min,
+                                             f[0], f[1], f[2]);
+    for (int b = 0; b < 3; b++) {
+      B_TRY(exclusive_scan<uint32_t>(s, f[b], p[b], n + 1));
+      CU_TRY(cudaMemcpy(&cnt[b], p[b] + n, 4, cudaMemcpyDeviceToHost));
+    }
+  }
+  uint64_t sell_padded_rows = ((uint64_t)cnt[0] + B2_SLICE - 1) / B2_SLICE * B2_SLICE;
+  if (!all_sell) {
+    CU_TRY(cudaMalloc(&ids[0], (sell_padded_rows + 1) * 4));
+    CU_TRY(cudaMalloc(&ids[1], (cnt[1] + 1ull) * 4));
+    CU_TRY(cudaMalloc(&ids[2], (cnt[2] + 1ull) * 4));
+    k_fill_u32<<<nblk(sell_padded_rows + 1), T256, 0, s>>>(ids[0], sell_padded_rows + 1, 0xffffffffu);
+    k_scatter_ids<<<nblk(n), T256, 0, s>>>(n, M->row_len, sell_max, long_min,
+                                           p[0], p[1], p[2], ids[0], ids[1], ids[2]);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(s));
+    for (int b = 0; b < 3; b++)
+      cudaFree(f[b]), cudaFree(p[b]);
+  }
+
+  // ---- SELL bin ----------------------------------------------------------------
+  M->sell_rows = cnt[0];
+  M->sell_slices = (uint32_t)(sell_padded_rows / B2_SLICE);
+  if (M->sell_slices) {
+    uint32_t ns = M->sell_slices;
+    uint32_t *width;
+    CU_TRY(cudaMalloc(&width, (ns + 1ull) * 4));
+    unsigned long long *d_true = d_hist;  // reuse
+    auto widths = [&](const uint32_t *list, uint64_t *padded, uint64_t *truth) -> int {
+      CU_TRY(cudaMemsetAsync(d_true, 0, 8, s));
+      k_slice_width<<<nblk((uint64_t)ns * 32), T256, 0, s>>>(ns, list, n, M->row_len, width, d_true);
+      B_TRY(exclusive_scan<uint32_t>(s, width, M->sell_off, ns + 1ull));
+      uint32_t tot = 0;
+      unsigned long long tr = 0;
+      CU_TRY(cudaMemcpy(&tot, M->sell_off + ns, 4, cudaMemcpyDeviceToHost));
+      CU_TRY(cudaMemcpy(&tr, d_true, 8, cudaMemcpyDeviceToHost));
+      *padded = (uint64_t)tot * B2_SLICE, *truth = tr;
+      return B200_OK;
+    };
+    B_TRY(dev_alloc(M, (void **)&M->sell_off, (ns + 1ull) * 4));
+    uint64_t padded = 0, truth = 0;
+    B_TRY(widths(ids[0], &padded, &truth));
+    bool sort = !(flags & B200_MAT_NO_SORT) && truth > 0 &&
+                (double)(padded - truth) > 0.03 * (double)truth;
+    if (sort) {
+      if (!ids[0]) {  // identity list so far: materialise it
+        CU_TRY(cudaMalloc(&ids[0], (sell_padded_rows + 1) * 4));
+        k_fill_u32<<<nblk(sell_padded_rows + 1), T256, 0, s>>>(ids[0], sell_padded_rows + 1, 0xffffffffu);
+        k_iota_u32<<<nblk(n), T256, 0, s>>>(ids[0], n);
+        CU_TRY(cudaGetLastError());
+      }
+      unsigned nwin = (unsigned)((sell_padded_rows + B2_SELL_SIGMA - 1) / B2_SELL_SIGMA);
+      k_window_sort<<<nwin, 256, 0, s>>>(ids[0], sell_padded_rows, M->row_len);
+      CU_TRY(cudaGetLastError());
+      B_TRY(widths(ids[0], &padded, &truth));
+      M->sell_sigma = B2_SELL_SIGMA;
+    }
+    M->sell_entries = padded;
+    B_TRY(dev_alloc(M, (void **)&M->sell_cols, (padded ? padded : 1) * 4));
+    B_TRY(dev_alloc(M, (void **)&M->sell_vals, (padded ? padded : 1) * 8));
+    k_sell_fill<<<nblk((uint64_t)ns * 32), T256, 0, s>>>(
+        ns, ids[0], n, M->row_len, M->sell_off, A->offs, A->cols, A->vals,
+        M->sell_cols, M->sell_vals);
+    CU_TRY(cudaGetLastError());
+    uint32_t wmax = 0;
+    {
+      void *tmp = nullptr;
+      size_t bytes = 0;
+      uint32_t *d_max;
+      CU_TRY(cudaMalloc(&d_max, 4));
+      CU_TRY(cub::DeviceReduce::Max(nullptr, bytes, width, d_max, (int)ns, s));
+      CU_TRY(cudaMalloc(&tmp, bytes ? bytes : 8));
+      CU_TRY(cub::DeviceReduce::Max(tmp, bytes, width, d_max, (int)ns, s));
+      CU_TRY(cudaMemcpyAsync(&wmax, d_max, 4, cudaMemcpyDeviceToHost, s));
+      CU_TRY(cudaStreamSynchronize(s));
+      cudaFree(tmp), cudaFree(d_max);
+    }
+    M->sell_max_width = wmax;
+    cudaFree(width);
+    if (ids[0]) {
+      M->sell_perm = ids[0];
+      M->device_bytes += (sell_padded_rows + 1) * 4;
+      ids[0] = nullptr;
+    }
+  }
+
+  // ---- vector and long bins: one shared row-major store ------------------------
+  M->vec_rows = cnt[1], M->long_rows = cnt[2];
+  if (cnt[1] + cnt[2]) {
+    uint64_t *len4[2] = {nullptr, nullptr};
+    uint64_t tot[2] = {0, 0};
+    uint64_t **offp[2] = {&M->vec_off, &M->long_off};
+    for (int b = 0; b < 2; b++) {
+      uint32_t nr = cnt[1 + b];
+      B_TRY(dev_alloc(M, (void **)offp[b], (nr + 1ull) * 8));
+      CU_TRY(cudaMalloc(&len4[b], (nr + 1ull) * 8));
+      CU_TRY(cudaMemsetAsync(d_hist, 0, 8, s));
+      k_pad4_len<<<nblk(nr + 1ull), T256, 0, s>>>(nr, ids[1 + b], M->row_len, len4[b], d_hist);
+      unsigned long long tn = 0;
+      CU_TRY(cudaMemcpyAsync(&tn, d_hist, 8, cudaMemcpyDeviceToHost, s));
+      CU_TRY(cudaStreamSynchronize(s));
+      (b == 0 ? M->vec_nnz : M->long_nnz) = tn;
+      B_TRY(exclusive_scan<uint64_t>(s, len4[b], *offp[b], nr + 1ull));
+      CU_TRY(cudaMemcpy(&tot[b], *offp[b] + nr, 8, cudaMemcpyDeviceToHost));
+      cudaFree(len4[b]);
+    }
+    // long rows live after the vector rows
+    if (cnt[2])
+      k_add_const_u64<<<nblk(cnt[2] + 1ull), T256, 0, s>>>(M->long_off, cnt[2] + 1ull, tot[0]);
+    M->vl_entries = tot[0] + tot[1];
+    B_TRY(dev_alloc(M, (void **)&M->vl_cols, (M->vl_entries + 4) * 4));
+    B_TRY(dev_alloc(M, (void **)&M->vl_vals, (M->vl_entries + 4) * 8));
+    if (cnt[1])
+      k_vl_fill<<<nblk((uint64_t)cnt[1] * 32), T256, 0, s>>>(
+          cnt[1], ids[1], M->row_len, M->vec_off, A->offs, A->cols, A->vals,
+          M->vl_cols, M->vl_vals);
+    if (cnt[2])
+      k_vl_fill<<<nblk((uint64_t)cnt[2] * 32), T256, 0, s>>>(
+          cnt[2], ids[2], M->row_len, M->long_off, A->offs, A->cols, A->vals,
+          M->vl_cols, M->vl_vals);
+    CU_TRY(cudaGetLastError());
+    M->vec_row_ids = ids[1], M->long_row_ids = ids[2];
+    M->device_bytes += (cnt[1] + cnt[2] + 2ull) * 4;
+    ids[1] = ids[2] = nullptr;
+  }
+
+  // ---- Jacobi preconditioner ------------------------------------------------------
+  // (columns are local ids here; the diagonal of local row i is column i)
+  B_TRY(dev_alloc(M, (void **)&M->dinv, (n + 1) * 8));
+  if (n)
+    k_inv_diag<<<nblk(n), T256, 0, s>>>(n, A->offs, A->cols, A->vals, M->dinv);
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaStreamSynchronize(s));
+  cudaFree(d_hist);
+  for (int b = 0; b < 3; b++)
+    if (ids[b]) cudaFree(ids[b]);
+  if (!M->halo.n_halo)
+    M->interior_begin = 0, M->interior_end = n;
+  return B200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// C ABI
+extern "C" int b200_mat_from_csr(b200_ctx *c, uint32_t nrows, uint32_t base,
+                                 const uint32_t *offs, const uint32_t *cols,
+                                 const double *vals, uint32_t flags,
+                                 b200_mat **out) {
+  if (!c || !offs || !cols || !vals || !out)
+    B_FAIL(B200_EINVAL, "b200_mat_from_csr: null argument");
+  if (base > 1 || nrows == 0)
+    B_FAIL(B200_EINVAL, "b200_mat_from_csr: nrows=%u base=%u", nrows, base);
+  if ((flags & B200_MAT_FORCE_SELL) && (flags & B200_MAT_FORCE_VECTOR))
+    B_FAIL(B200_EINVAL, "b200_mat_from_csr: contradictory FORCE flags");
+  CU_TRY(cudaSetDevice(c->device));
+  *out = nullptr;
+  PlainCsr A;
+  B_TRY(upload_csr(c, nrows, base, offs, cols, vals, &A));
+  uint32_t patsym = 1;
+  if (flags & B200_MAT_SYM_UPPER)
+    B_TRY(sym_upper(c, &A, &patsym));
+  b200_mat *M = new b200_mat();
+  M->pattern_symmetric = patsym;
+  M->ctx = c;
+  int rc = partition_and_renumber(c, &A, nrows, 0, M);
+  if (rc == B200_OK)
+    rc = build_layout(c, &A, nrows, M->row_begin, flags, &M);
+  plain_free(&A);
+  if (rc == B200_OK && c->nranks > 1)
+    rc = halo_setup(M);
+  if (rc != B200_OK) {
+    b200_mat_destroy(M);
+    return rc;
+  }
+  *out = M;
+  return B200_OK;
+}
+
+extern "C" int b200_mat_destroy(b200_mat *M) {
+  if (!M)
+    return B200_OK;
+  if (M->ctx)
+    cudaSetDevice(M->ctx->device);
+  cudaDeviceSynchronize();
+  small_free(M);
+  halo_free(M);
+  if (M->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)M->graph_exec);
+  void *ptrs[] = {M->sell_off, M->sell_cols, M->sell_vals, M->sell_perm,
+                  M->vec_row_ids, M->long_row_ids, M->vec_off, M->long_off,
+                  M->vl_cols, M->vl_vals, M->dinv, M->row_len, M->w_r, M->w_p,
+                  M->w_q, M->x_ext, M->partials, M->state};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  delete M;
+  return B200_OK;
+}
+
+extern "C" int b200_mat_get_info(const b200_mat *M, b200_mat_info *o) {
+  if (!M || !o)
+    B_FAIL(B200_EINVAL, "b200_mat_get_info: null argument");
+  memset(o, 0, sizeof *o);
+  o->n_global = M->n_global, o->row_begin = M->row_begin, o->n_local = M->n_local;
+  o->n_halo = M->halo.n_halo, o->nnz = M->nnz;
+  o->nnz_padded = M->sell_entries + M->vl_entries;
+  o->sell_rows = M->sell_rows, o->sell_slices = M->sell_slices;
+  o->sell_sigma = M->sell_sigma, o->sell_max_width = M->sell_max_width;
+  o->vec_rows = M->vec_rows, o->long_rows = M->long_rows;
+  o->vec_nnz = M->vec_nnz, o->long_nnz = M->long_nnz;
+  o->interior_begin = M->interior_begin, o->interior_end = M->interior_end;
+  memcpy(o->hist, M->hist, sizeof o->hist);
+  o->max_row_len = M->max_row_len;
+  o->pattern_symmetric = M->pattern_symmetric;
+  o->sell_perm = M->sell_perm != nullptr;
+  o->device_bytes = M->device_bytes;
+  return B200_OK;
+}
+
+extern "C" int b200_mat_algorithmic_bytes(const b200_mat *M, uint64_t *spmv,
+                                          uint64_t *pcg) {
+  if (!M)
+    B_FAIL(B200_EINVAL, "b200_mat_algorithmic_bytes: null matrix");
+  uint64_t mat = 12 * M->nnz + 4 * (M->n_local + 1);
+  if (spmv) *spmv = mat + 16 * M->n_local;
+  if (pcg) *pcg = mat + 104 * M->n_local;
+  return B200_OK;
+}
+
+// ---- export: what the layout represents, in original row order -----------------
+__global__ void k_export_sell(uint32_t nslices, const uint32_t *list, uint64_t n,
+                              const uint32_t *len, const uint32_t *sell_off,
+                              const uint32_t *scols, const double *svals,
+                              const uint64_t *ooffs, uint32_t *ocols, double *ovals) {
+  uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (s >= nslices)
+    return;
+  uint64_t pos = (uint64_t)s * B2_SLICE + lane;
+  uint32_t row = list ? list[pos] : (pos < n ? (uint32_t)pos : 0xffffffffu);
+  if (row == 0xffffffffu)
+    return;
+  uint64_t src = (uint64_t)sell_off[s] * B2_SLICE + lane, dst = ooffs[row];
+  for (uint32_t k = 0; k < len[row]; k++, src += B2_SLICE)
+    ocols[dst + k] = scols[src], ovals[dst + k] = svals[src];
+}
+
+__global__ void k_export_vl(uint32_t nrows, const uint32_t *ids,
+                            const uint32_t *len, const uint64_t *voff,
+                            const uint32_t *vcols, const double *vvals,
+                            const uint64_t *ooffs, uint32_t *ocols, double *ovals) {
+  uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= nrows)
+    return;
+  uint32_t row = ids[r];
+  uint64_t src = voff[r], dst = ooffs[row];
+  for (uint32_t k = lane; k < len[row]; k += 32)
+    ocols[dst + k] = vcols[src + k], ovals[dst + k] = vvals[src + k];
+}
+
+__global__ void k_u32_to_u64(const uint32_t *in, uint64_t *out, uint64_t n) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n)
+    out[i] = in[i];
+  if (i == n)
+    out[i] = 0;
+}
+
+extern "C" int b200_mat_export(const b200_mat *M, uint64_t *offs,
+                               uint32_t *cols, double *vals) {
+  if (!M)
+    B_FAIL(B200_EINVAL, "b200_mat_export: null matrix");
+  b200_ctx *c = M->ctx;
+  CU_TRY(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  uint64_t n = M->n_local;
+  uint64_t *l64, *ooffs;
+  CU_TRY(cudaMalloc(&l64, (n + 1) * 8));
+  CU_TRY(cudaMalloc(&ooffs, (n + 1) * 8));
+  k_u32_to_u64<<<nblk(n + 1), T256, 0, s>>>(M->row_len, l64, n);
+  B_TRY(exclusive_scan<uint64_t>(s, l64, ooffs, n + 1));
+  if (offs)
+    CU_TRY(cudaMemcpy(offs, ooffs, (n + 1) * 8, cudaMemcpyDeviceToHost));
+  if (cols && vals) {
+    uint32_t *oc;
+    double *ov;
+    CU_TRY(cudaMalloc(&oc, (M->nnz ? M->nnz : 1) * 4));
+    CU_TRY(cudaMalloc(&ov, (M->nnz ? M->nnz : 1) * 8));
+    if (M->sell_slices)
+      k_export_sell<<<nblk((uint64_t)M->sell_slices * 32), T256, 0, s>>>(
+          M->sell_slices, M->sell_perm, n, M->row_len, M->sell_off,
+          M->sell_cols, M->sell_vals, ooffs, oc, ov);
+    if (M->vec_rows)
+      k_export_vl<<<nblk((uint64_t)M->vec_rows * 32), T256, 0, s>>>(
+          M->vec_rows, M->vec_row_ids, M->row_len, M->vec_off, M->vl_cols,
+          M->vl_vals, ooffs, oc, ov);
+    if (M->long_rows)
+      k_export_vl<<<nblk((uint64_t)M->long_rows * 32), T256, 0, s>>>(
+          M->long_rows, M->long_row_ids, M->row_len, M->long_off, M->vl_cols,
+          M->vl_vals, ooffs, oc, ov);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(cols, oc, M->nnz * 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(vals, ov, M->nnz * 8, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    cudaFree(oc), cudaFree(ov);
+  }
+  cudaFree(l64), cudaFree(ooffs);
+  return B200_OK;
+}
+
+extern "C" int b200_mat_inv_diag(const b200_mat *M, double *h) {
+  if (!M || !h)
+    B_FAIL(B200_EINVAL, "b200_mat_inv_diag: null argument");
+  CU_TRY(cudaSetDevice(M->ctx->device));
+  CU_TRY(cudaMemcpy(h, M->dinv, M->n_local * 8, cudaMemcpyDeviceToHost));
+  return B200_OK;
+}

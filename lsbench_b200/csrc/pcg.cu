@@ -1,0 +1,376 @@
+// pcg.cu -- north_star piece (3): Jacobi-preconditioned CG with the vector
+// work fused into three HBM passes per iteration.
+//
+// Stands where the timed solve of a reference backend stands
+// (src/cusparse.c:189-197 cusolverSpDcsrlsvchol, src/cholmod-impl.h:58-63
+// cholmod_l_solve, src/ginkgo.cpp:91-99 solver->apply); protocol per the
+// Ginkgo wiring, the one Krylov precedent: Jacobi preconditioner, relative
+// residual stop (src/ginkgo.cpp:55-64), x reset by the caller per trial (:92).
+//
+//   K1  q = A p            + p.q          (spmv.cu, fused dot)
+//   K2  x += a p; r -= a q + r.D^-1 r, r.r
+//   K3  p = D^-1 r + b p
+//
+// Algorithmic bytes / iteration: 12 nnz + 4 (n+1) + 104 n.
+// alpha, beta, the convergence test and the iteration count live on the
+// device (PcgState); the host queues `check_every` iterations at a time and
+// only then looks at one pinned word, so there is no per-iteration sync, and
+// iterations queued past convergence return at their first instruction.
+// Every reduction has a fixed order (common.cuh grid_sum_finish), hence
+// bit-identical iterates and iteration counts run to run.
+#include "common.cuh"
+
+#define EW_THREADS 256
+#define EW_WARPS (EW_THREADS / 32)
+
+int spmv_full_internal(b200_mat *M, double *x_ext, double *y, bool dot);
+
+// r = b - q (q = A x0), p = D^-1 r; partial sums of r.z, r.r, b.b
+__global__ void __launch_bounds__(EW_THREADS)
+k_pcg_init(uint64_t n, const double *__restrict__ b, const double *__restrict__ q,
+           const double *__restrict__ dinv, double *__restrict__ r,
+           double *__restrict__ p, double *partials, unsigned stride,
+           PcgState *st) {
+  __shared__ double red[EW_WARPS];
+  double s[3] = {0.0, 0.0, 0.0};
+  for (uint64_t i = blockIdx.x * (uint64_t)EW_THREADS + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * EW_THREADS) {
+    double bi = b[i], ri = bi - q[i], zi = dinv[i] * ri;
+    r[i] = ri, p[i] = zi;
+    s[0] = fma(ri, zi, s[0]), s[1] = fma(ri, ri, s[1]), s[2] = fma(bi, bi, s[2]);
+  }
+  double bs[3];
+#pragma unroll
+  for (int v = 0; v < 3; v++)
+    bs[v] = block_sum<EW_WARPS>(s[v], red);
+  grid_sum_finish<3, EW_WARPS>(bs, partials, stride, blockIdx.x, gridDim.x,
+                               &st->ticket[1], &st->red[4], red);
+}
+
+__global__ void k_pcg_start(PcgState *st, double tol, int maxit) {
+  st->red[0] = st->red[4], st->red[1] = st->red[5];
+  st->bb = st->red[6];
+  st->tol = tol, st->thr2 = tol * tol * st->bb;
+  st->iter = 0, st->maxit = maxit, st->status = 1, st->done = 0;
+  st->pq = 0.0;
+  if (st->red[5] <= st->thr2)
+    st->done = 1, st->status = 0;  // x0 already solves it
+  else if (maxit <= 0)
+    st->done = 1;
+}
+
+// K2
+__global__ void __launch_bounds__(EW_THREADS)
+k_pcg_update(uint64_t n, double *__restrict__ x, double *__restrict__ r,
+             const double *__restrict__ p, const double *__restrict__ q,
+             const double *__restrict__ dinv, double *partials, unsigned stride,
+             PcgState *st, int par) {
+  if (st->done)
+    return;
+  __shared__ double red[EW_WARPS];
+  const double pq = st->pq, rz = st->red[par * 2];
+  if (!(pq > 0.0)) {  // not SPD, or NaN crept in: SURVEY 5 breakdown guard
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+      st->done = 1, st->status = 2;
+    return;
+  }
+  const double alpha = rz / pq;
+  double s[2] = {0.0, 0.0};
+  const uint64_t stride_e = (uint64_t)gridDim.x * EW_THREADS;
+  uint64_t i = blockIdx.x * (uint64_t)EW_THREADS + threadIdx.x;
+  // two elements in flight per thread
+  for (; i + stride_e < n; i += 2 * stride_e) {
+    const uint64_t j = i + stride_e;
+    double xi = x[i], pi = __ldcs(p + i), ri = r[i], qi = __ldcs(q + i), di = __ldcs(dinv + i);
+    double xj = x[j], pj = __ldcs(p + j), rj = r[j], qj = __ldcs(q + j), dj = __ldcs(dinv + j);
+    xi = fma(alpha, pi, xi), ri = fma(-alpha, qi, ri);
+    xj = fma(alpha, pj, xj), rj = fma(-alpha, qj, rj);
+    x[i] = xi, r[i] = ri, x[j] = xj, r[j] = rj;
+    s[0] = fma(ri, di * ri, s[0]), s[1] = fma(ri, ri, s[1]);
+    s[0] = fma(rj, dj * rj, s[0]), s[1] = fma(rj, rj, s[1]);
+  }
+  if (i < n) {
+    double xi = x[i], pi = p[i], ri = r[i], qi = q[i], di = dinv[i];
+    xi = fma(alpha, pi, xi), ri = fma(-alpha, qi, ri);
+    x[i] = xi, r[i] = ri;
+    s[0] = fma(ri, di * ri, s[0]), s[1] = fma(ri, ri, s[1]);
+  }
+  double bs[2];
+  bs[0] = block_sum<EW_WARPS>(s[0], red);
+  bs[1] = block_sum<EW_WARPS>(s[1], red);
+  grid_sum_finish<2, EW_WARPS>(bs, partials, stride, blockIdx.x, gridDim.x,
+                               &st->ticket[2], &st->red[(par ^ 1) * 2], red);
+}
+
+// K3 (also owns the convergence decision and the iteration counter)
+__global__ void __launch_bounds__(EW_THREADS)
+k_pcg_pupdate(uint64_t n, const double *__restrict__ r,
+              const double *__restrict__ dinv, double *__restrict__ p,
+              PcgState *st, int par) {
+  if (st->done)
+    return;
+  const double rzn = st->red[(par ^ 1) * 2], rr = st->red[(par ^ 1) * 2 + 1];
+  const double rz = st->red[par * 2];
+  const bool conv = rr <= st->thr2;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int it = st->iter + 1;
+    st->iter = it;
+    if (conv)
+      st->done = 1, st->status = 0;
+    else if (!(rr == rr))
+      st->done = 1, st->status = 2;
+    else if (it >= st->maxit)
+      st->done = 1, st->status = 1;
+  }
+  if (conv)
+    return;
+  const double beta = rzn / rz;
+  const uint64_t stride_e = (uint64_t)gridDim.x * EW_THREADS;
+  uint64_t i = blockIdx.x * (uint64_t)EW_THREADS + threadIdx.x;
+  for (; i + stride_e < n; i += 2 * stride_e) {
+    const uint64_t j = i + stride_e;
+    double ri = __ldcs(r + i), di = __ldcs(dinv + i), pi = p[i];
+    double rj = __ldcs(r + j), dj = __ldcs(dinv + j), pj = p[j];
+    p[i] = fma(beta, pi, di * ri);
+    p[j] = fma(beta, pj, dj * rj);
+  }
+  if (i < n)
+    p[i] = fma(beta, p[i], dinv[i] * r[i]);
+}
+
+// ||b - A x||^2 for the exit check (q = A x)
+__global__ void __launch_bounds__(EW_THREADS)
+k_true_resid(uint64_t n, const double *__restrict__ b, const double *__restrict__ q,
+             double *partials, unsigned stride, PcgState *st) {
+  __shared__ double red[EW_WARPS];
+  double s = 0.0;
+  for (uint64_t i = blockIdx.x * (uint64_t)EW_THREADS + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * EW_THREADS) {
+    double d = b[i] - q[i];
+    s = fma(d, d, s);
+  }
+  double bs[1] = {block_sum<EW_WARPS>(s, red)};
+  grid_sum_finish<1, EW_WARPS>(bs, partials, stride, blockIdx.x, gridDim.x,
+                               &st->ticket[3], &st->true_rr, red);
+}
+
+// ---------------------------------------------------------------------------
+int ensure_workspace(b200_mat *M) {
+  if (M->state)
+    return B200_OK;
+  b200_ctx *c = M->ctx;
+  uint64_t n = M->n_local, ne = n + M->halo.n_halo;
+  B_TRY(dev_alloc(M, (void **)&M->w_r, (n + 2) * 8));
+  B_TRY(dev_alloc(M, (void **)&M->w_p, (ne + 2) * 8));
+  B_TRY(dev_alloc(M, (void **)&M->w_q, (n + 2) * 8));
+  B_TRY(dev_alloc(M, (void **)&M->w_x, (n + 2) * 8));
+  B_TRY(dev_alloc(M, (void **)&M->x_ext, (ne + 2) * 8));
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_update,
+                                                    EW_THREADS, 0) != cudaSuccess ||
+      per_sm < 1)
+    per_sm = 4;
+  if (per_sm > 8)
+    per_sm = 8;
+  uint64_t g = (uint64_t)c->sm_count * per_sm;
+  uint64_t need = (n + EW_THREADS - 1) / EW_THREADS;
+  if (g > need)
+    g = need;
+  M->grid_ew = g < 1 ? 1 : (int)g;
+  // partial slots: the larger of the SpMV CTA count and the element-wise grid
+  unsigned slots = (unsigned)c->sm_count * 32 * 3 + 64;
+  M->partial_stride = slots;
+  B_TRY(dev_alloc(M, (void **)&M->partials, (size_t)slots * 3 * 8));
+  B_TRY(dev_alloc(M, (void **)&M->state, sizeof(PcgState)));
+  CU_TRY(cudaMemsetAsync(M->state, 0, sizeof(PcgState), c->stream));
+  return B200_OK;
+}
+
+static int reduce_ranks(b200_mat *M, double *d_vals, int count) {
+  if (M->ctx->nranks == 1)
+    return B200_OK;
+  return allreduce_sum(M->ctx, d_vals, count);
+}
+
+static int queue_iteration(b200_mat *M, int par) {
+  b200_ctx *c = M->ctx;
+  cudaStream_t s = c->stream;
+  uint64_t n = M->n_local;
+  B_TRY(spmv_full_internal(M, M->w_p, M->w_q, true));  // K1
+  B_TRY(reduce_ranks(M, &M->state->pq, 1));
+  k_pcg_update<<<M->grid_ew, EW_THREADS, 0, s>>>(n, M->w_x, M->w_r, M->w_p,
+                                                 M->w_q, M->dinv, M->partials,
+                                                 M->partial_stride, M->state, par);
+  B_TRY(reduce_ranks(M, &M->state->red[(par ^ 1) * 2], 2));
+  k_pcg_pupdate<<<M->grid_ew, EW_THREADS, 0, s>>>(n, M->w_r, M->dinv, M->w_p,
+                                                  M->state, par);
+  CU_TRY(cudaGetLastError());
+  return B200_OK;
+}
+
+// One graph = `chunk` (even) iterations; replayed until the device says done.
+static int ensure_graph(b200_mat *M, int chunk) {
+  if (M->graph_exec && M->graph_chunk == chunk && M->graph_stream == (void *)M->ctx->stream)
+    return B200_OK;
+  if (M->graph_exec) {
+    cudaGraphExecDestroy((cudaGraphExec_t)M->graph_exec);
+    M->graph_exec = nullptr;
+  }
+  cudaStream_t s = M->ctx->stream;
+  cudaGraph_t g = nullptr;
+  CU_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  int rc = B200_OK;
+  for (int i = 0; i < chunk && rc == B200_OK; i++)
+    rc = queue_iteration(M, i & 1);
+  cudaError_t e = cudaStreamEndCapture(s, &g);
+  if (rc != B200_OK)
+    return rc;
+  CU_TRY(e);
+  cudaGraphExec_t ge = nullptr;
+  CU_TRY(cudaGraphInstantiate(&ge, g, 0));
+  cudaGraphDestroy(g);
+  M->graph_exec = ge, M->graph_chunk = chunk, M->graph_stream = (void *)s;
+  return B200_OK;
+}
+
+extern "C" int b200_pcg_solve(b200_mat *M, const double *d_b, double *d_x,
+                              const b200_pcg_opts *o, b200_pcg_result *res) {
+  if (!M || !d_b || !d_x || !o || !res)
+    B_FAIL(B200_EINVAL, "b200_pcg_solve: null argument");
+  if (!(o->tol > 0.0) || o->maxit < 0)
+    B_FAIL(B200_EINVAL, "b200_pcg_solve: tol=%g maxit=%d", o->tol, o->maxit);
+  b200_ctx *c = M->ctx;
+  CU_TRY(cudaSetDevice(c->device));
+  memset(res, 0, sizeof *res);
+  if (!(o->flags & B200_PCG_NO_SMALL) && c->nranks == 1) {
+    B_TRY(small_try_build(M));
+    if (M->small)
+      return small_solve(M, d_b, d_x, o, res);
+  }
+  B_TRY(ensure_workspace(M));
+  cudaStream_t s = c->stream;
+  const uint64_t n = M->n_local;
+  const bool timing = o->flags & B200_PCG_TIME_KERNELS;
+  int chunk = o->check_every > 0 ? o->check_every : 32;
+  chunk = (chunk + 1) & ~1;  // even: the parity pattern repeats per chunk
+  const bool use_graph = !(o->flags & B200_PCG_NO_GRAPH) && !timing;
+  int launches = 0;
+
+  CU_TRY(cudaEventRecord(c->ev_a, s));
+  // ---- start-up: r = b - A x0, p = D^-1 r ---------------------------------------
+  CU_TRY(cudaMemcpyAsync(M->w_x, d_x, n * 8, cudaMemcpyDeviceToDevice, s));
+  CU_TRY(cudaMemcpyAsync(M->w_p, d_x, n * 8, cudaMemcpyDeviceToDevice, s));
+  B_TRY(spmv_full_internal(M, M->w_p, M->w_q, false));
+  k_pcg_init<<<M->grid_ew, EW_THREADS, 0, s>>>(n, d_b, M->w_q, M->dinv, M->w_r,
+                                               M->w_p, M->partials,
+                                               M->partial_stride, M->state);
+  B_TRY(reduce_ranks(M, &M->state->red[4], 3));
+  k_pcg_start<<<1, 1, 0, s>>>(M->state, o->tol, o->maxit);
+  CU_TRY(cudaGetLastError());
+  launches += 3;
+
+  // ---- iterations ---------------------------------------------------------------
+  volatile int *flag = c->h_flag;  // {iter, done, status, maxit}
+  int queued = 0;
+  float t_cls[3] = {0, 0, 0};
+  int timed_iters = 0;
+  for (;;) {
+    CU_TRY(cudaMemcpyAsync((void *)flag, &M->state->iter, 16, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaEventRecord(c->ev_ready, s));
+    CU_TRY(cudaEventSynchronize(c->ev_ready));
+    if (flag[1] || queued >= o->maxit)
+      break;
+    if (timing && timed_iters == 0) {
+      // per-class device time over one chunk, events on the launch stream
+      cudaEvent_t ev[4];
+      for (auto &e : ev)
+        CU_TRY(cudaEventCreate(&e));
+      for (int i = 0; i < chunk; i++) {
+        int par = i & 1;
+        CU_TRY(cudaEventRecord(ev[0], s));
+        B_TRY(spmv_full_internal(M, M->w_p, M->w_q, true));
+        B_TRY(reduce_ranks(M, &M->state->pq, 1));
+        CU_TRY(cudaEventRecord(ev[1], s));
+        k_pcg_update<<<M->grid_ew, EW_THREADS, 0, s>>>(
+            n, M->w_x, M->w_r, M->w_p, M->w_q, M->dinv, M->partials,
+            M->partial_stride, M->state, par);
+        B_TRY(reduce_ranks(M, &M->state->red[(par ^ 1) * 2], 2));
+        CU_TRY(cudaEventRecord(ev[2], s));
+        k_pcg_pupdate<<<M->grid_ew, EW_THREADS, 0, s>>>(n, M->w_r, M->dinv,
+                                                        M->w_p, M->state, par);
+        CU_TRY(cudaEventRecord(ev[3], s));
+        CU_TRY(cudaEventSynchronize(ev[3]));
+        for (int k = 0; k < 3; k++) {
+          float t;
+          CU_TRY(cudaEventElapsedTime(&t, ev[k], ev[k + 1]));
+          t_cls[k] += t;
+        }
+      }
+      timed_iters = chunk;
+      for (auto &e : ev)
+        cudaEventDestroy(e);
+    } else if (use_graph) {
+      B_TRY(ensure_graph(M, chunk));
+      CU_TRY(cudaGraphLaunch((cudaGraphExec_t)M->graph_exec, s));
+    } else {
+      for (int i = 0; i < chunk; i++)
+        B_TRY(queue_iteration(M, i & 1));
+    }
+    queued += chunk;
+    launches += chunk * 3;
+  }
+
+  // ---- exit: true residual with one more SpMV -----------------------------------
+  CU_TRY(cudaMemcpyAsync(M->w_p, M->w_x, n * 8, cudaMemcpyDeviceToDevice, s));
+  B_TRY(spmv_full_internal(M, M->w_p, M->w_q, false));
+  k_true_resid<<<M->grid_ew, EW_THREADS, 0, s>>>(n, d_b, M->w_q, M->partials,
+                                                 M->partial_stride, M->state);
+  B_TRY(reduce_ranks(M, &M->state->true_rr, 1));
+  CU_TRY(cudaMemcpyAsync(d_x, M->w_x, n * 8, cudaMemcpyDeviceToDevice, s));
+  launches += 2;
+  CU_TRY(cudaEventRecord(c->ev_b, s));
+  PcgState h;
+  CU_TRY(cudaMemcpyAsync(&h, M->state, sizeof h, cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  CU_TRY(cudaEventElapsedTime(&res->solve_ms, c->ev_a, c->ev_b));
+
+  const int parity = h.iter & 1;  // {rz, rr} of the last finished iteration
+  double rr = h.iter == 0 ? h.red[1] : h.red[parity * 2 + 1];
+  res->iters = h.iter, res->status = h.status;
+  res->bnorm = sqrt(h.bb);
+  res->relres = h.bb > 0 ? sqrt(rr / h.bb) : sqrt(rr);
+  res->true_relres = h.bb > 0 ? sqrt(h.true_rr / h.bb) : sqrt(h.true_rr);
+  res->kernel_launches = launches;
+  res->path = 0;
+  if (timed_iters) {
+    res->spmv_ms = t_cls[0] / timed_iters;
+    res->update_ms = t_cls[1] / timed_iters;
+    res->pupdate_ms = t_cls[2] / timed_iters;
+  }
+  if (h.status == 2)
+    B_FAIL(B200_ENOTSPD, "b200_pcg_solve: breakdown at iteration %d (p.Ap = %g)",
+           h.iter, h.pq);
+  return B200_OK;
+}
+
+extern "C" int b200_pcg_solve_host(b200_mat *M, const double *h_b, double *h_x,
+                                   const b200_pcg_opts *o, b200_pcg_result *res) {
+  if (!M || !h_b || !h_x || !o || !res)
+    B_FAIL(B200_EINVAL, "b200_pcg_solve_host: null argument");
+  b200_ctx *c = M->ctx;
+  CU_TRY(cudaSetDevice(c->device));
+  const uint64_t n = M->n_local;
+  double *d_b = nullptr, *d_x = nullptr;
+  CU_TRY(cudaMalloc(&d_b, (n + 1) * 8));
+  CU_TRY(cudaMalloc(&d_x, (n + 1) * 8));
+  cudaStream_t s = c->stream;
+  CU_TRY(cudaMemcpyAsync(d_b, h_b, n * 8, cudaMemcpyHostToDevice, s));
+  CU_TRY(cudaMemcpyAsync(d_x, h_x, n * 8, cudaMemcpyHostToDevice, s));
+  int rc = b200_pcg_solve(M, d_b, d_x, o, res);
+  if (rc == B200_OK || rc == B200_ENOTSPD) {
+    cudaMemcpyAsync(h_x, d_x, n * 8, cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+  }
+  cudaFree(d_b), cudaFree(d_x);
+  return rc;
+}

@@ -1,0 +1,355 @@
+// spmv.cu -- north_star piece (2): fp64 SpMV y = A x on the device layout of
+// convert.cu, optionally fused with the CG dot product p.Ap.
+//
+// No reference counterpart (the reference has no SpMV of its own;
+// its backends hand the CSR to cuSOLVER / CHOLMOD / Ginkgo).  HBM-bound:
+// algorithmic bytes 12 nnz + 4 (n+1) + 16 n, no tensor cores.
+//
+//   k_spmv_sell  one warp per 32-row slice, one row per lane, column-major
+//                slice: cols / vals warp loads are single aligned 128 B /
+//                256 B segments (read once, streaming hint), x is gathered
+//                through L1/L2 (__ldg), each lane sums its row left to right
+//                (same order as a host CSR loop => bit-identical to it when
+//                the host uses fma).
+//   k_spmv_vec   one warp per row, 128-bit col / val loads, fixed butterfly
+//                warp-shuffle reduction.
+//   k_spmv_long  one CTA per row for the power-law tail.
+//
+// All grids are persistent (a multiple of the SM count) so the per-CTA
+// partials of the fused dot have a fixed count and a fixed summation order.
+#include "common.cuh"
+
+#define SPMV_THREADS 256
+#define SPMV_WARPS (SPMV_THREADS / 32)
+
+template <bool DOT>
+__global__ void __launch_bounds__(SPMV_THREADS, 4)
+k_spmv_sell(const uint32_t *__restrict__ sell_off,
+            const uint32_t *__restrict__ cols, const double *__restrict__ vals,
+            const uint32_t *__restrict__ perm, const double *__restrict__ x,
+            double *__restrict__ y, uint32_t b0, uint32_t e0, uint32_t b1,
+            uint32_t e1, uint32_t n_rows, double *partials, unsigned slot_base,
+            unsigned total_slots, PcgState *st) {
+  if (DOT && st->done)
+    return;
+  __shared__ double red[SPMV_WARPS];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t n0 = e0 - b0, nv = n0 + (e1 - b1);
+  const uint32_t stride = gridDim.x * SPMV_WARPS;
+  double dot = 0.0;
+  for (uint32_t v = blockIdx.x * SPMV_WARPS + warp; v < nv; v += stride) {
+    const uint32_t s = v < n0 ? b0 + v : b1 + (v - n0);
+    const uint32_t o = __ldg(sell_off + s);
+    const uint32_t w = __ldg(sell_off + s + 1) - o;
+    const size_t base = (size_t)o * B2_SLICE + lane;
+    const uint32_t *cp = cols + base;
+    const double *vp = vals + base;
+    double sum = 0.0;
+    uint32_t k = 0;
+    for (; k + 8 <= w; k += 8) {
+      uint32_t c[8];
+      double a[8], xv[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        c[j] = ld_stream(cp + (size_t)(k + j) * B2_SLICE);
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        a[j] = ld_stream(vp + (size_t)(k + j) * B2_SLICE);
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        xv[j] = __ldg(x + c[j]);
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        sum = fma(a[j], xv[j], sum);
+    }
+    if (k < w) {
+      const uint32_t rem = w - k;
+      uint32_t c[8];
+      double a[8], xv[8];
+#pragma unroll
+      for (int j = 0; j < 7; j++)
+        c[j] = j < rem ? ld_stream(cp + (size_t)(k + j) * B2_SLICE) : 0u;
+#pragma unroll
+      for (int j = 0; j < 7; j++)
+        a[j] = j < rem ? ld_stream(vp + (size_t)(k + j) * B2_SLICE) : 0.0;
+#pragma unroll
+      for (int j = 0; j < 7; j++)
+        xv[j] = j < rem ? __ldg(x + c[j]) : 0.0;
+#pragma unroll
+      for (int j = 0; j < 7; j++)
+        if (j < rem)
+          sum = fma(a[j], xv[j], sum);
+    }
+    const uint32_t pos = s * B2_SLICE + lane;
+    const uint32_t row = perm ? __ldg(perm + pos) : pos;
+    if (row < n_rows) {
+      y[row] = sum;
+      if (DOT)
+        dot = fma(sum, __ldg(x + row), dot);
+    }
+  }
+  if (DOT) {
+    double b[1] = {block_sum<SPMV_WARPS>(dot, red)};
+    grid_sum_finish<1, SPMV_WARPS>(b, partials, 0, slot_base + blockIdx.x,
+                                   total_slots, &st->ticket[0], &st->pq, red);
+  }
+}
+
+template <bool DOT>
+__global__ void __launch_bounds__(SPMV_THREADS, 4)
+k_spmv_vec(uint32_t nrows, const uint32_t *__restrict__ ids,
+           const uint64_t *__restrict__ off, const uint32_t *__restrict__ cols,
+           const double *__restrict__ vals, const double *__restrict__ x,
+           double *__restrict__ y, double *partials, unsigned slot_base,
+           unsigned total_slots, PcgState *st) {
+  if (DOT && st->done)
+    return;
+  __shared__ double red[SPMV_WARPS];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t stride = gridDim.x * SPMV_WARPS;
+  double dot = 0.0;
+  for (uint32_t r = blockIdx.x * SPMV_WARPS + warp; r < nrows; r += stride) {
+    const uint64_t s = __ldg(off + r), e = __ldg(off + r + 1);
+    double sum = 0.0;
+    for (uint64_t k = s + lane * 4; k < e; k += 128) {
+      const uint4 c = __ldcs(reinterpret_cast<const uint4 *>(cols + k));
+      const double2 v01 = __ldcs(reinterpret_cast<const double2 *>(vals + k));
+      const double2 v23 = __ldcs(reinterpret_cast<const double2 *>(vals + k + 2));
+      const double x0 = __ldg(x + c.x), x1 = __ldg(x + c.y),
+                   x2 = __ldg(x + c.z), x3 = __ldg(x + c.w);
+      sum = fma(v01.x, x0, sum);
+      sum = fma(v01.y, x1, sum);
+      sum = fma(v23.x, x2, sum);
+      sum = fma(v23.y, x3, sum);
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) {
+      const uint32_t row = __ldg(ids + r);
+      y[row] = sum;
+      if (DOT)
+        dot = fma(sum, __ldg(x + row), dot);
+    }
+  }
+  if (DOT) {
+    double b[1] = {block_sum<SPMV_WARPS>(dot, red)};
+    grid_sum_finish<1, SPMV_WARPS>(b, partials, 0, slot_base + blockIdx.x,
+                                   total_slots, &st->ticket[0], &st->pq, red);
+  }
+}
+
+template <bool DOT>
+__global__ void __launch_bounds__(SPMV_THREADS, 4)
+k_spmv_long(uint32_t nrows, const uint32_t *__restrict__ ids,
+            const uint64_t *__restrict__ off, const uint32_t *__restrict__ cols,
+            const double *__restrict__ vals, const double *__restrict__ x,
+            double *__restrict__ y, double *partials, unsigned slot_base,
+            unsigned total_slots, PcgState *st) {
+  if (DOT && st->done)
+    return;
+  __shared__ double red[SPMV_WARPS];
+  double dot = 0.0;
+  for (uint32_t r = blockIdx.x; r < nrows; r += gridDim.x) {
+    const uint64_t s = __ldg(off + r), e = __ldg(off + r + 1);
+    double sum = 0.0;
+    for (uint64_t k = s + threadIdx.x * 4; k < e; k += SPMV_THREADS * 4) {
+      const uint4 c = __ldcs(reinterpret_cast<const uint4 *>(cols + k));
+      const double2 v01 = __ldcs(reinterpret_cast<const double2 *>(vals + k));
+      const double2 v23 = __ldcs(reinterpret_cast<const double2 *>(vals + k + 2));
+      const double x0 = __ldg(x + c.x), x1 = __ldg(x + c.y),
+                   x2 = __ldg(x + c.z), x3 = __ldg(x + c.w);
+      sum = fma(v01.x, x0, sum);
+      sum = fma(v01.y, x1, sum);
+      sum = fma(v23.x, x2, sum);
+      sum = fma(v23.y, x3, sum);
+    }
+    sum = block_sum<SPMV_WARPS>(sum, red);
+    if (threadIdx.x == 0) {
+      const uint32_t row = __ldg(ids + r);
+      y[row] = sum;
+      if (DOT)
+        dot = fma(sum, __ldg(x + row), dot);
+    }
+  }
+  if (DOT) {
+    // only thread 0 carries a value; block_sum keeps the protocol uniform
+    double b[1] = {block_sum<SPMV_WARPS>(dot, red)};
+    grid_sum_finish<1, SPMV_WARPS>(b, partials, 0, slot_base + blockIdx.x,
+                                   total_slots, &st->ticket[0], &st->pq, red);
+  }
+}
+
+// ---------------------------------------------------------------------------
+static int persistent_grid(b200_ctx *c, const void *kernel, uint64_t work_ctas) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel,
+                                                    SPMV_THREADS, 0) != cudaSuccess ||
+      per_sm < 1)
+    per_sm = 4;
+  uint64_t g = (uint64_t)c->sm_count * per_sm;
+  if (g > work_ctas)
+    g = work_ctas;
+  return g < 1 ? 1 : (int)g;
+}
+
+static SpmvPlan compute_plan(b200_mat *M, int phase) {
+  SpmvPlan P = {0, 0, 0, 0, 0, 0, 0};
+  b200_ctx *c = M->ctx;
+  uint32_t ns = M->sell_slices;
+  // Slices that hold only interior rows.  With a permuted SELL list the
+  // windows are B2_SELL_SIGMA rows wide, so round inward to window multiples.
+  uint32_t ib = 0, ie = ns;
+  if (M->halo.n_halo) {
+    if (M->sell_perm && (M->vec_rows || M->long_rows)) {
+      ib = ie = 0;  // compacted list: slice <-> row range is not monotone
+    } else {
+      uint64_t g = M->sell_perm ? M->sell_sigma : B2_SLICE;
+      uint64_t lo = (M->interior_begin + g - 1) / g * g;
+      uint64_t hi = M->interior_end / g * g;
+      if (hi > lo)
+        ib = (uint32_t)(lo / B2_SLICE), ie = (uint32_t)(hi / B2_SLICE);
+      else
+        ib = ie = 0;
+    }
+  }
+  bool others = true;
+  if (phase == 0)
+    P.b0 = 0, P.e0 = ns;
+  else if (phase == 1)
+    P.b0 = ib, P.e0 = ie, others = false;
+  else
+    P.b0 = 0, P.e0 = ib, P.b1 = ie, P.e1 = ns;
+  uint32_t nv = (P.e0 - P.b0) + (P.e1 - P.b1);
+  if (nv)
+    P.g_sell = persistent_grid(c, (const void *)k_spmv_sell<true>,
+                               (nv + SPMV_WARPS - 1) / SPMV_WARPS);
+  if (others && M->vec_rows)
+    P.g_vec = persistent_grid(c, (const void *)k_spmv_vec<true>,
+                              (M->vec_rows + SPMV_WARPS - 1) / SPMV_WARPS);
+  if (others && M->long_rows)
+    P.g_long = persistent_grid(c, (const void *)k_spmv_long<true>, M->long_rows);
+  return P;
+}
+
+static const SpmvPlan &plan_phase(b200_mat *M, int phase) {
+  if (!M->plan_ready) {
+    for (int p = 0; p < 3; p++)
+      M->plan[p] = compute_plan(M, p);
+    M->plan_ready = true;
+  }
+  return M->plan[phase];
+}
+
+// Partials layout for the fused dot: phase-1 CTAs first, then phase-2 (or the
+// phase-0 CTAs alone).  Totals are fixed per matrix => fixed summation order.
+int launch_spmv(b200_mat *M, const double *x, double *y, bool dot, int phase) {
+  b200_ctx *c = M->ctx;
+  cudaStream_t s = c->stream;
+  const SpmvPlan P = plan_phase(M, phase);
+  unsigned slot_base = 0, total = 0;
+  if (dot) {
+    if (phase == 0) {
+      total = P.g_sell + P.g_vec + P.g_long;
+    } else {
+      const SpmvPlan P1 = plan_phase(M, 1), P2 = plan_phase(M, 2);
+      unsigned t1 = P1.g_sell, t2 = P2.g_sell + P2.g_vec + P2.g_long;
+      total = t1 + t2;
+      slot_base = phase == 1 ? 0 : t1;
+    }
+    if (total == 0)
+      B_FAIL(B200_EINVAL, "launch_spmv: empty matrix");
+  }
+  uint32_t n = (uint32_t)M->n_local;
+  if (P.g_sell) {
+    if (dot)
+      k_spmv_sell<true><<<P.g_sell, SPMV_THREADS, 0, s>>>(
+          M->sell_off, M->sell_cols, M->sell_vals, M->sell_perm, x, y, P.b0,
+          P.e0, P.b1, P.e1, n, M->partials, slot_base, total, M->state);
+    else
+      k_spmv_sell<false><<<P.g_sell, SPMV_THREADS, 0, s>>>(
+          M->sell_off, M->sell_cols, M->sell_vals, M->sell_perm, x, y, P.b0,
+          P.e0, P.b1, P.e1, n, nullptr, 0, 0, nullptr);
+    slot_base += P.g_sell;
+  }
+  if (P.g_vec) {
+    if (dot)
+      k_spmv_vec<true><<<P.g_vec, SPMV_THREADS, 0, s>>>(
+          M->vec_rows, M->vec_row_ids, M->vec_off, M->vl_cols, M->vl_vals, x, y,
+          M->partials, slot_base, total, M->state);
+    else
+      k_spmv_vec<false><<<P.g_vec, SPMV_THREADS, 0, s>>>(
+          M->vec_rows, M->vec_row_ids, M->vec_off, M->vl_cols, M->vl_vals, x, y,
+          nullptr, 0, 0, nullptr);
+    slot_base += P.g_vec;
+  }
+  if (P.g_long) {
+    if (dot)
+      k_spmv_long<true><<<P.g_long, SPMV_THREADS, 0, s>>>(
+          M->long_rows, M->long_row_ids, M->long_off, M->vl_cols, M->vl_vals, x,
+          y, M->partials, slot_base, total, M->state);
+    else
+      k_spmv_long<false><<<P.g_long, SPMV_THREADS, 0, s>>>(
+          M->long_rows, M->long_row_ids, M->long_off, M->vl_cols, M->vl_vals, x,
+          y, nullptr, 0, 0, nullptr);
+  }
+  CU_TRY(cudaGetLastError());
+  return B200_OK;
+}
+
+// Full SpMV with halo exchange overlapped with the interior rows (piece 5).
+static int spmv_full(b200_mat *M, double *x_ext, double *y, bool dot) {
+  if (!M->halo.n_halo && M->ctx->nranks == 1)
+    return launch_spmv(M, x_ext, y, dot, 0);
+  B_TRY(halo_exchange_begin(M, x_ext));
+  B_TRY(launch_spmv(M, x_ext, y, dot, 1));
+  B_TRY(halo_exchange_wait(M));
+  return launch_spmv(M, x_ext, y, dot, 2);
+}
+
+int spmv_full_internal(b200_mat *M, double *x_ext, double *y, bool dot) {
+  return spmv_full(M, x_ext, y, dot);
+}
+
+extern "C" int b200_spmv(b200_mat *M, const double *d_x, double *d_y) {
+  if (!M || !d_x || !d_y)
+    B_FAIL(B200_EINVAL, "b200_spmv: null argument");
+  b200_ctx *c = M->ctx;
+  CU_TRY(cudaSetDevice(c->device));
+  if (c->nranks == 1)
+    return launch_spmv(M, d_x, d_y, false, 0);
+  B_TRY(ensure_workspace(M));
+  CU_TRY(cudaMemcpyAsync(M->x_ext, d_x, M->n_local * 8,
+                         cudaMemcpyDeviceToDevice, c->stream));
+  return spmv_full(M, M->x_ext, d_y, false);
+}
+
+extern "C" int b200_spmv_host(b200_mat *M, const double *h_x, double *h_y) {
+  if (!M || !h_x || !h_y)
+    B_FAIL(B200_EINVAL, "b200_spmv_host: null argument");
+  b200_ctx *c = M->ctx;
+  CU_TRY(cudaSetDevice(c->device));
+  B_TRY(ensure_workspace(M));
+  cudaStream_t s = c->stream;
+  CU_TRY(cudaMemcpyAsync(M->x_ext, h_x, M->n_local * 8, cudaMemcpyHostToDevice, s));
+  B_TRY(spmv_full(M, M->x_ext, M->w_q, false));
+  CU_TRY(cudaMemcpyAsync(h_y, M->w_q, M->n_local * 8, cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  return B200_OK;
+}
+
+extern "C" int b200_spmv_time(b200_mat *M, const double *d_x, double *d_y,
+                              int reps, float *ms) {
+  if (!M || !d_x || !d_y || !ms || reps < 1)
+    B_FAIL(B200_EINVAL, "b200_spmv_time: bad argument");
+  b200_ctx *c = M->ctx;
+  CU_TRY(cudaSetDevice(c->device));
+  B_TRY(b200_spmv(M, d_x, d_y));  // warm
+  CU_TRY(cudaEventRecord(c->ev_a, c->stream));
+  for (int i = 0; i < reps; i++)
+    B_TRY(b200_spmv(M, d_x, d_y));
+  CU_TRY(cudaEventRecord(c->ev_b, c->stream));
+  CU_TRY(cudaEventSynchronize(c->ev_b));
+  float t = 0;
+  CU_TRY(cudaEventElapsedTime(&t, c->ev_a, c->ev_b));
+  *ms = t / reps;
+  return B200_OK;
+}

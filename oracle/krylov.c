@@ -42,6 +42,18 @@ void orc_spmv(const orc_op *M, const double *x, double *y, double *yabs) {
   }
 }
 
+/* Same product with every multiply-add fused (one rounding per term), summed
+ * left to right: the arithmetic a GPU lane does in the SELL kernel, so that
+ * path can be compared bit for bit. */
+void orc_spmv_fma(const orc_op *M, const double *x, double *y) {
+  for (uint64_t i = 0; i < M->n; i++) {
+    double s = 0.0;
+    for (uint64_t k = M->offs[i]; k < M->offs[i + 1]; k++)
+      s = fma(M->vals[k], x[M->cols[k]], s);
+    y[i] = s;
+  }
+}
+
 void orc_spmv_omp(const orc_op *M, const double *x, double *y) {
   int64_t n = (int64_t)M->n;
 #pragma omp parallel for schedule(static)

@@ -63,6 +63,7 @@ void orc_rhs(uint64_t n, double *b);
 /* ---- SpMV (host CSR product in row order) ------------------ */
 /* y = M x; if yabs != NULL also yabs[i] = sum_j |a_ij x_j| (error scale). */
 void orc_spmv(const orc_op *M, const double *x, double *y, double *yabs);
+void orc_spmv_fma(const orc_op *M, const double *x, double *y);
 void orc_spmv_omp(const orc_op *M, const double *x, double *y);
 
 /* ---- Jacobi-preconditioned CG ----------------------------------------- */

@@ -59,6 +59,7 @@ def lib():
         L.orc_op_free.argtypes = [C.POINTER(_Op)]
         L.orc_spmv.argtypes = [C.POINTER(_Op)] + [C.c_void_p] * 3
         L.orc_spmv_omp.argtypes = [C.POINTER(_Op)] + [C.c_void_p] * 2
+        L.orc_spmv_fma.argtypes = [C.POINTER(_Op)] + [C.c_void_p] * 2
         for f in ("orc_pcg", "orc_pcg_omp"):
             getattr(L, f).restype = C.c_int
             getattr(L, f).argtypes = [C.POINTER(_Op), C.c_void_p, C.c_void_p,
@@ -226,6 +227,14 @@ def spmv(M, x, want_abs=False):
     lib().orc_spmv(C.byref(s), x.ctypes.data, y.ctypes.data,
                    ya.ctypes.data if want_abs else None)
     return (y, ya) if want_abs else y
+
+
+def spmv_fma(M, x):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty(M.n)
+    s = M.as_struct()
+    lib().orc_spmv_fma(C.byref(s), x.ctypes.data, y.ctypes.data)
+    return y
 
 
 def pcg(M, b, x0=None, tol=1e-10, maxit=10000, omp=False):

@@ -1,0 +1,277 @@
+"""GPU parity: the CUDA path, called through the C ABI (include/b200.h), against
+the CPU oracle and the golden fixtures.  Run on a B200: pytest -m gpu.
+
+Bars (BASELINE.json north_star):
+  layout conversion  bit-exact (integer / byte work)
+  SpMV               <= 1e-13 * sum_j |a_ij x_j| per entry; the SELL path, which
+                     sums each row left to right with fma, is bit-identical to
+                     the oracle's fma product
+  PCG                ||b-Ax||/||b|| <= 1e-10, x within 1e-8 (relative, 2-norm) of
+                     the direct solve, iteration counts identical run to run
+"""
+import os
+
+import numpy as np
+import pytest
+
+import orc
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+DIRECT = np.load(os.path.join(GOLD, "direct.npz"))
+
+
+@pytest.fixture(scope="module")
+def abi():
+    from lsbench_b200 import abi as m
+    m.load()
+    return m
+
+
+@pytest.fixture(scope="module")
+def ctx(abi):
+    c = abi.Context(0)
+    yield c
+    c.close()
+
+
+def host_csr(name):
+    return orc.matrix_read(orc.matrix_path(name))
+
+
+def op_to_csr(M):
+    """orc Op (0-based, u64 offs) -> the `struct csr` field layout, base 0."""
+    return orc.HostCsr(M.n, 0, M.offs.astype(np.uint32), M.cols, M.vals)
+
+
+def make(abi, ctx, A, flags=0):
+    return abi.Matrix.from_csr(ctx, A.nrows, A.base, A.offs, A.cols, A.vals, flags)
+
+
+def assert_same_operator(Md, M):
+    offs, cols, vals = Md.export()
+    assert np.array_equal(offs, M.offs)
+    assert np.array_equal(cols, M.cols)
+    assert vals.tobytes() == M.vals.tobytes()
+
+
+# --------------------------------------------------------------------------- layout
+@pytest.mark.parametrize("name", ["I1_05x05", "A0_02x02", "A1_02x02"] + orc.NEK)
+def test_layout_is_the_cholmod_operator(abi, ctx, name):
+    A = host_csr(name)
+    Md = make(abi, ctx, A, abi.MAT_SYM_UPPER)
+    M = orc.op_upper_mirror(A)
+    assert_same_operator(Md, M)
+    i = Md.info()
+    assert (i.n_global, i.n_local, i.nnz, i.n_halo) == (M.n, M.n, M.nnz, 0)
+    assert i.pattern_symmetric == 1
+    assert sum(i.hist) == M.n and i.max_row_len == M.rowlens().max()
+    assert i.sell_rows == M.n and i.vec_rows == 0 and i.long_rows == 0
+    d = np.array([M.vals[M.offs[r]:M.offs[r + 1]][M.cols[M.offs[r]:M.offs[r + 1]] == r][0]
+                  for r in range(M.n)])
+    assert np.array_equal(Md.inv_diag(), 1.0 / d)
+    Md.close()
+
+
+@pytest.mark.parametrize("name", ["tj7a_A_18", "xn3b_A_18"])
+def test_layout_as_stored(abi, ctx, name):
+    A = host_csr(name)
+    Md = make(abi, ctx, A, 0)
+    assert_same_operator(Md, orc.op_full(A))
+    Md.close()
+
+
+def test_layout_pattern_asymmetric_input(abi, ctx, tmp_path):
+    # a_13 present, a_31 absent; a_21 present, a_12 absent: the mirror of the
+    # upper triangle inserts (3,1) and drops (2,1)
+    p = tmp_path / "m.txt"
+    p.write_text("6 1\n1 1 4\n1 3 -1\n2 1 7\n2 2 5\n3 3 6\n3 2 9\n")
+    A = orc.matrix_read(str(p))
+    Md = make(abi, ctx, A, abi.MAT_SYM_UPPER)
+    M = orc.op_upper_mirror(A)
+    assert_same_operator(Md, M)
+    assert Md.info().pattern_symmetric == 0
+    assert M.scipy().toarray().tolist() == [[4, 0, -1], [0, 5, 0], [-1, 0, 6]]
+    Md.close()
+
+
+@pytest.mark.parametrize("flags", ["auto", "vector", "nosort"])
+def test_layout_powerlaw_bins(abi, ctx, flags):
+    n = 60000
+    P = orc.gen_powerlaw(n, 2)
+    f = {"auto": 0, "vector": abi.MAT_FORCE_VECTOR, "nosort": abi.MAT_NO_SORT}[flags]
+    Md = make(abi, ctx, op_to_csr(P), f)
+    assert_same_operator(Md, P)
+    i = Md.info()
+    rl = P.rowlens()
+    if flags == "vector":
+        assert i.sell_rows == 0 and i.vec_rows == n
+    else:
+        assert i.sell_rows == (rl <= 256).sum()
+        assert i.vec_rows == ((rl > 256) & (rl < 8192)).sum()
+        assert i.long_rows == (rl >= 8192).sum() and i.long_rows > 0
+        assert i.vec_nnz == rl[(rl > 256) & (rl < 8192)].sum()
+        assert i.long_nnz == rl[rl >= 8192].sum()
+    if flags == "auto":
+        assert i.sell_sigma == 1024 and i.sell_perm == 1
+        assert i.nnz_padded < 1.15 * i.nnz
+    Md.close()
+
+
+# --------------------------------------------------------------------------- SpMV
+def check_spmv(Md, M, x, exact):
+    y = Md.spmv_host(x)
+    if exact:
+        assert np.array_equal(y, orc.spmv_fma(M, x))
+    yr, ya = orc.spmv(M, x, want_abs=True)
+    err = np.abs(y - yr)
+    assert np.all(err <= 1e-13 * ya + 1e-300), float((err / (ya + 1e-300)).max())
+
+
+@pytest.mark.parametrize("name", ["I1_05x05"] + orc.NEK)
+def test_spmv_nek(abi, ctx, name):
+    A = host_csr(name)
+    Md = make(abi, ctx, A, abi.MAT_SYM_UPPER)
+    M = orc.op_upper_mirror(A)
+    rng = np.random.default_rng(7)
+    check_spmv(Md, M, rng.standard_normal(M.n), exact=True)
+    check_spmv(Md, M, orc.rhs(M.n), exact=True)
+    Md.close()
+
+
+@pytest.mark.parametrize("gen,N", [("poisson7", 24), ("poisson27", 20), ("poisson7", 33)])
+def test_spmv_poisson(abi, ctx, gen, N):
+    M = getattr(orc, "gen_" + gen)(N)
+    Md = make(abi, ctx, op_to_csr(M))
+    i = Md.info()
+    assert i.sell_perm == 0 and i.sell_max_width == (7 if gen == "poisson7" else 27)
+    rng = np.random.default_rng(N)
+    check_spmv(Md, M, rng.standard_normal(M.n), exact=True)
+    Md.close()
+
+
+@pytest.mark.parametrize("flags", ["auto", "vector", "nosort"])
+def test_spmv_powerlaw_all_kernels(abi, ctx, flags):
+    n = 60000
+    P = orc.gen_powerlaw(n, 5)
+    f = {"auto": 0, "vector": abi.MAT_FORCE_VECTOR, "nosort": abi.MAT_NO_SORT}[flags]
+    Md = make(abi, ctx, op_to_csr(P), f)
+    rng = np.random.default_rng(1)
+    check_spmv(Md, P, rng.standard_normal(n), exact=False)
+    Md.close()
+
+
+def test_spmv_device_pointers_and_timer(abi, ctx):
+    M = orc.gen_poisson7(32)
+    Md = make(abi, ctx, op_to_csr(M))
+    x = np.random.default_rng(3).standard_normal(M.n)
+    dx, dy = ctx.array(M.n).upload(x), ctx.array(M.n).zero()
+    Md.spmv(dx, dy)
+    ctx.sync()
+    assert np.array_equal(dy.download(), orc.spmv_fma(M, x))
+    assert Md.spmv_time(dx, dy, reps=5) > 0
+    sp, it = Md.algorithmic_bytes()
+    assert sp == 12 * M.nnz + 4 * (M.n + 1) + 16 * M.n
+    assert it == 12 * M.nnz + 4 * (M.n + 1) + 104 * M.n
+    Md.close()
+
+
+# --------------------------------------------------------------------------- PCG
+def test_pcg_i1_known_answer(abi, ctx):
+    A = host_csr("I1_05x05")
+    Md = make(abi, ctx, A, abi.MAT_SYM_UPPER)
+    x, r, rc = Md.pcg_host(orc.rhs(5), flags=abi.PCG_NO_SMALL)
+    assert rc == 0 and r.status == 0 and r.iters == 1
+    np.testing.assert_allclose(x, [0, 1 / 2, 2 / 3, 3 / 4, 4 / 5], rtol=1e-15)
+    Md.close()
+
+
+@pytest.mark.parametrize("name", orc.NEK)
+@pytest.mark.parametrize("graph", [True, False])
+def test_pcg_nek_vs_direct(abi, ctx, name, graph):
+    A = host_csr(name)
+    Md = make(abi, ctx, A, abi.MAT_SYM_UPPER)
+    M = orc.op_upper_mirror(A)
+    b = orc.rhs(M.n)
+    fl = abi.PCG_NO_SMALL | (0 if graph else abi.PCG_NO_GRAPH)
+    x, r, rc = Md.pcg_host(b, tol=1e-10, maxit=5000, flags=fl)
+    assert rc == 0 and r.status == 0
+    assert r.relres <= 1e-10
+    assert orc.true_relres(M, b, x) <= 1.05e-10   # the residual bar
+    assert abs(r.true_relres - orc.true_relres(M, b, x)) <= 1e-12
+    xg = DIRECT[name]
+    assert np.linalg.norm(x - xg) / np.linalg.norm(xg) <= 1e-8   # the parity bar
+    _, it_cpu, _, _ = orc.pcg(M, b, tol=1e-10)
+    assert abs(r.iters - it_cpu) <= 3, (r.iters, it_cpu)
+    # bit-for-bit reproducible, graph or not
+    x2, r2, _ = Md.pcg_host(b, tol=1e-10, maxit=5000, flags=fl)
+    assert r2.iters == r.iters and x2.tobytes() == x.tobytes()
+    Md.close()
+
+
+def test_pcg_graph_and_plain_agree_bitwise(abi, ctx):
+    A = host_csr("xn3b_A_18")
+    Md = make(abi, ctx, A, abi.MAT_SYM_UPPER)
+    b = orc.rhs(A.nrows)
+    xa, ra, _ = Md.pcg_host(b, flags=abi.PCG_NO_SMALL)
+    xb, rb, _ = Md.pcg_host(b, flags=abi.PCG_NO_SMALL | abi.PCG_NO_GRAPH, check_every=7)
+    xc, rc_, _ = Md.pcg_host(b, flags=abi.PCG_NO_SMALL | abi.PCG_TIME_KERNELS)
+    assert ra.iters == rb.iters == rc_.iters
+    assert xa.tobytes() == xb.tobytes() == xc.tobytes()
+    assert rc_.spmv_ms > 0 and rc_.update_ms > 0 and rc_.pupdate_ms > 0
+    Md.close()
+
+
+@pytest.mark.parametrize("gen,N,want", [("poisson7", 32, 125), ("poisson27", 32, 73)])
+def test_pcg_poisson(abi, ctx, gen, N, want):
+    M = getattr(orc, "gen_" + gen)(N)
+    Md = make(abi, ctx, op_to_csr(M))
+    b = orc.rhs(M.n)
+    x, r, rc = Md.pcg_host(b, flags=abi.PCG_NO_SMALL)
+    assert rc == 0 and abs(r.iters - want) <= 2
+    xc, itc, _, _ = orc.pcg(M, b)
+    assert np.linalg.norm(x - xc) / np.linalg.norm(xc) <= 1e-8
+    assert orc.true_relres(M, b, x) <= 1.05e-10
+    Md.close()
+
+
+def test_pcg_nonzero_start_and_maxit(abi, ctx):
+    M = orc.gen_poisson7(16)
+    Md = make(abi, ctx, op_to_csr(M))
+    b = orc.rhs(M.n)
+    xs, _, _ = Md.pcg_host(b, flags=abi.PCG_NO_SMALL)
+    # starting at the solution: zero iterations
+    x, r, rc = Md.pcg_host(b, x0=xs, tol=1e-9, flags=abi.PCG_NO_SMALL)
+    assert r.iters == 0 and r.status == 0
+    # a different start converges to the same solution
+    x0 = np.random.default_rng(5).standard_normal(M.n)
+    x, r, rc = Md.pcg_host(b, x0=x0, flags=abi.PCG_NO_SMALL)
+    assert r.status == 0 and np.linalg.norm(x - xs) / np.linalg.norm(xs) < 1e-8
+    # maxit: stops early, says so, iterate equals the oracle's after 5 steps
+    x, r, rc = Md.pcg_host(b, maxit=5, flags=abi.PCG_NO_SMALL)
+    assert (r.iters, r.status) == (5, 1)
+    xc, itc, _, rcc = orc.pcg(M, b, maxit=5)
+    assert (itc, rcc) == (5, 1) and np.linalg.norm(x - xc) / np.linalg.norm(xc) < 1e-12
+    Md.close()
+
+
+def test_pcg_rejects_indefinite(abi, ctx):
+    A = host_csr("A0_02x02")  # [[1,1],[1,-1]]: p.Ap <= 0 on the second step
+    Md = make(abi, ctx, A, abi.MAT_SYM_UPPER)
+    x, r, rc = Md.pcg_host(np.array([1.0, 2.0]), flags=abi.PCG_NO_SMALL)
+    assert rc == 5 and r.status == 2
+    assert orc.pcg(orc.op_upper_mirror(A), np.array([1.0, 2.0]))[3] == 2
+    Md.close()
+
+
+def test_bad_arguments(abi, ctx):
+    A = host_csr("I1_05x05")
+    with pytest.raises(abi.B200Error):
+        abi.Matrix.from_csr(ctx, A.nrows, 2, A.offs, A.cols, A.vals)
+    with pytest.raises(abi.B200Error):
+        make(abi, ctx, A, abi.MAT_FORCE_SELL | abi.MAT_FORCE_VECTOR)
+    Md = make(abi, ctx, A)
+    with pytest.raises(abi.B200Error):
+        Md.pcg_host(orc.rhs(5), tol=0.0)
+    Md.close()
