@@ -47,7 +47,7 @@ struct b200_ctx {
   cudaStream_t stream = nullptr;       // where kernels go (own or caller's)
   cudaStream_t comm_stream = nullptr;  // halo exchange, overlapped with interior
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_halo = nullptr,
-              ev_ready = nullptr;
+              ev_ready = nullptr, ev_poll = nullptr;
   void *nccl_comm = nullptr;
   const NcclApi *nccl = nullptr;
   int *h_flag = nullptr;  // pinned: PCG progress word read by the host

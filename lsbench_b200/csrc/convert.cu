@@ -272,30 +272,38 @@ __global__ void k_fill_u32(uint32_t *p, uint64_t n, uint32_t v) {
     p[i] = v;
 }
 
-// Sort the SELL row list by decreasing length inside windows of B2_SELL_SIGMA
-// entries; ties keep the original order (the key carries the position).
-__global__ void __launch_bounds__(256) k_window_sort(uint32_t *list,
-                                                     uint64_t padded,
-                                                     const uint32_t *len) {
-  typedef cub::BlockRadixSort<uint32_t, 256, 4, uint32_t> Sort;
-  __shared__ typename Sort::TempStorage tmp;
-  uint64_t base = (uint64_t)blockIdx.x * B2_SELL_SIGMA;
-  uint32_t key[4], val[4];
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    uint32_t idx = threadIdx.x * 4 + j;
-    uint32_t row = base + idx < padded ? list[base + idx] : 0xffffffffu;
-    uint32_t l = row == 0xffffffffu ? 0u : len[row];
-    key[j] = ((B2_SELL_MAX - l) << 10) | idx;  // B2_SELL_MAX - l in [0, 256]
-    val[j] = row;
-  }
-  Sort(tmp).Sort(key, val, 0, 20);
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    uint32_t idx = threadIdx.x * 4 + j;
-    if (base + idx < padded)
-      list[base + idx] = val[j];
-  }
+// Sort key for the SELL row list: (window, descending length, position), so a
+// device-wide radix sort orders every window of `sigma` list entries by
+// decreasing row length and keeps ties in their original order.
+__global__ void k_sort_keys(const uint32_t *list, uint64_t padded,
+                            const uint32_t *len, uint64_t sigma, uint64_t *keys) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= padded)
+    return;
+  uint32_t row = list[i];
+  uint64_t l = row == 0xffffffffu ? 0u : len[row];
+  keys[i] = ((i / sigma) << 41) | ((B2_SELL_MAX - l) << 32) | (i % sigma);
+}
+
+static int window_sort(cudaStream_t s, uint32_t *list, uint64_t padded,
+                       const uint32_t *len, uint64_t sigma) {
+  uint64_t *k_in, *k_out;
+  uint32_t *v_out;
+  CU_TRY(cudaMalloc(&k_in, (padded + 1) * 8));
+  CU_TRY(cudaMalloc(&k_out, (padded + 1) * 8));
+  CU_TRY(cudaMalloc(&v_out, (padded + 1) * 4));
+  k_sort_keys<<<nblk(padded), T256, 0, s>>>(list, padded, len, sigma, k_in);
+  void *tmp = nullptr;
+  size_t bytes = 0;
+  CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k_in, k_out, list, v_out,
+                                         padded, 0, 64, s));
+  CU_TRY(cudaMalloc(&tmp, bytes ? bytes : 8));
+  CU_TRY(cub::DeviceRadixSort::SortPairs(tmp, bytes, k_in, k_out, list, v_out,
+                                         padded, 0, 64, s));
+  CU_TRY(cudaMemcpyAsync(list, v_out, padded * 4, cudaMemcpyDeviceToDevice, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  cudaFree(tmp), cudaFree(k_in), cudaFree(k_out), cudaFree(v_out);
+  return B200_OK;
 }
 
 // one warp per slice: width = longest row in the slice
@@ -495,11 +503,16 @@ int build_layout(b200_ctx *c, PlainCsr *A, uint64_t n_global,
         k_iota_u32<<<nblk(n), T256, 0, s>>>(ids[0], n);
         CU_TRY(cudaGetLastError());
       }
-      unsigned nwin = (unsigned)((sell_padded_rows + B2_SELL_SIGMA - 1) / B2_SELL_SIGMA);
-      k_window_sort<<<nwin, 256, 0, s>>>(ids[0], sell_padded_rows, M->row_len);
-      CU_TRY(cudaGetLastError());
-      B_TRY(widths(ids[0], &padded, &truth));
-      M->sell_sigma = B2_SELL_SIGMA;
+      // widen the window until the padding is small: 1024 rows, 32768, all
+      const uint64_t sig[3] = {B2_SELL_SIGMA, 32 * B2_SELL_SIGMA, sell_padded_rows};
+      for (int t = 0; t < 3; t++) {
+        uint64_t sg = sig[t] < sell_padded_rows ? sig[t] : sell_padded_rows;
+        B_TRY(window_sort(s, ids[0], sell_padded_rows, M->row_len, sg));
+        B_TRY(widths(ids[0], &padded, &truth));
+        M->sell_sigma = (uint32_t)sg;
+        if ((double)(padded - truth) <= 0.03 * (double)truth || sg == sell_padded_rows)
+          break;
+      }
     }
     M->sell_entries = padded;
     B_TRY(dev_alloc(M, (void **)&M->sell_cols, (padded ? padded : 1) * 4));

@@ -46,6 +46,7 @@ static int ctx_common(int device, b200_ctx **out) {
   CU_TRY(cudaEventCreate(&c->ev_b));
   CU_TRY(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
   CU_TRY(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
+  CU_TRY(cudaEventCreateWithFlags(&c->ev_poll, cudaEventDisableTiming));
   CU_TRY(cudaHostAlloc((void **)&c->h_flag, 64, cudaHostAllocDefault));
   memset(c->h_flag, 0, 64);
   *out = c;
@@ -83,6 +84,7 @@ extern "C" int b200_ctx_destroy(b200_ctx *c) {
   if (c->ev_b) cudaEventDestroy(c->ev_b);
   if (c->ev_halo) cudaEventDestroy(c->ev_halo);
   if (c->ev_ready) cudaEventDestroy(c->ev_ready);
+  if (c->ev_poll) cudaEventDestroy(c->ev_poll);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   if (c->h_flag) cudaFreeHost(c->h_flag);

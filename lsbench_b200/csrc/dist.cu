@@ -1,33 +1,425 @@
-// dist.cu -- row-block partition, halo exchange and scalar all-reduce
-// (north_star piece 5).  STUB for the first single-GPU milestone.
+// dist.cu -- north_star piece (5): row-block partition over the ranks, halo
+// exchange overlapped with the interior SpMV, and the all-reduce of the CG
+// scalars.  One rank = one process (or host thread) = one GPU.
+//
+// No reference counterpart: every lsbench backend is single-device
+// (src/amgx.c:88-89, src/ginkgo.cpp:18, src/hypre.c:31).
+//
+//   partition   contiguous row blocks [cut(k), cut(k+1)), cuts rounded to 32
+//               rows (whole z-planes for the stencils when P divides N).
+//   renumber    owned columns -> [0, n_local); remote columns -> n_local + slot,
+//               slots in ascending global order (so grouped by owner).  The
+//               entry order inside a row is untouched: a row sums in the same
+//               order on 1 GPU and on P.
+//   interior    maximal middle run of rows without remote columns; it is
+//               multiplied while the halo is in flight on the comm stream.
+//   exchange    pack kernel + grouped ncclSend/ncclRecv over NVLink.
+//   scalars     ncclAllReduce(sum, fp64) on 1-3 values (latency-bound).
+//
+// NCCL is bound with dlopen so the library loads (and the single-GPU path
+// runs) on hosts without it, and so that inside a torch process the NCCL that
+// torch already loaded is the one used.
 #include "common.cuh"
+#include <cub/cub.cuh>
+#include <dlfcn.h>
+#include <nccl.h>
 
-int dist_comm_init(b200_ctx *c, const void *nccl_id) {
-  (void)c, (void)nccl_id;
-  B_FAIL(B200_ENCCL, "b200: multi-rank contexts are not built yet");
-}
-void dist_comm_destroy(b200_ctx *c) { (void)c; }
-
-extern "C" int b200_nccl_unique_id(void *id_out) {
-  (void)id_out;
-  B_FAIL(B200_ENCCL, "b200: multi-rank contexts are not built yet");
+#define T256 256
+static inline unsigned nblk(uint64_t n, unsigned t = T256) {
+  return (unsigned)((n + t - 1) / t);
 }
 
-int partition_and_renumber(b200_ctx *c, PlainCsr *A, uint64_t n_global,
-                           uint64_t row_begin, b200_mat *M) {
-  (void)A, (void)n_global;
-  if (c->nranks != 1)
-    B_FAIL(B200_ENCCL, "b200: multi-rank contexts are not built yet");
-  M->row_begin = row_begin;
+void b200_row_block(uint64_t n, int rank, int nranks, uint64_t *r0, uint64_t *r1);
+
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t,
+                            ncclRedOp_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t,
+                            ncclComm_t, cudaStream_t);
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t,
+                       cudaStream_t);
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t,
+                       cudaStream_t);
+  ncclResult_t (*GroupStart)();
+  ncclResult_t (*GroupEnd)();
+  const char *(*GetErrorString)(ncclResult_t);
+};
+
+static NcclApi g_nccl;
+static bool g_nccl_ok = false;
+
+static int nccl_bind() {
+  if (g_nccl_ok)
+    return B200_OK;
+  void *h = nullptr;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *nm : names)
+    if ((h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL)))
+      break;
+  if (!h)
+    B_FAIL(B200_ENCCL, "b200: cannot dlopen libnccl.so.2: %s", dlerror());
+#define BIND(field, sym)                                                       \
+  if (!(*(void **)(&g_nccl.field) = dlsym(h, sym)))                            \
+    B_FAIL(B200_ENCCL, "b200: libnccl lacks %s", sym);
+  BIND(GetUniqueId, "ncclGetUniqueId")
+  BIND(CommInitRank, "ncclCommInitRank")
+  BIND(CommDestroy, "ncclCommDestroy")
+  BIND(AllReduce, "ncclAllReduce")
+  BIND(AllGather, "ncclAllGather")
+  BIND(Send, "ncclSend")
+  BIND(Recv, "ncclRecv")
+  BIND(GroupStart, "ncclGroupStart")
+  BIND(GroupEnd, "ncclGroupEnd")
+  BIND(GetErrorString, "ncclGetErrorString")
+#undef BIND
+  g_nccl_ok = true;
   return B200_OK;
 }
-int halo_setup(b200_mat *M) { (void)M; return B200_OK; }
-int halo_exchange_begin(b200_mat *M, double *x) { (void)M, (void)x; return B200_OK; }
-int halo_exchange_wait(b200_mat *M) { (void)M; return B200_OK; }
-void halo_free(b200_mat *M) { (void)M; }
-int allreduce_sum(b200_ctx *c, double *v, int n) { (void)c, (void)v, (void)n; return B200_OK; }
+
+#define NC_TRY(expr)                                                           \
+  do {                                                                         \
+    ncclResult_t r_ = (expr);                                                  \
+    if (r_ != ncclSuccess) {                                                   \
+      b200_set_error("%s:%d nccl error: %s (%s)", __FILE__, __LINE__,          \
+                     g_nccl.GetErrorString(r_), #expr);                        \
+      return B200_ENCCL;                                                       \
+    }                                                                          \
+  } while (0)
+
+extern "C" int b200_nccl_unique_id(void *id_out) {
+  if (!id_out)
+    B_FAIL(B200_EINVAL, "b200_nccl_unique_id: null argument");
+  B_TRY(nccl_bind());
+  static_assert(sizeof(ncclUniqueId) == B200_NCCL_ID_BYTES, "nccl id size");
+  NC_TRY(g_nccl.GetUniqueId((ncclUniqueId *)id_out));
+  return B200_OK;
+}
+
+int dist_comm_init(b200_ctx *c, const void *nccl_id) {
+  B_TRY(nccl_bind());
+  ncclUniqueId id;
+  memcpy(&id, nccl_id, sizeof id);
+  ncclComm_t comm;
+  NC_TRY(g_nccl.CommInitRank(&comm, c->nranks, id, c->rank));
+  c->nccl_comm = comm, c->nccl = &g_nccl;
+  return B200_OK;
+}
+
+void dist_comm_destroy(b200_ctx *c) {
+  if (c->nccl_comm)
+    g_nccl.CommDestroy((ncclComm_t)c->nccl_comm);
+  c->nccl_comm = nullptr;
+}
+
+int allreduce_sum(b200_ctx *c, double *v, int n) {
+  if (c->nranks == 1)
+    return B200_OK;
+  NC_TRY(g_nccl.AllReduce(v, v, n, ncclDouble, ncclSum, (ncclComm_t)c->nccl_comm,
+                          c->stream));
+  return B200_OK;
+}
+
+// ---- partition / renumber ---------------------------------------------------------
+__global__ void k_mark_remote(uint64_t nloc, const uint64_t *offs,
+                              const uint32_t *cols, uint64_t r0, uint64_t r1,
+                              uint32_t *bits, unsigned long long *lo_max,
+                              unsigned long long *hi_min) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= nloc)
+    return;
+  bool remote = false;
+  for (uint64_t k = offs[i]; k < offs[i + 1]; k++) {
+    uint64_t c = cols[k];
+    if (c < r0 || c >= r1) {
+      atomicOr(&bits[c >> 5], 1u << (c & 31));
+      remote = true;
+    }
+  }
+  if (remote) {
+    // interior = the middle run between the last boundary row of the first
+    // half and the first boundary row of the second half
+    if (i < nloc / 2)
+      atomicMax(lo_max, (unsigned long long)(i + 1));
+    else
+      atomicMin(hi_min, (unsigned long long)i);
+  }
+}
+
+__global__ void k_popc(const uint32_t *bits, uint64_t nwords, uint32_t *cnt) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < nwords)
+    cnt[i] = __popc(bits[i]);
+  if (i == nwords)
+    cnt[i] = 0;
+}
+
+__global__ void k_emit_halo(const uint32_t *bits, uint64_t nwords,
+                            const uint32_t *rank_of_word, uint64_t *gcols) {
+  uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (w >= nwords)
+    return;
+  uint32_t b = bits[w];
+  uint64_t o = rank_of_word[w];
+  while (b) {
+    int bit = __ffs(b) - 1;
+    gcols[o++] = w * 32 + bit;
+    b &= b - 1;
+  }
+}
+
+__global__ void k_renumber(uint64_t nnz, uint32_t *cols, uint64_t r0, uint64_t r1,
+                           uint64_t nloc, const uint32_t *bits,
+                           const uint32_t *rank_of_word) {
+  uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (k >= nnz)
+    return;
+  uint64_t c = cols[k];
+  if (c >= r0 && c < r1)
+    cols[k] = (uint32_t)(c - r0);
+  else
+    cols[k] = (uint32_t)(nloc + rank_of_word[c >> 5] +
+                         __popc(bits[c >> 5] & ((1u << (c & 31)) - 1u)));
+}
+
+__global__ void k_shift_offs(const uint64_t *in, uint64_t *out, uint64_t n,
+                             uint64_t base) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n)
+    out[i] = in[i] - base;
+}
+
+// A holds rows [row_begin, row_begin + A->n) -- or, when it holds the whole
+// matrix on a multi-rank context, it is cut down to this rank's block first.
+int partition_and_renumber(b200_ctx *c, PlainCsr *A, uint64_t n_global,
+                           uint64_t row_begin, b200_mat *M) {
+  M->row_begin = row_begin;
+  if (c->nranks == 1)
+    return B200_OK;
+  cudaStream_t s = c->stream;
+  uint64_t r0, r1;
+  b200_row_block(n_global, c->rank, c->nranks, &r0, &r1);
+  if (A->n == n_global && !(r0 == 0 && r1 == n_global)) {
+    // cut the block out of the full matrix
+    uint64_t nloc = r1 - r0, k0 = 0, k1 = 0;
+    CU_TRY(cudaMemcpy(&k0, A->offs + r0, 8, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(&k1, A->offs + r1, 8, cudaMemcpyDeviceToHost));
+    PlainCsr B;
+    B.n = nloc, B.nnz = k1 - k0;
+    CU_TRY(cudaMalloc(&B.offs, (nloc + 1) * 8));
+    CU_TRY(cudaMalloc(&B.cols, (B.nnz ? B.nnz : 1) * 4));
+    CU_TRY(cudaMalloc(&B.vals, (B.nnz ? B.nnz : 1) * 8));
+    k_shift_offs<<<nblk(nloc + 1), T256, 0, s>>>(A->offs + r0, B.offs, nloc + 1, k0);
+    CU_TRY(cudaMemcpyAsync(B.cols, A->cols + k0, B.nnz * 4, cudaMemcpyDeviceToDevice, s));
+    CU_TRY(cudaMemcpyAsync(B.vals, A->vals + k0, B.nnz * 8, cudaMemcpyDeviceToDevice, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    plain_free(A);
+    *A = B;
+  } else if (row_begin != r0 || A->n != r1 - r0) {
+    B_FAIL(B200_EINVAL, "partition: rows [%llu,+%llu) are not this rank's block",
+           (unsigned long long)row_begin, (unsigned long long)A->n);
+  }
+  M->row_begin = r0;
+  const uint64_t nloc = A->n, nwords = (n_global + 31) / 32;
+  uint32_t *bits, *cnt, *rank_of_word;
+  unsigned long long *d_lohi, h_lohi[2] = {0ull, (unsigned long long)nloc};
+  CU_TRY(cudaMalloc(&bits, (nwords + 1) * 4));
+  CU_TRY(cudaMalloc(&cnt, (nwords + 1) * 4));
+  CU_TRY(cudaMalloc(&rank_of_word, (nwords + 1) * 4));
+  CU_TRY(cudaMalloc(&d_lohi, 16));
+  CU_TRY(cudaMemsetAsync(bits, 0, (nwords + 1) * 4, s));
+  CU_TRY(cudaMemcpyAsync(d_lohi, h_lohi, 16, cudaMemcpyHostToDevice, s));
+  if (nloc)
+    k_mark_remote<<<nblk(nloc), T256, 0, s>>>(nloc, A->offs, A->cols, r0, r1, bits,
+                                              d_lohi, d_lohi + 1);
+  k_popc<<<nblk(nwords + 1), T256, 0, s>>>(bits, nwords, cnt);
+  {
+    void *tmp = nullptr;
+    size_t bytes = 0;
+    CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, bytes, cnt, rank_of_word, nwords + 1, s));
+    CU_TRY(cudaMalloc(&tmp, bytes ? bytes : 8));
+    CU_TRY(cub::DeviceScan::ExclusiveSum(tmp, bytes, cnt, rank_of_word, nwords + 1, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    cudaFree(tmp);
+  }
+  uint32_t n_halo = 0;
+  CU_TRY(cudaMemcpy(&n_halo, rank_of_word + nwords, 4, cudaMemcpyDeviceToHost));
+  CU_TRY(cudaMemcpy(h_lohi, d_lohi, 16, cudaMemcpyDeviceToHost));
+  if (nloc + (uint64_t)n_halo >= 0xffffffffull)
+    B_FAIL(B200_ERANGE, "partition: local + halo columns exceed 32 bits");
+  M->halo.n_halo = n_halo;
+  CU_TRY(cudaMalloc(&M->halo.d_gcols, (n_halo + 1ull) * 8));
+  k_emit_halo<<<nblk(nwords), T256, 0, s>>>(bits, nwords, rank_of_word, M->halo.d_gcols);
+  if (A->nnz)
+    k_renumber<<<nblk(A->nnz), T256, 0, s>>>(A->nnz, A->cols, r0, r1, nloc, bits,
+                                             rank_of_word);
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaStreamSynchronize(s));
+  M->interior_begin = h_lohi[0];
+  M->interior_end = h_lohi[1] > h_lohi[0] ? h_lohi[1] : h_lohi[0];
+  cudaFree(bits), cudaFree(cnt), cudaFree(rank_of_word), cudaFree(d_lohi);
+  return B200_OK;
+}
+
+// ---- halo plan ----------------------------------------------------------------------
+__global__ void k_global_to_local_u32(const uint64_t *g, uint32_t *l, uint64_t n,
+                                      uint64_t r0) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n)
+    l[i] = (uint32_t)(g[i] - r0);
+}
+
+int halo_setup(b200_mat *M) {
+  b200_ctx *c = M->ctx;
+  HaloPlan &H = M->halo;
+  const int P = c->nranks, me = c->rank;
+  cudaStream_t s = c->stream;
+  ncclComm_t comm = (ncclComm_t)c->nccl_comm;
+  // how many of my halo slots each owner holds (slots are sorted by global id)
+  uint64_t *h_g = (uint64_t *)malloc((H.n_halo + 1) * 8);
+  CU_TRY(cudaMemcpy(h_g, H.d_gcols, H.n_halo * 8, cudaMemcpyDeviceToHost));
+  uint64_t *need = (uint64_t *)calloc((size_t)P * P, 8);  // need[r*P + o]
+  uint64_t *first = (uint64_t *)calloc(P + 1, 8);
+  {
+    uint64_t j = 0;
+    for (int o = 0; o < P; o++) {
+      uint64_t b0, b1;
+      b200_row_block(M->n_global, o, P, &b0, &b1);
+      first[o] = j;
+      while (j < H.n_halo && h_g[j] < b1)
+        j++;
+      need[(size_t)me * P + o] = j - first[o];
+    }
+    first[P] = j;
+  }
+  free(h_g);
+  uint64_t *d_need;
+  CU_TRY(cudaMalloc(&d_need, (size_t)P * P * 8));
+  CU_TRY(cudaMemcpy(d_need + (size_t)me * P, need + (size_t)me * P, P * 8,
+                    cudaMemcpyHostToDevice));
+  NC_TRY(g_nccl.AllGather(d_need + (size_t)me * P, d_need, P, ncclUint64, comm, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  CU_TRY(cudaMemcpy(need, d_need, (size_t)P * P * 8, cudaMemcpyDeviceToHost));
+  cudaFree(d_need);
+
+  H.peer = (int *)calloc(P, sizeof(int));
+  H.recv_off = (uint64_t *)calloc(P + 1, 8);
+  H.send_off = (uint64_t *)calloc(P + 1, 8);
+  H.n_peers = 0;
+  uint64_t ns = 0;
+  for (int o = 0; o < P; o++) {
+    uint64_t rcv = need[(size_t)me * P + o], snd = need[(size_t)o * P + me];
+    if (o == me || (rcv == 0 && snd == 0))
+      continue;
+    int k = H.n_peers++;
+    H.peer[k] = o;
+    H.recv_off[k] = first[o];
+    H.send_off[k] = ns;
+    ns += snd;
+    // lengths are recovered from need[] below; store ends in the next slot
+    H.recv_off[k + 1] = first[o] + rcv;
+    H.send_off[k + 1] = ns;
+  }
+  H.n_send = ns;
+  // recv ranges are not necessarily adjacent across skipped owners: keep
+  // explicit (begin, count) pairs
+  uint64_t *rb = (uint64_t *)calloc(2 * (size_t)P + 2, 8);
+  uint64_t *sb = (uint64_t *)calloc(2 * (size_t)P + 2, 8);
+  {
+    uint64_t acc = 0;
+    for (int k = 0; k < H.n_peers; k++) {
+      int o = H.peer[k];
+      rb[2 * k] = first[o], rb[2 * k + 1] = need[(size_t)me * P + o];
+      sb[2 * k] = acc, sb[2 * k + 1] = need[(size_t)o * P + me];
+      acc += sb[2 * k + 1];
+    }
+  }
+  free(H.recv_off), free(H.send_off);
+  H.recv_off = rb, H.send_off = sb;
+
+  // tell every owner which of its rows I read
+  uint64_t *d_send_g;
+  CU_TRY(cudaMalloc(&d_send_g, (ns + 1) * 8));
+  NC_TRY(g_nccl.GroupStart());
+  for (int k = 0; k < H.n_peers; k++) {
+    if (rb[2 * k + 1])
+      NC_TRY(g_nccl.Send(H.d_gcols + rb[2 * k], rb[2 * k + 1], ncclUint64, H.peer[k], comm, s));
+    if (sb[2 * k + 1])
+      NC_TRY(g_nccl.Recv(d_send_g + sb[2 * k], sb[2 * k + 1], ncclUint64, H.peer[k], comm, s));
+  }
+  NC_TRY(g_nccl.GroupEnd());
+  CU_TRY(cudaMalloc(&H.d_send_idx, (ns + 1) * 4));
+  CU_TRY(cudaMalloc(&H.d_send_buf, (ns + 1) * 8));
+  if (ns)
+    k_global_to_local_u32<<<nblk(ns), T256, 0, s>>>(d_send_g, H.d_send_idx, ns, M->row_begin);
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaStreamSynchronize(s));
+  cudaFree(d_send_g);
+  M->device_bytes += (ns + 1) * 12 + (H.n_halo + 1) * 8;
+  free(need), free(first);
+  return B200_OK;
+}
+
+void halo_free(b200_mat *M) {
+  HaloPlan &H = M->halo;
+  if (H.d_gcols) cudaFree(H.d_gcols);
+  if (H.d_send_idx) cudaFree(H.d_send_idx);
+  if (H.d_send_buf) cudaFree(H.d_send_buf);
+  free(H.peer), free(H.recv_off), free(H.send_off);
+  H = HaloPlan();
+}
+
+__global__ void k_halo_pack(const double *__restrict__ x,
+                            const uint32_t *__restrict__ idx,
+                            double *__restrict__ buf, uint64_t n) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n)
+    buf[i] = x[idx[i]];
+}
+
+// Owned part of x_ext is final on the compute stream; ship the entries the
+// neighbours read and receive mine into x_ext[n_local ...], all on the comm
+// stream so the interior SpMV runs meanwhile.
+int halo_exchange_begin(b200_mat *M, double *x_ext) {
+  b200_ctx *c = M->ctx;
+  if (c->nranks == 1)
+    return B200_OK;
+  HaloPlan &H = M->halo;
+  ncclComm_t comm = (ncclComm_t)c->nccl_comm;
+  CU_TRY(cudaEventRecord(c->ev_ready, c->stream));
+  CU_TRY(cudaStreamWaitEvent(c->comm_stream, c->ev_ready, 0));
+  if (H.n_send)
+    k_halo_pack<<<nblk(H.n_send), T256, 0, c->comm_stream>>>(x_ext, H.d_send_idx,
+                                                             H.d_send_buf, H.n_send);
+  CU_TRY(cudaGetLastError());
+  NC_TRY(g_nccl.GroupStart());
+  for (int k = 0; k < H.n_peers; k++) {
+    if (H.send_off[2 * k + 1])
+      NC_TRY(g_nccl.Send(H.d_send_buf + H.send_off[2 * k], H.send_off[2 * k + 1],
+                         ncclDouble, H.peer[k], comm, c->comm_stream));
+    if (H.recv_off[2 * k + 1])
+      NC_TRY(g_nccl.Recv(x_ext + M->n_local + H.recv_off[2 * k], H.recv_off[2 * k + 1],
+                         ncclDouble, H.peer[k], comm, c->comm_stream));
+  }
+  NC_TRY(g_nccl.GroupEnd());
+  CU_TRY(cudaEventRecord(c->ev_halo, c->comm_stream));
+  return B200_OK;
+}
+
+int halo_exchange_wait(b200_mat *M) {
+  b200_ctx *c = M->ctx;
+  if (c->nranks == 1)
+    return B200_OK;
+  CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+  return B200_OK;
+}
 
 extern "C" int b200_mat_halo_cols(const b200_mat *M, uint64_t *g) {
-  (void)M, (void)g;
+  if (!M || !g)
+    B_FAIL(B200_EINVAL, "b200_mat_halo_cols: null argument");
+  if (M->halo.n_halo)
+    CU_TRY(cudaMemcpy(g, M->halo.d_gcols, M->halo.n_halo * 8, cudaMemcpyDeviceToHost));
   return B200_OK;
 }

@@ -253,7 +253,8 @@ extern "C" int b200_pcg_solve(b200_mat *M, const double *d_b, double *d_x,
   const bool timing = o->flags & B200_PCG_TIME_KERNELS;
   int chunk = o->check_every > 0 ? o->check_every : 32;
   chunk = (chunk + 1) & ~1;  // even: the parity pattern repeats per chunk
-  const bool use_graph = !(o->flags & B200_PCG_NO_GRAPH) && !timing;
+  // (multi-rank: plain launches; the NCCL calls stay outside any capture)
+  const bool use_graph = !(o->flags & B200_PCG_NO_GRAPH) && !timing && c->nranks == 1;
   int launches = 0;
 
   CU_TRY(cudaEventRecord(c->ev_a, s));
@@ -276,8 +277,8 @@ extern "C" int b200_pcg_solve(b200_mat *M, const double *d_b, double *d_x,
   int timed_iters = 0;
   for (;;) {
     CU_TRY(cudaMemcpyAsync((void *)flag, &M->state->iter, 16, cudaMemcpyDeviceToHost, s));
-    CU_TRY(cudaEventRecord(c->ev_ready, s));
-    CU_TRY(cudaEventSynchronize(c->ev_ready));
+    CU_TRY(cudaEventRecord(c->ev_poll, s));
+    CU_TRY(cudaEventSynchronize(c->ev_poll));
     if (flag[1] || queued >= o->maxit)
       break;
     if (timing && timed_iters == 0) {

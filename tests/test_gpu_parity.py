@@ -114,8 +114,8 @@ def test_layout_powerlaw_bins(abi, ctx, flags):
         assert i.vec_nnz == rl[(rl > 256) & (rl < 8192)].sum()
         assert i.long_nnz == rl[rl >= 8192].sum()
     if flags == "auto":
-        assert i.sell_sigma == 1024 and i.sell_perm == 1
-        assert i.nnz_padded < 1.15 * i.nnz
+        assert i.sell_sigma >= 1024 and i.sell_perm == 1
+        assert i.nnz_padded < 1.05 * i.nnz
     Md.close()
 
 
@@ -274,4 +274,58 @@ def test_bad_arguments(abi, ctx):
     Md = make(abi, ctx, A)
     with pytest.raises(abi.B200Error):
         Md.pcg_host(orc.rhs(5), tol=0.0)
+    Md.close()
+
+
+# --------------------------------------------------------------------------- generators
+@pytest.mark.parametrize("kind,size", [("poisson7", 20), ("poisson27", 17), ("powerlaw", 50000)])
+def test_device_generators_match_the_specification(abi, ctx, kind, size):
+    k = {"poisson7": abi.GEN_POISSON7, "poisson27": abi.GEN_POISSON27,
+         "powerlaw": abi.GEN_POWERLAW}[kind]
+    Md = abi.Matrix.generate(ctx, k, size, seed=11)
+    M = (orc.gen_powerlaw(size, 11) if kind == "powerlaw"
+         else getattr(orc, "gen_" + kind)(size))
+    assert_same_operator(Md, M)
+    x = np.random.default_rng(2).standard_normal(M.n)
+    check_spmv(Md, M, x, exact=(kind != "powerlaw"))
+    Md.close()
+
+
+def test_generated_poisson_solves_like_the_oracle(abi, ctx):
+    Md = abi.Matrix.generate(ctx, abi.GEN_POISSON27, 32)
+    M = orc.gen_poisson27(32)
+    b = orc.rhs(M.n)
+    x, r, rc = Md.pcg_host(b, flags=abi.PCG_NO_SMALL)
+    xc, itc, _, _ = orc.pcg(M, b)
+    assert rc == 0 and abs(r.iters - itc) <= 2
+    assert np.linalg.norm(x - xc) / np.linalg.norm(xc) <= 1e-8
+    Md.close()
+
+
+def test_large_grid_properties(abi, ctx):
+    """Size-independent checks at a grid the CPU oracle is not asked to solve:
+    A*1 is the analytic row sum (0 inside, boundary rows positive), symmetry via
+    x.(A y) == y.(A x), and PCG on a manufactured solution recovers it."""
+    N = 128
+    n = N ** 3
+    Md = abi.Matrix.generate(ctx, abi.GEN_POISSON7, N)
+    i = Md.info()
+    assert i.nnz == 7 * n - 6 * N * N and i.n_local == n
+    y = Md.spmv_host(np.ones(n))
+    g = np.arange(n)
+    xx, yy, zz = g % N, (g // N) % N, g // (N * N)
+    missing = ((xx == 0).astype(int) + (xx == N - 1) + (yy == 0) + (yy == N - 1)
+               + (zz == 0) + (zz == N - 1))
+    assert np.array_equal(y, missing.astype(np.float64))
+    rng = np.random.default_rng(0)
+    u, v = rng.standard_normal(n), rng.standard_normal(n)
+    a, b_ = u @ Md.spmv_host(v), v @ Md.spmv_host(u)
+    assert abs(a - b_) <= 1e-12 * (abs(a) + abs(b_))
+    xstar = rng.standard_normal(n)
+    rhs = Md.spmv_host(xstar)
+    x, r, rc = Md.pcg_host(rhs, tol=1e-10)
+    assert rc == 0 and r.true_relres <= 1.05e-10
+    assert np.linalg.norm(x - xstar) / np.linalg.norm(xstar) <= 1e-8
+    x2, r2, _ = Md.pcg_host(rhs, tol=1e-10)
+    assert r2.iters == r.iters and x2.tobytes() == x.tobytes()
     Md.close()
