@@ -51,6 +51,7 @@ struct b200_ctx {
   void *nccl_comm = nullptr;
   const NcclApi *nccl = nullptr;
   int *h_flag = nullptr;  // pinned: PCG progress word read by the host
+  uint64_t launches = 0;  // kernels of this library queued so far
 };
 
 // Plain CSR on the device: the intermediate every input goes through.
@@ -132,6 +133,7 @@ struct b200_mat {
   void *small = nullptr;          // on-chip small-matrix plan (small.cu)
   void *graph_exec = nullptr;     // cudaGraphExec_t of one iteration chunk
   int graph_chunk = 0;
+  int graph_kernels = 0;         // kernel nodes in the captured chunk
   void *graph_stream = nullptr;
 };
 

@@ -393,6 +393,7 @@ int halo_exchange_begin(b200_mat *M, double *x_ext) {
   if (H.n_send)
     k_halo_pack<<<nblk(H.n_send), T256, 0, c->comm_stream>>>(x_ext, H.d_send_idx,
                                                              H.d_send_buf, H.n_send);
+  c->launches += H.n_send > 0;
   CU_TRY(cudaGetLastError());
   NC_TRY(g_nccl.GroupStart());
   for (int k = 0; k < H.n_peers; k++) {

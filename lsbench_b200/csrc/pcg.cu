@@ -204,6 +204,7 @@ static int queue_iteration(b200_mat *M, int par) {
   B_TRY(reduce_ranks(M, &M->state->red[(par ^ 1) * 2], 2));
   k_pcg_pupdate<<<M->grid_ew, EW_THREADS, 0, s>>>(n, M->w_r, M->dinv, M->w_p,
                                                   M->state, par);
+  c->launches += 2;
   CU_TRY(cudaGetLastError());
   return B200_OK;
 }
@@ -220,9 +221,12 @@ static int ensure_graph(b200_mat *M, int chunk) {
   cudaGraph_t g = nullptr;
   CU_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
   int rc = B200_OK;
+  const uint64_t before = M->ctx->launches;
   for (int i = 0; i < chunk && rc == B200_OK; i++)
     rc = queue_iteration(M, i & 1);
   cudaError_t e = cudaStreamEndCapture(s, &g);
+  M->graph_kernels = (int)(M->ctx->launches - before);
+  M->ctx->launches = before;  // captured, not launched
   if (rc != B200_OK)
     return rc;
   CU_TRY(e);
@@ -254,8 +258,8 @@ extern "C" int b200_pcg_solve(b200_mat *M, const double *d_b, double *d_x,
   int chunk = o->check_every > 0 ? o->check_every : 32;
   chunk = (chunk + 1) & ~1;  // even: the parity pattern repeats per chunk
   // (multi-rank: plain launches; the NCCL calls stay outside any capture)
-  const bool use_graph = !(o->flags & B200_PCG_NO_GRAPH) && !timing && c->nranks == 1;
-  int launches = 0;
+  const bool use_graph = !(o->flags & B200_PCG_NO_GRAPH) && c->nranks == 1;
+  const uint64_t launches0 = c->launches;
 
   CU_TRY(cudaEventRecord(c->ev_a, s));
   // ---- start-up: r = b - A x0, p = D^-1 r ---------------------------------------
@@ -267,8 +271,8 @@ extern "C" int b200_pcg_solve(b200_mat *M, const double *d_b, double *d_x,
                                                M->partial_stride, M->state);
   B_TRY(reduce_ranks(M, &M->state->red[4], 3));
   k_pcg_start<<<1, 1, 0, s>>>(M->state, o->tol, o->maxit);
+  c->launches += 2;
   CU_TRY(cudaGetLastError());
-  launches += 3;
 
   // ---- iterations ---------------------------------------------------------------
   volatile int *flag = c->h_flag;  // {iter, done, status, maxit}
@@ -300,6 +304,7 @@ extern "C" int b200_pcg_solve(b200_mat *M, const double *d_b, double *d_x,
         k_pcg_pupdate<<<M->grid_ew, EW_THREADS, 0, s>>>(n, M->w_r, M->dinv,
                                                         M->w_p, M->state, par);
         CU_TRY(cudaEventRecord(ev[3], s));
+        c->launches += 2;
         CU_TRY(cudaEventSynchronize(ev[3]));
         for (int k = 0; k < 3; k++) {
           float t;
@@ -313,12 +318,12 @@ extern "C" int b200_pcg_solve(b200_mat *M, const double *d_b, double *d_x,
     } else if (use_graph) {
       B_TRY(ensure_graph(M, chunk));
       CU_TRY(cudaGraphLaunch((cudaGraphExec_t)M->graph_exec, s));
+      c->launches += M->graph_kernels;
     } else {
       for (int i = 0; i < chunk; i++)
         B_TRY(queue_iteration(M, i & 1));
     }
     queued += chunk;
-    launches += chunk * 3;
   }
 
   // ---- exit: true residual with one more SpMV -----------------------------------
@@ -328,7 +333,7 @@ extern "C" int b200_pcg_solve(b200_mat *M, const double *d_b, double *d_x,
                                                  M->partial_stride, M->state);
   B_TRY(reduce_ranks(M, &M->state->true_rr, 1));
   CU_TRY(cudaMemcpyAsync(d_x, M->w_x, n * 8, cudaMemcpyDeviceToDevice, s));
-  launches += 2;
+  c->launches += 1;
   CU_TRY(cudaEventRecord(c->ev_b, s));
   PcgState h;
   CU_TRY(cudaMemcpyAsync(&h, M->state, sizeof h, cudaMemcpyDeviceToHost, s));
@@ -341,7 +346,7 @@ extern "C" int b200_pcg_solve(b200_mat *M, const double *d_b, double *d_x,
   res->bnorm = sqrt(h.bb);
   res->relres = h.bb > 0 ? sqrt(rr / h.bb) : sqrt(rr);
   res->true_relres = h.bb > 0 ? sqrt(h.true_rr / h.bb) : sqrt(h.true_rr);
-  res->kernel_launches = launches;
+  res->kernel_launches = (int32_t)(c->launches - launches0);
   res->path = 0;
   if (timed_iters) {
     res->spmv_ms = t_cls[0] / timed_iters;

@@ -291,6 +291,7 @@ int launch_spmv(b200_mat *M, const double *x, double *y, bool dot, int phase) {
           M->long_rows, M->long_row_ids, M->long_off, M->vl_cols, M->vl_vals, x,
           y, nullptr, 0, 0, nullptr);
   }
+  c->launches += (P.g_sell > 0) + (P.g_vec > 0) + (P.g_long > 0);
   CU_TRY(cudaGetLastError());
   return B200_OK;
 }

@@ -145,7 +145,9 @@ def test_spmv_poisson(abi, ctx, gen, N):
     M = getattr(orc, "gen_" + gen)(N)
     Md = make(abi, ctx, op_to_csr(M))
     i = Md.info()
-    assert i.sell_perm == 0 and i.sell_max_width == (7 if gen == "poisson7" else 27)
+    # (tiny grids have enough short boundary rows to trigger the length sort)
+    assert i.sell_max_width == (7 if gen == "poisson7" else 27)
+    assert i.nnz_padded <= 1.04 * i.nnz
     rng = np.random.default_rng(N)
     check_spmv(Md, M, rng.standard_normal(M.n), exact=True)
     Md.close()
