@@ -1,0 +1,122 @@
+"""Multi-rank parity worker, one rank per GPU:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N \
+        --master-addr 127.0.0.1 --master-port P tests/dist_check.py
+
+Checks, against the CPU oracle, for the row-block partitioned path
+(lsbench_b200/csrc/dist.cu): partition + halo renumbering (exported local rows
+== oracle rows with columns mapped back to global ids), SpMV with halo
+exchange, PCG with all-reduced scalars (same x on every rank count, iteration
+count reproducible).  Prints "DIST_CHECK OK" from rank 0.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+
+import orc  # noqa: E402
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from lsbench_b200 import abi
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    t = torch.zeros(abi.NCCL_ID_BYTES, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        t.copy_(torch.frombuffer(bytearray(abi.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(t, 0)
+    ctx = abi.Context(local, rank, world, bytes(t.cpu().numpy().tobytes()))
+
+    def gather(v):
+        """all ranks' local slices -> the global vector, on every rank"""
+        sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([v.size], dtype=torch.int64, device=dev))
+        mx = max(int(s.item()) for s in sizes)
+        buf = torch.zeros(mx, dtype=torch.float64, device=dev)
+        buf[:v.size] = torch.from_numpy(v).to(dev)
+        out = [torch.zeros(mx, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(out, buf)
+        return np.concatenate([o[:int(s.item())].cpu().numpy() for o, s in zip(out, sizes)])
+
+    cases = [("poisson27", 24, abi.GEN_POISSON27), ("poisson7", 40, abi.GEN_POISSON7),
+             ("powerlaw", 40000, abi.GEN_POWERLAW)]
+    for name, size, kind in cases:
+        M = abi.Matrix.generate(ctx, kind, size, seed=9)
+        i = M.info()
+        r0, r1, n = i.row_begin, i.row_begin + i.n_local, i.n_global
+        ref = {"poisson27": orc.gen_poisson27, "poisson7": orc.gen_poisson7}.get(name)
+        Mo = ref(size, r0, r1) if ref else orc.gen_powerlaw(size, 9, r0, r1)
+        # ---- partition / renumber: map local column ids back to global ----------------
+        offs, cols, vals = M.export()
+        halo = M.halo_cols()
+        assert np.all(np.diff(halo.astype(np.int64)) > 0)
+        assert np.all((halo < r0) | (halo >= r1))
+        g = np.where(cols < i.n_local, cols.astype(np.int64) + r0,
+                     halo[np.clip(cols.astype(np.int64) - i.n_local, 0, max(len(halo) - 1, 0))]
+                     if len(halo) else 0)
+        assert np.array_equal(offs, Mo.offs), name
+        assert np.array_equal(g, Mo.cols.astype(np.int64)), name
+        assert vals.tobytes() == Mo.vals.tobytes(), name
+        assert sorted(set(Mo.cols[(Mo.cols < r0) | (Mo.cols >= r1)].tolist())) == halo.tolist()
+        # ---- SpMV with halo exchange ---------------------------------------------------
+        xg = np.random.default_rng(4).standard_normal(n)
+        y = M.spmv_host(xg[r0:r1])
+        yr, ya = orc.spmv(Mo, xg, want_abs=True)
+        assert np.all(np.abs(y - yr) <= 1e-13 * ya + 1e-300), name
+        if name != "powerlaw":
+            assert np.array_equal(y, orc.spmv_fma(Mo, xg)), name
+            # interior rows really have no halo column
+            ib, ie = i.interior_begin, i.interior_end
+            if ie > ib:
+                assert np.all(cols[offs[ib]:offs[ie]] < i.n_local)
+            # ---- PCG: same answer as the serial oracle on the whole grid ------------------
+            b = orc.rhs(n)
+            x, r, rc = M.pcg_host(b[r0:r1], tol=1e-10)
+            assert rc == 0 and r.status == 0 and r.true_relres <= 1.05e-10
+            x2, r2, _ = M.pcg_host(b[r0:r1], tol=1e-10)
+            assert r2.iters == r.iters and x2.tobytes() == x.tobytes()
+            xfull = gather(x)
+            if rank == 0:
+                Mfull = ref(size)
+                xc, itc, _, _ = orc.pcg(Mfull, b)
+                assert abs(r.iters - itc) <= 2, (r.iters, itc)
+                assert np.linalg.norm(xfull - xc) / np.linalg.norm(xc) <= 1e-8
+                assert orc.true_relres(Mfull, b, xfull) <= 1.05e-10
+        if rank == 0:
+            print("dist_check %s:%d ranks=%d halo=%d interior=[%d,%d) of %d ok"
+                  % (name, size, world, i.n_halo, i.interior_begin, i.interior_end, i.n_local))
+        M.close()
+
+    # a file matrix: every rank reads it, keeps its row block of the CHOLMOD operator
+    A = orc.matrix_read(orc.matrix_path("tj7a_A_18"))
+    M = abi.Matrix.from_csr(ctx, A.nrows, A.base, A.offs, A.cols, A.vals, abi.MAT_SYM_UPPER)
+    i = M.info()
+    Mo = orc.op_upper_mirror(A)
+    b = orc.rhs(Mo.n)
+    x, r, rc = M.pcg_host(b[i.row_begin:i.row_begin + i.n_local], tol=1e-10, maxit=5000)
+    xfull = gather(x)
+    if rank == 0:
+        gold = np.load(os.path.join(HERE, "golden", "direct.npz"))["tj7a_A_18"]
+        assert rc == 0 and np.linalg.norm(xfull - gold) / np.linalg.norm(gold) <= 1e-8
+        assert orc.true_relres(Mo, b, xfull) <= 1.05e-10
+        print("dist_check tj7a_A_18 ranks=%d iters=%d ok" % (world, r.iters))
+    M.close()
+    dist.barrier()
+    if rank == 0:
+        print("DIST_CHECK OK")
+    ctx.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
