@@ -175,9 +175,10 @@ def matrix_path(name, tmpdir=None):
     os.makedirs(d, exist_ok=True)
     out = os.path.join(d, name + ".txt")
     if not os.path.exists(out):
-        with lzma.open(packed, "rb") as f, open(out + ".part", "wb") as g:
+        part = "%s.%d.part" % (out, os.getpid())  # ranks may unpack concurrently
+        with lzma.open(packed, "rb") as f, open(part, "wb") as g:
             g.write(f.read())
-        os.replace(out + ".part", out)
+        os.replace(part, out)
     return out
 
 
