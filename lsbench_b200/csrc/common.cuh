@@ -84,9 +84,15 @@ struct SpmvPlan {
 // Device-resident scalars of one PCG solve.  red[] holds the values that are
 // all-reduced across ranks: {rz, rr} for iteration parity 0 at [0..1], parity
 // 1 at [2..3], and the start-up triple {rz, rr, bb} at [4..6].
+// loc[] / pq_loc / true_rr_loc are this rank's partial sums; on a multi-rank
+// context they are all-reduced out of place into red[] / pq / true_rr, so a
+// repeated all-reduce (iterations queued past convergence are no-ops that
+// leave loc[] untouched) reproduces the same values instead of compounding.
 struct PcgState {
-  double pq;
+  double pq, pq_loc;
   double red[7];
+  double loc[7];
+  double true_rr_loc;
   double bb, thr2, tol;
   double true_rr;
   int iter, done, status, maxit;
@@ -151,7 +157,7 @@ void halo_free(b200_mat *M);
 int ensure_workspace(b200_mat *M);
 int launch_spmv(b200_mat *M, const double *x_ext, double *y, bool fuse_dot,
                 int phase /*0 all, 1 interior, 2 boundary*/);
-int allreduce_sum(b200_ctx *ctx, double *d_vals, int count);
+int allreduce_sum(b200_ctx *ctx, const double *d_src, double *d_dst, int count);
 int small_try_build(b200_mat *M);
 void small_free(b200_mat *M);
 int small_solve(b200_mat *M, const double *d_b, double *d_x,

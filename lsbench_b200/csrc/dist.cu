@@ -114,11 +114,11 @@ void dist_comm_destroy(b200_ctx *c) {
   c->nccl_comm = nullptr;
 }
 
-int allreduce_sum(b200_ctx *c, double *v, int n) {
+int allreduce_sum(b200_ctx *c, const double *src, double *dst, int n) {
   if (c->nranks == 1)
     return B200_OK;
-  NC_TRY(g_nccl.AllReduce(v, v, n, ncclDouble, ncclSum, (ncclComm_t)c->nccl_comm,
-                          c->stream));
+  NC_TRY(g_nccl.AllReduce(src, dst, n, ncclDouble, ncclSum,
+                          (ncclComm_t)c->nccl_comm, c->stream));
   return B200_OK;
 }
 

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(EW_THREADS)
 k_pcg_init(uint64_t n, const double *__restrict__ b, const double *__restrict__ q,
            const double *__restrict__ dinv, double *__restrict__ r,
            double *__restrict__ p, double *partials, unsigned stride,
-           PcgState *st) {
+           PcgState *st, double *out) {
   __shared__ double red[EW_WARPS];
   double s[3] = {0.0, 0.0, 0.0};
   for (uint64_t i = blockIdx.x * (uint64_t)EW_THREADS + threadIdx.x; i < n;
@@ -44,7 +44,7 @@ k_pcg_init(uint64_t n, const double *__restrict__ b, const double *__restrict__ 
   for (int v = 0; v < 3; v++)
     bs[v] = block_sum<EW_WARPS>(s[v], red);
   grid_sum_finish<3, EW_WARPS>(bs, partials, stride, blockIdx.x, gridDim.x,
-                               &st->ticket[1], &st->red[4], red);
+                               &st->ticket[1], out, red);
 }
 
 __global__ void k_pcg_start(PcgState *st, double tol, int maxit) {
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(EW_THREADS)
 k_pcg_update(uint64_t n, double *__restrict__ x, double *__restrict__ r,
              const double *__restrict__ p, const double *__restrict__ q,
              const double *__restrict__ dinv, double *partials, unsigned stride,
-             PcgState *st, int par) {
+             PcgState *st, int par, double *out) {
   if (st->done)
     return;
   __shared__ double red[EW_WARPS];
@@ -99,7 +99,7 @@ k_pcg_update(uint64_t n, double *__restrict__ x, double *__restrict__ r,
   bs[0] = block_sum<EW_WARPS>(s[0], red);
   bs[1] = block_sum<EW_WARPS>(s[1], red);
   grid_sum_finish<2, EW_WARPS>(bs, partials, stride, blockIdx.x, gridDim.x,
-                               &st->ticket[2], &st->red[(par ^ 1) * 2], red);
+                               &st->ticket[2], out, red);
 }
 
 // K3 (also owns the convergence decision and the iteration counter)
@@ -141,7 +141,7 @@ k_pcg_pupdate(uint64_t n, const double *__restrict__ r,
 // ||b - A x||^2 for the exit check (q = A x)
 __global__ void __launch_bounds__(EW_THREADS)
 k_true_resid(uint64_t n, const double *__restrict__ b, const double *__restrict__ q,
-             double *partials, unsigned stride, PcgState *st) {
+             double *partials, unsigned stride, PcgState *st, double *out) {
   __shared__ double red[EW_WARPS];
   double s = 0.0;
   for (uint64_t i = blockIdx.x * (uint64_t)EW_THREADS + threadIdx.x; i < n;
@@ -151,7 +151,7 @@ k_true_resid(uint64_t n, const double *__restrict__ b, const double *__restrict_
   }
   double bs[1] = {block_sum<EW_WARPS>(s, red)};
   grid_sum_finish<1, EW_WARPS>(bs, partials, stride, blockIdx.x, gridDim.x,
-                               &st->ticket[3], &st->true_rr, red);
+                               &st->ticket[3], out, red);
 }
 
 // ---------------------------------------------------------------------------
@@ -186,10 +186,15 @@ int ensure_workspace(b200_mat *M) {
   return B200_OK;
 }
 
-static int reduce_ranks(b200_mat *M, double *d_vals, int count) {
+// where a reduction kernel stores its sum: straight into `red` on one rank,
+// into the matching `loc` slot (all-reduced into `red` afterwards) on several
+static double *sum_target(b200_mat *M, double *red, double *loc) {
+  return M->ctx->nranks > 1 ? loc : red;
+}
+static int reduce_ranks(b200_mat *M, double *red, double *loc, int count) {
   if (M->ctx->nranks == 1)
     return B200_OK;
-  return allreduce_sum(M->ctx, d_vals, count);
+  return allreduce_sum(M->ctx, loc, red, count);
 }
 
 static int queue_iteration(b200_mat *M, int par) {
@@ -197,11 +202,13 @@ static int queue_iteration(b200_mat *M, int par) {
   cudaStream_t s = c->stream;
   uint64_t n = M->n_local;
   B_TRY(spmv_full_internal(M, M->w_p, M->w_q, true));  // K1
-  B_TRY(reduce_ranks(M, &M->state->pq, 1));
-  k_pcg_update<<<M->grid_ew, EW_THREADS, 0, s>>>(n, M->w_x, M->w_r, M->w_p,
-                                                 M->w_q, M->dinv, M->partials,
-                                                 M->partial_stride, M->state, par);
-  B_TRY(reduce_ranks(M, &M->state->red[(par ^ 1) * 2], 2));
+  PcgState *st = M->state;
+  const int nx = (par ^ 1) * 2;
+  B_TRY(reduce_ranks(M, &st->pq, &st->pq_loc, 1));
+  k_pcg_update<<<M->grid_ew, EW_THREADS, 0, s>>>(
+      n, M->w_x, M->w_r, M->w_p, M->w_q, M->dinv, M->partials, M->partial_stride,
+      st, par, sum_target(M, &st->red[nx], &st->loc[nx]));
+  B_TRY(reduce_ranks(M, &st->red[nx], &st->loc[nx], 2));
   k_pcg_pupdate<<<M->grid_ew, EW_THREADS, 0, s>>>(n, M->w_r, M->dinv, M->w_p,
                                                   M->state, par);
   c->launches += 2;
@@ -268,8 +275,9 @@ extern "C" int b200_pcg_solve(b200_mat *M, const double *d_b, double *d_x,
   B_TRY(spmv_full_internal(M, M->w_p, M->w_q, false));
   k_pcg_init<<<M->grid_ew, EW_THREADS, 0, s>>>(n, d_b, M->w_q, M->dinv, M->w_r,
                                                M->w_p, M->partials,
-                                               M->partial_stride, M->state);
-  B_TRY(reduce_ranks(M, &M->state->red[4], 3));
+                                               M->partial_stride, M->state,
+                                               sum_target(M, &M->state->red[4], &M->state->loc[4]));
+  B_TRY(reduce_ranks(M, &M->state->red[4], &M->state->loc[4], 3));
   k_pcg_start<<<1, 1, 0, s>>>(M->state, o->tol, o->maxit);
   c->launches += 2;
   CU_TRY(cudaGetLastError());
@@ -294,12 +302,14 @@ extern "C" int b200_pcg_solve(b200_mat *M, const double *d_b, double *d_x,
         int par = i & 1;
         CU_TRY(cudaEventRecord(ev[0], s));
         B_TRY(spmv_full_internal(M, M->w_p, M->w_q, true));
-        B_TRY(reduce_ranks(M, &M->state->pq, 1));
+        PcgState *st = M->state;
+        const int nx = (par ^ 1) * 2;
+        B_TRY(reduce_ranks(M, &st->pq, &st->pq_loc, 1));
         CU_TRY(cudaEventRecord(ev[1], s));
         k_pcg_update<<<M->grid_ew, EW_THREADS, 0, s>>>(
             n, M->w_x, M->w_r, M->w_p, M->w_q, M->dinv, M->partials,
-            M->partial_stride, M->state, par);
-        B_TRY(reduce_ranks(M, &M->state->red[(par ^ 1) * 2], 2));
+            M->partial_stride, st, par, sum_target(M, &st->red[nx], &st->loc[nx]));
+        B_TRY(reduce_ranks(M, &st->red[nx], &st->loc[nx], 2));
         CU_TRY(cudaEventRecord(ev[2], s));
         k_pcg_pupdate<<<M->grid_ew, EW_THREADS, 0, s>>>(n, M->w_r, M->dinv,
                                                         M->w_p, M->state, par);
@@ -329,9 +339,10 @@ extern "C" int b200_pcg_solve(b200_mat *M, const double *d_b, double *d_x,
   // ---- exit: true residual with one more SpMV -----------------------------------
   CU_TRY(cudaMemcpyAsync(M->w_p, M->w_x, n * 8, cudaMemcpyDeviceToDevice, s));
   B_TRY(spmv_full_internal(M, M->w_p, M->w_q, false));
-  k_true_resid<<<M->grid_ew, EW_THREADS, 0, s>>>(n, d_b, M->w_q, M->partials,
-                                                 M->partial_stride, M->state);
-  B_TRY(reduce_ranks(M, &M->state->true_rr, 1));
+  k_true_resid<<<M->grid_ew, EW_THREADS, 0, s>>>(
+      n, d_b, M->w_q, M->partials, M->partial_stride, M->state,
+      sum_target(M, &M->state->true_rr, &M->state->true_rr_loc));
+  B_TRY(reduce_ranks(M, &M->state->true_rr, &M->state->true_rr_loc, 1));
   CU_TRY(cudaMemcpyAsync(d_x, M->w_x, n * 8, cudaMemcpyDeviceToDevice, s));
   c->launches += 1;
   CU_TRY(cudaEventRecord(c->ev_b, s));

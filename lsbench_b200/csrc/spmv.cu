@@ -29,7 +29,7 @@ k_spmv_sell(const uint32_t *__restrict__ sell_off,
             const uint32_t *__restrict__ perm, const double *__restrict__ x,
             double *__restrict__ y, uint32_t b0, uint32_t e0, uint32_t b1,
             uint32_t e1, uint32_t n_rows, double *partials, unsigned slot_base,
-            unsigned total_slots, PcgState *st) {
+            unsigned total_slots, PcgState *st, double *dot_out) {
   if (DOT && st->done)
     return;
   __shared__ double red[SPMV_WARPS];
@@ -91,7 +91,7 @@ k_spmv_sell(const uint32_t *__restrict__ sell_off,
   if (DOT) {
     double b[1] = {block_sum<SPMV_WARPS>(dot, red)};
     grid_sum_finish<1, SPMV_WARPS>(b, partials, 0, slot_base + blockIdx.x,
-                                   total_slots, &st->ticket[0], &st->pq, red);
+                                   total_slots, &st->ticket[0], dot_out, red);
   }
 }
 
@@ -101,7 +101,7 @@ k_spmv_vec(uint32_t nrows, const uint32_t *__restrict__ ids,
            const uint64_t *__restrict__ off, const uint32_t *__restrict__ cols,
            const double *__restrict__ vals, const double *__restrict__ x,
            double *__restrict__ y, double *partials, unsigned slot_base,
-           unsigned total_slots, PcgState *st) {
+           unsigned total_slots, PcgState *st, double *dot_out) {
   if (DOT && st->done)
     return;
   __shared__ double red[SPMV_WARPS];
@@ -133,7 +133,7 @@ k_spmv_vec(uint32_t nrows, const uint32_t *__restrict__ ids,
   if (DOT) {
     double b[1] = {block_sum<SPMV_WARPS>(dot, red)};
     grid_sum_finish<1, SPMV_WARPS>(b, partials, 0, slot_base + blockIdx.x,
-                                   total_slots, &st->ticket[0], &st->pq, red);
+                                   total_slots, &st->ticket[0], dot_out, red);
   }
 }
 
@@ -143,7 +143,7 @@ k_spmv_long(uint32_t nrows, const uint32_t *__restrict__ ids,
             const uint64_t *__restrict__ off, const uint32_t *__restrict__ cols,
             const double *__restrict__ vals, const double *__restrict__ x,
             double *__restrict__ y, double *partials, unsigned slot_base,
-            unsigned total_slots, PcgState *st) {
+            unsigned total_slots, PcgState *st, double *dot_out) {
   if (DOT && st->done)
     return;
   __shared__ double red[SPMV_WARPS];
@@ -174,7 +174,7 @@ k_spmv_long(uint32_t nrows, const uint32_t *__restrict__ ids,
     // only thread 0 carries a value; block_sum keeps the protocol uniform
     double b[1] = {block_sum<SPMV_WARPS>(dot, red)};
     grid_sum_finish<1, SPMV_WARPS>(b, partials, 0, slot_base + blockIdx.x,
-                                   total_slots, &st->ticket[0], &st->pq, red);
+                                   total_slots, &st->ticket[0], dot_out, red);
   }
 }
 
@@ -259,37 +259,38 @@ int launch_spmv(b200_mat *M, const double *x, double *y, bool dot, int phase) {
       B_FAIL(B200_EINVAL, "launch_spmv: empty matrix");
   }
   uint32_t n = (uint32_t)M->n_local;
+  double *dot_out = dot ? (c->nranks > 1 ? &M->state->pq_loc : &M->state->pq) : nullptr;
   if (P.g_sell) {
     if (dot)
       k_spmv_sell<true><<<P.g_sell, SPMV_THREADS, 0, s>>>(
           M->sell_off, M->sell_cols, M->sell_vals, M->sell_perm, x, y, P.b0,
-          P.e0, P.b1, P.e1, n, M->partials, slot_base, total, M->state);
+          P.e0, P.b1, P.e1, n, M->partials, slot_base, total, M->state, dot_out);
     else
       k_spmv_sell<false><<<P.g_sell, SPMV_THREADS, 0, s>>>(
           M->sell_off, M->sell_cols, M->sell_vals, M->sell_perm, x, y, P.b0,
-          P.e0, P.b1, P.e1, n, nullptr, 0, 0, nullptr);
+          P.e0, P.b1, P.e1, n, nullptr, 0, 0, nullptr, nullptr);
     slot_base += P.g_sell;
   }
   if (P.g_vec) {
     if (dot)
       k_spmv_vec<true><<<P.g_vec, SPMV_THREADS, 0, s>>>(
           M->vec_rows, M->vec_row_ids, M->vec_off, M->vl_cols, M->vl_vals, x, y,
-          M->partials, slot_base, total, M->state);
+          M->partials, slot_base, total, M->state, dot_out);
     else
       k_spmv_vec<false><<<P.g_vec, SPMV_THREADS, 0, s>>>(
           M->vec_rows, M->vec_row_ids, M->vec_off, M->vl_cols, M->vl_vals, x, y,
-          nullptr, 0, 0, nullptr);
+          nullptr, 0, 0, nullptr, nullptr);
     slot_base += P.g_vec;
   }
   if (P.g_long) {
     if (dot)
       k_spmv_long<true><<<P.g_long, SPMV_THREADS, 0, s>>>(
           M->long_rows, M->long_row_ids, M->long_off, M->vl_cols, M->vl_vals, x,
-          y, M->partials, slot_base, total, M->state);
+          y, M->partials, slot_base, total, M->state, dot_out);
     else
       k_spmv_long<false><<<P.g_long, SPMV_THREADS, 0, s>>>(
           M->long_rows, M->long_row_ids, M->long_off, M->vl_cols, M->vl_vals, x,
-          y, nullptr, 0, 0, nullptr);
+          y, nullptr, 0, 0, nullptr, nullptr);
   }
   c->launches += (P.g_sell > 0) + (P.g_vec > 0) + (P.g_long > 0);
   CU_TRY(cudaGetLastError());

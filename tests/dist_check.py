@@ -83,6 +83,7 @@ def main():
             b = orc.rhs(n)
             x, r, rc = M.pcg_host(b[r0:r1], tol=1e-10)
             assert rc == 0 and r.status == 0 and r.true_relres <= 1.05e-10
+            assert r.relres <= 1e-10, r.relres
             x2, r2, _ = M.pcg_host(b[r0:r1], tol=1e-10)
             assert r2.iters == r.iters and x2.tobytes() == x.tobytes()
             xfull = gather(x)
