@@ -1,0 +1,102 @@
+"""The C host path on a GPU: `driver --solver b200` (host C -> C ABI -> CUDA),
+i.e. the call a user of the reference makes, against the golden direct solve.
+Also runs the reference's own, unmodified bin/driver.c when it was built."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import orc
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DIRECT = np.load(os.path.join(ROOT, "tests", "golden", "direct.npz"))
+
+
+@pytest.fixture(scope="module")
+def bh():
+    from lsbench_b200 import build, build_host
+    build.build()
+    build_host.build()
+    return build_host
+
+
+def parse(stdout):
+    lines = stdout.strip().splitlines()
+    i = lines.index("===matrix,n,nnz,trials,solver,ordering,elapsed===")
+    row = lines[i + 1].split(",")
+    j = [k for k, l in enumerate(lines) if l.startswith("===b200:")][0]
+    ext = lines[j + 1].split(",")
+    return row, ext
+
+
+@pytest.mark.parametrize("name", ["I1_05x05", "tj7a_A_12", "xn3b_A_10", "xn3b_A_18"])
+def test_driver_b200_matches_direct_solve(bh, name, tmp_path):
+    A = orc.matrix_read(orc.matrix_path(name))
+    out = str(tmp_path / "x.bin")
+    r = subprocess.run([bh.DRIVER, "--solver", "b200", "--matrix", orc.matrix_path(name),
+                        "--trials=3", "--verbose=1", "--dump-x", out],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    row, ext = parse(r.stdout)
+    # matrix,n,nnz,trials,solver,ordering,elapsed  (src/cusparse.c:207-209)
+    assert row[1:6] == [str(A.nrows), str(A.nnz), "3", "6", "0"] and float(row[6]) > 0
+    gpus, iters, status, relres, true_relres = int(ext[0]), int(ext[1]), int(ext[2]), float(ext[3]), float(ext[4])
+    assert (gpus, status) == (1, 0) and relres <= 1e-10 and true_relres <= 1.05e-10
+    x = np.fromfile(out)
+    g = DIRECT[name]
+    assert np.linalg.norm(x - g) / np.linalg.norm(g) <= 1e-8
+    M = orc.op_upper_mirror(A)
+    assert orc.true_relres(M, orc.rhs(M.n), x) <= 1.05e-10
+
+
+def test_unmodified_reference_driver_runs_b200(bh):
+    if not os.path.exists(bh.DRIVER_REF):
+        pytest.skip("driver_ref was not built (no reference tree at build time)")
+    r = subprocess.run([bh.DRIVER_REF, "--solver", "b200", "--matrix",
+                        orc.matrix_path("tj7a_A_18"), "--trials=2"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    row, ext = parse(r.stdout)
+    assert row[1] == "3707" and int(ext[2]) == 0 and float(ext[4]) <= 1.05e-10
+
+
+def test_driver_full_operator_switch(bh, tmp_path):
+    """LSBENCH_B200_OPERATOR=full solves the matrix as stored (what cuSOLVER is
+    handed): a different answer, by ~1e-7."""
+    name = "tj7a_A_18"
+    out = str(tmp_path / "x.bin")
+    env = dict(os.environ, LSBENCH_B200_OPERATOR="full")
+    r = subprocess.run([bh.DRIVER, "--solver", "b200", "--matrix", orc.matrix_path(name),
+                        "--trials=1", "--dump-x", out], capture_output=True, text=True,
+                       env=env, timeout=600)
+    assert r.returncode == 0, r.stderr
+    x, g = np.fromfile(out), DIRECT[name]
+    d = np.linalg.norm(x - g) / np.linalg.norm(g)
+    assert 1e-8 < d < 1e-5
+    A = orc.matrix_read(orc.matrix_path(name))
+    assert orc.true_relres(orc.op_full(A), orc.rhs(A.nrows), x) <= 1.05e-10
+
+
+def test_driver_synthetic_and_multi_gpu(bh, tmp_path):
+    from lsbench_b200 import abi
+    out = str(tmp_path / "x.bin")
+    r = subprocess.run([bh.DRIVER, "--solver", "b200", "--matrix", "poisson27:40",
+                        "--trials=2", "--dump-x", out], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    row, ext = parse(r.stdout)
+    M = orc.gen_poisson27(40)
+    assert row[1:3] == [str(M.n), str(M.nnz)] and int(ext[2]) == 0
+    x1 = np.fromfile(out)
+    assert orc.true_relres(M, orc.rhs(M.n), x1) <= 1.05e-10
+    if abi.device_count() >= 2:
+        env = dict(os.environ, LSBENCH_B200_NGPUS="2")
+        r = subprocess.run([bh.DRIVER, "--solver", "b200", "--matrix", "poisson27:40",
+                            "--trials=2", "--dump-x", out], capture_output=True, text=True,
+                           env=env, timeout=600)
+        assert r.returncode == 0, r.stderr
+        row2, ext2 = parse(r.stdout)
+        assert int(ext2[0]) == 2 and int(ext2[2]) == 0 and row2[2] == row[2]
+        x2 = np.fromfile(out)
+        assert np.linalg.norm(x2 - x1) / np.linalg.norm(x1) <= 1e-9

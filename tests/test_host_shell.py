@@ -1,0 +1,193 @@
+"""The C host shell around the backend (lsbench_b200/host): public API, CLI,
+reader, registration of `--solver b200` -- everything that runs without a GPU.
+
+Anchors: src/lsbench.h:31-40 (API), src/lsbench.c:82-150 (CLI), :156-187
+(dispatch), src/lsbench-csr.c:29-92 (reader), bin/driver.c (must build
+unchanged), BASELINE.json config 1 (cholmod plumbing on CPU).
+"""
+import ctypes as C
+import hashlib
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+READER = json.load(open(os.path.join(GOLD, "reader.json")))
+
+
+class Csr(C.Structure):
+    _fields_ = [("nrows", C.c_uint), ("base", C.c_uint), ("offs", C.POINTER(C.c_uint)),
+                ("cols", C.POINTER(C.c_uint)), ("vals", C.POINTER(C.c_double)),
+                ("gen_kind", C.c_int), ("gen_size", C.c_ulonglong),
+                ("gen_seed", C.c_ulonglong), ("gen_nnz", C.c_ulonglong)]
+
+
+class Lsbench(C.Structure):
+    _fields_ = [("matrix", C.c_char_p), ("solver", C.c_int), ("ordering", C.c_int),
+                ("precision", C.c_int), ("verbose", C.c_uint), ("trials", C.c_uint)]
+
+
+@pytest.fixture(scope="module")
+def host():
+    from lsbench_b200 import build, build_host
+    build.build()
+    build_host.build()
+    L = C.CDLL(build_host.LIB)
+    L.lsbench_matrix_read.restype = C.POINTER(Csr)
+    L.lsbench_matrix_read.argtypes = [C.c_char_p]
+    L.lsbench_matrix_free.argtypes = [C.POINTER(Csr)]
+    L.lsbench_init.restype = C.POINTER(Lsbench)
+    L.lsbench_init.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+    L.lsbench_finalize.argtypes = [C.POINTER(Lsbench)]
+    L.lsbench_get_matrix_name.restype = C.c_char_p
+    L.lsbench_get_matrix_name.argtypes = [C.POINTER(Lsbench)]
+    L.lsbench_matrix_nnz.restype = C.c_ulonglong
+    L.lsbench_matrix_nnz.argtypes = [C.POINTER(Csr)]
+    return L, build_host
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def init(L, *words):
+    argv = (C.c_char_p * (len(words) + 2))(b"driver", *[w.encode() for w in words], None)
+    return L.lsbench_init(len(words) + 1, argv)
+
+
+def test_public_api_is_the_reference_api(host):
+    L, _ = host
+    for f in ("lsbench_matrix_read", "lsbench_matrix_print", "lsbench_matrix_free",
+              "lsbench_init", "lsbench_get_matrix_name", "lsbench_bench", "lsbench_finalize",
+              "b200_init", "b200_bench", "b200_finalize"):
+        assert hasattr(L, f), f
+    hdr = open(os.path.join(ROOT, "include", "lsbench.h")).read()
+    for name, val in (("CUSOLVER", 0), ("HYPRE", 1), ("AMGX", 2), ("CHOLMOD", 3),
+                      ("PARALMOND", 4), ("GINKGO", 5), ("B200", 6)):
+        assert "LSBENCH_SOLVER_%s = %d" % (name, val) in hdr
+
+
+@pytest.mark.parametrize("name", orc.TOY + orc.NEK)
+def test_host_reader_is_bit_identical_to_the_reference(host, name):
+    L, _ = host
+    p = L.lsbench_matrix_read(orc.matrix_path(name).encode())
+    a, g = p.contents, READER[name]
+    nnz = a.offs[a.nrows]
+    assert (a.nrows, nnz, a.base) == (g["n"], g["nnz"], g["base"])
+    assert sha(np.ctypeslib.as_array(a.offs, (a.nrows + 1,))) == g["offs"]
+    assert sha(np.ctypeslib.as_array(a.cols, (nnz,))) == g["cols"]
+    assert sha(np.ctypeslib.as_array(a.vals, (nnz,))) == g["vals"]
+    assert L.lsbench_matrix_nnz(p) == nnz and a.gen_kind == 0
+    L.lsbench_matrix_free(p)
+
+
+def test_host_reader_sorts_folds_and_compresses(host, tmp_path):
+    L, _ = host
+    f = tmp_path / "m.txt"
+    f.write_text("6 1\n3 1 5.0\n1 2 1.5\n1 1 2.0\n1 2 0.25\n4 4 7\n3 3 -1e0\n")
+    p = L.lsbench_matrix_read(str(f).encode())
+    a = p.contents
+    assert a.nrows == 3 and [a.offs[i] for i in range(4)] == [0, 2, 4, 5]
+    assert [a.cols[i] for i in range(5)] == [1, 2, 1, 3, 4]
+    assert [a.vals[i] for i in range(5)] == [2.0, 1.75, 5.0, -1.0, 7.0]
+    L.lsbench_matrix_free(p)
+
+
+def test_synthetic_descriptor(host):
+    L, _ = host
+    p = L.lsbench_matrix_read(b"poisson27:512")
+    a = p.contents
+    assert (a.nrows, a.gen_kind, a.gen_size) == (512 ** 3, 2, 512) and not a.offs
+    L.lsbench_matrix_free(p)
+    p = L.lsbench_matrix_read(b"powerlaw:50000000:3")
+    assert (p.contents.nrows, p.contents.gen_kind, p.contents.gen_seed) == (50000000, 3, 3)
+    L.lsbench_matrix_free(p)
+
+
+def test_cli_defaults_and_both_option_forms(host):
+    L, _ = host
+    cb = init(L, "--matrix", "m.txt")
+    c = cb.contents  # defaults: src/lsbench.c:95-96
+    assert (c.solver, c.ordering, c.precision, c.verbose, c.trials) == (0, 0, 0, 0, 100)
+    assert L.lsbench_get_matrix_name(cb) == b"m.txt"
+    L.lsbench_finalize(cb)
+    cb = init(L, "--test", "t.txt", "--solver", "b200", "--trials", "7", "--verbose=2",
+              "--ordering", "amd")
+    c = cb.contents
+    assert (c.matrix, c.solver, c.trials, c.verbose, c.ordering) == (b"t.txt", 6, 7, 2, 1)
+    L.lsbench_finalize(cb)
+    cb = init(L, "--matrix", "m", "--solver", "CuSolver", "--trials=3")
+    assert (cb.contents.solver, cb.contents.trials) == (0, 3)
+    L.lsbench_finalize(cb)
+    cb = init(L, "--matrix", "m", "--solver", "cusparse")  # src/lsbench.c:31-33
+    assert cb.contents.solver == 3
+    L.lsbench_finalize(cb)
+
+
+def test_driver_cli_errors(host):
+    _, bh = host
+    r = subprocess.run([bh.DRIVER, "--help"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("Usage: " + bh.DRIVER)
+    r = subprocess.run([bh.DRIVER, "--solver", "b200"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Input matrix file not provided" in r.stderr
+    r = subprocess.run([bh.DRIVER, "--matrix", "x", "--precision=FP32"],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "FP64" in r.stderr
+    r = subprocess.run([bh.DRIVER, "--matrix", "/nonexistent.txt", "--solver", "b200"],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "Unable to open file" in r.stderr
+    r = subprocess.run([bh.DRIVER, "--bogus"], capture_output=True, text=True)
+    assert r.returncode == 1
+
+
+def test_reference_driver_source_builds_unchanged(host):
+    _, bh = host
+    if not os.path.exists(bh.DRIVER_REF):
+        pytest.skip("reference tree not mounted when the host shell was built")
+    r = subprocess.run([bh.DRIVER_REF, "--help"], capture_output=True, text=True)
+    assert r.returncode == 0 and "--solver" in r.stdout
+
+
+def test_cpu_only_host_still_runs_the_cholmod_configuration(host):
+    """BASELINE.json config 1.  In the product library cholmod is 'not built'
+    (like the reference with ENABLE_CHOLMOD=OFF) and the run must survive on a
+    GPU-less host even though b200 is compiled in."""
+    _, bh = host
+    r = subprocess.run([bh.DRIVER, "--solver", "cholmod", "--test",
+                        orc.matrix_path("I1_05x05")], capture_output=True, text=True)
+    assert r.returncode == 0 and "did not run" in r.stderr
+
+
+def test_config1_with_the_direct_solve_standin(host, tmp_path):
+    """Same command with the test-only CHOLMOD stand-in linked in: CSV row in
+    the reference's format and the analytic I1 solution."""
+    _, bh = host
+    from lsbench_b200 import build_host as b
+    orc.lib()
+    lib = str(tmp_path / "liblsbench.so")
+    drv = str(tmp_path / "driver")
+    host_dir = os.path.join(ROOT, "lsbench_b200", "host")
+    inc = ["-I", os.path.join(ROOT, "include"), "-I", host_dir, "-I", orc.ORACLE_DIR]
+    subprocess.run([b._cc(), "-O2", "-std=c11", "-fPIC", "-shared", "-DLSBENCH_CHOLMOD_STANDIN",
+                    "-o", lib] + inc +
+                   [os.path.join(host_dir, f) for f in ("lsbench.c", "lsbench-csr.c", "b200.c")] +
+                   [os.path.join(ROOT, "tests", "cholmod_standin.c"), orc.LIB,
+                    "-Wl,-rpath," + os.path.dirname(orc.LIB)], check=True)
+    subprocess.run([b._cc(), "-O2", "-std=c11"] + inc + [os.path.join(host_dir, "main.c"), "-o", drv,
+                    lib, "-Wl,-rpath," + str(tmp_path)], check=True)
+    out = str(tmp_path / "x.bin")
+    r = subprocess.run([drv, "--solver", "cholmod", "--test", orc.matrix_path("I1_05x05"),
+                        "--trials=4", "--dump-x", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    assert lines[0] == "===matrix,n,nnz,trials,solver,ordering,elapsed==="
+    f = lines[1].split(",")
+    assert f[0].endswith("I1_05x05.txt") and f[1:6] == ["5", "5", "4", "3", "0"]
+    assert float(f[6]) >= 0
+    np.testing.assert_allclose(np.fromfile(out), [0, 1 / 2, 2 / 3, 3 / 4, 4 / 5], rtol=1e-15)
