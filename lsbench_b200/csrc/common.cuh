@@ -137,6 +137,7 @@ struct b200_mat {
   SpmvPlan plan[3];              // phase 0 all, 1 interior, 2 boundary
   bool plan_ready = false;
   void *small = nullptr;          // on-chip small-matrix plan (small.cu)
+  bool small_tried = false;
   void *graph_exec = nullptr;     // cudaGraphExec_t of one iteration chunk
   int graph_chunk = 0;
   int graph_kernels = 0;         // kernel nodes in the captured chunk

@@ -1,10 +1,472 @@
-// small.cu -- on-chip PCG for matrices that fit in distributed shared memory.
-// STUB for the first milestone: never selected.
+// small.cu -- the coarse-grid regime (BASELINE.json config 2: Nek matrices,
+// n ~ 3.5-6.4 k, nnz ~ 77-146 k): the whole Jacobi-PCG solve in ONE kernel on
+// ONE thread-block cluster, matrix resident in (distributed) shared memory.
+//
+// Why: with three streaming kernels per iteration a 300-iteration solve is
+// ~900 launches of ~3 us each -- launch-bound (3.4 ms measured) although the
+// data is 1.7 MB.  Here the matrix is split over the shared memory of the C
+// CTAs of a cluster (C = 16, else 8), each CTA keeps its rows' x, r, D^-1 in
+// shared memory too, and an iteration costs three hardware cluster barriers:
+//
+//   stage   the slice of p this CTA's columns touch: L2 -> shared memory
+//   SpMV    4 lanes per row, 8 rows per warp, operands from shared memory,
+//           4-lane shuffle reduction; p.q partial per CTA
+//   -- partials to every CTA's shared memory over DSMEM; cluster barrier 1 --
+//   update  x += a p, r -= a q, partials of r.D^-1 r and r.r
+//   -- DSMEM exchange; cluster barrier 2; convergence test (same in all CTAs) --
+//   p       p = D^-1 r + b p for the owned rows -> global (L2)
+//   -- cluster barrier 3 --
+//
+// All sums have a fixed order (4-lane butterfly, warp butterfly, warps in
+// order, CTAs in rank order), so iterates and iteration counts are
+// bit-reproducible.  Same recurrences and stopping rule as pcg.cu; stands
+// where the timed solve of src/cholmod-impl.h:58-63 / src/cusparse.c:189-197
+// stands for these matrices.
 #include "common.cuh"
-int small_try_build(b200_mat *M) { (void)M; return B200_OK; }
-void small_free(b200_mat *M) { (void)M; }
-int small_solve(b200_mat *M, const double *b, double *x, const b200_pcg_opts *o,
-                b200_pcg_result *r) {
-  (void)M, (void)b, (void)x, (void)o, (void)r;
-  B_FAIL(B200_EINVAL, "small path not built");
+#include <cooperative_groups.h>
+#include <algorithm>
+#include <vector>
+
+namespace cg = cooperative_groups;
+
+#define SM_THREADS 1024
+#define SM_WARPS (SM_THREADS / 32)
+#define SM_MAX_CLUSTER 16
+#define SM_MAX_ROWS 16384
+#define SM_MAX_NNZ 600000
+
+struct SmallCta {         // one per CTA, in global memory
+  uint32_t n_groups;      // 8-row groups owned
+  uint32_t n_rows;        // rows owned (<= 8 n_groups)
+  uint32_t ent;           // padded entries = 32 * sum of group widths
+  uint32_t col_lo, col_n; // staged column window [col_lo, col_lo + col_n)
+  uint32_t goff_at;       // into goff[]   (n_groups + 1 values, units of 32 entries)
+  uint32_t row_at;        // into rowid[] / dinv[] (8 n_groups values, 0xffffffff = none)
+  uint32_t pad;
+  uint64_t ent_at;        // into vals[] / cols[]
+};
+
+struct SmallPlan {
+  int C = 0;
+  uint32_t n = 0;
+  size_t smem = 0;
+  SmallCta *d_cta = nullptr;
+  uint32_t *d_goff = nullptr, *d_rowid = nullptr;
+  double *d_vals = nullptr, *d_dinv = nullptr;
+  uint16_t *d_cols = nullptr;
+  double *d_p = nullptr, *d_xg = nullptr;  // global p and x staging (L2)
+  PcgState *d_state = nullptr;
+  // largest per-CTA extents (shared memory carve-up is uniform)
+  uint32_t max_ent = 0, max_groups = 0, max_stage = 0;
+};
+
+struct SmemMap {
+  size_t stage, vals, xs, rs, ds, qs, slots, wred, goff, rowid, cols, total;
+};
+
+__host__ __device__ inline SmemMap smem_map(uint32_t max_ent, uint32_t max_groups,
+                                            uint32_t max_stage) {
+  SmemMap m;
+  size_t rows = (size_t)max_groups * 8, o = 0;
+  m.stage = o, o += ((size_t)max_stage + 1) / 2 * 2 * 8;
+  m.vals = o, o += (size_t)max_ent * 8;
+  m.xs = o, o += rows * 8;
+  m.rs = o, o += rows * 8;
+  m.ds = o, o += rows * 8;
+  m.qs = o, o += rows * 8;
+  m.slots = o, o += 4 * SM_MAX_CLUSTER * 8;  // pq | rz | rr | bb
+  m.wred = o, o += 3 * SM_WARPS * 8;
+  m.goff = o, o += ((size_t)max_groups + 2) * 4;
+  m.rowid = o, o += rows * 4;
+  m.cols = o, o += (size_t)max_ent * 2;
+  m.total = (o + 15) / 16 * 16;
+  return m;
+}
+
+// y[lr] = sum_k a(lr,k) * v[col(lr,k)] for the rows of this CTA; v staged in
+// shared memory.  4 lanes per row; the value lands in every lane of the group.
+__device__ __forceinline__ void small_spmv(const SmallCta &me, const uint32_t *goff,
+                                           const double *vals, const uint16_t *cols,
+                                           const double *v_s, double *q_s) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint32_t j = warp; j < me.n_groups; j += SM_WARPS) {
+    const uint32_t o = goff[j], w = goff[j + 1] - o;
+    const uint32_t base = o * 32 + lane;
+    double s = 0.0;
+    for (uint32_t t = 0; t < w; t++)
+      s = fma(vals[base + t * 32], v_s[cols[base + t * 32]], s);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if ((lane & 3) == 0)
+      q_s[j * 8 + (lane >> 2)] = s;
+  }
+}
+
+// CTA sum of NV per-thread values -> slot[v][my rank] in EVERY CTA of the
+// cluster (DSMEM), then the cluster barrier; on return tot[v] = sum over the
+// CTAs in rank order, identical in all threads of all CTAs.
+template <int NV>
+__device__ __forceinline__ void cluster_sum(cg::cluster_group &cl, double (&val)[NV],
+                                            double *wred, double *slots, int slot0,
+                                            double (&tot)[NV]) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned C = cl.num_blocks(), me = cl.block_rank();
+#pragma unroll
+  for (int v = 0; v < NV; v++) {
+    double s = warp_sum(val[v]);
+    if (lane == 0)
+      wred[v * SM_WARPS + warp] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < C) {
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+      double s = 0.0;
+      for (int w = 0; w < SM_WARPS; w++)
+        s += wred[v * SM_WARPS + w];
+      double *remote = cl.map_shared_rank(slots + (slot0 + v) * SM_MAX_CLUSTER, threadIdx.x);
+      remote[me] = s;
+    }
+  }
+  cl.sync();
+#pragma unroll
+  for (int v = 0; v < NV; v++) {
+    double s = 0.0;
+    for (unsigned c = 0; c < C; c++)
+      s += slots[(slot0 + v) * SM_MAX_CLUSTER + c];
+    tot[v] = s;
+  }
+}
+
+__global__ void __launch_bounds__(SM_THREADS, 1)
+k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_goff,
+            const uint32_t *__restrict__ g_rowid, const double *__restrict__ g_vals,
+            const uint16_t *__restrict__ g_cols, const double *__restrict__ g_dinv,
+            const double *__restrict__ b, double *__restrict__ x, double *p_g,
+            double *x_g, PcgState *st, uint32_t max_ent, uint32_t max_groups,
+            uint32_t max_stage, double tol, int maxit) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  cg::cluster_group cl = cg::this_cluster();
+  const SmallCta me = ctas[cl.block_rank()];
+  const SmemMap mp = smem_map(max_ent, max_groups, max_stage);
+  double *v_s = (double *)(smem + mp.stage), *vals = (double *)(smem + mp.vals);
+  double *x_s = (double *)(smem + mp.xs), *r_s = (double *)(smem + mp.rs);
+  double *d_s = (double *)(smem + mp.ds), *q_s = (double *)(smem + mp.qs);
+  double *slots = (double *)(smem + mp.slots), *wred = (double *)(smem + mp.wred);
+  uint32_t *goff = (uint32_t *)(smem + mp.goff), *rowid = (uint32_t *)(smem + mp.rowid);
+  uint16_t *cols = (uint16_t *)(smem + mp.cols);
+  const uint32_t tid = threadIdx.x, nslot = me.n_groups * 8;
+
+  // ---- make the matrix resident ----------------------------------------------------
+  for (uint32_t i = tid; i < me.ent; i += SM_THREADS)
+    vals[i] = g_vals[me.ent_at + i], cols[i] = g_cols[me.ent_at + i];
+  for (uint32_t i = tid; i <= me.n_groups; i += SM_THREADS)
+    goff[i] = g_goff[me.goff_at + i];
+  for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
+    uint32_t row = g_rowid[me.row_at + i];
+    rowid[i] = row;
+    d_s[i] = g_dinv[me.row_at + i];
+    x_s[i] = row != 0xffffffffu ? x[row] : 0.0;
+  }
+  __syncthreads();
+
+  // ---- r = b - A x0, p = D^-1 r ------------------------------------------------------
+  for (uint32_t i = tid; i < me.col_n; i += SM_THREADS)
+    v_s[i] = x[me.col_lo + i];
+  __syncthreads();
+  small_spmv(me, goff, vals, cols, v_s, q_s);
+  __syncthreads();
+  double acc3[3] = {0.0, 0.0, 0.0}, tot3[3];
+  for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
+    uint32_t row = rowid[i];
+    if (row == 0xffffffffu)
+      continue;
+    double bi = b[row], ri = bi - q_s[i], zi = d_s[i] * ri;
+    r_s[i] = ri;
+    p_g[row] = zi;
+    acc3[0] = fma(ri, zi, acc3[0]), acc3[1] = fma(ri, ri, acc3[1]), acc3[2] = fma(bi, bi, acc3[2]);
+  }
+  __threadfence();
+  cluster_sum<3>(cl, acc3, wred, slots, 1, tot3);  // slots 1,2,3 = rz, rr, bb
+  double rz = tot3[0], rr = tot3[1];
+  const double bb = tot3[2], thr2 = tol * tol * bb;
+  int it = 0, status = 1;
+  double pq = 0.0;
+  if (rr <= thr2)
+    status = 0;
+
+  // ---- iterations ----------------------------------------------------------------------
+  while (status == 1 && it < maxit) {
+    for (uint32_t i = tid; i < me.col_n; i += SM_THREADS)
+      v_s[i] = __ldcg(p_g + me.col_lo + i);
+    __syncthreads();
+    small_spmv(me, goff, vals, cols, v_s, q_s);
+    __syncthreads();
+    double a1[1] = {0.0}, t1[1];
+    for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
+      uint32_t row = rowid[i];
+      if (row != 0xffffffffu)
+        a1[0] = fma(q_s[i], v_s[row - me.col_lo], a1[0]);
+    }
+    cluster_sum<1>(cl, a1, wred, slots, 0, t1);
+    pq = t1[0];
+    if (!(pq > 0.0)) {
+      status = 2;
+      break;
+    }
+    const double alpha = rz / pq;
+    double a2[2] = {0.0, 0.0}, t2[2];
+    for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
+      uint32_t row = rowid[i];
+      if (row == 0xffffffffu)
+        continue;
+      double pi = v_s[row - me.col_lo];
+      x_s[i] = fma(alpha, pi, x_s[i]);
+      double ri = fma(-alpha, q_s[i], r_s[i]);
+      r_s[i] = ri;
+      a2[0] = fma(ri, d_s[i] * ri, a2[0]), a2[1] = fma(ri, ri, a2[1]);
+    }
+    cluster_sum<2>(cl, a2, wred, slots, 1, t2);
+    const double rzn = t2[0];
+    rr = t2[1];
+    it++;
+    if (rr <= thr2) {
+      status = 0;
+      break;
+    }
+    if (!(rr == rr)) {
+      status = 2;
+      break;
+    }
+    const double beta = rzn / rz;
+    rz = rzn;
+    for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
+      uint32_t row = rowid[i];
+      if (row != 0xffffffffu)
+        p_g[row] = fma(beta, v_s[row - me.col_lo], d_s[i] * r_s[i]);
+    }
+    __threadfence();
+    cl.sync();
+  }
+
+  // ---- x out, true residual ---------------------------------------------------------------
+  for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
+    uint32_t row = rowid[i];
+    if (row != 0xffffffffu)
+      x[row] = x_s[i], x_g[row] = x_s[i];
+  }
+  __threadfence();
+  cl.sync();
+  for (uint32_t i = tid; i < me.col_n; i += SM_THREADS)
+    v_s[i] = __ldcg(x_g + me.col_lo + i);
+  __syncthreads();
+  small_spmv(me, goff, vals, cols, v_s, q_s);
+  __syncthreads();
+  double a4[1] = {0.0}, t4[1];
+  for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
+    uint32_t row = rowid[i];
+    if (row != 0xffffffffu) {
+      double d = b[row] - q_s[i];
+      a4[0] = fma(d, d, a4[0]);
+    }
+  }
+  cluster_sum<1>(cl, a4, wred, slots, 0, t4);
+  if (cl.block_rank() == 0 && tid == 0) {
+    st->iter = it, st->status = status, st->done = 1;
+    st->bb = bb, st->red[1] = rr, st->pq = pq, st->true_rr = t4[0];
+  }
+}
+
+// ---------------------------------------------------------------------------
+void small_free(b200_mat *M) {
+  SmallPlan *P = (SmallPlan *)M->small;
+  if (!P)
+    return;
+  void *ptrs[] = {P->d_cta, P->d_goff, P->d_rowid, P->d_vals, P->d_dinv,
+                  P->d_cols, P->d_p, P->d_xg, P->d_state};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  delete P;
+  M->small = nullptr;
+}
+
+static int small_launch_config(SmallPlan *P, cudaLaunchConfig_t *cfg,
+                               cudaLaunchAttribute *attr, cudaStream_t s) {
+  memset(cfg, 0, sizeof *cfg);
+  cfg->gridDim = dim3(P->C), cfg->blockDim = dim3(SM_THREADS);
+  cfg->dynamicSmemBytes = P->smem, cfg->stream = s;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = P->C, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg->attrs = attr, cfg->numAttrs = 1;
+  return B200_OK;
+}
+
+// Builds the on-chip plan when the matrix qualifies; leaves M->small null
+// (streaming path) when it does not.  Never an error just for not fitting.
+int small_try_build(b200_mat *M) {
+  if (M->small || M->small_tried)
+    return B200_OK;
+  M->small_tried = true;
+  b200_ctx *c = M->ctx;
+  const uint64_t n = M->n_local;
+  if (c->nranks != 1 || n > SM_MAX_ROWS || M->nnz > SM_MAX_NNZ || M->vec_rows ||
+      M->long_rows || n == 0)
+    return B200_OK;
+
+  std::vector<uint64_t> offs(n + 1);
+  std::vector<uint32_t> cols(M->nnz ? M->nnz : 1);
+  std::vector<double> vals(M->nnz ? M->nnz : 1), dinv(n);
+  B_TRY(b200_mat_export(M, offs.data(), cols.data(), vals.data()));
+  B_TRY(b200_mat_inv_diag(M, dinv.data()));
+
+  int dev_smem = 0;
+  CU_TRY(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+  CU_TRY(cudaFuncSetAttribute(k_pcg_small, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+
+  for (int C : {16, 8}) {
+    // contiguous row chunks; inside a chunk rows sorted by decreasing length
+    std::vector<SmallCta> ctas(C);
+    std::vector<uint32_t> goff, rowid;
+    std::vector<double> pv, pd;
+    std::vector<uint16_t> pc;
+    uint32_t max_ent = 0, max_groups = 0, max_stage = 0;
+    bool ok = true;
+    for (int k = 0; k < C && ok; k++) {
+      uint64_t r0 = n * k / C, r1 = n * (k + 1) / C;
+      std::vector<uint32_t> rows;
+      for (uint64_t r = r0; r < r1; r++)
+        rows.push_back((uint32_t)r);
+      std::stable_sort(rows.begin(), rows.end(), [&](uint32_t a, uint32_t b) {
+        return offs[a + 1] - offs[a] > offs[b + 1] - offs[b];
+      });
+      uint32_t lo = 0xffffffffu, hi = 0;
+      for (uint32_t r : rows) {
+        lo = std::min(lo, r), hi = std::max(hi, r);  // own p entries are read too
+        for (uint64_t e = offs[r]; e < offs[r + 1]; e++)
+          lo = std::min(lo, cols[e]), hi = std::max(hi, cols[e]);
+      }
+      if (rows.empty())
+        lo = 0, hi = 0;
+      SmallCta &T = ctas[k];
+      T.n_rows = (uint32_t)rows.size();
+      T.n_groups = (T.n_rows + 7) / 8;
+      T.col_lo = lo, T.col_n = rows.empty() ? 0 : hi - lo + 1;
+      T.goff_at = (uint32_t)goff.size(), T.row_at = (uint32_t)rowid.size();
+      T.ent_at = pv.size(), T.pad = 0;
+      if (T.col_n > 65536)
+        ok = false;
+      uint32_t units = 0;
+      for (uint32_t g = 0; g < T.n_groups; g++) {
+        uint32_t w = 0;
+        for (uint32_t i = 0; i < 8; i++) {
+          uint32_t s = g * 8 + i;
+          if (s < T.n_rows) {
+            uint32_t len = (uint32_t)(offs[rows[s] + 1] - offs[rows[s]]);
+            w = std::max(w, (len + 3) / 4);
+          }
+        }
+        goff.push_back(units);
+        size_t base = pv.size();
+        pv.resize(base + (size_t)w * 32, 0.0);
+        pc.resize(base + (size_t)w * 32, 0);
+        for (uint32_t i = 0; i < 8; i++) {
+          uint32_t s = g * 8 + i;
+          if (s >= T.n_rows)
+            continue;
+          uint32_t r = rows[s];
+          uint64_t e0 = offs[r], len = offs[r + 1] - e0;
+          for (uint64_t e = 0; e < len; e++) {
+            // entry e of the row: lane 4i + (e % 4), step e / 4 -- so the four
+            // lanes walk the row interleaved and the butterfly adds them
+            size_t at = base + (e / 4) * 32 + i * 4 + (e % 4);
+            pv[at] = vals[e0 + e], pc[at] = (uint16_t)(cols[e0 + e] - lo);
+          }
+        }
+        units += w;
+      }
+      goff.push_back(units);
+      T.ent = units * 32;
+      for (uint32_t s = 0; s < T.n_groups * 8; s++) {
+        rowid.push_back(s < T.n_rows ? rows[s] : 0xffffffffu);
+        pd.push_back(s < T.n_rows ? dinv[rows[s]] : 1.0);
+      }
+      max_ent = std::max(max_ent, T.ent), max_groups = std::max(max_groups, T.n_groups);
+      max_stage = std::max(max_stage, T.col_n);
+    }
+    if (!ok)
+      continue;
+    SmemMap mp = smem_map(max_ent, max_groups, max_stage);
+    if (mp.total > (size_t)dev_smem)
+      continue;
+    SmallPlan *P = new SmallPlan();
+    P->C = C, P->n = (uint32_t)n, P->smem = mp.total;
+    P->max_ent = max_ent, P->max_groups = max_groups, P->max_stage = max_stage;
+    if (cudaFuncSetAttribute(k_pcg_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)mp.total) != cudaSuccess) {
+      cudaGetLastError();
+      delete P;
+      continue;
+    }
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    small_launch_config(P, &cfg, attr, c->stream);
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, k_pcg_small, &cfg) != cudaSuccess ||
+        nclusters < 1) {
+      cudaGetLastError();
+      delete P;
+      continue;
+    }
+    auto up = [&](void **d, const void *h, size_t bytes) -> int {
+      CU_TRY(cudaMalloc(d, bytes ? bytes : 8));
+      CU_TRY(cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice));
+      M->device_bytes += bytes;
+      return B200_OK;
+    };
+    B_TRY(up((void **)&P->d_cta, ctas.data(), ctas.size() * sizeof(SmallCta)));
+    B_TRY(up((void **)&P->d_goff, goff.data(), goff.size() * 4));
+    B_TRY(up((void **)&P->d_rowid, rowid.data(), rowid.size() * 4));
+    B_TRY(up((void **)&P->d_vals, pv.data(), pv.size() * 8));
+    B_TRY(up((void **)&P->d_cols, pc.data(), pc.size() * 2));
+    B_TRY(up((void **)&P->d_dinv, pd.data(), pd.size() * 8));
+    CU_TRY(cudaMalloc(&P->d_p, (n + 2) * 8));
+    CU_TRY(cudaMalloc(&P->d_xg, (n + 2) * 8));
+    CU_TRY(cudaMalloc(&P->d_state, sizeof(PcgState)));
+    M->small = P;
+    return B200_OK;
+  }
+  return B200_OK;
+}
+
+int small_solve(b200_mat *M, const double *d_b, double *d_x,
+                const b200_pcg_opts *o, b200_pcg_result *res) {
+  SmallPlan *P = (SmallPlan *)M->small;
+  b200_ctx *c = M->ctx;
+  cudaStream_t s = c->stream;
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  small_launch_config(P, &cfg, attr, s);
+  CU_TRY(cudaEventRecord(c->ev_a, s));
+  CU_TRY(cudaLaunchKernelEx(&cfg, k_pcg_small, (const SmallCta *)P->d_cta,
+                            (const uint32_t *)P->d_goff, (const uint32_t *)P->d_rowid,
+                            (const double *)P->d_vals, (const uint16_t *)P->d_cols,
+                            (const double *)P->d_dinv, d_b, d_x, P->d_p, P->d_xg,
+                            P->d_state, P->max_ent, P->max_groups, P->max_stage,
+                            o->tol, (int)o->maxit));
+  c->launches += 1;
+  CU_TRY(cudaEventRecord(c->ev_b, s));
+  PcgState h;
+  CU_TRY(cudaMemcpyAsync(&h, P->d_state, sizeof h, cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  CU_TRY(cudaEventElapsedTime(&res->solve_ms, c->ev_a, c->ev_b));
+  res->iters = h.iter, res->status = h.status;
+  res->bnorm = sqrt(h.bb);
+  res->relres = h.bb > 0 ? sqrt(h.red[1] / h.bb) : sqrt(h.red[1]);
+  res->true_relres = h.bb > 0 ? sqrt(h.true_rr / h.bb) : sqrt(h.true_rr);
+  res->kernel_launches = 1;
+  res->path = 1;
+  if (h.status == 2)
+    B_FAIL(B200_ENOTSPD, "b200_pcg_solve: breakdown at iteration %d (p.Ap = %g)",
+           h.iter, h.pq);
+  return B200_OK;
 }

@@ -331,3 +331,57 @@ def test_large_grid_properties(abi, ctx):
     x2, r2, _ = Md.pcg_host(rhs, tol=1e-10)
     assert r2.iters == r.iters and x2.tobytes() == x.tobytes()
     Md.close()
+
+
+# --------------------------------------------------------------------------- on-chip path
+@pytest.mark.parametrize("name", ["I1_05x05"] + orc.NEK)
+def test_small_matrix_cluster_path(abi, ctx, name):
+    """Coarse-grid regime: the single-kernel cluster/DSMEM solve (csrc/small.cu)
+    is what b200_pcg_solve picks for the Nek matrices; same bars as the
+    streaming path."""
+    A = host_csr(name)
+    Md = make(abi, ctx, A, abi.MAT_SYM_UPPER)
+    M = orc.op_upper_mirror(A)
+    b = orc.rhs(M.n)
+    x, r, rc = Md.pcg_host(b, tol=1e-10, maxit=5000)
+    assert rc == 0 and r.status == 0 and r.path == 1 and r.kernel_launches == 1
+    assert r.relres <= 1e-10 and orc.true_relres(M, b, x) <= 1.05e-10
+    assert abs(r.true_relres - orc.true_relres(M, b, x)) <= 1e-12
+    xg = DIRECT[name]
+    assert np.linalg.norm(x - xg) / np.linalg.norm(xg) <= 1e-8
+    _, it_cpu, _, _ = orc.pcg(M, b, tol=1e-10)
+    assert abs(r.iters - it_cpu) <= 3, (r.iters, it_cpu)
+    x2, r2, _ = Md.pcg_host(b, tol=1e-10, maxit=5000)
+    assert r2.iters == r.iters and x2.tobytes() == x.tobytes()
+    # streaming path on the same matrix: same answer to rounding
+    x3, r3, _ = Md.pcg_host(b, tol=1e-10, maxit=5000, flags=abi.PCG_NO_SMALL)
+    assert r3.path == 0 and abs(r3.iters - r.iters) <= 3
+    assert np.linalg.norm(x3 - x) / np.linalg.norm(x) <= 1e-9
+    Md.close()
+
+
+def test_small_path_edge_cases(abi, ctx):
+    M = orc.gen_poisson7(12)
+    Md = make(abi, ctx, op_to_csr(M))
+    b = orc.rhs(M.n)
+    xs, r, _ = Md.pcg_host(b)
+    assert r.path == 1 and r.status == 0
+    x, r, _ = Md.pcg_host(b, x0=xs, tol=1e-9)            # start at the solution
+    assert (r.iters, r.status, r.path) == (0, 0, 1)
+    x0 = np.random.default_rng(8).standard_normal(M.n)   # arbitrary start
+    x, r, _ = Md.pcg_host(b, x0=x0)
+    assert r.status == 0 and np.linalg.norm(x - xs) / np.linalg.norm(xs) < 1e-8
+    x, r, _ = Md.pcg_host(b, maxit=4)                    # maxit
+    assert (r.iters, r.status) == (4, 1)
+    xc, itc, _, _ = orc.pcg(M, b, maxit=4)
+    assert np.linalg.norm(x - xc) / np.linalg.norm(xc) < 1e-12
+    Md.close()
+    A = host_csr("A0_02x02")                             # indefinite: breakdown
+    Md = make(abi, ctx, A, abi.MAT_SYM_UPPER)
+    x, r, rc = Md.pcg_host(np.array([1.0, 2.0]))
+    assert rc == 5 and r.status == 2 and r.path == 1
+    Md.close()
+    P = orc.gen_powerlaw(20000, 2)                       # long rows: not eligible
+    Md = make(abi, ctx, op_to_csr(P))
+    assert Md.info().long_rows + Md.info().vec_rows > 0
+    Md.close()
