@@ -28,6 +28,7 @@ def build_oracle():
     subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True)
     if os.path.isdir("/root/reference/src"):
         subprocess.run(["make", "-s", "-C", ORACLE_DIR, "ref"], check=True)
+        subprocess.run(["make", "-s", "-C", ORACLE_DIR, "ref-cusolver"], check=True)
 
 
 class _Csr(C.Structure):
