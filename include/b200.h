@@ -18,6 +18,10 @@
  *                                  B200_MAT_SYM_UPPER the operator is the one
  *                                  CHOLMOD factorises, src/cholmod-impl.h:5-21
  *   b200_mat_destroy               csr_finalize, src/cusparse.c:127-136
+ *   b200_coo_to_csr / _mat_from_coo the sort / fold / row-compress / fill body
+ *                                  of lsbench_matrix_read once the text is
+ *                                  tokenised, src/lsbench-csr.c:54-86
+ *                                  (device-side ingest)
  *   b200_pcg_solve                 the solve inside the X_bench timed loop,
  *                                  src/cusparse.c:189-197 /
  *                                  src/cholmod-impl.h:58-63 /
@@ -97,6 +101,24 @@ enum {
  * rounded to 32 rows. */
 int b200_mat_from_csr(b200_ctx *ctx, uint32_t nrows, uint32_t base,
                       const uint32_t *offs, const uint32_t *cols,
+                      const double *vals, uint32_t flags, b200_mat **M);
+
+/* ---- device-side ingest ---------------------------------- */
+/* The records of a COO text file in file order (rows / cols as written, i.e.
+ * still carrying the file's base) -> CSR with the reference reader's
+ * semantics (src/lsbench-csr.c:54-86): ordered by (row, col) with a stable
+ * sort, equal (row, col) records summed left to right in file order, absent
+ * row ids compressed away, offs 0-based, cols keep the base.  Sort, fold and
+ * fill run on the device.  0 < nnz < 2^32 (the reference's `unsigned nnz`).
+ * Output arrays are caller-owned with room for nnz+1 / nnz / nnz elements;
+ * pass NULL for all three to get the sizes only. */
+int b200_coo_to_csr(b200_ctx *ctx, uint64_t nnz, const uint32_t *rows,
+                    const uint32_t *cols, const double *vals,
+                    uint32_t *nrows_out, uint64_t *nnz_out, uint32_t *offs,
+                    uint32_t *cols_out, double *vals_out);
+/* Same ingest, then straight into the device layout (no host CSR). */
+int b200_mat_from_coo(b200_ctx *ctx, uint64_t nnz, uint32_t base,
+                      const uint32_t *rows, const uint32_t *cols,
                       const double *vals, uint32_t flags, b200_mat **M);
 
 enum { B200_GEN_POISSON7 = 1, B200_GEN_POISSON27 = 2, B200_GEN_POWERLAW = 3 };

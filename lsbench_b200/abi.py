@@ -34,6 +34,7 @@ SYMBOLS = [
     "b200_malloc", "b200_free", "b200_memcpy_h2d", "b200_memcpy_d2h",
     "b200_memset", "b200_host_alloc", "b200_host_free",
     "b200_mat_from_csr", "b200_mat_generate", "b200_mat_destroy",
+    "b200_coo_to_csr", "b200_mat_from_coo",
     "b200_mat_get_info", "b200_mat_export", "b200_mat_halo_cols",
     "b200_mat_inv_diag", "b200_spmv", "b200_spmv_host", "b200_spmv_time",
     "b200_pcg_solve", "b200_pcg_solve_host", "b200_mat_algorithmic_bytes",
@@ -106,6 +107,8 @@ def load():
         "b200_host_free": [vp],
         "b200_mat_from_csr": [vp, u32, u32, vp, vp, vp, u32, C.POINTER(vp)],
         "b200_mat_generate": [vp, i32, u64, u64, u32, C.POINTER(vp)],
+        "b200_coo_to_csr": [vp, u64, vp, vp, vp, C.POINTER(u32), C.POINTER(u64), vp, vp, vp],
+        "b200_mat_from_coo": [vp, u64, u32, vp, vp, vp, u32, C.POINTER(vp)],
         "b200_mat_destroy": [vp],
         "b200_mat_get_info": [vp, C.POINTER(MatInfo)],
         "b200_mat_export": [vp, vp, vp, vp],
@@ -142,6 +145,23 @@ def nccl_unique_id():
     buf = C.create_string_buffer(NCCL_ID_BYTES)
     _chk(load().b200_nccl_unique_id(buf))
     return bytes(buf.raw)
+
+
+def coo_to_csr(ctx, rows, cols, vals):
+    """Device-side restatement of the reader body (src/lsbench-csr.c:54-86):
+    returns (nrows, offs u32, cols u32 with the base kept, vals)."""
+    rows = np.ascontiguousarray(rows, dtype=np.uint32)
+    cols = np.ascontiguousarray(cols, dtype=np.uint32)
+    vals = np.ascontiguousarray(vals, dtype=np.float64)
+    nnz = rows.size
+    offs = np.empty(nnz + 1, dtype=np.uint32)
+    oc = np.empty(max(nnz, 1), dtype=np.uint32)
+    ov = np.empty(max(nnz, 1), dtype=np.float64)
+    nr, m = C.c_uint32(0), C.c_uint64(0)
+    _chk(load().b200_coo_to_csr(ctx.h, nnz, rows.ctypes.data, cols.ctypes.data,
+                                vals.ctypes.data, C.byref(nr), C.byref(m),
+                                offs.ctypes.data, oc.ctypes.data, ov.ctypes.data))
+    return nr.value, offs[:nr.value + 1].copy(), oc[:m.value].copy(), ov[:m.value].copy()
 
 
 class DeviceArray:
@@ -217,6 +237,19 @@ class Matrix:
         vals = np.ascontiguousarray(vals, dtype=np.float64)
         h = C.c_void_p()
         _chk(load().b200_mat_from_csr(ctx.h, nrows, base, offs.ctypes.data,
+                                      cols.ctypes.data, vals.ctypes.data, flags,
+                                      C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def from_coo(cls, ctx, base, rows, cols, vals, flags=0):
+        """COO records in file order (src/lsbench-csr.c:49-53) -> device
+        layout; sort / fold / row-compress on the device."""
+        rows = np.ascontiguousarray(rows, dtype=np.uint32)
+        cols = np.ascontiguousarray(cols, dtype=np.uint32)
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        h = C.c_void_p()
+        _chk(load().b200_mat_from_coo(ctx.h, rows.size, base, rows.ctypes.data,
                                       cols.ctypes.data, vals.ctypes.data, flags,
                                       C.byref(h)))
         return cls(ctx, h)

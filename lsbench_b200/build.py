@@ -18,7 +18,7 @@ CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "_obj")
 LIB = os.path.join(PKG, "libb200.so")
 SOURCES = ["ctx.cu", "convert.cu", "spmv.cu", "pcg.cu", "generate.cu",
-           "dist.cu", "small.cu"]
+           "dist.cu", "small.cu", "ingest.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -600,6 +600,34 @@ int build_layout(b200_ctx *c, PlainCsr *A, uint64_t n_global,
 
 // ---------------------------------------------------------------------------
 // C ABI
+// plain device CSR (0-based columns, global rows) -> matrix; consumes A
+int mat_from_plain(b200_ctx *c, PlainCsr *A, uint32_t flags, b200_mat **out) {
+  const uint64_t nrows = A->n;
+  uint32_t patsym = 1;
+  int rc = B200_OK;
+  if (flags & B200_MAT_SYM_UPPER)
+    rc = sym_upper(c, A, &patsym);
+  if (rc != B200_OK) {
+    plain_free(A);
+    return rc;
+  }
+  b200_mat *M = new b200_mat();
+  M->pattern_symmetric = patsym;
+  M->ctx = c;
+  rc = partition_and_renumber(c, A, nrows, 0, M);
+  if (rc == B200_OK)
+    rc = build_layout(c, A, nrows, M->row_begin, flags, &M);
+  plain_free(A);
+  if (rc == B200_OK && c->nranks > 1)
+    rc = halo_setup(M);
+  if (rc != B200_OK) {
+    b200_mat_destroy(M);
+    return rc;
+  }
+  *out = M;
+  return B200_OK;
+}
+
 extern "C" int b200_mat_from_csr(b200_ctx *c, uint32_t nrows, uint32_t base,
                                  const uint32_t *offs, const uint32_t *cols,
                                  const double *vals, uint32_t flags,
@@ -613,25 +641,12 @@ extern "C" int b200_mat_from_csr(b200_ctx *c, uint32_t nrows, uint32_t base,
   CU_TRY(cudaSetDevice(c->device));
   *out = nullptr;
   PlainCsr A;
-  B_TRY(upload_csr(c, nrows, base, offs, cols, vals, &A));
-  uint32_t patsym = 1;
-  if (flags & B200_MAT_SYM_UPPER)
-    B_TRY(sym_upper(c, &A, &patsym));
-  b200_mat *M = new b200_mat();
-  M->pattern_symmetric = patsym;
-  M->ctx = c;
-  int rc = partition_and_renumber(c, &A, nrows, 0, M);
-  if (rc == B200_OK)
-    rc = build_layout(c, &A, nrows, M->row_begin, flags, &M);
-  plain_free(&A);
-  if (rc == B200_OK && c->nranks > 1)
-    rc = halo_setup(M);
+  int rc = upload_csr(c, nrows, base, offs, cols, vals, &A);
   if (rc != B200_OK) {
-    b200_mat_destroy(M);
+    plain_free(&A);
     return rc;
   }
-  *out = M;
-  return B200_OK;
+  return mat_from_plain(c, &A, flags, out);
 }
 
 extern "C" int b200_mat_destroy(b200_mat *M) {

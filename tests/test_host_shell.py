@@ -191,3 +191,61 @@ def test_config1_with_the_direct_solve_standin(host, tmp_path):
     assert f[0].endswith("I1_05x05.txt") and f[1:6] == ["5", "5", "4", "3", "0"]
     assert float(f[6]) >= 0
     np.testing.assert_allclose(np.fromfile(out), [0, 1 / 2, 2 / 3, 3 / 4, 4 / 5], rtol=1e-15)
+
+
+def test_binary_cache_round_trip(host, tmp_path, monkeypatch):
+    """LSBENCH_MATRIX_CACHE: the cached CSR is byte-identical to the parsed one,
+    is written beside the text file, and is dropped when the text is newer
+    (reader semantics src/lsbench-csr.c:29-92)."""
+    L, _ = host
+    f = tmp_path / "m.txt"
+    f.write_text("6 1\n3 1 5.0\n1 2 1.5\n1 1 2.0\n1 2 0.25\n4 4 7\n3 3 -1e0\n")
+
+    def grab():
+        p = L.lsbench_matrix_read(str(f).encode())
+        a = p.contents
+        nnz = a.offs[a.nrows]
+        out = (a.nrows, a.base, [a.offs[i] for i in range(a.nrows + 1)],
+               [a.cols[i] for i in range(nnz)], [a.vals[i] for i in range(nnz)])
+        L.lsbench_matrix_free(p)
+        return out
+
+    plain = grab()
+    assert not os.path.exists(str(f) + ".lsbcsr")
+    monkeypatch.setenv("LSBENCH_MATRIX_CACHE", "1")
+    assert grab() == plain and os.path.exists(str(f) + ".lsbcsr")
+    # second read comes from the cache: make the text unreadable as a matrix,
+    # keep its mtime older than the cache
+    st = os.stat(str(f))
+    f.write_text("garbage\n")
+    os.utime(str(f), (st.st_atime, st.st_mtime - 10))
+    assert grab() == plain
+    # a text file newer than the cache wins
+    f.write_text("1 0\n0 0 3.5\n")
+    os.utime(str(f), (st.st_atime + 100, st.st_mtime + 100))
+    assert grab() == (1, 0, [0, 1], [0], [3.5])
+    # a truncated cache is ignored, not trusted
+    with open(str(f) + ".lsbcsr", "r+b") as g:
+        g.truncate(20)
+    os.utime(str(f) + ".lsbcsr", (st.st_atime + 200, st.st_mtime + 200))
+    assert grab() == (1, 0, [0, 1], [0], [3.5])
+
+
+@pytest.mark.parametrize("name", ["tj7a_A_18"])
+def test_binary_cache_real_matrix(host, name, tmp_path, monkeypatch):
+    L, _ = host
+    import shutil
+    f = str(tmp_path / (name + ".txt"))
+    shutil.copy(orc.matrix_path(name), f)
+    monkeypatch.setenv("LSBENCH_MATRIX_CACHE", "1")
+    for _ in range(2):   # parse + store, then load
+        p = L.lsbench_matrix_read(f.encode())
+        a = p.contents
+        nnz = a.offs[a.nrows]
+        got = {"n": a.nrows, "base": a.base, "nnz": int(nnz),
+               "offs": sha(np.ctypeslib.as_array(a.offs, (a.nrows + 1,))),
+               "cols": sha(np.ctypeslib.as_array(a.cols, (nnz,))),
+               "vals": sha(np.ctypeslib.as_array(a.vals, (nnz,)))}
+        L.lsbench_matrix_free(p)
+        for k, v in got.items():
+            assert READER[name][k] == v, k
