@@ -92,7 +92,8 @@ enum {
   B200_MAT_SYM_UPPER = 1u << 0, /* solve the upper triangle mirrored */
   B200_MAT_FORCE_VECTOR = 1u << 1, /* kernel sweep: no SELL bin */
   B200_MAT_FORCE_SELL = 1u << 2,   /* kernel sweep: everything in SELL */
-  B200_MAT_NO_SORT = 1u << 3       /* SELL without the length-sort window */
+  B200_MAT_NO_SORT = 1u << 3,      /* SELL without the length-sort window */
+  B200_MAT_NO_COMPRESS = 1u << 4   /* keep one explicit u32 column per entry */
 };
 
 /* Host CSR exactly as lsbench_matrix_read leaves it: offs 0-based, cols
@@ -145,6 +146,11 @@ typedef struct {
   uint32_t pattern_symmetric;     /* SYM_UPPER: mirror slots all existed */
   uint32_t sell_perm;             /* 1 if SELL rows are permuted */
   uint64_t device_bytes;
+  /* index compression: SELL slices stored as w column deltas instead of
+   * 32 w columns, and the bytes of matrix streams (offsets, columns, values,
+   * permutation) one SpMV actually reads -- compare with 12 nnz + 4 (n+1) */
+  uint64_t sell_uniform_slices;
+  uint64_t matrix_stream_bytes;
 } b200_mat_info;
 int b200_mat_get_info(const b200_mat *M, b200_mat_info *info);
 

@@ -19,6 +19,7 @@ MAT_SYM_UPPER = 1 << 0
 MAT_FORCE_VECTOR = 1 << 1
 MAT_FORCE_SELL = 1 << 2
 MAT_NO_SORT = 1 << 3
+MAT_NO_COMPRESS = 1 << 4
 
 GEN_POISSON7, GEN_POISSON27, GEN_POWERLAW = 1, 2, 3
 
@@ -55,7 +56,8 @@ class MatInfo(C.Structure):
         "interior_begin", "interior_end")] + [
         ("hist", C.c_uint64 * HIST_BINS), ("max_row_len", C.c_uint64),
         ("pattern_symmetric", C.c_uint32), ("sell_perm", C.c_uint32),
-        ("device_bytes", C.c_uint64)]
+        ("device_bytes", C.c_uint64), ("sell_uniform_slices", C.c_uint64),
+        ("matrix_stream_bytes", C.c_uint64)]
 
 
 class PcgOpts(C.Structure):

@@ -109,6 +109,12 @@ struct b200_mat {
   uint32_t *sell_cols = nullptr;
   double *sell_vals = nullptr;
   uint32_t *sell_perm = nullptr;  // nullptr == identity (row = 32 s + lane)
+  // index compression (nullptr == off): sell_meta[s] = {o, w | uniform << 31,
+  // column offset, 0} (uint4 per slice), the deltas of the uniform slices;
+  // sell_cols then holds only the explicit slices
+  uint32_t *sell_meta = nullptr;
+  int32_t *sell_dcols = nullptr;
+  uint64_t sell_uniform_slices = 0, sell_col_entries = 0, sell_delta_entries = 0;
   uint64_t sell_entries = 0;      // padded
   // --- warp-per-row and block-per-row bins: row-major, rows padded to 4 ----
   uint32_t vec_rows = 0, long_rows = 0;

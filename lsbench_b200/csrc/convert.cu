@@ -19,10 +19,17 @@
 //                 one warp per row.
 //   long bin      len >= B2_LONG_MIN: same storage, one CTA per row.
 //
+// Index compression (on unless B200_MAT_NO_COMPRESS): a SELL slice whose 32
+// rows all have the slice width and the same column-minus-row pattern stores
+// its w deltas once instead of 32 w columns (k_slice_uniform / k_compact_cols).
+// Lossless -- b200_mat_export gives back the same CSR bit for bit -- and the
+// values and summation order are untouched.
+//
 // With B200_MAT_SYM_UPPER the operator is first replaced by the one CHOLMOD
 // factorises (src/cholmod-impl.h:5-21): entries with col >= row, mirrored.
 #include "common.cuh"
 #include <cub/cub.cuh>
+#include <vector>
 
 #define B2_SELL_MAX 256u
 #define B2_LONG_MIN 8192u
@@ -354,6 +361,62 @@ __global__ void k_sell_fill(uint32_t nslices, const uint32_t *list, uint64_t n,
   }
 }
 
+// ---- index compression of the SELL column stream -----------------------------
+// One warp per slice.  A slice is "uniform" when every lane holds a real row
+// of exactly the slice width and, for every k, col(lane, k) - row(lane) is the
+// same in all 32 lanes.  Such a slice needs w deltas, not 32 w columns.
+__global__ void k_slice_uniform(uint32_t nslices, const uint32_t *list, uint64_t n,
+                                const uint32_t *len, const uint32_t *sell_off,
+                                const uint32_t *scols, uint32_t *cnt_u,
+                                uint32_t *cnt_e) {
+  uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (s >= nslices)
+    return;
+  uint64_t pos = (uint64_t)s * B2_SLICE + lane;
+  uint32_t row = list ? list[pos] : (pos < n ? (uint32_t)pos : 0xffffffffu);
+  uint32_t o = sell_off[s], w = sell_off[s + 1] - o;
+  bool ok = row != 0xffffffffu && w > 0 && len[row] == w;
+  ok = __all_sync(0xffffffffu, ok);
+  if (ok) {
+    uint64_t src = (uint64_t)o * B2_SLICE + lane;
+    for (uint32_t k = 0; k < w; k++, src += B2_SLICE) {
+      const uint32_t d = scols[src] - row;
+      const uint32_t d0 = __shfl_sync(0xffffffffu, d, 0);  // every lane, every k
+      ok = ok && d == d0;
+    }
+    ok = __all_sync(0xffffffffu, ok);
+  }
+  if (lane == 0) {
+    cnt_u[s] = ok ? w : 0u, cnt_e[s] = ok ? 0u : w;
+    if (s == nslices - 1)
+      cnt_u[nslices] = 0u, cnt_e[nslices] = 0u;
+  }
+}
+
+__global__ void k_compact_cols(uint32_t nslices, const uint32_t *list,
+                               const uint32_t *sell_off, const uint32_t *scols,
+                               const uint32_t *cnt_u, const uint32_t *off_u,
+                               const uint32_t *off_e, int32_t *dcols,
+                               uint32_t *ecols, uint4 *meta) {
+  uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (s >= nslices)
+    return;
+  uint32_t o = sell_off[s], w = sell_off[s + 1] - o;
+  if (cnt_u[s]) {
+    uint32_t row0 = list ? list[(uint64_t)s * B2_SLICE] : s * B2_SLICE;
+    for (uint32_t k = lane; k < w; k += 32)
+      dcols[off_u[s] + k] = (int32_t)(scols[(uint64_t)(o + k) * B2_SLICE] - row0);
+    if (lane == 0)
+      meta[s] = make_uint4(o, w | 0x80000000u, off_u[s], 0u);
+  } else {
+    uint64_t src = (uint64_t)o * B2_SLICE + lane, dst = (uint64_t)off_e[s] * B2_SLICE + lane;
+    for (uint32_t k = 0; k < w; k++, src += B2_SLICE, dst += B2_SLICE)
+      ecols[dst] = scols[src];
+    if (lane == 0)
+      meta[s] = make_uint4(o, w, off_e[s], 0u);
+  }
+}
+
 __global__ void k_pad4_len(uint32_t nrows, const uint32_t *ids,
                            const uint32_t *len, uint64_t *out,
                            unsigned long long *true_nnz) {
@@ -536,6 +599,56 @@ int build_layout(b200_ctx *c, PlainCsr *A, uint64_t n_global,
     }
     M->sell_max_width = wmax;
     cudaFree(width);
+    // ---- index compression: uniform slices keep w deltas instead of 32 w columns
+    M->sell_col_entries = padded;
+    if (!(flags & B200_MAT_NO_COMPRESS) && padded) {
+      uint32_t *cnt_u, *cnt_e, *off_u, *off_e;
+      CU_TRY(cudaMalloc(&cnt_u, (ns + 1ull) * 4));
+      CU_TRY(cudaMalloc(&cnt_e, (ns + 1ull) * 4));
+      CU_TRY(cudaMalloc(&off_u, (ns + 1ull) * 4));
+      CU_TRY(cudaMalloc(&off_e, (ns + 1ull) * 4));
+      k_slice_uniform<<<nblk((uint64_t)ns * 32), T256, 0, s>>>(
+          ns, ids[0], n, M->row_len, M->sell_off, M->sell_cols, cnt_u, cnt_e);
+      CU_TRY(cudaGetLastError());
+      B_TRY(exclusive_scan<uint32_t>(s, cnt_u, off_u, ns + 1ull));
+      B_TRY(exclusive_scan<uint32_t>(s, cnt_e, off_e, ns + 1ull));
+      uint32_t tot_u = 0, tot_e = 0;
+      CU_TRY(cudaMemcpy(&tot_u, off_u + ns, 4, cudaMemcpyDeviceToHost));
+      CU_TRY(cudaMemcpy(&tot_e, off_e + ns, 4, cudaMemcpyDeviceToHost));
+      // worth it when at least a tenth of the column stream goes away; both
+      // offsets must leave bit 31 free
+      if ((uint64_t)tot_u * 10 >= (uint64_t)tot_u + tot_e && tot_u < 0x80000000u &&
+          tot_e < 0x80000000u) {
+        uint32_t *ecols = nullptr;
+        int32_t *dcols = nullptr;
+        uint4 *meta = nullptr;
+        CU_TRY(cudaMalloc(&ecols, ((uint64_t)tot_e * B2_SLICE + 1) * 4));
+        CU_TRY(cudaMalloc(&dcols, ((uint64_t)tot_u + 40) * 4));
+        CU_TRY(cudaMalloc(&meta, (ns + 1ull) * 16));
+        CU_TRY(cudaMemsetAsync(dcols + tot_u, 0, 40 * 4, s));
+        CU_TRY(cudaMemsetAsync(meta + ns, 0, 16, s));
+        k_compact_cols<<<nblk((uint64_t)ns * 32), T256, 0, s>>>(
+            ns, ids[0], M->sell_off, M->sell_cols, cnt_u, off_u, off_e, dcols, ecols, meta);
+        CU_TRY(cudaGetLastError());
+        // how many slices went uniform (for the info block)
+        {
+          std::vector<uint32_t> h(ns);
+          CU_TRY(cudaMemcpy(h.data(), cnt_u, (size_t)ns * 4, cudaMemcpyDeviceToHost));
+          uint64_t nu = 0;
+          for (uint32_t v : h)
+            nu += v != 0;
+          M->sell_uniform_slices = nu;
+        }
+        CU_TRY(cudaStreamSynchronize(s));
+        cudaFree(M->sell_cols);
+        M->device_bytes -= (padded ? padded : 1) * 4;
+        M->sell_cols = ecols, M->sell_dcols = dcols, M->sell_meta = (uint32_t *)meta;
+        M->sell_col_entries = (uint64_t)tot_e * B2_SLICE, M->sell_delta_entries = tot_u;
+        M->device_bytes += ((uint64_t)tot_e * B2_SLICE + 1) * 4 + ((uint64_t)tot_u + 40) * 4 +
+                           (ns + 1ull) * 16;
+      }
+      cudaFree(cnt_u), cudaFree(cnt_e), cudaFree(off_u), cudaFree(off_e);
+    }
     if (ids[0]) {
       M->sell_perm = ids[0];
       M->device_bytes += (sell_padded_rows + 1) * 4;
@@ -659,6 +772,7 @@ extern "C" int b200_mat_destroy(b200_mat *M) {
   halo_free(M);
   if (M->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)M->graph_exec);
   void *ptrs[] = {M->sell_off, M->sell_cols, M->sell_vals, M->sell_perm,
+                  M->sell_meta, M->sell_dcols,
                   M->vec_row_ids, M->long_row_ids, M->vec_off, M->long_off,
                   M->vl_cols, M->vl_vals, M->dinv, M->row_len, M->w_r, M->w_p,
                   M->w_q, M->x_ext, M->partials, M->state};
@@ -685,6 +799,15 @@ extern "C" int b200_mat_get_info(const b200_mat *M, b200_mat_info *o) {
   o->pattern_symmetric = M->pattern_symmetric;
   o->sell_perm = M->sell_perm != nullptr;
   o->device_bytes = M->device_bytes;
+  o->sell_uniform_slices = M->sell_uniform_slices;
+  // what one SpMV streams from the matrix: values, columns / deltas, slice and
+  // row offsets, the row permutation
+  o->matrix_stream_bytes =
+      8 * (M->sell_entries + M->vl_entries) +
+      4 * (M->sell_col_entries + M->sell_delta_entries + M->vl_entries) +
+      (M->sell_meta ? 16 : 4) * (uint64_t)(M->sell_slices + 1) +
+      (M->sell_perm ? 4 * (uint64_t)M->sell_slices * B2_SLICE : 0) +
+      12 * ((uint64_t)M->vec_rows + M->long_rows);
   return B200_OK;
 }
 
@@ -701,7 +824,8 @@ extern "C" int b200_mat_algorithmic_bytes(const b200_mat *M, uint64_t *spmv,
 // ---- export: what the layout represents, in original row order -----------------
 __global__ void k_export_sell(uint32_t nslices, const uint32_t *list, uint64_t n,
                               const uint32_t *len, const uint32_t *sell_off,
-                              const uint32_t *scols, const double *svals,
+                              const uint4 *meta, const uint32_t *scols,
+                              const int32_t *dcols, const double *svals,
                               const uint64_t *ooffs, uint32_t *ocols, double *ovals) {
   uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (s >= nslices)
@@ -711,8 +835,17 @@ __global__ void k_export_sell(uint32_t nslices, const uint32_t *list, uint64_t n
   if (row == 0xffffffffu)
     return;
   uint64_t src = (uint64_t)sell_off[s] * B2_SLICE + lane, dst = ooffs[row];
-  for (uint32_t k = 0; k < len[row]; k++, src += B2_SLICE)
-    ocols[dst + k] = scols[src], ovals[dst + k] = svals[src];
+  const uint4 m = meta ? meta[s] : make_uint4(0u, 0u, 0u, 0u);
+  const uint32_t c = m.z;
+  if (meta && (m.y >> 31)) {  // uniform slice: column = row + delta
+    const int32_t *dp = dcols + c;
+    for (uint32_t k = 0; k < len[row]; k++, src += B2_SLICE)
+      ocols[dst + k] = row + (uint32_t)dp[k], ovals[dst + k] = svals[src];
+    return;
+  }
+  uint64_t csrc = meta ? (uint64_t)c * B2_SLICE + lane : src;
+  for (uint32_t k = 0; k < len[row]; k++, src += B2_SLICE, csrc += B2_SLICE)
+    ocols[dst + k] = scols[csrc], ovals[dst + k] = svals[src];
 }
 
 __global__ void k_export_vl(uint32_t nrows, const uint32_t *ids,
@@ -759,7 +892,7 @@ extern "C" int b200_mat_export(const b200_mat *M, uint64_t *offs,
     if (M->sell_slices)
       k_export_sell<<<nblk((uint64_t)M->sell_slices * 32), T256, 0, s>>>(
           M->sell_slices, M->sell_perm, n, M->row_len, M->sell_off,
-          M->sell_cols, M->sell_vals, ooffs, oc, ov);
+          (const uint4 *)M->sell_meta, M->sell_cols, M->sell_dcols, M->sell_vals, ooffs, oc, ov);
     if (M->vec_rows)
       k_export_vl<<<nblk((uint64_t)M->vec_rows * 32), T256, 0, s>>>(
           M->vec_rows, M->vec_row_ids, M->row_len, M->vec_off, M->vl_cols,

@@ -11,6 +11,8 @@
 //                through L1/L2 (__ldg), each lane sums its row left to right
 //                (same order as a host CSR loop => bit-identical to it when
 //                the host uses fma).
+//                With index compression (the default) uniform slices read w
+//                column deltas instead of 32 w columns.
 //   k_spmv_vec   one warp per row, 128-bit col / val loads, fixed butterfly
 //                warp-shuffle reduction.
 //   k_spmv_long  one CTA per row for the power-law tail.
@@ -21,6 +23,30 @@
 
 #define SPMV_THREADS 256
 #define SPMV_WARPS (SPMV_THREADS / 32)
+
+// One k-chunk of up to 8 entries of a slice: columns -> values -> gathers ->
+// fma in row order.  `colf(j)` yields the column of entry k + j.
+template <bool FULL, typename ColF>
+__device__ __forceinline__ double sell_chunk(const double *vp, const double *__restrict__ x,
+                                             uint32_t k, uint32_t rem, double sum, ColF colf) {
+  constexpr int N = FULL ? 8 : 7;
+  uint32_t c[8];
+  double a[8], xv[8];
+#pragma unroll
+  for (int j = 0; j < N; j++)
+    c[j] = (FULL || j < rem) ? colf(j) : 0u;
+#pragma unroll
+  for (int j = 0; j < N; j++)
+    a[j] = (FULL || j < rem) ? ld_stream(vp + (size_t)(k + j) * B2_SLICE) : 0.0;
+#pragma unroll
+  for (int j = 0; j < N; j++)
+    xv[j] = (FULL || j < rem) ? __ldg(x + c[j]) : 0.0;
+#pragma unroll
+  for (int j = 0; j < N; j++)
+    if (FULL || j < rem)
+      sum = fma(a[j], xv[j], sum);
+  return sum;
+}
 
 template <bool DOT>
 __global__ void __launch_bounds__(SPMV_THREADS, 4)
@@ -46,42 +72,89 @@ k_spmv_sell(const uint32_t *__restrict__ sell_off,
     const double *vp = vals + base;
     double sum = 0.0;
     uint32_t k = 0;
-    for (; k + 8 <= w; k += 8) {
-      uint32_t c[8];
-      double a[8], xv[8];
-#pragma unroll
-      for (int j = 0; j < 8; j++)
-        c[j] = ld_stream(cp + (size_t)(k + j) * B2_SLICE);
-#pragma unroll
-      for (int j = 0; j < 8; j++)
-        a[j] = ld_stream(vp + (size_t)(k + j) * B2_SLICE);
-#pragma unroll
-      for (int j = 0; j < 8; j++)
-        xv[j] = __ldg(x + c[j]);
-#pragma unroll
-      for (int j = 0; j < 8; j++)
-        sum = fma(a[j], xv[j], sum);
-    }
-    if (k < w) {
-      const uint32_t rem = w - k;
-      uint32_t c[8];
-      double a[8], xv[8];
-#pragma unroll
-      for (int j = 0; j < 7; j++)
-        c[j] = j < rem ? ld_stream(cp + (size_t)(k + j) * B2_SLICE) : 0u;
-#pragma unroll
-      for (int j = 0; j < 7; j++)
-        a[j] = j < rem ? ld_stream(vp + (size_t)(k + j) * B2_SLICE) : 0.0;
-#pragma unroll
-      for (int j = 0; j < 7; j++)
-        xv[j] = j < rem ? __ldg(x + c[j]) : 0.0;
-#pragma unroll
-      for (int j = 0; j < 7; j++)
-        if (j < rem)
-          sum = fma(a[j], xv[j], sum);
-    }
+    for (; k + 8 <= w; k += 8)
+      sum = sell_chunk<true>(vp, x, k, 8, sum, [&](int j) {
+        return ld_stream(cp + (size_t)(k + j) * B2_SLICE);
+      });
+    if (k < w)
+      sum = sell_chunk<false>(vp, x, k, w - k, sum, [&](int j) {
+        return ld_stream(cp + (size_t)(k + j) * B2_SLICE);
+      });
     const uint32_t pos = s * B2_SLICE + lane;
     const uint32_t row = perm ? __ldg(perm + pos) : pos;
+    if (row < n_rows) {
+      y[row] = sum;
+      if (DOT)
+        dot = fma(sum, __ldg(x + row), dot);
+    }
+  }
+  if (DOT) {
+    double b[1] = {block_sum<SPMV_WARPS>(dot, red)};
+    grid_sum_finish<1, SPMV_WARPS>(b, partials, 0, slot_base + blockIdx.x,
+                                   total_slots, &st->ticket[0], dot_out, red);
+  }
+}
+
+// Index-compressed SELL (convert.cu, step 6).  A slice whose 32 rows all have
+// the slice's width and whose k-th column is `row + d_k` with the same d_k in
+// every lane (the interior of any stencil or banded operator, in any numbering
+// that keeps neighbouring rows together) stores its w deltas once -- 4 w bytes
+// instead of 128 w -- and its gathers become one coalesced warp access each.
+// Other slices keep explicit columns.  meta[s] = {o, w | uniform << 31, c, 0}:
+// o as in sell_off; c = offset into dcols (entries) for a uniform slice, into
+// cols (units of 32 entries) otherwise.  Values and the order of the additions
+// are untouched, so the result is bit-identical to the uncompressed kernel.
+//
+// Measured alternatives that lost to this plain loop on 27-point 512^3 (5.99 ms
+// in PCG): deltas prefetched one slice ahead and broadcast by shuffle (6.38),
+// next-chunk values prefetched into registers (8.0-8.4), a bulk-copy
+// (cp.async.bulk + mbarrier) ring of value tiles in shared memory (10.3), and
+// balanced 9+9+9 chunks instead of 8+8+8+3 (6.25).
+template <bool DOT>
+__global__ void __launch_bounds__(SPMV_THREADS, 4)
+k_spmv_sellc(const uint4 *__restrict__ meta, const uint32_t *__restrict__ cols,
+             const int32_t *__restrict__ dcols, const double *__restrict__ vals,
+             const uint32_t *__restrict__ perm, const double *__restrict__ x,
+             double *__restrict__ y, uint32_t b0, uint32_t e0, uint32_t b1,
+             uint32_t e1, uint32_t n_rows, double *partials, unsigned slot_base,
+             unsigned total_slots, PcgState *st, double *dot_out) {
+  if (DOT && st->done)
+    return;
+  __shared__ double red[SPMV_WARPS];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t n0 = e0 - b0, nv = n0 + (e1 - b1);
+  const uint32_t stride = gridDim.x * SPMV_WARPS;
+  double dot = 0.0;
+  for (uint32_t v = blockIdx.x * SPMV_WARPS + warp; v < nv; v += stride) {
+    const uint32_t s = v < n0 ? b0 + v : b1 + (v - n0);
+    const uint4 m = __ldg(meta + s);
+    const uint32_t o = m.x, w = m.y & 0x7fffffffu;
+    const double *vp = vals + (size_t)o * B2_SLICE + lane;
+    const uint32_t pos = s * B2_SLICE + lane;
+    const uint32_t row = perm ? __ldg(perm + pos) : pos;
+    double sum = 0.0;
+    uint32_t k = 0;
+    if (m.y >> 31) {
+      const int32_t *dp = dcols + m.z;
+      for (; k + 8 <= w; k += 8)
+        sum = sell_chunk<true>(vp, x, k, 8, sum, [&](int j) {
+          return row + (uint32_t)__ldg(dp + k + j);
+        });
+      if (k < w)
+        sum = sell_chunk<false>(vp, x, k, w - k, sum, [&](int j) {
+          return row + (uint32_t)__ldg(dp + k + j);
+        });
+    } else {
+      const uint32_t *cp = cols + (size_t)m.z * B2_SLICE + lane;
+      for (; k + 8 <= w; k += 8)
+        sum = sell_chunk<true>(vp, x, k, 8, sum, [&](int j) {
+          return ld_stream(cp + (size_t)(k + j) * B2_SLICE);
+        });
+      if (k < w)
+        sum = sell_chunk<false>(vp, x, k, w - k, sum, [&](int j) {
+          return ld_stream(cp + (size_t)(k + j) * B2_SLICE);
+        });
+    }
     if (row < n_rows) {
       y[row] = sum;
       if (DOT)
@@ -179,10 +252,11 @@ k_spmv_long(uint32_t nrows, const uint32_t *__restrict__ ids,
 }
 
 // ---------------------------------------------------------------------------
-static int persistent_grid(b200_ctx *c, const void *kernel, uint64_t work_ctas) {
+static int persistent_grid(b200_ctx *c, const void *kernel, uint64_t work_ctas,
+                           int threads = SPMV_THREADS, size_t smem = 0) {
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel,
-                                                    SPMV_THREADS, 0) != cudaSuccess ||
+                                                    threads, smem) != cudaSuccess ||
       per_sm < 1)
     per_sm = 4;
   uint64_t g = (uint64_t)c->sm_count * per_sm;
@@ -220,7 +294,9 @@ static SpmvPlan compute_plan(b200_mat *M, int phase) {
     P.b0 = 0, P.e0 = ib, P.b1 = ie, P.e1 = ns;
   uint32_t nv = (P.e0 - P.b0) + (P.e1 - P.b1);
   if (nv)
-    P.g_sell = persistent_grid(c, (const void *)k_spmv_sell<true>,
+    P.g_sell = persistent_grid(c,
+                               M->sell_meta ? (const void *)k_spmv_sellc<true>
+                                            : (const void *)k_spmv_sell<true>,
                                (nv + SPMV_WARPS - 1) / SPMV_WARPS);
   if (others && M->vec_rows)
     P.g_vec = persistent_grid(c, (const void *)k_spmv_vec<true>,
@@ -261,14 +337,24 @@ int launch_spmv(b200_mat *M, const double *x, double *y, bool dot, int phase) {
   uint32_t n = (uint32_t)M->n_local;
   double *dot_out = dot ? (c->nranks > 1 ? &M->state->pq_loc : &M->state->pq) : nullptr;
   if (P.g_sell) {
-    if (dot)
+#define B2_SELL_ARGS(DOTV)                                                        \
+  M->sell_perm, x, y, P.b0, P.e0, P.b1, P.e1, n, DOTV ? M->partials : nullptr,    \
+      DOTV ? slot_base : 0u, DOTV ? total : 0u, DOTV ? M->state : nullptr,        \
+      DOTV ? dot_out : nullptr
+    const uint4 *meta = (const uint4 *)M->sell_meta;
+    if (dot && meta)
+      k_spmv_sellc<true><<<P.g_sell, SPMV_THREADS, 0, s>>>(
+          meta, M->sell_cols, M->sell_dcols, M->sell_vals, B2_SELL_ARGS(true));
+    else if (dot)
       k_spmv_sell<true><<<P.g_sell, SPMV_THREADS, 0, s>>>(
-          M->sell_off, M->sell_cols, M->sell_vals, M->sell_perm, x, y, P.b0,
-          P.e0, P.b1, P.e1, n, M->partials, slot_base, total, M->state, dot_out);
+          M->sell_off, M->sell_cols, M->sell_vals, B2_SELL_ARGS(true));
+    else if (meta)
+      k_spmv_sellc<false><<<P.g_sell, SPMV_THREADS, 0, s>>>(
+          meta, M->sell_cols, M->sell_dcols, M->sell_vals, B2_SELL_ARGS(false));
     else
       k_spmv_sell<false><<<P.g_sell, SPMV_THREADS, 0, s>>>(
-          M->sell_off, M->sell_cols, M->sell_vals, M->sell_perm, x, y, P.b0,
-          P.e0, P.b1, P.e1, n, nullptr, 0, 0, nullptr, nullptr);
+          M->sell_off, M->sell_cols, M->sell_vals, B2_SELL_ARGS(false));
+#undef B2_SELL_ARGS
     slot_base += P.g_sell;
   }
   if (P.g_vec) {

@@ -34,8 +34,8 @@ def test_library_exports_every_declared_symbol(abi):
 
 
 def test_struct_sizes_match_header(abi):
-    # b200_mat_info: 16 u64 + 24 u64 hist + u64 + 2 u32 + u64
-    assert ctypes.sizeof(abi.MatInfo) == 8 * (16 + 24 + 1) + 8 + 8
+    # b200_mat_info: 16 u64 + 24 u64 hist + u64 + 2 u32 + 3 u64
+    assert ctypes.sizeof(abi.MatInfo) == 8 * (16 + 24 + 1) + 8 + 8 * 3
     assert ctypes.sizeof(abi.PcgOpts) == 24
     assert ctypes.sizeof(abi.PcgResult) == 56
 

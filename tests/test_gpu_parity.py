@@ -385,3 +385,80 @@ def test_small_path_edge_cases(abi, ctx):
     Md = make(abi, ctx, op_to_csr(P))
     assert Md.info().long_rows + Md.info().vec_rows > 0
     Md.close()
+
+
+# --------------------------------------------------------------------------- index compression
+@pytest.mark.parametrize("gen,N", [("poisson7", 96), ("poisson27", 96), ("poisson7", 33)])
+def test_index_compression_is_lossless(abi, ctx, gen, N):
+    """Uniform SELL slices store w column deltas instead of 32 w columns
+    (convert.cu): the exported operator, the SpMV result and the PCG iterates
+    are bit-identical with and without it."""
+    M = getattr(orc, "gen_" + gen)(N)
+    x = np.random.default_rng(N).standard_normal(M.n)
+    b = orc.rhs(M.n)
+    out = {}
+    for label, fl in (("on", 0), ("off", abi.MAT_NO_COMPRESS)):
+        Md = make(abi, ctx, op_to_csr(M), fl)
+        assert_same_operator(Md, M)
+        i = Md.info()
+        y = Md.spmv_host(x)
+        assert np.array_equal(y, orc.spmv_fma(M, x))
+        xs, r, rc = Md.pcg_host(b, tol=1e-10, flags=abi.PCG_NO_SMALL)
+        assert rc == 0 and r.status == 0
+        out[label] = (y, xs, r.iters, i.sell_uniform_slices, i.matrix_stream_bytes, i.sell_slices)
+        Md.close()
+    assert out["on"][0].tobytes() == out["off"][0].tobytes()
+    assert out["on"][1].tobytes() == out["off"][1].tobytes() and out["on"][2] == out["off"][2]
+    assert out["off"][3] == 0
+    if N == 96:
+        # x-lines of three slices: the middle one holds no line end => uniform
+        assert out["on"][3] == 96 * 96 and out["on"][4] < out["off"][4]
+    else:
+        assert out["on"][3] == 0    # lines not slice-aligned: stays explicit, still exact
+
+
+def test_index_compression_counts_on_an_aligned_grid(abi, ctx):
+    """64^3, x-lines of two slices: a slice is uniform unless it contains the
+    x = 0 or x = N-1 end of its line -- here none is (both halves of every line
+    touch an end), while at 96 the middle slice of every line is."""
+    for N, want in ((64, 0), (96, 96 * 96)):
+        Md = abi.Matrix.generate(ctx, abi.GEN_POISSON7, N)
+        i = Md.info()
+        assert i.sell_perm == 0
+        assert i.sell_uniform_slices == want, (N, i.sell_uniform_slices)
+        Md.close()
+
+
+@pytest.mark.parametrize("name", ["tj7a_A_12", "xn3b_A_10"])
+def test_index_compression_leaves_irregular_matrices_alone(abi, ctx, name):
+    A = host_csr(name)
+    Md = make(abi, ctx, A, abi.MAT_SYM_UPPER)
+    i = Md.info()
+    assert i.sell_uniform_slices == 0       # nothing to gain: stays explicit
+    assert_same_operator(Md, orc.op_upper_mirror(A))
+    Md.close()
+
+
+def test_index_compression_mixed_slices(abi, ctx):
+    """a banded matrix with a few perturbed rows: uniform and explicit slices
+    interleave; export and SpMV stay exact"""
+    import scipy.sparse as sp
+    n = 32 * 40
+    rng = np.random.default_rng(8)
+    diags = [rng.standard_normal(n) for _ in range(5)]
+    Asp = sp.diags(diags, [-40, -1, 0, 1, 40], shape=(n, n), format="lil")
+    for r in (5, 333, 700, 1279):          # break four slices
+        Asp[r, (r * 7 + 3) % n] = 2.5
+    Asp = Asp.tocsr()
+    Asp.sort_indices()
+    M = orc.Op(n, Asp.indptr.astype(np.uint64), Asp.indices.astype(np.uint32),
+               Asp.data.astype(np.float64))
+    Md = make(abi, ctx, op_to_csr(M), abi.MAT_NO_SORT)
+    assert_same_operator(Md, M)
+    i = Md.info()
+    # rows 0..39 and n-40..n-1 are shorter (band truncated): slices 0,1 and 38,39
+    # are non-uniform, plus the two perturbed rows that sit elsewhere (333, 700)
+    assert i.sell_uniform_slices == 40 - 4 - 2
+    x = rng.standard_normal(n)
+    assert np.array_equal(Md.spmv_host(x), orc.spmv_fma(M, x))
+    Md.close()

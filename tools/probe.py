@@ -14,9 +14,11 @@ ctx = abi.Context(0)
 t = time.time()
 M = abi.Matrix.generate(ctx, k, size, seed=1, flags=flags)
 i = M.info()
-print("generate+convert %.2fs n=%d nnz=%d padded=%d sell_rows=%d vec=%d long=%d sigma=%d perm=%d wmax=%d dev=%.2fGB" % (
+print("generate+convert %.2fs n=%d nnz=%d padded=%d sell_rows=%d vec=%d long=%d sigma=%d perm=%d wmax=%d dev=%.2fGB "
+      "uniform_slices=%d/%d stream=%.3f B/nnz" % (
     time.time() - t, i.n_local, i.nnz, i.nnz_padded, i.sell_rows, i.vec_rows, i.long_rows,
-    i.sell_sigma, i.sell_perm, i.sell_max_width, i.device_bytes / 1e9))
+    i.sell_sigma, i.sell_perm, i.sell_max_width, i.device_bytes / 1e9,
+    i.sell_uniform_slices, i.sell_slices, i.matrix_stream_bytes / max(i.nnz, 1)))
 n = i.n_local
 sp, it = M.algorithmic_bytes()
 dx, dy = ctx.array(n), ctx.array(n)
