@@ -14,7 +14,10 @@ The JSON line also carries
   roofline      the dominant kernel (SELL SpMV fused with p.Ap): algorithmic
                 bytes per launch / mean launch duration, CUDA events on the
                 launch stream, taken INSIDE the timed solves (first 32
-                iterations of each) -- against MEASURED_PEAKS.json
+                iterations of each) -- against MEASURED_PEAKS.json.  With the
+                index-compressed layout (default) the kernel moves fewer bytes
+                than the algorithmic count; stored_bytes / stored_frac give the
+                DRAM-side view and `uncompressed` the same solve without it
   spmv_7pt_256  stand-alone fp64 SpMV GB/s on the 7-point 256^3 operator (the
                 configuration the >= 75 % of 8 TB/s target is quoted on), N = 1
   e2e           the same solve through b200_pcg_solve_host (the X_bench call
@@ -163,6 +166,10 @@ def main():
     ap.add_argument("--ref-iters", type=int, default=1176,
                     help="iterations the full solve needs (measured on the GPU path)")
     ap.add_argument("--no-spmv", action="store_true")
+    ap.add_argument("--no-compress", action="store_true",
+                    help="keep one explicit u32 column per entry (B200_MAT_NO_COMPRESS)")
+    ap.add_argument("--no-uncompressed-leg", action="store_true",
+                    help="skip the extra NO_COMPRESS solve reported beside the headline")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -201,7 +208,8 @@ def main():
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
     t_setup = time.perf_counter()
-    M = abi.Matrix.generate(ctx, gen, size)
+    mflags = abi.MAT_NO_COMPRESS if args.no_compress else 0
+    M = abi.Matrix.generate(ctx, gen, size, flags=mflags)
     info = M.info()
     torch.cuda.synchronize()
     t_setup = time.perf_counter() - t_setup
@@ -265,29 +273,64 @@ def main():
 
     peak, peak_src = peaks()
     achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else None
+    compressed = info.sell_uniform_slices > 0
+    kernel_key = "k_spmv_sellc_dot" if compressed else "k_spmv_sell_dot"
     traffic = None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and world == 1:
         try:
-            traffic = json.load(open(tp)).get(args.workload, {}).get("k_spmv_sell_dot")
+            traffic = json.load(open(tp)).get(args.workload, {}).get(kernel_key)
         except Exception:
             traffic = None
+    # bytes one launch must move with the layout actually stored (index-compressed
+    # or not): matrix streams + x read once + y written once
+    stored_bytes = info.matrix_stream_bytes + 16 * n
 
     extra = {}
     if rank == 0 and world == 1 and not args.no_spmv:
         # the SpMV target configuration, stand-alone (matrix 1.5 GB >> 126 MB L2)
         M.close()
-        M7 = abi.Matrix.generate(ctx, abi.GEN_POISSON7, 256)
-        n7 = M7.info().n_local
-        x7 = torch.randn(n7, dtype=torch.float64, device=dev)
-        y7 = torch.empty(n7, dtype=torch.float64, device=dev)
-        sb7, _ = M7.algorithmic_bytes()
-        ms7 = min(M7.spmv_time(x7, y7, reps=50) for _ in range(3))
-        extra["spmv_7pt_256"] = {"ms": ms7, "gbs": sb7 / ms7 / 1e6,
-                                 "frac_of_measured": sb7 / ms7 / 1e6 / peak,
-                                 "frac_of_nominal_8TBs": sb7 / ms7 / 1e6 / 8000.0,
-                                 "algorithmic_bytes": sb7}
-        M7.close()
+        legs = [("spmv_7pt_256", mflags)]
+        if not args.no_compress:
+            legs.append(("spmv_7pt_256_uncompressed", abi.MAT_NO_COMPRESS))
+        for label, fl in legs:
+            M7 = abi.Matrix.generate(ctx, abi.GEN_POISSON7, 256, flags=fl)
+            i7 = M7.info()
+            n7 = i7.n_local
+            x7 = torch.randn(n7, dtype=torch.float64, device=dev)
+            y7 = torch.empty(n7, dtype=torch.float64, device=dev)
+            sb7, _ = M7.algorithmic_bytes()
+            ms7 = min(M7.spmv_time(x7, y7, reps=50) for _ in range(3))
+            extra[label] = {"ms": ms7, "gbs": sb7 / ms7 / 1e6,
+                            "frac_of_measured": sb7 / ms7 / 1e6 / peak,
+                            "frac_of_nominal_8TBs": sb7 / ms7 / 1e6 / 8000.0,
+                            "algorithmic_bytes": sb7,
+                            "stored_bytes": i7.matrix_stream_bytes + 16 * n7,
+                            "index_compressed_slices": "%d/%d" % (i7.sell_uniform_slices, i7.sell_slices)}
+            M7.close()
+            del x7, y7
+        if compressed and not args.no_uncompressed_leg:
+            # the same solve with one explicit column per entry, beside the headline
+            Mu = abi.Matrix.generate(ctx, gen, size, flags=abi.MAT_NO_COMPRESS)
+            d_x.zero_()
+            Mu.pcg(d_b, d_x, tol=TOL, maxit=MAXIT, flags=flags)
+            torch.cuda.synchronize()
+            d_x.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            ru, _ = Mu.pcg(d_b, d_x, tol=TOL, maxit=MAXIT, flags=flags)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            su = e0.elapsed_time(e1) / 1e3
+            extra["uncompressed"] = {
+                "value": su, "unit": UNIT, "iterations": ru.iters,
+                "ms_per_iteration": su * 1e3 / max(ru.iters, 1),
+                "algorithmic_gbs_per_gpu": iter_bytes * ru.iters / su / 1e9,
+                "kernel_ms": {"spmv_dot": ru.spmv_ms, "update": ru.update_ms, "pupdate": ru.pupdate_ms},
+                "spmv_achieved_gbs": spmv_bytes / (ru.spmv_ms * 1e-3) / 1e9 if ru.spmv_ms > 0 else None,
+                "spmv_frac_of_measured": spmv_bytes / (ru.spmv_ms * 1e-3) / 1e9 / peak if ru.spmv_ms > 0 else None,
+                "note": "B200_MAT_NO_COMPRESS: 12 B/nnz streams, the layout the algorithmic-byte count describes"}
+            Mu.close()
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_pcg_sample(kind, size, iters)
@@ -308,12 +351,23 @@ def main():
                     "ms_per_iteration": sec_per_solve * 1e3 / max(iters, 1),
                     "algorithmic_gbs_per_gpu": iter_bytes * iters / sec_per_solve / 1e9,
                     "kernel_ms": {"spmv_dot": spmv_ms, "update": upd_ms, "pupdate": pupd_ms}},
-            "roofline": {"bound": "hbm", "kernel": "k_spmv_sell<dot> (q = A p, p.q)",
+            "roofline": {"bound": "hbm",
+                         "kernel": ("k_spmv_sellc<dot>" if compressed else "k_spmv_sell<dot>")
+                                   + " (q = A p, p.q)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if achieved else None,
                          "frac_of_nominal_8TBs": achieved / 8000.0 if achieved else None,
                          "peak_source": peak_src, "traffic": traffic,
                          "algorithmic_bytes_per_launch": spmv_bytes,
+                         "stored_bytes_per_launch": stored_bytes,
+                         "stored_gbs": stored_bytes / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else None,
+                         "stored_frac": stored_bytes / (spmv_ms * 1e-3) / 1e9 / peak if spmv_ms > 0 else None,
+                         "index_compressed_slices": "%d/%d" % (info.sell_uniform_slices, info.sell_slices),
+                         "note": ("achieved counts the ALGORITHMIC bytes (12 nnz + 4 (n+1) + 16 n); "
+                                  "uniform SELL slices store w column deltas instead of 32 w columns, "
+                                  "so the kernel moves stored_bytes (< algorithmic) and frac can "
+                                  "exceed the copy peak; stored_frac is the DRAM-side fraction"
+                                  if compressed else "explicit u32 column per entry"),
                          "launch_ms": spmv_ms},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 2 * n * 8 * world,
                     "d2h_bytes_per_step": n * 8 * world,
