@@ -76,6 +76,10 @@ int b200_ctx_destroy(b200_ctx *ctx);
 int b200_ctx_set_stream(b200_ctx *ctx, void *cuda_stream);
 int b200_ctx_sync(b200_ctx *ctx);
 int b200_ctx_rank(const b200_ctx *ctx, int *rank, int *nranks);
+/* The row block [r0, r1) rank `rank` of `nranks` owns of an n-row operator:
+ * contiguous, cuts at n*k/nranks rounded to 32 rows.  Pure host arithmetic
+ * (no device needed): callers use it to slice b and x per rank. */
+int b200_row_block(uint64_t n, int rank, int nranks, uint64_t *r0, uint64_t *r1);
 
 /* Device memory owned by the library (so a C host needs no CUDA headers). */
 int b200_malloc(b200_ctx *ctx, size_t bytes, void **dptr);

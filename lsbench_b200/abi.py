@@ -32,6 +32,7 @@ SYMBOLS = [
     "b200_last_error", "b200_abi_version", "b200_device_count",
     "b200_ctx_create", "b200_nccl_unique_id", "b200_ctx_create_dist",
     "b200_ctx_destroy", "b200_ctx_set_stream", "b200_ctx_sync", "b200_ctx_rank",
+    "b200_row_block",
     "b200_malloc", "b200_free", "b200_memcpy_h2d", "b200_memcpy_d2h",
     "b200_memset", "b200_host_alloc", "b200_host_free",
     "b200_mat_from_csr", "b200_mat_generate", "b200_mat_destroy",
@@ -100,6 +101,7 @@ def load():
         "b200_ctx_set_stream": [vp, vp],
         "b200_ctx_sync": [vp],
         "b200_ctx_rank": [vp, C.POINTER(i32), C.POINTER(i32)],
+        "b200_row_block": [u64, i32, i32, C.POINTER(u64), C.POINTER(u64)],
         "b200_malloc": [vp, C.c_size_t, C.POINTER(vp)],
         "b200_free": [vp, vp],
         "b200_memcpy_h2d": [vp, vp, vp, C.c_size_t],
@@ -141,6 +143,13 @@ def device_count():
     n = C.c_int(0)
     _chk(load().b200_device_count(C.byref(n)))
     return n.value
+
+
+def row_block(n, rank, nranks):
+    """[r0, r1) owned by `rank` (host arithmetic, no GPU)."""
+    a, b = C.c_uint64(0), C.c_uint64(0)
+    _chk(load().b200_row_block(n, rank, nranks, C.byref(a), C.byref(b)))
+    return a.value, b.value
 
 
 def nccl_unique_id():

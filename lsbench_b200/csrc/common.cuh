@@ -135,6 +135,7 @@ struct b200_mat {
   // --- solver workspace (lazily allocated) ----------------------------------
   double *w_r = nullptr, *w_p = nullptr, *w_q = nullptr;  // p has halo room
   double *w_x = nullptr;          // iterate (graph-stable pointer)
+  double *stage_b = nullptr, *stage_x = nullptr;  // b200_pcg_solve_host staging
   int grid_ew = 0;                // element-wise kernels
   unsigned partial_stride = 0;
   double *x_ext = nullptr;        // spmv staging: n_local + n_halo

@@ -775,7 +775,7 @@ extern "C" int b200_mat_destroy(b200_mat *M) {
                   M->sell_meta, M->sell_dcols,
                   M->vec_row_ids, M->long_row_ids, M->vec_off, M->long_off,
                   M->vl_cols, M->vl_vals, M->dinv, M->row_len, M->w_r, M->w_p,
-                  M->w_q, M->x_ext, M->partials, M->state};
+                  M->w_q, M->x_ext, M->partials, M->state, M->stage_b, M->stage_x};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   delete M;

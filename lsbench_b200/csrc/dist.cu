@@ -29,7 +29,6 @@ static inline unsigned nblk(uint64_t n, unsigned t = T256) {
   return (unsigned)((n + t - 1) / t);
 }
 
-void b200_row_block(uint64_t n, int rank, int nranks, uint64_t *r0, uint64_t *r1);
 
 struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId *);

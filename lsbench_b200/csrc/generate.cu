@@ -169,7 +169,10 @@ static int scan_u64(cudaStream_t s, const uint64_t *in, uint64_t *out, uint64_t 
 
 // Row block owned by `rank`: contiguous, boundaries rounded to 32 rows (and so
 // to whole z-planes for the stencils whenever P divides N).
-void b200_row_block(uint64_t n, int rank, int nranks, uint64_t *r0, uint64_t *r1) {
+extern "C" int b200_row_block(uint64_t n, int rank, int nranks, uint64_t *r0,
+                              uint64_t *r1) {
+  if (!r0 || !r1 || nranks < 1 || rank < 0 || rank >= nranks)
+    B_FAIL(B200_EINVAL, "b200_row_block: rank %d of %d", rank, nranks);
   auto cut = [&](int k) -> uint64_t {
     if (k <= 0) return 0;
     if (k >= nranks) return n;
@@ -178,6 +181,7 @@ void b200_row_block(uint64_t n, int rank, int nranks, uint64_t *r0, uint64_t *r1
     return c > n ? n : c;
   };
   *r0 = cut(rank), *r1 = cut(rank + 1);
+  return B200_OK;
 }
 
 extern "C" int b200_mat_generate(b200_ctx *c, int kind, uint64_t size,

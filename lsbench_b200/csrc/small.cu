@@ -31,6 +31,7 @@ namespace cg = cooperative_groups;
 
 #define SM_THREADS 1024
 #define SM_WARPS (SM_THREADS / 32)
+static_assert(SM_THREADS == 1024, "cluster_sum reduces exactly 32 warp sums");
 #define SM_MAX_CLUSTER 16
 #define SM_MAX_ROWS 16384
 #define SM_MAX_NNZ 600000
@@ -84,27 +85,50 @@ __host__ __device__ inline SmemMap smem_map(uint32_t max_ent, uint32_t max_group
 }
 
 // y[lr] = sum_k a(lr,k) * v[col(lr,k)] for the rows of this CTA; v staged in
-// shared memory.  4 lanes per row; the value lands in every lane of the group.
-__device__ __forceinline__ void small_spmv(const SmallCta &me, const uint32_t *goff,
-                                           const double *vals, const uint16_t *cols,
-                                           const double *v_s, double *q_s) {
+// shared memory.  4 lanes per row, two steps in flight per lane; the row value
+// lands in every lane of its group of four.  With DOT the lane that owns the
+// row also returns its share of y . v (the CG p.Ap): rows it handled, in
+// order.
+template <bool DOT>
+__device__ __forceinline__ double small_spmv(const SmallCta &me, const uint32_t *goff,
+                                             const double *vals, const uint16_t *cols,
+                                             const uint32_t *rowid, const double *v_s,
+                                             double *q_s) {
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double dot = 0.0;
   for (uint32_t j = warp; j < me.n_groups; j += SM_WARPS) {
     const uint32_t o = goff[j], w = goff[j + 1] - o;
     const uint32_t base = o * 32 + lane;
     double s = 0.0;
-    for (uint32_t t = 0; t < w; t++)
+    uint32_t t = 0;
+    for (; t + 2 <= w; t += 2) {
+      const double a0 = vals[base + t * 32], a1 = vals[base + t * 32 + 32];
+      const double x0 = v_s[cols[base + t * 32]], x1 = v_s[cols[base + t * 32 + 32]];
+      s = fma(a0, x0, s);
+      s = fma(a1, x1, s);
+    }
+    if (t < w)
       s = fma(vals[base + t * 32], v_s[cols[base + t * 32]], s);
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
-    if ((lane & 3) == 0)
-      q_s[j * 8 + (lane >> 2)] = s;
+    if ((lane & 3) == 0) {
+      const uint32_t slot = j * 8 + (lane >> 2);
+      q_s[slot] = s;
+      if (DOT) {
+        const uint32_t row = rowid[slot];
+        if (row != 0xffffffffu)
+          dot = fma(s, v_s[row - me.col_lo], dot);
+      }
+    }
   }
+  return dot;
 }
 
 // CTA sum of NV per-thread values -> slot[v][my rank] in EVERY CTA of the
 // cluster (DSMEM), then the cluster barrier; on return tot[v] = sum over the
-// CTAs in rank order, identical in all threads of all CTAs.
+// CTAs, identical in all threads of all CTAs.  Every level is a fixed
+// butterfly (lanes, then the 32 warp sums, then the <= 16 CTA sums), so the
+// order of the additions depends on nothing but the launch shape.
 template <int NV>
 __device__ __forceinline__ void cluster_sum(cg::cluster_group &cl, double (&val)[NV],
                                             double *wred, double *slots, int slot0,
@@ -118,22 +142,23 @@ __device__ __forceinline__ void cluster_sum(cg::cluster_group &cl, double (&val)
       wred[v * SM_WARPS + warp] = s;
   }
   __syncthreads();
-  if (threadIdx.x < C) {
+  if (warp == 0) {
 #pragma unroll
     for (int v = 0; v < NV; v++) {
-      double s = 0.0;
-      for (int w = 0; w < SM_WARPS; w++)
-        s += wred[v * SM_WARPS + w];
-      double *remote = cl.map_shared_rank(slots + (slot0 + v) * SM_MAX_CLUSTER, threadIdx.x);
-      remote[me] = s;
+      const double s = warp_sum(wred[v * SM_WARPS + lane]);  // SM_WARPS == 32
+      if (lane < C) {
+        double *remote = cl.map_shared_rank(slots + (slot0 + v) * SM_MAX_CLUSTER, lane);
+        remote[me] = s;
+      }
     }
   }
   cl.sync();
 #pragma unroll
   for (int v = 0; v < NV; v++) {
-    double s = 0.0;
-    for (unsigned c = 0; c < C; c++)
-      s += slots[(slot0 + v) * SM_MAX_CLUSTER + c];
+    double s = (lane & 15u) < C ? slots[(slot0 + v) * SM_MAX_CLUSTER + (lane & 15u)] : 0.0;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1)
+      s += __shfl_xor_sync(0xffffffffu, s, o);
     tot[v] = s;
   }
 }
@@ -174,7 +199,7 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
   for (uint32_t i = tid; i < me.col_n; i += SM_THREADS)
     v_s[i] = x[me.col_lo + i];
   __syncthreads();
-  small_spmv(me, goff, vals, cols, v_s, q_s);
+  small_spmv<false>(me, goff, vals, cols, rowid, v_s, q_s);
   __syncthreads();
   double acc3[3] = {0.0, 0.0, 0.0}, tot3[3];
   for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
@@ -186,7 +211,8 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
     p_g[row] = zi;
     acc3[0] = fma(ri, zi, acc3[0]), acc3[1] = fma(ri, ri, acc3[1]), acc3[2] = fma(bi, bi, acc3[2]);
   }
-  __threadfence();
+  // (the cluster barrier inside cluster_sum is a release/acquire at cluster
+  // scope: the p_g stores above are visible to the other CTAs' __ldcg after it)
   cluster_sum<3>(cl, acc3, wred, slots, 1, tot3);  // slots 1,2,3 = rz, rr, bb
   double rz = tot3[0], rr = tot3[1];
   const double bb = tot3[2], thr2 = tol * tol * bb;
@@ -200,15 +226,9 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
     for (uint32_t i = tid; i < me.col_n; i += SM_THREADS)
       v_s[i] = __ldcg(p_g + me.col_lo + i);
     __syncthreads();
-    small_spmv(me, goff, vals, cols, v_s, q_s);
-    __syncthreads();
-    double a1[1] = {0.0}, t1[1];
-    for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
-      uint32_t row = rowid[i];
-      if (row != 0xffffffffu)
-        a1[0] = fma(q_s[i], v_s[row - me.col_lo], a1[0]);
-    }
-    cluster_sum<1>(cl, a1, wred, slots, 0, t1);
+    double a1[1], t1[1];
+    a1[0] = small_spmv<true>(me, goff, vals, cols, rowid, v_s, q_s);
+    cluster_sum<1>(cl, a1, wred, slots, 0, t1);  // (its __syncthreads publishes q_s)
     pq = t1[0];
     if (!(pq > 0.0)) {
       status = 2;
@@ -245,7 +265,6 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
       if (row != 0xffffffffu)
         p_g[row] = fma(beta, v_s[row - me.col_lo], d_s[i] * r_s[i]);
     }
-    __threadfence();
     cl.sync();
   }
 
@@ -255,12 +274,11 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
     if (row != 0xffffffffu)
       x[row] = x_s[i], x_g[row] = x_s[i];
   }
-  __threadfence();
   cl.sync();
   for (uint32_t i = tid; i < me.col_n; i += SM_THREADS)
     v_s[i] = __ldcg(x_g + me.col_lo + i);
   __syncthreads();
-  small_spmv(me, goff, vals, cols, v_s, q_s);
+  small_spmv<false>(me, goff, vals, cols, rowid, v_s, q_s);
   __syncthreads();
   double a4[1] = {0.0}, t4[1];
   for (uint32_t i = tid; i < nslot; i += SM_THREADS) {

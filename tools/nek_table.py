@@ -23,7 +23,7 @@ CU_DRIVER = os.path.join(ROOT, "oracle", "_ref", "driver_cusolver")
 def cusolver_ms(path):
     """elapsed column of the reference's CSV row (total clock() seconds over
     `trials` solves, src/cusparse.c:207-209) -> ms per solve."""
-    if not os.path.exists(CU_DRIVER):
+    if not os.path.exists(CU_DRIVER) or cu_trials < 1:
         return None
     try:
         r = subprocess.run([CU_DRIVER, "--solver", "cusolver", "--matrix", path,
