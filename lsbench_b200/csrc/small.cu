@@ -1,25 +1,34 @@
 // small.cu -- the coarse-grid regime (BASELINE.json config 2: Nek matrices,
 // n ~ 3.5-6.4 k, nnz ~ 77-146 k): the whole Jacobi-PCG solve in ONE kernel on
-// ONE thread-block cluster, matrix resident in (distributed) shared memory.
+// ONE thread-block cluster, matrix and vectors resident in (distributed)
+// shared memory, no global-memory traffic and no cluster-wide barrier inside
+// the iteration.
 //
 // Why: with three streaming kernels per iteration a 300-iteration solve is
-// ~900 launches of ~3 us each -- launch-bound (3.4 ms measured) although the
-// data is 1.7 MB.  Here the matrix is split over the shared memory of the C
-// CTAs of a cluster (C = 16, else 8), each CTA keeps its rows' x, r, D^-1 in
-// shared memory too, and an iteration costs three hardware cluster barriers:
+// ~900 launches -- launch-bound (3.4 ms measured) although the data is 1.7 MB.
+// Here the matrix is split over the shared memory of the C CTAs of a cluster
+// (C = 16, else 8); each CTA keeps x, r, D^-1 of its rows and p on the window
+// of columns its rows touch.  CTAs talk through DSMEM only:
 //
-//   stage   the slice of p this CTA's columns touch: L2 -> shared memory
-//   SpMV    4 lanes per row, 8 rows per warp, operands from shared memory,
-//           4-lane shuffle reduction; p.q partial per CTA
-//   -- partials to every CTA's shared memory over DSMEM; cluster barrier 1 --
-//   update  x += a p, r -= a q, partials of r.D^-1 r and r.r
-//   -- DSMEM exchange; cluster barrier 2; convergence test (same in all CTAs) --
-//   p       p = D^-1 r + b p for the owned rows -> global (L2)
-//   -- cluster barrier 3 --
+//   SpMV    q = A p on the local window, 4 lanes per row; p.q partial
+//   -- all-reduce 1: every CTA writes its partial into every CTA's slot with
+//      st.async (data + mbarrier transaction bytes in one DSMEM hop); a CTA
+//      goes on when its own mbarrier has counted 8 C bytes --
+//   update  x += a p, r -= a q, z = D^-1 r; partials of r.z and r.r; z is
+//           pushed (st.async) into the window of every CTA that reads the row
+//   -- all-reduce 2 + halo in one wait: 16 C + 8 col_n bytes on mbarrier B --
+//   p       p = z + b p on the whole local window (redundantly, instead of a
+//           third synchronisation)
 //
-// All sums have a fixed order (4-lane butterfly, warp butterfly, warps in
-// order, CTAs in rank order), so iterates and iteration counts are
-// bit-reproducible.  Same recurrences and stopping rule as pcg.cu; stands
+// Measured per-iteration cost on tj7a_A_12 (clock64, B200_SMALL_PROFILE=1): the
+// first version of this kernel -- p exchanged through L2, three cluster
+// barriers -- spent 1400-1850 cycles in each barrier.cluster and 12 400 cycles
+// per iteration.  Two mbarriers used in strict alternation are enough to
+// order every reuse of the slots and windows (see the kernel).
+//
+// All sums have a fixed order (4-lane butterfly, warp butterfly, 32 warp sums
+// by butterfly, <= 16 CTA sums by butterfly), so iterates and iteration counts
+// are bit-reproducible.  Same recurrences and stopping rule as pcg.cu; stands
 // where the timed solve of src/cholmod-impl.h:58-63 / src/cusparse.c:189-197
 // stands for these matrices.
 #include "common.cuh"
@@ -42,8 +51,8 @@ struct SmallCta {         // one per CTA, in global memory
   uint32_t ent;           // padded entries = 32 * sum of group widths
   uint32_t col_lo, col_n; // staged column window [col_lo, col_lo + col_n)
   uint32_t goff_at;       // into goff[]   (n_groups + 1 values, units of 32 entries)
-  uint32_t row_at;        // into rowid[] / dinv[] (8 n_groups values, 0xffffffff = none)
-  uint32_t pad;
+  uint32_t row_at;        // into rowid[] / dinv[] / dmask[] (8 n_groups values, 0xffffffff = none)
+  uint32_t n_recv;        // window entries some row of this CTA reads (incl. its own rows)
   uint64_t ent_at;        // into vals[] / cols[]
 };
 
@@ -52,17 +61,17 @@ struct SmallPlan {
   uint32_t n = 0;
   size_t smem = 0;
   SmallCta *d_cta = nullptr;
-  uint32_t *d_goff = nullptr, *d_rowid = nullptr;
+  uint32_t *d_goff = nullptr, *d_rowid = nullptr, *d_dmask = nullptr;
   double *d_vals = nullptr, *d_dinv = nullptr;
   uint16_t *d_cols = nullptr;
-  double *d_p = nullptr, *d_xg = nullptr;  // global p and x staging (L2)
+  long long *d_prof = nullptr;
   PcgState *d_state = nullptr;
   // largest per-CTA extents (shared memory carve-up is uniform)
   uint32_t max_ent = 0, max_groups = 0, max_stage = 0;
 };
 
 struct SmemMap {
-  size_t stage, vals, xs, rs, ds, qs, slots, wred, goff, rowid, cols, total;
+  size_t stage, zwin, vals, xs, rs, ds, qs, slots, wred, bars, win, goff, rowid, dmask, cols, total;
 };
 
 __host__ __device__ inline SmemMap smem_map(uint32_t max_ent, uint32_t max_groups,
@@ -70,6 +79,7 @@ __host__ __device__ inline SmemMap smem_map(uint32_t max_ent, uint32_t max_group
   SmemMap m;
   size_t rows = (size_t)max_groups * 8, o = 0;
   m.stage = o, o += ((size_t)max_stage + 1) / 2 * 2 * 8;
+  m.zwin = o, o += ((size_t)max_stage + 1) / 2 * 2 * 8;
   m.vals = o, o += (size_t)max_ent * 8;
   m.xs = o, o += rows * 8;
   m.rs = o, o += rows * 8;
@@ -77,8 +87,11 @@ __host__ __device__ inline SmemMap smem_map(uint32_t max_ent, uint32_t max_group
   m.qs = o, o += rows * 8;
   m.slots = o, o += 4 * SM_MAX_CLUSTER * 8;  // pq | rz | rr | bb
   m.wred = o, o += 3 * SM_WARPS * 8;
+  m.bars = o, o += 2 * 8;
+  m.win = o, o += 2 * SM_MAX_CLUSTER * 4;
   m.goff = o, o += ((size_t)max_groups + 2) * 4;
   m.rowid = o, o += rows * 4;
+  m.dmask = o, o += rows * 4;
   m.cols = o, o += (size_t)max_ent * 2;
   m.total = (o + 15) / 16 * 16;
   return m;
@@ -124,17 +137,55 @@ __device__ __forceinline__ double small_spmv(const SmallCta &me, const uint32_t 
   return dot;
 }
 
-// CTA sum of NV per-thread values -> slot[v][my rank] in EVERY CTA of the
-// cluster (DSMEM), then the cluster barrier; on return tot[v] = sum over the
-// CTAs, identical in all threads of all CTAs.  Every level is a fixed
-// butterfly (lanes, then the 32 warp sums, then the <= 16 CTA sums), so the
-// order of the additions depends on nothing but the launch shape.
+// ---- DSMEM / mbarrier primitives ----------------------------------------------
+__device__ __forceinline__ uint32_t s_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+// shared::cluster address of the same variable in CTA `rank`
+__device__ __forceinline__ uint32_t s_remote(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void bar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count) : "memory");
+}
+// the one arrival of a phase, announcing how many bytes st.async will deliver
+__device__ __forceinline__ void bar_arm(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const uint32_t a = s_u32(bar);
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// 8 bytes into another CTA's shared memory; the same hop adds 8 to the
+// transaction count of that CTA's mbarrier
+__device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(
+                   remote_addr),
+               "l"(__double_as_longlong(v)), "r"(remote_bar)
+               : "memory");
+}
+
+// CTA sum of NV per-thread values, delivered to slot[v][my rank] of EVERY CTA of
+// the cluster together with 8 NV transaction bytes on that CTA's `bar`.  Fixed
+// butterflies at every level.  (The __syncthreads inside also publishes what the
+// callers wrote to shared memory before the call.)
 template <int NV>
-__device__ __forceinline__ void cluster_sum(cg::cluster_group &cl, double (&val)[NV],
-                                            double *wred, double *slots, int slot0,
-                                            double (&tot)[NV]) {
+__device__ __forceinline__ void send_partials(unsigned C, unsigned me, double (&val)[NV],
+                                              double *wred, double *slots, int slot0,
+                                              uint64_t *bar) {
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned C = cl.num_blocks(), me = cl.block_rank();
 #pragma unroll
   for (int v = 0; v < NV; v++) {
     double s = warp_sum(val[v]);
@@ -143,16 +194,20 @@ __device__ __forceinline__ void cluster_sum(cg::cluster_group &cl, double (&val)
   }
   __syncthreads();
   if (warp == 0) {
+    const uint32_t rbar = s_remote(s_u32(bar), lane < C ? lane : 0);
 #pragma unroll
     for (int v = 0; v < NV; v++) {
       const double s = warp_sum(wred[v * SM_WARPS + lane]);  // SM_WARPS == 32
-      if (lane < C) {
-        double *remote = cl.map_shared_rank(slots + (slot0 + v) * SM_MAX_CLUSTER, lane);
-        remote[me] = s;
-      }
+      if (lane < C)
+        st_async_f64(s_remote(s_u32(slots + (slot0 + v) * SM_MAX_CLUSTER + me), lane), s, rbar);
     }
   }
-  cl.sync();
+}
+// after bar_wait: the <= 16 CTA sums by butterfly, identical in every thread
+template <int NV>
+__device__ __forceinline__ void read_totals(unsigned C, const double *slots, int slot0,
+                                            double (&tot)[NV]) {
+  const uint32_t lane = threadIdx.x & 31;
 #pragma unroll
   for (int v = 0; v < NV; v++) {
     double s = (lane & 15u) < C ? slots[(slot0 + v) * SM_MAX_CLUSTER + (lane & 15u)] : 0.0;
@@ -163,24 +218,39 @@ __device__ __forceinline__ void cluster_sum(cg::cluster_group &cl, double (&val)
   }
 }
 
+// PROF: thread 0 of CTA 0 accumulates clock64() per phase into prof[0..5]
+// (spmv, wait 1, update + push, wait 2, p window, -) -- B200_SMALL_PROFILE=1.
+template <bool PROF>
 __global__ void __launch_bounds__(SM_THREADS, 1)
 k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_goff,
-            const uint32_t *__restrict__ g_rowid, const double *__restrict__ g_vals,
+            const uint32_t *__restrict__ g_rowid, const uint32_t *__restrict__ g_dmask,
+            const double *__restrict__ g_vals,
             const uint16_t *__restrict__ g_cols, const double *__restrict__ g_dinv,
-            const double *__restrict__ b, double *__restrict__ x, double *p_g,
-            double *x_g, PcgState *st, uint32_t max_ent, uint32_t max_groups,
-            uint32_t max_stage, double tol, int maxit) {
+            const double *__restrict__ b, double *__restrict__ x, PcgState *st,
+            uint32_t max_ent, uint32_t max_groups, uint32_t max_stage, double tol,
+            int maxit, long long *prof) {
   extern __shared__ __align__(16) unsigned char smem[];
   cg::cluster_group cl = cg::this_cluster();
-  const SmallCta me = ctas[cl.block_rank()];
+  const unsigned C = cl.num_blocks(), rank = cl.block_rank();
+  const SmallCta me = ctas[rank];
   const SmemMap mp = smem_map(max_ent, max_groups, max_stage);
-  double *v_s = (double *)(smem + mp.stage), *vals = (double *)(smem + mp.vals);
+  double *p_w = (double *)(smem + mp.stage), *z_w = (double *)(smem + mp.zwin);
+  double *vals = (double *)(smem + mp.vals);
   double *x_s = (double *)(smem + mp.xs), *r_s = (double *)(smem + mp.rs);
   double *d_s = (double *)(smem + mp.ds), *q_s = (double *)(smem + mp.qs);
   double *slots = (double *)(smem + mp.slots), *wred = (double *)(smem + mp.wred);
+  uint64_t *bar_a = (uint64_t *)(smem + mp.bars), *bar_b = bar_a + 1;
+  uint32_t *win_lo = (uint32_t *)(smem + mp.win), *win_n = win_lo + SM_MAX_CLUSTER;
   uint32_t *goff = (uint32_t *)(smem + mp.goff), *rowid = (uint32_t *)(smem + mp.rowid);
+  uint32_t *dmask = (uint32_t *)(smem + mp.dmask);
   uint16_t *cols = (uint16_t *)(smem + mp.cols);
   const uint32_t tid = threadIdx.x, nslot = me.n_groups * 8;
+  long long pt[6] = {0, 0, 0, 0, 0, 0}, t0 = 0;
+#define B2_TICK(i)                                                                \
+  if (PROF) {                                                                     \
+    long long t1 = clock64();                                                     \
+    pt[i] += t1 - t0, t0 = t1;                                                    \
+  }
 
   // ---- make the matrix resident ----------------------------------------------------
   for (uint32_t i = tid; i < me.ent; i += SM_THREADS)
@@ -190,17 +260,44 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
   for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
     uint32_t row = g_rowid[me.row_at + i];
     rowid[i] = row;
+    dmask[i] = g_dmask[me.row_at + i];
     d_s[i] = g_dinv[me.row_at + i];
     x_s[i] = row != 0xffffffffu ? x[row] : 0.0;
   }
-  __syncthreads();
-
-  // ---- r = b - A x0, p = D^-1 r ------------------------------------------------------
+  if (tid < SM_MAX_CLUSTER)  // window base of every CTA, as a byte offset into its z window
+    win_lo[tid] = tid < C ? ctas[tid].col_lo : 0u, win_n[tid] = tid < C ? ctas[tid].col_n : 0u;
   for (uint32_t i = tid; i < me.col_n; i += SM_THREADS)
-    v_s[i] = x[me.col_lo + i];
+    p_w[i] = x[me.col_lo + i], z_w[i] = 0.0;  // the window of x0, for r = b - A x0
+  if (tid == 0) {
+    bar_init(bar_a, 1), bar_init(bar_b, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
-  small_spmv<false>(me, goff, vals, cols, rowid, v_s, q_s);
+  cl.sync();  // every CTA's barriers exist before anyone stores into a neighbour
+
+  // Two mbarriers, used in strict alternation B A B A ... B | B A.  A CTA sends
+  // the data of phase k+1 of one barrier only after it has passed phase k of
+  // the other one, which needed a contribution every CTA sends only after it
+  // has itself passed phase k of the first: so no store can land in a phase,
+  // a slot or a window that its receiver has not finished with.
+  uint32_t par_a = 0, par_b = 0;
+  const uint32_t my_bar_b = s_u32(bar_b), my_zw = s_u32(z_w);
+  // the value of owned row `row`, into the window of every CTA that reads it
+  // (mask: bit k set when some row of CTA k has an entry in column `row`, or
+  // owns it)
+  auto push = [&](uint32_t row, uint32_t mask, double v) {
+    while (mask) {
+      const unsigned k = __ffs(mask) - 1;
+      mask &= mask - 1;
+      st_async_f64(s_remote(my_zw + (row - win_lo[k]) * 8u, k), v, s_remote(my_bar_b, k));
+    }
+  };
+
+  // ---- r = b - A x0, z = D^-1 r, p = z ----------------------------------------------
+  small_spmv<false>(me, goff, vals, cols, rowid, p_w, q_s);
   __syncthreads();
+  if (tid == 0)
+    bar_arm(bar_b, (3 * C + me.n_recv) * 8);
   double acc3[3] = {0.0, 0.0, 0.0}, tot3[3];
   for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
     uint32_t row = rowid[i];
@@ -208,12 +305,15 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
       continue;
     double bi = b[row], ri = bi - q_s[i], zi = d_s[i] * ri;
     r_s[i] = ri;
-    p_g[row] = zi;
+    push(row, dmask[i], zi);
     acc3[0] = fma(ri, zi, acc3[0]), acc3[1] = fma(ri, ri, acc3[1]), acc3[2] = fma(bi, bi, acc3[2]);
   }
-  // (the cluster barrier inside cluster_sum is a release/acquire at cluster
-  // scope: the p_g stores above are visible to the other CTAs' __ldcg after it)
-  cluster_sum<3>(cl, acc3, wred, slots, 1, tot3);  // slots 1,2,3 = rz, rr, bb
+  send_partials<3>(C, rank, acc3, wred, slots, 1, bar_b);  // slots 1,2,3 = rz, rr, bb
+  bar_wait(bar_b, par_b), par_b ^= 1;
+  read_totals<3>(C, slots, 1, tot3);
+  for (uint32_t i = tid; i < me.col_n; i += SM_THREADS)
+    p_w[i] = z_w[i];
+  __syncthreads();
   double rz = tot3[0], rr = tot3[1];
   const double bb = tot3[2], thr2 = tol * tol * bb;
   int it = 0, status = 1;
@@ -222,31 +322,44 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
     status = 0;
 
   // ---- iterations ----------------------------------------------------------------------
+  if (PROF)
+    t0 = clock64();
   while (status == 1 && it < maxit) {
-    for (uint32_t i = tid; i < me.col_n; i += SM_THREADS)
-      v_s[i] = __ldcg(p_g + me.col_lo + i);
-    __syncthreads();
+    if (tid == 0)
+      bar_arm(bar_a, C * 8);
     double a1[1], t1[1];
-    a1[0] = small_spmv<true>(me, goff, vals, cols, rowid, v_s, q_s);
-    cluster_sum<1>(cl, a1, wred, slots, 0, t1);  // (its __syncthreads publishes q_s)
+    a1[0] = small_spmv<true>(me, goff, vals, cols, rowid, p_w, q_s);
+    B2_TICK(0)
+    send_partials<1>(C, rank, a1, wred, slots, 0, bar_a);
+    bar_wait(bar_a, par_a), par_a ^= 1;
+    read_totals<1>(C, slots, 0, t1);
+    B2_TICK(1)
     pq = t1[0];
     if (!(pq > 0.0)) {
       status = 2;
       break;
     }
     const double alpha = rz / pq;
+    if (tid == 0)
+      bar_arm(bar_b, (2 * C + me.n_recv) * 8);
     double a2[2] = {0.0, 0.0}, t2[2];
     for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
       uint32_t row = rowid[i];
       if (row == 0xffffffffu)
         continue;
-      double pi = v_s[row - me.col_lo];
+      double pi = p_w[row - me.col_lo];
       x_s[i] = fma(alpha, pi, x_s[i]);
       double ri = fma(-alpha, q_s[i], r_s[i]);
       r_s[i] = ri;
-      a2[0] = fma(ri, d_s[i] * ri, a2[0]), a2[1] = fma(ri, ri, a2[1]);
+      const double zi = d_s[i] * ri;
+      push(row, dmask[i], zi);
+      a2[0] = fma(ri, zi, a2[0]), a2[1] = fma(ri, ri, a2[1]);
     }
-    cluster_sum<2>(cl, a2, wred, slots, 1, t2);
+    B2_TICK(2)
+    send_partials<2>(C, rank, a2, wred, slots, 1, bar_b);
+    bar_wait(bar_b, par_b), par_b ^= 1;
+    read_totals<2>(C, slots, 1, t2);
+    B2_TICK(3)
     const double rzn = t2[0];
     rr = t2[1];
     it++;
@@ -260,25 +373,31 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
     }
     const double beta = rzn / rz;
     rz = rzn;
-    for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
-      uint32_t row = rowid[i];
-      if (row != 0xffffffffu)
-        p_g[row] = fma(beta, v_s[row - me.col_lo], d_s[i] * r_s[i]);
-    }
-    cl.sync();
+    for (uint32_t i = tid; i < me.col_n; i += SM_THREADS)
+      p_w[i] = fma(beta, p_w[i], z_w[i]);  // p = z + b p on the whole window
+    __syncthreads();
+    B2_TICK(4)
   }
+#undef B2_TICK
+  if (PROF && rank == 0 && tid == 0)
+    for (int i = 0; i < 6; i++)
+      prof[i] = pt[i];
 
   // ---- x out, true residual ---------------------------------------------------------------
+  cl.sync();  // the loop may end on barrier B; the next use below is B again
+  if (tid == 0)
+    bar_arm(bar_b, me.n_recv * 8);
   for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
     uint32_t row = rowid[i];
-    if (row != 0xffffffffu)
-      x[row] = x_s[i], x_g[row] = x_s[i];
+    if (row != 0xffffffffu) {
+      x[row] = x_s[i];
+      push(row, dmask[i], x_s[i]);
+    }
   }
-  cl.sync();
-  for (uint32_t i = tid; i < me.col_n; i += SM_THREADS)
-    v_s[i] = __ldcg(x_g + me.col_lo + i);
-  __syncthreads();
-  small_spmv<false>(me, goff, vals, cols, rowid, v_s, q_s);
+  bar_wait(bar_b, par_b), par_b ^= 1;
+  if (tid == 0)
+    bar_arm(bar_a, C * 8);
+  small_spmv<false>(me, goff, vals, cols, rowid, z_w, q_s);
   __syncthreads();
   double a4[1] = {0.0}, t4[1];
   for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
@@ -288,11 +407,14 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
       a4[0] = fma(d, d, a4[0]);
     }
   }
-  cluster_sum<1>(cl, a4, wred, slots, 0, t4);
-  if (cl.block_rank() == 0 && tid == 0) {
+  send_partials<1>(C, rank, a4, wred, slots, 0, bar_a);
+  bar_wait(bar_a, par_a), par_a ^= 1;
+  read_totals<1>(C, slots, 0, t4);
+  if (rank == 0 && tid == 0) {
     st->iter = it, st->status = status, st->done = 1;
     st->bb = bb, st->red[1] = rr, st->pq = pq, st->true_rr = t4[0];
   }
+  cl.sync();  // nobody leaves while a neighbour may still be storing into it
 }
 
 // ---------------------------------------------------------------------------
@@ -301,7 +423,7 @@ void small_free(b200_mat *M) {
   if (!P)
     return;
   void *ptrs[] = {P->d_cta, P->d_goff, P->d_rowid, P->d_vals, P->d_dinv,
-                  P->d_cols, P->d_p, P->d_xg, P->d_state};
+                  P->d_cols, P->d_state, P->d_prof, P->d_dmask};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   delete P;
@@ -339,9 +461,16 @@ int small_try_build(b200_mat *M) {
 
   int dev_smem = 0;
   CU_TRY(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
-  CU_TRY(cudaFuncSetAttribute(k_pcg_small, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  CU_TRY(cudaFuncSetAttribute(k_pcg_small<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  CU_TRY(cudaFuncSetAttribute(k_pcg_small<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
 
+  // B200_SMALL_CLUSTER=8|16 pins the cluster size (experiment switch)
+  int only = 0;
+  if (const char *e = getenv("B200_SMALL_CLUSTER"))
+    only = atoi(e);
   for (int C : {16, 8}) {
+    if (only && C != only)
+      continue;
     // contiguous row chunks; inside a chunk rows sorted by decreasing length
     std::vector<SmallCta> ctas(C);
     std::vector<uint32_t> goff, rowid;
@@ -370,7 +499,7 @@ int small_try_build(b200_mat *M) {
       T.n_groups = (T.n_rows + 7) / 8;
       T.col_lo = lo, T.col_n = rows.empty() ? 0 : hi - lo + 1;
       T.goff_at = (uint32_t)goff.size(), T.row_at = (uint32_t)rowid.size();
-      T.ent_at = pv.size(), T.pad = 0;
+      T.ent_at = pv.size(), T.n_recv = 0;
       if (T.col_n > 65536)
         ok = false;
       uint32_t units = 0;
@@ -413,13 +542,33 @@ int small_try_build(b200_mat *M) {
     }
     if (!ok)
       continue;
+    // who reads which column: mask of CTAs per row, and per CTA the number of
+    // window entries it receives each iteration
+    std::vector<uint32_t> readers(n, 0u), dmask(rowid.size(), 0u);
+    for (int k = 0; k < C; k++) {
+      uint64_t r0 = n * k / C, r1 = n * (k + 1) / C;
+      for (uint64_t r = r0; r < r1; r++) {
+        readers[r] |= 1u << k;
+        for (uint64_t e = offs[r]; e < offs[r + 1]; e++)
+          readers[cols[e]] |= 1u << k;
+      }
+    }
+    for (int k = 0; k < C; k++)
+      ctas[k].n_recv = 0;
+    for (uint64_t r = 0; r < n; r++)
+      for (int k = 0; k < C; k++)
+        ctas[k].n_recv += (readers[r] >> k) & 1u;
+    for (size_t i = 0; i < rowid.size(); i++)
+      dmask[i] = rowid[i] == 0xffffffffu ? 0u : readers[rowid[i]];
     SmemMap mp = smem_map(max_ent, max_groups, max_stage);
     if (mp.total > (size_t)dev_smem)
       continue;
     SmallPlan *P = new SmallPlan();
     P->C = C, P->n = (uint32_t)n, P->smem = mp.total;
     P->max_ent = max_ent, P->max_groups = max_groups, P->max_stage = max_stage;
-    if (cudaFuncSetAttribute(k_pcg_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(k_pcg_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)mp.total) != cudaSuccess ||
+        cudaFuncSetAttribute(k_pcg_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)mp.total) != cudaSuccess) {
       cudaGetLastError();
       delete P;
@@ -429,7 +578,7 @@ int small_try_build(b200_mat *M) {
     cudaLaunchAttribute attr[1];
     small_launch_config(P, &cfg, attr, c->stream);
     int nclusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&nclusters, k_pcg_small, &cfg) != cudaSuccess ||
+    if (cudaOccupancyMaxActiveClusters(&nclusters, k_pcg_small<false>, &cfg) != cudaSuccess ||
         nclusters < 1) {
       cudaGetLastError();
       delete P;
@@ -444,12 +593,12 @@ int small_try_build(b200_mat *M) {
     B_TRY(up((void **)&P->d_cta, ctas.data(), ctas.size() * sizeof(SmallCta)));
     B_TRY(up((void **)&P->d_goff, goff.data(), goff.size() * 4));
     B_TRY(up((void **)&P->d_rowid, rowid.data(), rowid.size() * 4));
+    B_TRY(up((void **)&P->d_dmask, dmask.data(), dmask.size() * 4));
     B_TRY(up((void **)&P->d_vals, pv.data(), pv.size() * 8));
     B_TRY(up((void **)&P->d_cols, pc.data(), pc.size() * 2));
     B_TRY(up((void **)&P->d_dinv, pd.data(), pd.size() * 8));
-    CU_TRY(cudaMalloc(&P->d_p, (n + 2) * 8));
-    CU_TRY(cudaMalloc(&P->d_xg, (n + 2) * 8));
     CU_TRY(cudaMalloc(&P->d_state, sizeof(PcgState)));
+    CU_TRY(cudaMalloc(&P->d_prof, 16 * sizeof(long long)));
     M->small = P;
     return B200_OK;
   }
@@ -465,12 +614,14 @@ int small_solve(b200_mat *M, const double *d_b, double *d_x,
   cudaLaunchAttribute attr[1];
   small_launch_config(P, &cfg, attr, s);
   CU_TRY(cudaEventRecord(c->ev_a, s));
-  CU_TRY(cudaLaunchKernelEx(&cfg, k_pcg_small, (const SmallCta *)P->d_cta,
+  static const bool prof = getenv("B200_SMALL_PROFILE") != nullptr;
+  CU_TRY(cudaLaunchKernelEx(&cfg, prof ? k_pcg_small<true> : k_pcg_small<false>,
+                            (const SmallCta *)P->d_cta,
                             (const uint32_t *)P->d_goff, (const uint32_t *)P->d_rowid,
-                            (const double *)P->d_vals, (const uint16_t *)P->d_cols,
-                            (const double *)P->d_dinv, d_b, d_x, P->d_p, P->d_xg,
+                            (const uint32_t *)P->d_dmask, (const double *)P->d_vals, (const uint16_t *)P->d_cols,
+                            (const double *)P->d_dinv, d_b, d_x,
                             P->d_state, P->max_ent, P->max_groups, P->max_stage,
-                            o->tol, (int)o->maxit));
+                            o->tol, (int)o->maxit, P->d_prof));
   c->launches += 1;
   CU_TRY(cudaEventRecord(c->ev_b, s));
   PcgState h;
@@ -483,6 +634,13 @@ int small_solve(b200_mat *M, const double *d_b, double *d_x,
   res->true_relres = h.bb > 0 ? sqrt(h.true_rr / h.bb) : sqrt(h.true_rr);
   res->kernel_launches = 1;
   res->path = 1;
+  if (prof && h.iter > 0) {
+    long long hp[6];
+    CU_TRY(cudaMemcpy(hp, P->d_prof, sizeof hp, cudaMemcpyDeviceToHost));
+    fprintf(stderr, "b200 small: C=%d iters=%d cycles/iter spmv=%lld reduce1=%lld update+push=%lld "
+                    "reduce2+halo=%lld pwindow=%lld\n", P->C, h.iter, hp[0] / h.iter,
+            hp[1] / h.iter, hp[2] / h.iter, hp[3] / h.iter, hp[4] / h.iter);
+  }
   if (h.status == 2)
     B_FAIL(B200_ENOTSPD, "b200_pcg_solve: breakdown at iteration %d (p.Ap = %g)",
            h.iter, h.pq);
