@@ -38,9 +38,10 @@
 
 namespace cg = cooperative_groups;
 
-#define SM_THREADS 1024
+#define SM_THREADS 512
 #define SM_WARPS (SM_THREADS / 32)
-static_assert(SM_THREADS == 1024, "cluster_sum reduces exactly 32 warp sums");
+#define SM_REG_STEPS 24  // matrix entries per lane kept in registers
+static_assert(SM_WARPS <= 32, "send_partials reduces the warp sums with one butterfly");
 #define SM_MAX_CLUSTER 16
 #define SM_MAX_ROWS 16384
 #define SM_MAX_NNZ 600000
@@ -97,19 +98,103 @@ __host__ __device__ inline SmemMap smem_map(uint32_t max_ent, uint32_t max_group
   return m;
 }
 
+// The SpMV of a CTA is shared-memory-bandwidth bound when values (8 B), columns
+// (2 B) and the gathered vector entry (8 B) all come from shared memory
+// (3 200 of 8 800 cycles per iteration on tj7a_A_12).  So each lane keeps the
+// first SM_REG_STEPS entries it multiplies in registers: a warp's groups j =
+// warp, warp + SM_WARPS, ... are covered in that order while they fit; the
+// rest stay in shared memory.  Slots are walked with compile-time indices
+// (full unroll) and warp-uniform group boundaries.
+struct RegMat {
+  double a[SM_REG_STEPS];
+  uint32_t c[SM_REG_STEPS / 2];  // two 16-bit window offsets per register
+  uint32_t nsteps;               // register slots in use (warp-uniform)
+  uint32_t j_rest;               // first group of this warp left in shared memory
+};
+
+__device__ __forceinline__ void regmat_load(RegMat &R, const SmallCta &me, const uint32_t *goff,
+                                            const double *vals, const uint16_t *cols) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t total = 0, j = warp;
+  for (; j < me.n_groups; j += SM_WARPS) {
+    const uint32_t w = goff[j + 1] - goff[j];
+    if (total + w > SM_REG_STEPS)
+      break;
+    total += w;
+  }
+  R.nsteps = total, R.j_rest = j;
+  uint32_t g = warp, o = g < me.n_groups ? goff[g] : 0u, w = g < me.n_groups ? goff[g + 1] - o : 1u, t = 0;
+#pragma unroll
+  for (int i = 0; i < SM_REG_STEPS; i++) {
+    double a = 0.0;
+    uint32_t c = 0;
+    if ((uint32_t)i < total) {
+      const uint32_t idx = (o + t) * 32 + lane;
+      a = vals[idx], c = cols[idx];
+      if (++t == w) {
+        g += SM_WARPS, t = 0;
+        if (g < me.n_groups)
+          o = goff[g], w = goff[g + 1] - o;
+      }
+    }
+    R.a[i] = a;
+    if (i & 1)
+      R.c[i / 2] |= c << 16;
+    else
+      R.c[i / 2] = c;
+  }
+}
+
 // y[lr] = sum_k a(lr,k) * v[col(lr,k)] for the rows of this CTA; v staged in
-// shared memory.  4 lanes per row, two steps in flight per lane; the row value
-// lands in every lane of its group of four.  With DOT the lane that owns the
-// row also returns its share of y . v (the CG p.Ap): rows it handled, in
-// order.
+// shared memory.  4 lanes per row; the row value lands in every lane of its
+// group of four.  With DOT the lane that owns the row also returns its share
+// of y . v (the CG p.Ap): rows it handled, in order.  Every group has at
+// least one step (the host pads).
 template <bool DOT>
-__device__ __forceinline__ double small_spmv(const SmallCta &me, const uint32_t *goff,
-                                             const double *vals, const uint16_t *cols,
-                                             const uint32_t *rowid, const double *v_s,
-                                             double *q_s) {
+__device__ __forceinline__ double small_spmv(const SmallCta &me, const RegMat &R,
+                                             const uint32_t *goff, const double *vals,
+                                             const uint16_t *cols, const uint32_t *rowid,
+                                             const double *v_s, double *q_s) {
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double dot = 0.0;
-  for (uint32_t j = warp; j < me.n_groups; j += SM_WARPS) {
+  auto finish = [&](uint32_t j, double s) {
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if ((lane & 3) == 0) {
+      const uint32_t slot = j * 8 + (lane >> 2);
+      q_s[slot] = s;
+      if (DOT) {
+        const uint32_t row = rowid[slot];
+        if (row != 0xffffffffu)
+          dot = fma(s, v_s[row - me.col_lo], dot);
+      }
+    }
+  };
+  // ---- groups held in registers ------------------------------------------------------
+  // (Measured with clock64: the 64-bit gathers from the window are what this
+  // loop waits for -- ~3.5 LDS-pipe cycles per warp gather with the bank
+  // conflicts of eight unrelated rows -- so batching the loads or keeping the
+  // values in shared memory changes nothing; registers only free the
+  // shared-memory port for the gathers.)
+  {
+    uint32_t g = warp, w = g < me.n_groups ? goff[g + 1] - goff[g] : 1u, t = 0;
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < SM_REG_STEPS; i++) {
+      if ((uint32_t)i < R.nsteps) {
+        const uint32_t c = (i & 1) ? R.c[i / 2] >> 16 : R.c[i / 2] & 0xffffu;
+        s = fma(R.a[i], v_s[c], s);
+        if (++t == w) {
+          finish(g, s);
+          s = 0.0, t = 0, g += SM_WARPS;
+          if (g < me.n_groups)
+            w = goff[g + 1] - goff[g];
+        }
+      }
+    }
+  }
+  // ---- the rest, from shared memory ----------------------------------------------------
+  for (uint32_t j = R.j_rest; j < me.n_groups; j += SM_WARPS) {
     const uint32_t o = goff[j], w = goff[j + 1] - o;
     const uint32_t base = o * 32 + lane;
     double s = 0.0;
@@ -122,17 +207,7 @@ __device__ __forceinline__ double small_spmv(const SmallCta &me, const uint32_t 
     }
     if (t < w)
       s = fma(vals[base + t * 32], v_s[cols[base + t * 32]], s);
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    if ((lane & 3) == 0) {
-      const uint32_t slot = j * 8 + (lane >> 2);
-      q_s[slot] = s;
-      if (DOT) {
-        const uint32_t row = rowid[slot];
-        if (row != 0xffffffffu)
-          dot = fma(s, v_s[row - me.col_lo], dot);
-      }
-    }
+    finish(j, s);
   }
   return dot;
 }
@@ -197,7 +272,7 @@ __device__ __forceinline__ void send_partials(unsigned C, unsigned me, double (&
     const uint32_t rbar = s_remote(s_u32(bar), lane < C ? lane : 0);
 #pragma unroll
     for (int v = 0; v < NV; v++) {
-      const double s = warp_sum(wred[v * SM_WARPS + lane]);  // SM_WARPS == 32
+      const double s = warp_sum(lane < SM_WARPS ? wred[v * SM_WARPS + lane] : 0.0);
       if (lane < C)
         st_async_f64(s_remote(s_u32(slots + (slot0 + v) * SM_MAX_CLUSTER + me), lane), s, rbar);
     }
@@ -273,6 +348,8 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  RegMat R;
+  regmat_load(R, me, goff, vals, cols);
   cl.sync();  // every CTA's barriers exist before anyone stores into a neighbour
 
   // Two mbarriers, used in strict alternation B A B A ... B | B A.  A CTA sends
@@ -294,7 +371,7 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
   };
 
   // ---- r = b - A x0, z = D^-1 r, p = z ----------------------------------------------
-  small_spmv<false>(me, goff, vals, cols, rowid, p_w, q_s);
+  small_spmv<false>(me, R, goff, vals, cols, rowid, p_w, q_s);
   __syncthreads();
   if (tid == 0)
     bar_arm(bar_b, (3 * C + me.n_recv) * 8);
@@ -328,7 +405,7 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
     if (tid == 0)
       bar_arm(bar_a, C * 8);
     double a1[1], t1[1];
-    a1[0] = small_spmv<true>(me, goff, vals, cols, rowid, p_w, q_s);
+    a1[0] = small_spmv<true>(me, R, goff, vals, cols, rowid, p_w, q_s);
     B2_TICK(0)
     send_partials<1>(C, rank, a1, wred, slots, 0, bar_a);
     bar_wait(bar_a, par_a), par_a ^= 1;
@@ -397,7 +474,7 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
   bar_wait(bar_b, par_b), par_b ^= 1;
   if (tid == 0)
     bar_arm(bar_a, C * 8);
-  small_spmv<false>(me, goff, vals, cols, rowid, z_w, q_s);
+  small_spmv<false>(me, R, goff, vals, cols, rowid, z_w, q_s);
   __syncthreads();
   double a4[1] = {0.0}, t4[1];
   for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
@@ -512,6 +589,7 @@ int small_try_build(b200_mat *M) {
             w = std::max(w, (len + 3) / 4);
           }
         }
+        w = std::max(w, 1u);  // the register walk of small_spmv needs w >= 1
         goff.push_back(units);
         size_t base = pv.size();
         pv.resize(base + (size_t)w * 32, 0.0);
