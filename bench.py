@@ -125,7 +125,7 @@ def cpu_pcg_sample(kind, size, full_iters):
             "sample_seconds": dt}
 
 
-def run_reference(args):
+def run_reference(args, out):
     """--impl reference: the reference's CPU path for this metric.  Its own
     solve is CHOLMOD (src/cholmod-impl.h:58-63), which cannot be built offline
     and cannot factor a 134 M-row grid anyway; the arm therefore times the
@@ -152,11 +152,28 @@ def run_reference(args):
                        "iterations_assumed": full_iters},
             "cpu_baseline": info,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    out.emit(json.dumps(line))
     return 0
 
 
+class OneLineStdout:
+    """The contract is ONE JSON line on stdout.  Libraries loaded later (NCCL
+    prints its version line there) write to file descriptor 1, so fd 1 is
+    pointed at stderr for the duration of the run and the line goes to the
+    saved descriptor."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.fd = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.fd, (text + "\n").encode())
+
+
 def main():
+    out = OneLineStdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
@@ -173,7 +190,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, out)
 
     import numpy as np
     import torch
@@ -377,7 +394,7 @@ def main():
         line.update(extra)
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        out.emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
