@@ -10,7 +10,7 @@ set(B200_CSRC ${CMAKE_CURRENT_LIST_DIR}/../lsbench_b200/csrc)
 add_library(b200 SHARED
   ${B200_CSRC}/ctx.cu ${B200_CSRC}/convert.cu ${B200_CSRC}/spmv.cu
   ${B200_CSRC}/pcg.cu ${B200_CSRC}/generate.cu ${B200_CSRC}/dist.cu
-  ${B200_CSRC}/small.cu)
+  ${B200_CSRC}/small.cu ${B200_CSRC}/ingest.cu)
 target_include_directories(b200 PUBLIC ${CMAKE_CURRENT_LIST_DIR}/../include
   PRIVATE ${B200_CSRC})
 # sm_100a only: no multi-arch dispatch

@@ -110,8 +110,13 @@ k_spmv_sell(const uint32_t *__restrict__ sell_off,
 // next-chunk values prefetched into registers (8.0-8.4), a bulk-copy
 // (cp.async.bulk + mbarrier) ring of value tiles in shared memory (10.3), and
 // balanced 9+9+9 chunks instead of 8+8+8+3 (6.25).
+//
+// Compiled for 5 CTAs per SM (48 registers, 40 warps): the uniform path needs no
+// column registers, and the extra warps are worth 6 % (27-point 512^3: 6.07 ->
+// 5.73 ms in PCG; 6 CTAs/SM spills and loses again).
+#define SELLC_MINB 5
 template <bool DOT>
-__global__ void __launch_bounds__(SPMV_THREADS, 4)
+__global__ void __launch_bounds__(SPMV_THREADS, SELLC_MINB)
 k_spmv_sellc(const uint4 *__restrict__ meta, const uint32_t *__restrict__ cols,
              const int32_t *__restrict__ dcols, const double *__restrict__ vals,
              const uint32_t *__restrict__ perm, const double *__restrict__ x,
@@ -345,12 +350,12 @@ int launch_spmv(b200_mat *M, const double *x, double *y, bool dot, int phase) {
     if (dot && meta)
       k_spmv_sellc<true><<<P.g_sell, SPMV_THREADS, 0, s>>>(
           meta, M->sell_cols, M->sell_dcols, M->sell_vals, B2_SELL_ARGS(true));
-    else if (dot)
-      k_spmv_sell<true><<<P.g_sell, SPMV_THREADS, 0, s>>>(
-          M->sell_off, M->sell_cols, M->sell_vals, B2_SELL_ARGS(true));
     else if (meta)
       k_spmv_sellc<false><<<P.g_sell, SPMV_THREADS, 0, s>>>(
           meta, M->sell_cols, M->sell_dcols, M->sell_vals, B2_SELL_ARGS(false));
+    else if (dot)
+      k_spmv_sell<true><<<P.g_sell, SPMV_THREADS, 0, s>>>(
+          M->sell_off, M->sell_cols, M->sell_vals, B2_SELL_ARGS(true));
     else
       k_spmv_sell<false><<<P.g_sell, SPMV_THREADS, 0, s>>>(
           M->sell_off, M->sell_cols, M->sell_vals, B2_SELL_ARGS(false));

@@ -391,8 +391,10 @@ def test_small_path_edge_cases(abi, ctx):
 @pytest.mark.parametrize("gen,N", [("poisson7", 96), ("poisson27", 96), ("poisson7", 33)])
 def test_index_compression_is_lossless(abi, ctx, gen, N):
     """Uniform SELL slices store w column deltas instead of 32 w columns
-    (convert.cu): the exported operator, the SpMV result and the PCG iterates
-    are bit-identical with and without it."""
+    (convert.cu): the exported operator and the SpMV result are bit-identical
+    with and without it; PCG takes the same number of iterations to the same
+    solution (the two kernels run different grids, so the fixed order in which
+    the p.Ap partials are added differs)."""
     M = getattr(orc, "gen_" + gen)(N)
     x = np.random.default_rng(N).standard_normal(M.n)
     b = orc.rhs(M.n)
@@ -408,7 +410,8 @@ def test_index_compression_is_lossless(abi, ctx, gen, N):
         out[label] = (y, xs, r.iters, i.sell_uniform_slices, i.matrix_stream_bytes, i.sell_slices)
         Md.close()
     assert out["on"][0].tobytes() == out["off"][0].tobytes()
-    assert out["on"][1].tobytes() == out["off"][1].tobytes() and out["on"][2] == out["off"][2]
+    assert out["on"][2] == out["off"][2]
+    assert np.linalg.norm(out["on"][1] - out["off"][1]) <= 1e-10 * np.linalg.norm(out["off"][1])
     assert out["off"][3] == 0
     if N == 96:
         # x-lines of three slices: the middle one holds no line end => uniform
