@@ -111,7 +111,7 @@ def cpu_pcg_sample(kind, size, full_iters):
         orc.pcg(_CPU_CACHE[key], orc.rhs(_CPU_CACHE[key].n), maxit=2, omp=True)  # touch pages
     M = _CPU_CACHE[key]
     b = orc.rhs(M.n)
-    its = 150
+    its = 600   # ~10-30 s of CPU work on the GPU box's host cores
     t0 = time.perf_counter()
     _, it, _, _ = orc.pcg(M, b, tol=1e-30, maxit=its, omp=True)
     dt = time.perf_counter() - t0

@@ -63,6 +63,8 @@ struct SmallPlan {
   size_t smem = 0;
   SmallCta *d_cta = nullptr;
   uint32_t *d_goff = nullptr, *d_rowid = nullptr, *d_dmask = nullptr;
+  uint32_t *d_orig = nullptr, *d_perm = nullptr;  // slot -> caller's row; on-chip row -> caller's row
+  bool reordered = false;
   double *d_vals = nullptr, *d_dinv = nullptr;
   uint16_t *d_cols = nullptr;
   long long *d_prof = nullptr;
@@ -72,7 +74,7 @@ struct SmallPlan {
 };
 
 struct SmemMap {
-  size_t stage, zwin, vals, xs, rs, ds, qs, slots, wred, bars, win, goff, rowid, dmask, cols, total;
+  size_t stage, zwin, vals, xs, rs, ds, qs, slots, wred, bars, win, goff, rowid, orig, dmask, cols, total;
 };
 
 __host__ __device__ inline SmemMap smem_map(uint32_t max_ent, uint32_t max_groups,
@@ -92,6 +94,7 @@ __host__ __device__ inline SmemMap smem_map(uint32_t max_ent, uint32_t max_group
   m.win = o, o += 2 * SM_MAX_CLUSTER * 4;
   m.goff = o, o += ((size_t)max_groups + 2) * 4;
   m.rowid = o, o += rows * 4;
+  m.orig = o, o += rows * 4;
   m.dmask = o, o += rows * 4;
   m.cols = o, o += (size_t)max_ent * 2;
   m.total = (o + 15) / 16 * 16;
@@ -299,6 +302,7 @@ template <bool PROF>
 __global__ void __launch_bounds__(SM_THREADS, 1)
 k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_goff,
             const uint32_t *__restrict__ g_rowid, const uint32_t *__restrict__ g_dmask,
+            const uint32_t *__restrict__ g_orig, const uint32_t *__restrict__ g_perm,
             const double *__restrict__ g_vals,
             const uint16_t *__restrict__ g_cols, const double *__restrict__ g_dinv,
             const double *__restrict__ b, double *__restrict__ x, PcgState *st,
@@ -317,7 +321,7 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
   uint64_t *bar_a = (uint64_t *)(smem + mp.bars), *bar_b = bar_a + 1;
   uint32_t *win_lo = (uint32_t *)(smem + mp.win), *win_n = win_lo + SM_MAX_CLUSTER;
   uint32_t *goff = (uint32_t *)(smem + mp.goff), *rowid = (uint32_t *)(smem + mp.rowid);
-  uint32_t *dmask = (uint32_t *)(smem + mp.dmask);
+  uint32_t *dmask = (uint32_t *)(smem + mp.dmask), *orig = (uint32_t *)(smem + mp.orig);
   uint16_t *cols = (uint16_t *)(smem + mp.cols);
   const uint32_t tid = threadIdx.x, nslot = me.n_groups * 8;
   long long pt[6] = {0, 0, 0, 0, 0, 0}, t0 = 0;
@@ -334,15 +338,16 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
     goff[i] = g_goff[me.goff_at + i];
   for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
     uint32_t row = g_rowid[me.row_at + i];
-    rowid[i] = row;
+    const uint32_t og = g_orig[me.row_at + i];  // the caller's numbering, for b and x
+    rowid[i] = row, orig[i] = og;
     dmask[i] = g_dmask[me.row_at + i];
     d_s[i] = g_dinv[me.row_at + i];
-    x_s[i] = row != 0xffffffffu ? x[row] : 0.0;
+    x_s[i] = row != 0xffffffffu ? x[og] : 0.0;
   }
   if (tid < SM_MAX_CLUSTER)  // window base of every CTA, as a byte offset into its z window
     win_lo[tid] = tid < C ? ctas[tid].col_lo : 0u, win_n[tid] = tid < C ? ctas[tid].col_n : 0u;
   for (uint32_t i = tid; i < me.col_n; i += SM_THREADS)
-    p_w[i] = x[me.col_lo + i], z_w[i] = 0.0;  // the window of x0, for r = b - A x0
+    p_w[i] = x[g_perm[me.col_lo + i]], z_w[i] = 0.0;  // the window of x0, for r = b - A x0
   if (tid == 0) {
     bar_init(bar_a, 1), bar_init(bar_b, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -380,7 +385,7 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
     uint32_t row = rowid[i];
     if (row == 0xffffffffu)
       continue;
-    double bi = b[row], ri = bi - q_s[i], zi = d_s[i] * ri;
+    double bi = b[orig[i]], ri = bi - q_s[i], zi = d_s[i] * ri;
     r_s[i] = ri;
     push(row, dmask[i], zi);
     acc3[0] = fma(ri, zi, acc3[0]), acc3[1] = fma(ri, ri, acc3[1]), acc3[2] = fma(bi, bi, acc3[2]);
@@ -467,7 +472,7 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
   for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
     uint32_t row = rowid[i];
     if (row != 0xffffffffu) {
-      x[row] = x_s[i];
+      x[orig[i]] = x_s[i];
       push(row, dmask[i], x_s[i]);
     }
   }
@@ -480,7 +485,7 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
   for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
     uint32_t row = rowid[i];
     if (row != 0xffffffffu) {
-      double d = b[row] - q_s[i];
+      double d = b[orig[i]] - q_s[i];
       a4[0] = fma(d, d, a4[0]);
     }
   }
@@ -500,7 +505,7 @@ void small_free(b200_mat *M) {
   if (!P)
     return;
   void *ptrs[] = {P->d_cta, P->d_goff, P->d_rowid, P->d_vals, P->d_dinv,
-                  P->d_cols, P->d_state, P->d_prof, P->d_dmask};
+                  P->d_cols, P->d_state, P->d_prof, P->d_dmask, P->d_orig, P->d_perm};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   delete P;
@@ -516,6 +521,66 @@ static int small_launch_config(SmallPlan *P, cudaLaunchConfig_t *cfg,
   attr[0].val.clusterDim.x = P->C, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
   cfg->attrs = attr, cfg->numAttrs = 1;
   return B200_OK;
+}
+
+// Reverse Cuthill-McKee on the pattern of A + A^T (used here for
+// one purpose: a CTA's window is [min column, max column] of its row chunk, and
+// both the shared memory it takes and the z entries pushed to it every
+// iteration grow with the bandwidth -- xn3b has bandwidth 2 343 at n = 6 408).
+// Returns perm[new] = old.  Deterministic: ties by original index.
+static std::vector<uint32_t> rcm_order(uint64_t n, const std::vector<uint64_t> &offs,
+                                       const std::vector<uint32_t> &cols) {
+  std::vector<std::vector<uint32_t>> adj(n);
+  for (uint64_t r = 0; r < n; r++)
+    for (uint64_t e = offs[r]; e < offs[r + 1]; e++)
+      if (cols[e] != r && cols[e] < n)
+        adj[r].push_back(cols[e]), adj[cols[e]].push_back((uint32_t)r);
+  for (auto &a : adj) {
+    std::sort(a.begin(), a.end());
+    a.erase(std::unique(a.begin(), a.end()), a.end());
+  }
+  auto by_degree = [&](uint32_t a, uint32_t b) {
+    return adj[a].size() != adj[b].size() ? adj[a].size() < adj[b].size() : a < b;
+  };
+  std::vector<uint32_t> order, byd(n);
+  std::vector<char> seen(n, 0);
+  order.reserve(n);
+  for (uint64_t i = 0; i < n; i++)
+    byd[i] = (uint32_t)i;
+  std::sort(byd.begin(), byd.end(), by_degree);
+  for (uint32_t start : byd) {  // one BFS per connected component, lowest degree first
+    if (seen[start])
+      continue;
+    size_t head = order.size();
+    order.push_back(start), seen[start] = 1;
+    while (head < order.size()) {
+      const uint32_t u = order[head++];
+      std::vector<uint32_t> nb;
+      for (uint32_t v : adj[u])
+        if (!seen[v])
+          nb.push_back(v), seen[v] = 1;
+      std::sort(nb.begin(), nb.end(), by_degree);
+      order.insert(order.end(), nb.begin(), nb.end());
+    }
+  }
+  std::reverse(order.begin(), order.end());
+  return order;
+}
+
+// sum over the C row chunks of the column window each one needs
+static uint64_t window_cost(uint64_t n, int C, const std::vector<uint64_t> &offs,
+                            const std::vector<uint32_t> &cols) {
+  uint64_t total = 0;
+  for (int k = 0; k < C; k++) {
+    uint64_t r0 = n * k / C, r1 = n * (k + 1) / C;
+    if (r1 == r0)
+      continue;
+    uint64_t lo = r0, hi = r1 - 1;
+    for (uint64_t e = offs[r0]; e < offs[r1]; e++)
+      lo = std::min<uint64_t>(lo, cols[e]), hi = std::max<uint64_t>(hi, cols[e]);
+    total += hi - lo + 1;
+  }
+  return total;
 }
 
 // Builds the on-chip plan when the matrix qualifies; leaves M->small null
@@ -535,6 +600,41 @@ int small_try_build(b200_mat *M) {
   std::vector<double> vals(M->nnz ? M->nnz : 1), dinv(n);
   B_TRY(b200_mat_export(M, offs.data(), cols.data(), vals.data()));
   B_TRY(b200_mat_inv_diag(M, dinv.data()));
+
+  // Renumber with RCM when that shrinks the windows by a fifth or more; the
+  // kernel then works in the new numbering and only b and x are addressed in
+  // the caller's (orig / perm).
+  std::vector<uint32_t> perm(n);
+  for (uint64_t i = 0; i < n; i++)
+    perm[i] = (uint32_t)i;
+  bool reordered = false;
+  if (!getenv("B200_SMALL_NO_RCM")) {
+    std::vector<uint32_t> cand = rcm_order(n, offs, cols), inv(n);
+    for (uint64_t i = 0; i < n; i++)
+      inv[cand[i]] = (uint32_t)i;
+    std::vector<uint64_t> o2(n + 1, 0);
+    std::vector<uint32_t> c2(cols.size());
+    std::vector<double> v2(vals.size()), d2(n);
+    for (uint64_t i = 0; i < n; i++)
+      o2[i + 1] = o2[i] + (offs[cand[i] + 1] - offs[cand[i]]);
+    for (uint64_t i = 0; i < n; i++) {
+      const uint64_t r = cand[i], len = offs[r + 1] - offs[r];
+      std::vector<std::pair<uint32_t, double>> row(len);
+      for (uint64_t e = 0; e < len; e++)
+        row[e] = {inv[cols[offs[r] + e]], vals[offs[r] + e]};
+      std::sort(row.begin(), row.end(),
+                [](const std::pair<uint32_t, double> &a, const std::pair<uint32_t, double> &b) {
+                  return a.first < b.first;
+                });
+      for (uint64_t e = 0; e < len; e++)
+        c2[o2[i] + e] = row[e].first, v2[o2[i] + e] = row[e].second;
+      d2[i] = dinv[r];
+    }
+    if (5 * window_cost(n, 16, o2, c2) <= 4 * window_cost(n, 16, offs, cols)) {
+      offs.swap(o2), cols.swap(c2), vals.swap(v2), dinv.swap(d2), perm.swap(cand);
+      reordered = true;
+    }
+  }
 
   int dev_smem = 0;
   CU_TRY(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
@@ -622,7 +722,10 @@ int small_try_build(b200_mat *M) {
       continue;
     // who reads which column: mask of CTAs per row, and per CTA the number of
     // window entries it receives each iteration
-    std::vector<uint32_t> readers(n, 0u), dmask(rowid.size(), 0u);
+    std::vector<uint32_t> readers(n, 0u), dmask(rowid.size(), 0u), orig(rowid.size(), 0xffffffffu);
+    for (size_t i = 0; i < rowid.size(); i++)
+      if (rowid[i] != 0xffffffffu)
+        orig[i] = perm[rowid[i]];
     for (int k = 0; k < C; k++) {
       uint64_t r0 = n * k / C, r1 = n * (k + 1) / C;
       for (uint64_t r = r0; r < r1; r++) {
@@ -672,6 +775,9 @@ int small_try_build(b200_mat *M) {
     B_TRY(up((void **)&P->d_goff, goff.data(), goff.size() * 4));
     B_TRY(up((void **)&P->d_rowid, rowid.data(), rowid.size() * 4));
     B_TRY(up((void **)&P->d_dmask, dmask.data(), dmask.size() * 4));
+    B_TRY(up((void **)&P->d_orig, orig.data(), orig.size() * 4));
+    B_TRY(up((void **)&P->d_perm, perm.data(), perm.size() * 4));
+    P->reordered = reordered;
     B_TRY(up((void **)&P->d_vals, pv.data(), pv.size() * 8));
     B_TRY(up((void **)&P->d_cols, pc.data(), pc.size() * 2));
     B_TRY(up((void **)&P->d_dinv, pd.data(), pd.size() * 8));
@@ -696,7 +802,8 @@ int small_solve(b200_mat *M, const double *d_b, double *d_x,
   CU_TRY(cudaLaunchKernelEx(&cfg, prof ? k_pcg_small<true> : k_pcg_small<false>,
                             (const SmallCta *)P->d_cta,
                             (const uint32_t *)P->d_goff, (const uint32_t *)P->d_rowid,
-                            (const uint32_t *)P->d_dmask, (const double *)P->d_vals, (const uint16_t *)P->d_cols,
+                            (const uint32_t *)P->d_dmask, (const uint32_t *)P->d_orig,
+                            (const uint32_t *)P->d_perm, (const double *)P->d_vals, (const uint16_t *)P->d_cols,
                             (const double *)P->d_dinv, d_b, d_x,
                             P->d_state, P->max_ent, P->max_groups, P->max_stage,
                             o->tol, (int)o->maxit, P->d_prof));
@@ -715,8 +822,8 @@ int small_solve(b200_mat *M, const double *d_b, double *d_x,
   if (prof && h.iter > 0) {
     long long hp[6];
     CU_TRY(cudaMemcpy(hp, P->d_prof, sizeof hp, cudaMemcpyDeviceToHost));
-    fprintf(stderr, "b200 small: C=%d iters=%d cycles/iter spmv=%lld reduce1=%lld update+push=%lld "
-                    "reduce2+halo=%lld pwindow=%lld\n", P->C, h.iter, hp[0] / h.iter,
+    fprintf(stderr, "b200 small: C=%d rcm=%d iters=%d cycles/iter spmv=%lld reduce1=%lld update+push=%lld "
+                    "reduce2+halo=%lld pwindow=%lld\n", P->C, (int)P->reordered, h.iter, hp[0] / h.iter,
             hp[1] / h.iter, hp[2] / h.iter, hp[3] / h.iter, hp[4] / h.iter);
   }
   if (h.status == 2)

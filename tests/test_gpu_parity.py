@@ -465,3 +465,74 @@ def test_index_compression_mixed_slices(abi, ctx):
     x = rng.standard_normal(n)
     assert np.array_equal(Md.spmv_host(x), orc.spmv_fma(M, x))
     Md.close()
+
+
+# --------------------------------------------------------------------------- BASELINE.json full sizes
+def _boundary_count(N, rows):
+    """number of missing neighbours of grid point `rows` in a 7-point stencil"""
+    xx, yy, zz = rows % N, (rows // N) % N, rows // (N * N)
+    return ((xx == 0).astype(np.int64) + (xx == N - 1) + (yy == 0) + (yy == N - 1)
+            + (zz == 0) + (zz == N - 1))
+
+
+def test_full_size_config3_poisson7_256(abi, ctx):
+    """BASELINE.json config 3 at its full size (16.7 M rows, 117 M nnz), where the
+    CPU oracle is not asked to solve: nnz is the closed form, A*1 is the analytic
+    row sum, x.(Ay) == y.(Ax), sampled rows equal the oracle's generator, and
+    PCG takes the same number of iterations twice and recovers a manufactured
+    solution."""
+    N = 256
+    n = N ** 3
+    Md = abi.Matrix.generate(ctx, abi.GEN_POISSON7, N)
+    i = Md.info()
+    assert (i.n_local, i.nnz) == (n, 7 * n - 6 * N * N)
+    assert i.sell_uniform_slices == 6 * N * N        # 8 slices per x-line, the two ends are not uniform
+    y = Md.spmv_host(np.ones(n))
+    assert np.array_equal(y, _boundary_count(N, np.arange(n)).astype(np.float64))
+    rng = np.random.default_rng(256)
+    u, v = rng.standard_normal(n), rng.standard_normal(n)
+    Au, Av = Md.spmv_host(u), Md.spmv_host(v)
+    assert abs(v @ Au - u @ Av) <= 1e-12 * (abs(v @ Au) + abs(u @ Av))
+    lin = Md.spmv_host(2.0 * u - 3.0 * v)
+    assert np.max(np.abs(lin - (2.0 * Au - 3.0 * Av))) <= 1e-12 * np.max(np.abs(lin))
+    # a window of rows against the CPU generator (row-block form), bit for bit
+    r0, r1 = 5 * N * N + 7 * N, 5 * N * N + 9 * N + 64
+    Mo = orc.gen_poisson7(N, r0, r1)
+    want = np.array([Mo.vals[Mo.offs[k]:Mo.offs[k + 1]] @ u[Mo.cols[Mo.offs[k]:Mo.offs[k + 1]]]
+                     for k in range(r1 - r0)])
+    assert np.max(np.abs(Au[r0:r1] - want)) <= 1e-13 * 7 * np.max(np.abs(u))
+    xstar = rng.standard_normal(n)
+    rhs = Md.spmv_host(xstar)
+    x, r, rc = Md.pcg_host(rhs, tol=1e-10)
+    assert rc == 0 and r.status == 0 and r.true_relres <= 1.05e-10
+    assert np.linalg.norm(x - xstar) / np.linalg.norm(xstar) <= 1e-8
+    x2, r2, _ = Md.pcg_host(rhs, tol=1e-10)
+    assert r2.iters == r.iters and x2.tobytes() == x.tobytes()
+    Md.close()
+
+
+def test_full_size_config4_poisson27_512(abi, ctx):
+    """BASELINE.json config 4 at its full size on one GPU (134 M rows, 3.61 G nnz:
+    past 2^31 entries, 64-bit offsets inside): closed-form nnz, A*1 = 26 minus
+    the number of present neighbours (0 in the interior), linearity."""
+    N = 512
+    n = N ** 3
+    try:
+        Md = abi.Matrix.generate(ctx, abi.GEN_POISSON27, N)
+    except abi.B200Error as e:            # a smaller device: not this test's subject
+        pytest.skip("poisson27:512 does not fit: %s" % e)
+    i = Md.info()
+    assert (i.n_local, i.nnz) == (n, (3 * N - 2) ** 3)
+    assert i.nnz > 2 ** 31 and i.sell_uniform_slices == 14 * N * N
+    y = Md.spmv_host(np.ones(n))
+    g = np.arange(n)
+    ext = lambda c: 3 - (c == 0) - (c == N - 1)     # neighbours present along one axis (incl. self)
+    present = ext(g % N) * ext((g // N) % N) * ext(g // (N * N))
+    assert np.array_equal(y, (27 - present).astype(np.float64))
+    del g, present
+    rng = np.random.default_rng(512)
+    u = rng.standard_normal(n)
+    Au = Md.spmv_host(u)
+    lin = Md.spmv_host(-1.5 * u + 1.0)
+    assert np.max(np.abs(lin - (-1.5 * Au + y))) <= 1e-12 * np.max(np.abs(lin))
+    Md.close()
