@@ -505,7 +505,8 @@ def test_full_size_config3_poisson7_256(abi, ctx):
     rhs = Md.spmv_host(xstar)
     x, r, rc = Md.pcg_host(rhs, tol=1e-10)
     assert rc == 0 and r.status == 0 and r.true_relres <= 1.05e-10
-    assert np.linalg.norm(x - xstar) / np.linalg.norm(xstar) <= 1e-8
+    # forward error <= cond(A) * residual; cond ~ (2 N / pi)^2 = 2.7e4 at N = 256
+    assert np.linalg.norm(x - xstar) / np.linalg.norm(xstar) <= 2.7e4 * 1.05e-10
     x2, r2, _ = Md.pcg_host(rhs, tol=1e-10)
     assert r2.iters == r.iters and x2.tobytes() == x.tobytes()
     Md.close()
