@@ -97,12 +97,15 @@ class ClockSampler(threading.Thread):
 _CPU_CACHE = {}
 
 
+CPU_SAMPLE = {"n": None, "its": 600}   # overridden by --cpu-sample-n / --cpu-sample-its
+
+
 def cpu_pcg_sample(kind, size, full_iters):
     """Oracle OpenMP Jacobi-PCG on a smaller cube of the same stencil; seconds
     per iteration per row, scaled to the full operator and iteration count."""
     import numpy as np
     import orc
-    Ns = 192 if kind == "poisson27" else 256   # ~2.3 GB / ~1.5 GB of CSR: well past the LLC
+    Ns = CPU_SAMPLE["n"] or (192 if kind == "poisson27" else 256)   # ~2.3 / ~1.5 GB of CSR: past the LLC
     gen = orc.gen_poisson27 if kind == "poisson27" else orc.gen_poisson7
     key = (kind, Ns)
     if key not in _CPU_CACHE:  # built once; every step re-times the iterations
@@ -111,7 +114,7 @@ def cpu_pcg_sample(kind, size, full_iters):
         orc.pcg(_CPU_CACHE[key], orc.rhs(_CPU_CACHE[key].n), maxit=2, omp=True)  # touch pages
     M = _CPU_CACHE[key]
     b = orc.rhs(M.n)
-    its = 600   # ~10-30 s of CPU work on the GPU box's host cores
+    its = CPU_SAMPLE["its"]   # default: ~10-30 s of CPU work on the GPU box's host cores
     t0 = time.perf_counter()
     _, it, _, _ = orc.pcg(M, b, tol=1e-30, maxit=its, omp=True)
     dt = time.perf_counter() - t0
@@ -182,6 +185,8 @@ def main():
     ap.add_argument("--workload", default="poisson27:512")
     ap.add_argument("--ref-iters", type=int, default=1176,
                     help="iterations the full solve needs (measured on the GPU path)")
+    ap.add_argument("--cpu-sample-n", type=int, default=0, help="grid edge of the CPU sample (0 = default)")
+    ap.add_argument("--cpu-sample-its", type=int, default=600)
     ap.add_argument("--no-spmv", action="store_true")
     ap.add_argument("--no-compress", action="store_true",
                     help="keep one explicit u32 column per entry (B200_MAT_NO_COMPRESS)")
@@ -189,6 +194,7 @@ def main():
                     help="skip the extra NO_COMPRESS solve reported beside the headline")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    CPU_SAMPLE["n"], CPU_SAMPLE["its"] = args.cpu_sample_n or None, args.cpu_sample_its
     if args.impl == "reference":
         return run_reference(args, out)
 
