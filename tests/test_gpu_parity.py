@@ -537,3 +537,70 @@ def test_full_size_config4_poisson27_512(abi, ctx):
     lin = Md.spmv_host(-1.5 * u + 1.0)
     assert np.max(np.abs(lin - (-1.5 * Au + y))) <= 1e-12 * np.max(np.abs(lin))
     Md.close()
+
+
+# --------------------------------------------------------------------------- ragged / edge shapes
+def _random_rows(n, lens, seed):
+    """CSR with prescribed row lengths, sorted distinct columns, random values"""
+    rng = np.random.default_rng(seed)
+    offs = np.zeros(n + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum(lens)
+    cols = np.concatenate([np.sort(rng.choice(n, size=int(l), replace=False)) for l in lens]
+                          + [np.zeros(0, dtype=np.int64)]).astype(np.uint32)
+    vals = rng.standard_normal(int(offs[-1]))
+    return orc.Op(n, offs, cols, vals)
+
+
+@pytest.mark.parametrize("flags", ["auto", "nocompress"])
+def test_bin_edges_empty_rows_and_odd_sizes(abi, ctx, flags):
+    """row lengths on both sides of every kernel-selection threshold (256 | 257 for
+    SELL -> warp-per-row, 8191 | 8192 for warp -> CTA-per-row), empty rows, a row
+    count that is not a multiple of the slice height: the layout exports the same
+    CSR bit for bit and every kernel multiplies it to 1e-13."""
+    n = 9001                                   # 281 slices + 9 rows
+    lens = np.full(n, 3, dtype=np.int64)
+    lens[[0, 5, 40, 41, 8999, 9000]] = 0       # empty rows, incl. first and last
+    lens[[7, 100]] = 256
+    lens[[8, 101]] = 257
+    lens[[9]] = 8191
+    lens[[10, 4000]] = 8192
+    lens[[11]] = 1
+    M = _random_rows(n, lens, 77)
+    f = {"auto": 0, "nocompress": abi.MAT_NO_COMPRESS}[flags]
+    Md = make(abi, ctx, op_to_csr(M), f)
+    assert_same_operator(Md, M)
+    i = Md.info()
+    assert i.long_rows == 2 and i.vec_rows == 3 and i.sell_rows == n - 5
+    assert i.max_row_len == 8192 and i.hist[0] == 6 + 1          # len 0..1
+    x = np.random.default_rng(5).standard_normal(n)
+    y = Md.spmv_host(x)
+    assert np.all(y[[0, 5, 40, 41, 8999, 9000]] == 0.0)
+    yr, ya = orc.spmv(M, x, want_abs=True)
+    assert np.all(np.abs(y - yr) <= 1e-13 * ya + 1e-300)
+    Md.close()
+
+
+def test_single_row_and_tiny_operators(abi, ctx):
+    for n in (1, 2, 31, 32, 33):
+        d = np.arange(1, n + 1, dtype=np.float64)
+        M = orc.Op(n, np.arange(n + 1, dtype=np.uint64), np.arange(n, dtype=np.uint32), d)
+        Md = make(abi, ctx, op_to_csr(M))
+        assert_same_operator(Md, M)
+        b = orc.rhs(n) + 1.0
+        for fl in (0, abi.PCG_NO_SMALL):
+            x, r, rc = Md.pcg_host(b, flags=fl)
+            assert rc == 0 and r.status == 0 and r.iters <= 1
+            assert np.allclose(x, b / d, rtol=4e-15, atol=0)
+        Md.close()
+
+
+def test_zero_diagonal_is_preconditioned_with_one(abi, ctx):
+    """a row without a diagonal entry gets D^-1 = 1 (convert.cu k_inv_diag), it does
+    not divide by zero"""
+    import scipy.sparse as sp
+    A = sp.csr_matrix(np.array([[0.0, 1.0, 0.0], [1.0, 4.0, 0.0], [0.0, 0.0, 2.0]]))
+    A.eliminate_zeros()
+    M = orc.Op(3, A.indptr.astype(np.uint64), A.indices.astype(np.uint32), A.data)
+    Md = make(abi, ctx, op_to_csr(M))
+    assert np.array_equal(Md.inv_diag(), np.array([1.0, 0.25, 0.5]))
+    Md.close()
