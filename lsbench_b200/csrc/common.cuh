@@ -39,6 +39,24 @@ void b200_set_error(const char *fmt, ...);
 // ---- NCCL, bound at run time (dist.cu) ------------------------------------
 struct NcclApi;
 
+// ---- peer-memory all-reduce of the CG scalars (dist.cu xr_setup) ---------------
+// Every rank owns a mailbox [kind][source rank][4 doubles: v0, v1, v2, seq] that
+// all ranks can write over NVLink (same process: peer access; other process:
+// CUDA IPC).  The CTA that finishes a rank-local sum stores it, then a sequence
+// number, into EVERY rank's mailbox (common.cuh xr_push, inside
+// grid_sum_finish); the kernel that needs the global sum waits for that
+// sequence number from all ranks in its own mailbox and adds the values in
+// rank order (xr_wait_sum) -- the same additions on every rank.  No collective
+// kernel, no extra launch: the reduction is fused into producer and consumer.
+#define B2_XR_MAX_RANKS 16
+#define B2_XR_KINDS 2  // 0: p.q    1: r.z, r.r
+struct XrArgs {
+  double *const *peers;  // device array, peers[r] = rank r's mailbox; nullptr = off
+  double *mine;          // this rank's mailbox
+  int nranks, me, kind;
+  unsigned long long seq;
+};
+
 struct b200_ctx {
   int device = 0;
   int sm_count = B200_SM_COUNT_FALLBACK;
@@ -50,6 +68,12 @@ struct b200_ctx {
               ev_ready = nullptr, ev_poll = nullptr;
   void *nccl_comm = nullptr;
   const NcclApi *nccl = nullptr;
+  // peer-memory all-reduce (nullptr / false: NCCL all-reduce)
+  double *xr_mail = nullptr;      // my mailbox
+  double **xr_peers = nullptr;    // device array of the ranks' mailboxes
+  void *xr_opened[B2_XR_MAX_RANKS] = {nullptr};  // IPC mappings to close
+  bool xr_on = false;
+  unsigned long long xr_seq = 0;  // last sequence number handed out
   int *h_flag = nullptr;  // pinned: PCG progress word read by the host
   uint64_t launches = 0;  // kernels of this library queued so far
 };
@@ -164,7 +188,7 @@ int halo_exchange_wait(b200_mat *M);
 void halo_free(b200_mat *M);
 int ensure_workspace(b200_mat *M);
 int launch_spmv(b200_mat *M, const double *x_ext, double *y, bool fuse_dot,
-                int phase /*0 all, 1 interior, 2 boundary*/);
+                int phase /*0 all, 1 interior, 2 boundary*/, const XrArgs *xr);
 int allreduce_sum(b200_ctx *ctx, const double *d_src, double *d_dst, int count);
 int small_try_build(b200_mat *M);
 void small_free(b200_mat *M);
@@ -199,17 +223,93 @@ __device__ __forceinline__ double block_sum(double v, double *smem /*NWARPS*/) {
   return t;
 }
 
+// ---- peer-memory all-reduce, device side --------------------------------------
+__device__ __forceinline__ void st_relaxed_sys(double *p, double v) {
+  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double *p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// One CTA, after its __syncthreads: thread r < nranks stores the NV values and
+// then the sequence number into rank r's mailbox slot [kind][me].
+template <int NV>
+__device__ __forceinline__ void xr_push(const XrArgs &xr, const double *vals /*smem, NV*/) {
+  const int r = threadIdx.x;
+  if (r < xr.nranks) {
+    double *slot = xr.peers[r] + ((size_t)xr.kind * B2_XR_MAX_RANKS + xr.me) * 4;
+#pragma unroll
+    for (int v = 0; v < NV; v++)
+      st_relaxed_sys(slot + v, vals[v]);
+    __threadfence_system();
+    st_relaxed_sys(reinterpret_cast<unsigned long long *>(slot) + 3, xr.seq);
+  }
+}
+
+// Every thread of the CTA calls it.  Waits until all ranks' values of sequence
+// xr.seq are in my mailbox, then tot[v] = sum over the ranks in rank order
+// (identical on every rank).  smem: NV * B2_XR_MAX_RANKS doubles + 1 int.
+// Returns false when a peer did not deliver within ~4 s (never hang the GPU).
+template <int NV>
+__device__ __forceinline__ bool xr_wait_sum(const XrArgs &xr, double (&tot)[NV], double *smem) {
+  int *ok = reinterpret_cast<int *>(smem + NV * B2_XR_MAX_RANKS);
+  const int r = threadIdx.x;
+  if (r == 0)
+    *ok = 1;
+  __syncthreads();
+  if (r < xr.nranks) {
+    const double *slot = xr.mine + ((size_t)xr.kind * B2_XR_MAX_RANKS + r) * 4;
+    const unsigned long long *flag = reinterpret_cast<const unsigned long long *>(slot) + 3;
+    const long long t0 = clock64();
+    bool got = true;
+    while (ld_acquire_sys(flag) != xr.seq)
+      if (clock64() - t0 > 8000000000ll) {
+        got = false;
+        break;
+      }
+    if (!got)
+      *ok = 0;
+#pragma unroll
+    for (int v = 0; v < NV; v++)
+      smem[v * B2_XR_MAX_RANKS + r] = ld_relaxed_sys(slot + v);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int v = 0; v < NV; v++) {
+    double s = 0.0;
+    for (int k = 0; k < xr.nranks; k++)
+      s += smem[v * B2_XR_MAX_RANKS + k];
+    tot[v] = s;
+  }
+  const bool good = *ok != 0;
+  __syncthreads();
+  return good;
+}
+
 // Grid-wide deterministic sum of NV values per CTA.  Each CTA stores its
 // block sums to partials[v * stride + slot]; the CTA drawing the last ticket
 // adds the `total` partials of every lane in a fixed order (strided per
 // thread, then the block tree) and writes out[v].  The order depends only on
-// `total`, i.e. on the launch geometry -- never on scheduling.
+// `total`, i.e. on the launch geometry -- never on scheduling.  With xr.peers
+// set, that CTA also ships the sums to every rank's mailbox (xr_push).
 template <int NV, int NWARPS>
 __device__ __forceinline__ void grid_sum_finish(const double (&block_val)[NV],
                                                 double *partials,
                                                 unsigned stride, unsigned slot,
                                                 unsigned total, unsigned *ticket,
-                                                double *out, double *smem) {
+                                                double *out, double *smem,
+                                                const XrArgs xr = XrArgs{nullptr, nullptr, 1, 0, 0, 0ull}) {
+  static_assert(NV <= NWARPS, "the sums are staged in the warp-sum scratch");
   __shared__ bool is_last;
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -223,17 +323,28 @@ __device__ __forceinline__ void grid_sum_finish(const double (&block_val)[NV],
   if (!is_last)
     return;
   __threadfence();
+  double res[NV];
 #pragma unroll
   for (int v = 0; v < NV; v++) {
     double acc = 0.0;
     for (unsigned i = threadIdx.x; i < total; i += blockDim.x)
       acc += __ldcg(partials + v * stride + i);
     acc = block_sum<NWARPS>(acc, smem);
+    res[v] = acc;
     if (threadIdx.x == 0)
       out[v] = acc;
   }
   if (threadIdx.x == 0)
     *ticket = 0;
+  if (xr.peers) {
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int v = 0; v < NV; v++)
+        smem[v] = res[v];
+    }
+    __syncthreads();
+    xr_push<NV>(xr, smem);
+  }
 }
 
 // streaming (read-once) loads: keep them out of L1, evict-first in L2

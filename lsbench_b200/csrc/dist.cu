@@ -23,6 +23,8 @@
 #include <cub/cub.cuh>
 #include <dlfcn.h>
 #include <nccl.h>
+#include <unistd.h>
+#include <vector>
 
 #define T256 256
 static inline unsigned nblk(uint64_t n, unsigned t = T256) {
@@ -97,6 +99,88 @@ extern "C" int b200_nccl_unique_id(void *id_out) {
   return B200_OK;
 }
 
+// ---- peer-memory all-reduce: mailboxes every rank can write (common.cuh) -----------
+// Called once per context after the communicator exists.  All ranks must end up
+// on the same path, so the decision is itself all-reduced (min).  Not an error
+// when peer memory cannot be mapped: the NCCL all-reduce stays in use.
+// B200_ALLREDUCE=nccl switches it off.
+struct XrInfo {
+  long long pid;
+  int dev, ok;
+  unsigned long long ptr;
+  cudaIpcMemHandle_t handle;
+};
+
+static int xr_setup(b200_ctx *c) {
+  const char *e = getenv("B200_ALLREDUCE");
+  int want = !(e && strcmp(e, "nccl") == 0) && c->nranks <= B2_XR_MAX_RANKS;
+  ncclComm_t comm = (ncclComm_t)c->nccl_comm;
+  cudaStream_t s = c->stream;
+  const size_t mail_bytes = (size_t)B2_XR_KINDS * B2_XR_MAX_RANKS * 4 * sizeof(double);
+  XrInfo mine;
+  memset(&mine, 0, sizeof mine);
+  mine.pid = (long long)getpid(), mine.dev = c->device, mine.ok = want;
+  if (want) {
+    CU_TRY(cudaMalloc(&c->xr_mail, mail_bytes));
+    CU_TRY(cudaMemset(c->xr_mail, 0, mail_bytes));
+    mine.ptr = (unsigned long long)c->xr_mail;
+    if (cudaIpcGetMemHandle(&mine.handle, c->xr_mail) != cudaSuccess)
+      cudaGetLastError(), mine.ok = 0;
+  }
+  // everybody's record to everybody
+  XrInfo *d_all = nullptr;
+  std::vector<XrInfo> all(c->nranks);
+  CU_TRY(cudaMalloc(&d_all, sizeof(XrInfo) * c->nranks));
+  CU_TRY(cudaMemcpyAsync(d_all + c->rank, &mine, sizeof mine, cudaMemcpyHostToDevice, s));
+  NC_TRY(g_nccl.AllGather(d_all + c->rank, d_all, sizeof(XrInfo), ncclChar, comm, s));
+  CU_TRY(cudaMemcpyAsync(all.data(), d_all, sizeof(XrInfo) * c->nranks, cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  std::vector<double *> peers(B2_XR_MAX_RANKS, nullptr);
+  int ok = 1;
+  for (int r = 0; r < c->nranks && ok; r++) {
+    if (!all[r].ok) {
+      ok = 0;
+    } else if (r == c->rank) {
+      peers[r] = c->xr_mail;
+    } else if (all[r].pid == mine.pid) {  // another host thread of this process
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, c->device, all[r].dev) != cudaSuccess || !can) {
+        cudaGetLastError(), ok = 0;
+        break;
+      }
+      cudaError_t pe = cudaDeviceEnablePeerAccess(all[r].dev, 0);
+      if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled)
+        ok = 0;
+      cudaGetLastError();
+      peers[r] = (double *)all[r].ptr;
+    } else {
+      void *p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError(), ok = 0;
+        break;
+      }
+      c->xr_opened[r] = p, peers[r] = (double *)p;
+    }
+  }
+  // one decision for all ranks
+  int *d_ok = (int *)d_all;
+  CU_TRY(cudaMemcpyAsync(d_ok, &ok, sizeof ok, cudaMemcpyHostToDevice, s));
+  NC_TRY(g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, comm, s));
+  CU_TRY(cudaMemcpyAsync(&ok, d_ok, sizeof ok, cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  cudaFree(d_all);
+  if (ok) {
+    CU_TRY(cudaMalloc(&c->xr_peers, sizeof(double *) * B2_XR_MAX_RANKS));
+    CU_TRY(cudaMemcpy(c->xr_peers, peers.data(), sizeof(double *) * B2_XR_MAX_RANKS,
+                      cudaMemcpyHostToDevice));
+  }
+  c->xr_on = ok != 0;
+  if (getenv("B200_VERBOSE") && c->rank == 0)
+    fprintf(stderr, "b200: CG scalars all-reduced over %s\n",
+            c->xr_on ? "peer memory (fused into producer / consumer kernels)" : "NCCL");
+  return B200_OK;
+}
+
 int dist_comm_init(b200_ctx *c, const void *nccl_id) {
   B_TRY(nccl_bind());
   ncclUniqueId id;
@@ -104,10 +188,16 @@ int dist_comm_init(b200_ctx *c, const void *nccl_id) {
   ncclComm_t comm;
   NC_TRY(g_nccl.CommInitRank(&comm, c->nranks, id, c->rank));
   c->nccl_comm = comm, c->nccl = &g_nccl;
-  return B200_OK;
+  return xr_setup(c);
 }
 
 void dist_comm_destroy(b200_ctx *c) {
+  for (void *&p : c->xr_opened)
+    if (p)
+      cudaIpcCloseMemHandle(p), p = nullptr;
+  if (c->xr_peers) cudaFree(c->xr_peers);
+  if (c->xr_mail) cudaFree(c->xr_mail);
+  c->xr_peers = nullptr, c->xr_mail = nullptr, c->xr_on = false;
   if (c->nccl_comm)
     g_nccl.CommDestroy((ncclComm_t)c->nccl_comm);
   c->nccl_comm = nullptr;

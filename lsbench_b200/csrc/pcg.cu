@@ -23,7 +23,8 @@
 #define EW_THREADS 256
 #define EW_WARPS (EW_THREADS / 32)
 
-int spmv_full_internal(b200_mat *M, double *x_ext, double *y, bool dot);
+int spmv_full_internal(b200_mat *M, double *x_ext, double *y, bool dot,
+                       const XrArgs *xr = nullptr);
 
 // r = b - q (q = A x0), p = D^-1 r; partial sums of r.z, r.r, b.b
 __global__ void __launch_bounds__(EW_THREADS)
@@ -59,16 +60,30 @@ __global__ void k_pcg_start(PcgState *st, double tol, int maxit) {
     st->done = 1;
 }
 
-// K2
+// K2.  xin: where p.q comes from when the ranks all-reduce over peer memory
+// (common.cuh xr_wait_sum); xout: where this kernel's {r.z, r.r} go.
 __global__ void __launch_bounds__(EW_THREADS)
 k_pcg_update(uint64_t n, double *__restrict__ x, double *__restrict__ r,
              const double *__restrict__ p, const double *__restrict__ q,
              const double *__restrict__ dinv, double *partials, unsigned stride,
-             PcgState *st, int par, double *out) {
+             PcgState *st, int par, double *out, const XrArgs xin, const XrArgs xout) {
   if (st->done)
     return;
   __shared__ double red[EW_WARPS];
-  const double pq = st->pq, rz = st->red[par * 2];
+  __shared__ double xr_s[B2_XR_MAX_RANKS + 1];
+  double pq = st->pq;
+  const double rz = st->red[par * 2];
+  if (xin.peers) {
+    double t[1];
+    if (!xr_wait_sum<1>(xin, t, xr_s)) {  // a peer never delivered: stop, do not hang
+      if (blockIdx.x == 0 && threadIdx.x == 0)
+        st->done = 1, st->status = 3;
+      return;
+    }
+    pq = t[0];
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+      st->pq = pq;
+  }
   if (!(pq > 0.0)) {  // not SPD, or NaN crept in: SURVEY 5 breakdown guard
     if (blockIdx.x == 0 && threadIdx.x == 0)
       st->done = 1, st->status = 2;
@@ -99,17 +114,30 @@ k_pcg_update(uint64_t n, double *__restrict__ x, double *__restrict__ r,
   bs[0] = block_sum<EW_WARPS>(s[0], red);
   bs[1] = block_sum<EW_WARPS>(s[1], red);
   grid_sum_finish<2, EW_WARPS>(bs, partials, stride, blockIdx.x, gridDim.x,
-                               &st->ticket[2], out, red);
+                               &st->ticket[2], out, red, xout);
 }
 
-// K3 (also owns the convergence decision and the iteration counter)
+// K3 (also owns the convergence decision and the iteration counter).  xin: the
+// {r.z, r.r} of all ranks over peer memory, when that path is on.
 __global__ void __launch_bounds__(EW_THREADS)
 k_pcg_pupdate(uint64_t n, const double *__restrict__ r,
               const double *__restrict__ dinv, double *__restrict__ p,
-              PcgState *st, int par) {
+              PcgState *st, int par, const XrArgs xin) {
   if (st->done)
     return;
-  const double rzn = st->red[(par ^ 1) * 2], rr = st->red[(par ^ 1) * 2 + 1];
+  __shared__ double xr_s[2 * B2_XR_MAX_RANKS + 1];
+  double rzn = st->red[(par ^ 1) * 2], rr = st->red[(par ^ 1) * 2 + 1];
+  if (xin.peers) {
+    double t[2];
+    if (!xr_wait_sum<2>(xin, t, xr_s)) {
+      if (blockIdx.x == 0 && threadIdx.x == 0)
+        st->done = 1, st->status = 3;
+      return;
+    }
+    rzn = t[0], rr = t[1];
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+      st->red[(par ^ 1) * 2] = rzn, st->red[(par ^ 1) * 2 + 1] = rr;
+  }
   const double rz = st->red[par * 2];
   const bool conv = rr <= st->thr2;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -197,20 +225,40 @@ static int reduce_ranks(b200_mat *M, double *red, double *loc, int count) {
   return allreduce_sum(M->ctx, loc, red, count);
 }
 
-static int queue_iteration(b200_mat *M, int par) {
+static XrArgs xr_args(b200_ctx *c, int kind) {
+  XrArgs a = {nullptr, nullptr, c->nranks, c->rank, kind, 0ull};
+  if (c->xr_on)
+    a.peers = c->xr_peers, a.mine = c->xr_mail, a.seq = ++c->xr_seq;
+  return a;
+}
+
+// One iteration.  ev (4 events) brackets the three kernel classes when the
+// caller times them.  With the peer-memory all-reduce the two NCCL calls
+// disappear: K1's last CTA ships p.q to every rank and K2 collects it, K2's
+// last CTA ships {r.z, r.r} and K3 collects them.
+static int queue_iteration(b200_mat *M, int par, cudaEvent_t *ev = nullptr) {
   b200_ctx *c = M->ctx;
   cudaStream_t s = c->stream;
   uint64_t n = M->n_local;
-  B_TRY(spmv_full_internal(M, M->w_p, M->w_q, true));  // K1
   PcgState *st = M->state;
   const int nx = (par ^ 1) * 2;
-  B_TRY(reduce_ranks(M, &st->pq, &st->pq_loc, 1));
+  const XrArgs x_pq = xr_args(c, 0), x_rz = xr_args(c, 1);
+  const XrArgs none = {nullptr, nullptr, 1, 0, 0, 0ull};
+  if (ev) CU_TRY(cudaEventRecord(ev[0], s));
+  B_TRY(spmv_full_internal(M, M->w_p, M->w_q, true, c->xr_on ? &x_pq : nullptr));  // K1
+  if (!c->xr_on)
+    B_TRY(reduce_ranks(M, &st->pq, &st->pq_loc, 1));
+  if (ev) CU_TRY(cudaEventRecord(ev[1], s));
   k_pcg_update<<<M->grid_ew, EW_THREADS, 0, s>>>(
       n, M->w_x, M->w_r, M->w_p, M->w_q, M->dinv, M->partials, M->partial_stride,
-      st, par, sum_target(M, &st->red[nx], &st->loc[nx]));
-  B_TRY(reduce_ranks(M, &st->red[nx], &st->loc[nx], 2));
+      st, par, sum_target(M, &st->red[nx], &st->loc[nx]), c->xr_on ? x_pq : none,
+      c->xr_on ? x_rz : none);
+  if (!c->xr_on)
+    B_TRY(reduce_ranks(M, &st->red[nx], &st->loc[nx], 2));
+  if (ev) CU_TRY(cudaEventRecord(ev[2], s));
   k_pcg_pupdate<<<M->grid_ew, EW_THREADS, 0, s>>>(n, M->w_r, M->dinv, M->w_p,
-                                                  M->state, par);
+                                                  M->state, par, c->xr_on ? x_rz : none);
+  if (ev) CU_TRY(cudaEventRecord(ev[3], s));
   c->launches += 2;
   CU_TRY(cudaGetLastError());
   return B200_OK;
@@ -299,22 +347,7 @@ extern "C" int b200_pcg_solve(b200_mat *M, const double *d_b, double *d_x,
       for (auto &e : ev)
         CU_TRY(cudaEventCreate(&e));
       for (int i = 0; i < chunk; i++) {
-        int par = i & 1;
-        CU_TRY(cudaEventRecord(ev[0], s));
-        B_TRY(spmv_full_internal(M, M->w_p, M->w_q, true));
-        PcgState *st = M->state;
-        const int nx = (par ^ 1) * 2;
-        B_TRY(reduce_ranks(M, &st->pq, &st->pq_loc, 1));
-        CU_TRY(cudaEventRecord(ev[1], s));
-        k_pcg_update<<<M->grid_ew, EW_THREADS, 0, s>>>(
-            n, M->w_x, M->w_r, M->w_p, M->w_q, M->dinv, M->partials,
-            M->partial_stride, st, par, sum_target(M, &st->red[nx], &st->loc[nx]));
-        B_TRY(reduce_ranks(M, &st->red[nx], &st->loc[nx], 2));
-        CU_TRY(cudaEventRecord(ev[2], s));
-        k_pcg_pupdate<<<M->grid_ew, EW_THREADS, 0, s>>>(n, M->w_r, M->dinv,
-                                                        M->w_p, M->state, par);
-        CU_TRY(cudaEventRecord(ev[3], s));
-        c->launches += 2;
+        B_TRY(queue_iteration(M, i & 1, ev));
         CU_TRY(cudaEventSynchronize(ev[3]));
         for (int k = 0; k < 3; k++) {
           float t;
@@ -367,6 +400,9 @@ extern "C" int b200_pcg_solve(b200_mat *M, const double *d_b, double *d_x,
   if (h.status == 2)
     B_FAIL(B200_ENOTSPD, "b200_pcg_solve: breakdown at iteration %d (p.Ap = %g)",
            h.iter, h.pq);
+  if (h.status == 3)
+    B_FAIL(B200_ENCCL, "b200_pcg_solve: a rank's partial sums did not arrive over peer "
+                       "memory (iteration %d)", h.iter);
   return B200_OK;
 }
 

@@ -55,7 +55,7 @@ k_spmv_sell(const uint32_t *__restrict__ sell_off,
             const uint32_t *__restrict__ perm, const double *__restrict__ x,
             double *__restrict__ y, uint32_t b0, uint32_t e0, uint32_t b1,
             uint32_t e1, uint32_t n_rows, double *partials, unsigned slot_base,
-            unsigned total_slots, PcgState *st, double *dot_out) {
+            unsigned total_slots, PcgState *st, double *dot_out, const XrArgs xr) {
   if (DOT && st->done)
     return;
   __shared__ double red[SPMV_WARPS];
@@ -91,7 +91,7 @@ k_spmv_sell(const uint32_t *__restrict__ sell_off,
   if (DOT) {
     double b[1] = {block_sum<SPMV_WARPS>(dot, red)};
     grid_sum_finish<1, SPMV_WARPS>(b, partials, 0, slot_base + blockIdx.x,
-                                   total_slots, &st->ticket[0], dot_out, red);
+                                   total_slots, &st->ticket[0], dot_out, red, xr);
   }
 }
 
@@ -122,7 +122,7 @@ k_spmv_sellc(const uint4 *__restrict__ meta, const uint32_t *__restrict__ cols,
              const uint32_t *__restrict__ perm, const double *__restrict__ x,
              double *__restrict__ y, uint32_t b0, uint32_t e0, uint32_t b1,
              uint32_t e1, uint32_t n_rows, double *partials, unsigned slot_base,
-             unsigned total_slots, PcgState *st, double *dot_out) {
+             unsigned total_slots, PcgState *st, double *dot_out, const XrArgs xr) {
   if (DOT && st->done)
     return;
   __shared__ double red[SPMV_WARPS];
@@ -169,7 +169,7 @@ k_spmv_sellc(const uint4 *__restrict__ meta, const uint32_t *__restrict__ cols,
   if (DOT) {
     double b[1] = {block_sum<SPMV_WARPS>(dot, red)};
     grid_sum_finish<1, SPMV_WARPS>(b, partials, 0, slot_base + blockIdx.x,
-                                   total_slots, &st->ticket[0], dot_out, red);
+                                   total_slots, &st->ticket[0], dot_out, red, xr);
   }
 }
 
@@ -179,7 +179,7 @@ k_spmv_vec(uint32_t nrows, const uint32_t *__restrict__ ids,
            const uint64_t *__restrict__ off, const uint32_t *__restrict__ cols,
            const double *__restrict__ vals, const double *__restrict__ x,
            double *__restrict__ y, double *partials, unsigned slot_base,
-           unsigned total_slots, PcgState *st, double *dot_out) {
+           unsigned total_slots, PcgState *st, double *dot_out, const XrArgs xr) {
   if (DOT && st->done)
     return;
   __shared__ double red[SPMV_WARPS];
@@ -211,7 +211,7 @@ k_spmv_vec(uint32_t nrows, const uint32_t *__restrict__ ids,
   if (DOT) {
     double b[1] = {block_sum<SPMV_WARPS>(dot, red)};
     grid_sum_finish<1, SPMV_WARPS>(b, partials, 0, slot_base + blockIdx.x,
-                                   total_slots, &st->ticket[0], dot_out, red);
+                                   total_slots, &st->ticket[0], dot_out, red, xr);
   }
 }
 
@@ -221,7 +221,7 @@ k_spmv_long(uint32_t nrows, const uint32_t *__restrict__ ids,
             const uint64_t *__restrict__ off, const uint32_t *__restrict__ cols,
             const double *__restrict__ vals, const double *__restrict__ x,
             double *__restrict__ y, double *partials, unsigned slot_base,
-            unsigned total_slots, PcgState *st, double *dot_out) {
+            unsigned total_slots, PcgState *st, double *dot_out, const XrArgs xr) {
   if (DOT && st->done)
     return;
   __shared__ double red[SPMV_WARPS];
@@ -252,7 +252,7 @@ k_spmv_long(uint32_t nrows, const uint32_t *__restrict__ ids,
     // only thread 0 carries a value; block_sum keeps the protocol uniform
     double b[1] = {block_sum<SPMV_WARPS>(dot, red)};
     grid_sum_finish<1, SPMV_WARPS>(b, partials, 0, slot_base + blockIdx.x,
-                                   total_slots, &st->ticket[0], dot_out, red);
+                                   total_slots, &st->ticket[0], dot_out, red, xr);
   }
 }
 
@@ -322,7 +322,9 @@ static const SpmvPlan &plan_phase(b200_mat *M, int phase) {
 
 // Partials layout for the fused dot: phase-1 CTAs first, then phase-2 (or the
 // phase-0 CTAs alone).  Totals are fixed per matrix => fixed summation order.
-int launch_spmv(b200_mat *M, const double *x, double *y, bool dot, int phase) {
+int launch_spmv(b200_mat *M, const double *x, double *y, bool dot, int phase,
+                const XrArgs *xrp) {
+  const XrArgs xr = (dot && xrp) ? *xrp : XrArgs{nullptr, nullptr, 1, 0, 0, 0ull};
   b200_ctx *c = M->ctx;
   cudaStream_t s = c->stream;
   const SpmvPlan P = plan_phase(M, phase);
@@ -345,7 +347,7 @@ int launch_spmv(b200_mat *M, const double *x, double *y, bool dot, int phase) {
 #define B2_SELL_ARGS(DOTV)                                                        \
   M->sell_perm, x, y, P.b0, P.e0, P.b1, P.e1, n, DOTV ? M->partials : nullptr,    \
       DOTV ? slot_base : 0u, DOTV ? total : 0u, DOTV ? M->state : nullptr,        \
-      DOTV ? dot_out : nullptr
+      DOTV ? dot_out : nullptr, xr
     const uint4 *meta = (const uint4 *)M->sell_meta;
     if (dot && meta)
       k_spmv_sellc<true><<<P.g_sell, SPMV_THREADS, 0, s>>>(
@@ -366,22 +368,22 @@ int launch_spmv(b200_mat *M, const double *x, double *y, bool dot, int phase) {
     if (dot)
       k_spmv_vec<true><<<P.g_vec, SPMV_THREADS, 0, s>>>(
           M->vec_rows, M->vec_row_ids, M->vec_off, M->vl_cols, M->vl_vals, x, y,
-          M->partials, slot_base, total, M->state, dot_out);
+          M->partials, slot_base, total, M->state, dot_out, xr);
     else
       k_spmv_vec<false><<<P.g_vec, SPMV_THREADS, 0, s>>>(
           M->vec_rows, M->vec_row_ids, M->vec_off, M->vl_cols, M->vl_vals, x, y,
-          nullptr, 0, 0, nullptr, nullptr);
+          nullptr, 0, 0, nullptr, nullptr, xr);
     slot_base += P.g_vec;
   }
   if (P.g_long) {
     if (dot)
       k_spmv_long<true><<<P.g_long, SPMV_THREADS, 0, s>>>(
           M->long_rows, M->long_row_ids, M->long_off, M->vl_cols, M->vl_vals, x,
-          y, M->partials, slot_base, total, M->state, dot_out);
+          y, M->partials, slot_base, total, M->state, dot_out, xr);
     else
       k_spmv_long<false><<<P.g_long, SPMV_THREADS, 0, s>>>(
           M->long_rows, M->long_row_ids, M->long_off, M->vl_cols, M->vl_vals, x,
-          y, nullptr, 0, 0, nullptr, nullptr);
+          y, nullptr, 0, 0, nullptr, nullptr, xr);
   }
   c->launches += (P.g_sell > 0) + (P.g_vec > 0) + (P.g_long > 0);
   CU_TRY(cudaGetLastError());
@@ -389,17 +391,18 @@ int launch_spmv(b200_mat *M, const double *x, double *y, bool dot, int phase) {
 }
 
 // Full SpMV with halo exchange overlapped with the interior rows (piece 5).
-static int spmv_full(b200_mat *M, double *x_ext, double *y, bool dot) {
+static int spmv_full(b200_mat *M, double *x_ext, double *y, bool dot,
+                     const XrArgs *xr = nullptr) {
   if (!M->halo.n_halo && M->ctx->nranks == 1)
-    return launch_spmv(M, x_ext, y, dot, 0);
+    return launch_spmv(M, x_ext, y, dot, 0, nullptr);
   B_TRY(halo_exchange_begin(M, x_ext));
-  B_TRY(launch_spmv(M, x_ext, y, dot, 1));
+  B_TRY(launch_spmv(M, x_ext, y, dot, 1, xr));
   B_TRY(halo_exchange_wait(M));
-  return launch_spmv(M, x_ext, y, dot, 2);
+  return launch_spmv(M, x_ext, y, dot, 2, xr);
 }
 
-int spmv_full_internal(b200_mat *M, double *x_ext, double *y, bool dot) {
-  return spmv_full(M, x_ext, y, dot);
+int spmv_full_internal(b200_mat *M, double *x_ext, double *y, bool dot, const XrArgs *xr) {
+  return spmv_full(M, x_ext, y, dot, xr);
 }
 
 extern "C" int b200_spmv(b200_mat *M, const double *d_x, double *d_y) {
@@ -408,7 +411,7 @@ extern "C" int b200_spmv(b200_mat *M, const double *d_x, double *d_y) {
   b200_ctx *c = M->ctx;
   CU_TRY(cudaSetDevice(c->device));
   if (c->nranks == 1)
-    return launch_spmv(M, d_x, d_y, false, 0);
+    return launch_spmv(M, d_x, d_y, false, 0, nullptr);
   B_TRY(ensure_workspace(M));
   CU_TRY(cudaMemcpyAsync(M->x_ext, d_x, M->n_local * 8,
                          cudaMemcpyDeviceToDevice, c->stream));
