@@ -14,7 +14,10 @@
 //   interior    maximal middle run of rows without remote columns; it is
 //               multiplied while the halo is in flight on the comm stream.
 //   exchange    pack kernel + grouped ncclSend/ncclRecv over NVLink.
-//   scalars     ncclAllReduce(sum, fp64) on 1-3 values (latency-bound).
+//   scalars     1-3 fp64 sums per reduction: written by the producing kernel's last
+//               CTA into every rank's mailbox over NVLink peer memory and summed
+//               by the consuming kernel (xr_setup here, xr_push / xr_wait_sum in
+//               common.cuh); ncclAllReduce when peer memory cannot be mapped.
 //
 // NCCL is bound with dlopen so the library loads (and the single-GPU path
 // runs) on hosts without it, and so that inside a torch process the NCCL that
