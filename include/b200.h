@@ -18,6 +18,8 @@
  *                                  B200_MAT_SYM_UPPER the operator is the one
  *                                  CHOLMOD factorises, src/cholmod-impl.h:5-21
  *   b200_mat_destroy               csr_finalize, src/cusparse.c:127-136
+ *   b200_text_to_csr               the record loop of lsbench_matrix_read,
+ *                                  src/lsbench-csr.c:49-53, plus the body below
  *   b200_coo_to_csr / _mat_from_coo the sort / fold / row-compress / fill body
  *                                  of lsbench_matrix_read once the text is
  *                                  tokenised, src/lsbench-csr.c:54-86
@@ -121,6 +123,17 @@ int b200_coo_to_csr(b200_ctx *ctx, uint64_t nnz, const uint32_t *rows,
                     const uint32_t *cols, const double *vals,
                     uint32_t *nrows_out, uint64_t *nnz_out, uint32_t *offs,
                     uint32_t *cols_out, double *vals_out);
+/* The same from text: `body` is the file content after the header line
+ * ("nnz base\n"), len bytes; its first nnz lines are the records.  Lines are
+ * found and parsed on the device by a strict, exact parser (one record per
+ * line, "row col val\n"; doubles on Clinger's exact path); the lines it does
+ * not accept are parsed by strtoul / strtod on the host (*n_host_parsed of
+ * them).  B200_EINVAL when the text is not one strict record per line -- the
+ * caller then tokenises with fscanf semantics and uses b200_coo_to_csr. */
+int b200_text_to_csr(b200_ctx *ctx, const char *body, uint64_t len, uint64_t nnz,
+                     uint32_t *nrows_out, uint64_t *nnz_out, uint32_t *offs,
+                     uint32_t *cols_out, double *vals_out,
+                     uint64_t *n_host_parsed);
 /* Same ingest, then straight into the device layout (no host CSR). */
 int b200_mat_from_coo(b200_ctx *ctx, uint64_t nnz, uint32_t base,
                       const uint32_t *rows, const uint32_t *cols,

@@ -36,7 +36,7 @@ SYMBOLS = [
     "b200_malloc", "b200_free", "b200_memcpy_h2d", "b200_memcpy_d2h",
     "b200_memset", "b200_host_alloc", "b200_host_free",
     "b200_mat_from_csr", "b200_mat_generate", "b200_mat_destroy",
-    "b200_coo_to_csr", "b200_mat_from_coo",
+    "b200_coo_to_csr", "b200_mat_from_coo", "b200_text_to_csr",
     "b200_mat_get_info", "b200_mat_export", "b200_mat_halo_cols",
     "b200_mat_inv_diag", "b200_spmv", "b200_spmv_host", "b200_spmv_time",
     "b200_pcg_solve", "b200_pcg_solve_host", "b200_mat_algorithmic_bytes",
@@ -113,6 +113,8 @@ def load():
         "b200_mat_generate": [vp, i32, u64, u64, u32, C.POINTER(vp)],
         "b200_coo_to_csr": [vp, u64, vp, vp, vp, C.POINTER(u32), C.POINTER(u64), vp, vp, vp],
         "b200_mat_from_coo": [vp, u64, u32, vp, vp, vp, u32, C.POINTER(vp)],
+        "b200_text_to_csr": [vp, C.c_char_p, u64, u64, C.POINTER(u32), C.POINTER(u64), vp, vp, vp,
+                             C.POINTER(u64)],
         "b200_mat_destroy": [vp],
         "b200_mat_get_info": [vp, C.POINTER(MatInfo)],
         "b200_mat_export": [vp, vp, vp, vp],
@@ -173,6 +175,18 @@ def coo_to_csr(ctx, rows, cols, vals):
                                 vals.ctypes.data, C.byref(nr), C.byref(m),
                                 offs.ctypes.data, oc.ctypes.data, ov.ctypes.data))
     return nr.value, offs[:nr.value + 1].copy(), oc[:m.value].copy(), ov[:m.value].copy()
+
+
+def text_to_csr(ctx, body, nnz):
+    """COO text (everything after the header line, bytes) -> (nrows, offs, cols,
+    vals, lines parsed by the host); lines and numbers are parsed on the device."""
+    offs = np.empty(nnz + 1, dtype=np.uint32)
+    oc = np.empty(max(nnz, 1), dtype=np.uint32)
+    ov = np.empty(max(nnz, 1), dtype=np.float64)
+    nr, m, nh = C.c_uint32(0), C.c_uint64(0), C.c_uint64(0)
+    _chk(load().b200_text_to_csr(ctx.h, body, len(body), nnz, C.byref(nr), C.byref(m),
+                                 offs.ctypes.data, oc.ctypes.data, ov.ctypes.data, C.byref(nh)))
+    return nr.value, offs[:nr.value + 1].copy(), oc[:m.value].copy(), ov[:m.value].copy(), nh.value
 
 
 class DeviceArray:

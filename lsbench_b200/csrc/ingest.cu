@@ -17,7 +17,11 @@
 // merge sort at these sizes, hence stable as well; tests/ compare against the
 // reference's own reader).
 #include "common.cuh"
+#include "parse.cuh"
 #include <cub/cub.cuh>
+#include <cerrno>
+#include <string>
+#include <vector>
 
 #define T256 256
 static inline unsigned nblk(uint64_t n, unsigned t = T256) {
@@ -99,7 +103,7 @@ static int scan_excl(cudaStream_t s, const T *in, T *out, uint64_t n) {
 }
 
 struct IngestTmp {
-  void *p[12] = {nullptr};
+  void *p[24] = {nullptr};
   int n = 0;
   template <typename T> int get(T **out, size_t count) {
     void *q = nullptr;
@@ -123,28 +127,22 @@ struct IngestTmp {
 // file's base, as `struct csr` does; `base` gives the 0-based ids the device
 // layout wants).  Row ids are dropped: row r of the result is the r-th
 // distinct row id of the input.
-int coo_to_plain(b200_ctx *c, uint64_t nnz, const uint32_t *h_rows,
-                 const uint32_t *h_cols, const double *h_vals, uint32_t sub,
-                 PlainCsr *A, uint32_t *was_sorted) {
+// device core: d_rows / d_cols / d_vals are the records in file order
+static int coo_dev_to_plain(b200_ctx *c, uint64_t nnz, const uint32_t *d_rows,
+                            const uint32_t *d_cols, const double *d_vals, uint32_t sub,
+                            PlainCsr *A, uint32_t *was_sorted) {
   if (nnz == 0 || nnz >= 0xffffffffull)
     B_FAIL(B200_ERANGE, "ingest: nnz=%llu outside (0, 2^32)", (unsigned long long)nnz);
   cudaStream_t s = c->stream;
   IngestTmp T;
-  uint32_t *d_rows, *d_cols, *idx, *idx2, *head, *pos;
-  double *d_vals;
+  uint32_t *idx, *idx2, *head, *pos;
   uint64_t *keys, *keys2;
   unsigned *d_flag;
   unsigned long long *d_or;
-  B_TRY(T.get(&d_rows, nnz));
-  B_TRY(T.get(&d_cols, nnz));
-  B_TRY(T.get(&d_vals, nnz));
   B_TRY(T.get(&keys, nnz));
   B_TRY(T.get(&idx, nnz));
   B_TRY(T.get(&d_flag, 2));
   B_TRY(T.get(&d_or, 1));
-  CU_TRY(cudaMemcpyAsync(d_rows, h_rows, nnz * 4, cudaMemcpyHostToDevice, s));
-  CU_TRY(cudaMemcpyAsync(d_cols, h_cols, nnz * 4, cudaMemcpyHostToDevice, s));
-  CU_TRY(cudaMemcpyAsync(d_vals, h_vals, nnz * 8, cudaMemcpyHostToDevice, s));
   CU_TRY(cudaMemsetAsync(d_flag, 0, 8, s));
   CU_TRY(cudaMemsetAsync(d_or, 0, 8, s));
   k_coo_keys<<<nblk(nnz), T256, 0, s>>>(nnz, d_rows, d_cols, keys, idx, d_flag, d_or);
@@ -230,6 +228,173 @@ int coo_to_plain(b200_ctx *c, uint64_t nnz, const uint32_t *h_rows,
   return B200_OK;
 }
 
+int coo_to_plain(b200_ctx *c, uint64_t nnz, const uint32_t *h_rows,
+                 const uint32_t *h_cols, const double *h_vals, uint32_t sub,
+                 PlainCsr *A, uint32_t *was_sorted) {
+  if (nnz == 0 || nnz >= 0xffffffffull)
+    B_FAIL(B200_ERANGE, "ingest: nnz=%llu outside (0, 2^32)", (unsigned long long)nnz);
+  cudaStream_t s = c->stream;
+  IngestTmp T;
+  uint32_t *d_rows, *d_cols;
+  double *d_vals;
+  B_TRY(T.get(&d_rows, nnz));
+  B_TRY(T.get(&d_cols, nnz));
+  B_TRY(T.get(&d_vals, nnz));
+  CU_TRY(cudaMemcpyAsync(d_rows, h_rows, nnz * 4, cudaMemcpyHostToDevice, s));
+  CU_TRY(cudaMemcpyAsync(d_cols, h_cols, nnz * 4, cudaMemcpyHostToDevice, s));
+  CU_TRY(cudaMemcpyAsync(d_vals, h_vals, nnz * 8, cudaMemcpyHostToDevice, s));
+  return coo_dev_to_plain(c, nnz, d_rows, d_cols, d_vals, sub, A, was_sorted);
+}
+
+// ---- text -> records on the device ------------------------------------------------
+// One thread per line with the exact, strict parser of parse.cuh; lines it does
+// not accept are listed for the host, which runs strtoul / strtod on them.
+struct FlagToU64 {
+  __host__ __device__ uint64_t operator()(uint8_t f) const { return f; }
+};
+
+__global__ void k_flag_newlines(const char *__restrict__ text, uint64_t len, uint8_t *flag) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < len)
+    flag[i] = text[i] == '\n';
+}
+
+__global__ void k_parse_lines(uint64_t nnz, const char *__restrict__ text,
+                              const uint64_t *__restrict__ nlpos, uint32_t *rows,
+                              uint32_t *cols, double *vals, uint8_t *ask) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= nnz)
+    return;
+  const char *p = text + (i ? nlpos[i - 1] + 1 : 0), *nl = text + nlpos[i];
+  uint32_t r = 0, c = 0;
+  double v = 0.0;
+  ask[i] = (uint8_t)b2_parse_record(p, nl, r, c, v);
+  rows[i] = r, cols[i] = c, vals[i] = v;
+}
+
+__global__ void k_patch_records(uint64_t n, const uint64_t *__restrict__ at,
+                                const uint32_t *__restrict__ pr, const uint32_t *__restrict__ pc,
+                                const double *__restrict__ pv, uint32_t *rows, uint32_t *cols,
+                                double *vals) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i < n)
+    rows[at[i]] = pr[i], cols[at[i]] = pc[i], vals[at[i]] = pv[i];
+}
+
+// body: the text after the header line, `len` bytes, in host memory.  The first
+// nnz lines are the records.  Returns B200_EINVAL (nothing else touched) when
+// the text is not one strict record per line -- the caller then tokenises it
+// the slow way, with the semantics of fscanf.
+static int text_to_plain(b200_ctx *c, const char *body, uint64_t len, uint64_t nnz,
+                         uint32_t sub, PlainCsr *A, uint64_t *n_host) {
+  if (nnz == 0 || nnz >= 0xffffffffull)
+    B_FAIL(B200_ERANGE, "ingest: nnz=%llu outside (0, 2^32)", (unsigned long long)nnz);
+  if (len == 0)
+    B_FAIL(B200_EINVAL, "ingest: empty matrix body");
+  cudaStream_t s = c->stream;
+  IngestTmp T;
+  char *d_text;
+  uint8_t *d_flag, *d_ask;
+  uint64_t *d_pos, *d_count;
+  B_TRY(T.get(&d_text, len));
+  B_TRY(T.get(&d_flag, len));
+  B_TRY(T.get(&d_count, 1));
+  CU_TRY(cudaMemcpyAsync(d_text, body, len, cudaMemcpyHostToDevice, s));
+  k_flag_newlines<<<nblk(len), T256, 0, s>>>(d_text, len, d_flag);
+  {  // how many lines, then where they end
+    void *tmp = nullptr;
+    size_t bytes = 0;
+    cub::TransformInputIterator<uint64_t, FlagToU64, const uint8_t *> wide(d_flag, FlagToU64());
+    CU_TRY(cub::DeviceReduce::Sum(nullptr, bytes, wide, d_count, len, s));
+    CU_TRY(cudaMalloc(&tmp, bytes ? bytes : 8));
+    cudaError_t e = cub::DeviceReduce::Sum(tmp, bytes, wide, d_count, len, s);
+    cudaStreamSynchronize(s);
+    cudaFree(tmp);
+    CU_TRY(e);
+  }
+  uint64_t nlines = 0;
+  CU_TRY(cudaMemcpy(&nlines, d_count, 8, cudaMemcpyDeviceToHost));
+  if (nlines < nnz)
+    B_FAIL(B200_EINVAL, "ingest: %llu records announced, %llu lines", (unsigned long long)nnz,
+           (unsigned long long)nlines);
+  B_TRY(T.get(&d_pos, nlines + 1));
+  {
+    void *tmp = nullptr;
+    size_t bytes = 0;
+    cub::CountingInputIterator<uint64_t> it(0);
+    CU_TRY(cub::DeviceSelect::Flagged(nullptr, bytes, it, d_flag, d_pos, d_count, len, s));
+    CU_TRY(cudaMalloc(&tmp, bytes ? bytes : 8));
+    cudaError_t e = cub::DeviceSelect::Flagged(tmp, bytes, it, d_flag, d_pos, d_count, len, s);
+    cudaStreamSynchronize(s);
+    cudaFree(tmp);
+    CU_TRY(e);
+  }
+  uint32_t *d_rows, *d_cols;
+  double *d_vals;
+  B_TRY(T.get(&d_rows, nnz));
+  B_TRY(T.get(&d_cols, nnz));
+  B_TRY(T.get(&d_vals, nnz));
+  B_TRY(T.get(&d_ask, nnz));
+  k_parse_lines<<<nblk(nnz), T256, 0, s>>>(nnz, d_text, d_pos, d_rows, d_cols, d_vals, d_ask);
+  CU_TRY(cudaGetLastError());
+  // lines for the host
+  uint64_t *d_list;
+  B_TRY(T.get(&d_list, nnz));
+  {
+    void *tmp = nullptr;
+    size_t bytes = 0;
+    cub::CountingInputIterator<uint64_t> it(0);
+    CU_TRY(cub::DeviceSelect::Flagged(nullptr, bytes, it, d_ask, d_list, d_count, nnz, s));
+    CU_TRY(cudaMalloc(&tmp, bytes ? bytes : 8));
+    cudaError_t e = cub::DeviceSelect::Flagged(tmp, bytes, it, d_ask, d_list, d_count, nnz, s);
+    cudaStreamSynchronize(s);
+    cudaFree(tmp);
+    CU_TRY(e);
+  }
+  uint64_t nask = 0;
+  CU_TRY(cudaMemcpy(&nask, d_count, 8, cudaMemcpyDeviceToHost));
+  if (n_host)
+    *n_host = nask;
+  if (nask) {
+    std::vector<uint64_t> list(nask), nl(2 * nask);
+    CU_TRY(cudaMemcpy(list.data(), d_list, nask * 8, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> pr(nask), pc(nask);
+    std::vector<double> pv(nask);
+    for (uint64_t k = 0; k < nask; k++) {
+      uint64_t b = 0, e = 0;  // [b, e]: the line, e at its newline
+      if (list[k]) {
+        CU_TRY(cudaMemcpy(&b, d_pos + list[k] - 1, 8, cudaMemcpyDeviceToHost));
+        b += 1;
+      }
+      CU_TRY(cudaMemcpy(&e, d_pos + list[k], 8, cudaMemcpyDeviceToHost));
+      // libc on this one line; the value must end exactly at the newline
+      const std::string line(body + b, body + e + 1);
+      const char *p0 = line.c_str(), *last = p0 + line.size() - 1;
+      char *q1, *q2, *q3;
+      const unsigned long r = strtoul(p0, &q1, 10);
+      const unsigned long cc = strtoul(q1, &q2, 10);
+      const double v = strtod(q2, &q3);
+      const bool strict = !(*p0 == ' ' || *p0 == '\t' || *p0 == '\n' || *p0 == '\r');
+      if (!strict || q1 == p0 || q2 == q1 || q3 == q2 || q3 != last)
+        B_FAIL(B200_EINVAL, "ingest: record %llu is not one strict line",
+               (unsigned long long)list[k]);
+      pr[k] = (uint32_t)r, pc[k] = (uint32_t)cc, pv[k] = v;
+    }
+    uint32_t *d_pr, *d_pc;
+    double *d_pv;
+    B_TRY(T.get(&d_pr, nask));
+    B_TRY(T.get(&d_pc, nask));
+    B_TRY(T.get(&d_pv, nask));
+    CU_TRY(cudaMemcpyAsync(d_pr, pr.data(), nask * 4, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(d_pc, pc.data(), nask * 4, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(d_pv, pv.data(), nask * 8, cudaMemcpyHostToDevice, s));
+    k_patch_records<<<nblk(nask), T256, 0, s>>>(nask, d_list, d_pr, d_pc, d_pv, d_rows, d_cols, d_vals);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(s));
+  }
+  return coo_dev_to_plain(c, nnz, d_rows, d_cols, d_vals, sub, A, nullptr);
+}
+
 __global__ void k_narrow_offs(const uint64_t *in, uint32_t *out, uint64_t n) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i < n)
@@ -264,6 +429,37 @@ extern "C" int b200_coo_to_csr(b200_ctx *c, uint64_t nnz, const uint32_t *rows,
   }
   plain_free(&A);
   return B200_OK;
+}
+
+static int plain_to_host(b200_ctx *c, PlainCsr &A, uint32_t *nrows_out, uint64_t *nnz_out,
+                         uint32_t *offs, uint32_t *cols_out, double *vals_out) {
+  *nrows_out = (uint32_t)A.n, *nnz_out = A.nnz;
+  if (offs && cols_out && vals_out) {
+    cudaStream_t s = c->stream;
+    uint32_t *o32 = nullptr;
+    CU_TRY(cudaMalloc(&o32, (A.n + 1) * 4));
+    k_narrow_offs<<<nblk(A.n + 1), T256, 0, s>>>(A.offs, o32, A.n + 1);
+    CU_TRY(cudaMemcpyAsync(offs, o32, (A.n + 1) * 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(cols_out, A.cols, A.nnz * 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(vals_out, A.vals, A.nnz * 8, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    cudaFree(o32);
+  }
+  return B200_OK;
+}
+
+extern "C" int b200_text_to_csr(b200_ctx *c, const char *body, uint64_t len, uint64_t nnz,
+                                uint32_t *nrows_out, uint64_t *nnz_out, uint32_t *offs,
+                                uint32_t *cols_out, double *vals_out, uint64_t *n_host_parsed) {
+  if (!c || !body || !nrows_out || !nnz_out)
+    B_FAIL(B200_EINVAL, "b200_text_to_csr: null argument");
+  CU_TRY(cudaSetDevice(c->device));
+  PlainCsr A;
+  int rc = text_to_plain(c, body, len, nnz, 0, &A, n_host_parsed);
+  if (rc == B200_OK)
+    rc = plain_to_host(c, A, nrows_out, nnz_out, offs, cols_out, vals_out);
+  plain_free(&A);
+  return rc;
 }
 
 int mat_from_plain(b200_ctx *c, PlainCsr *A, uint32_t flags, b200_mat **out);

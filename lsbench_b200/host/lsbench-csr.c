@@ -182,6 +182,43 @@ static struct csr *device_ingest(size_t nnz, unsigned base, const uint32_t *rows
 }
 #endif
 
+#if defined(LSBENCH_B200)
+/* Text straight to CSR on the device (b200_text_to_csr).  NULL when the body
+ * is not one strict record per line (the caller tokenises it instead); any
+ * other failure is fatal. */
+static struct csr *device_text_ingest(const char *body, size_t len, size_t nnz,
+                                      unsigned base) {
+  const char *v = getenv("LSBENCH_B200_DEVICE");
+  b200_ctx *ctx = NULL;
+  if (b200_ctx_create(v ? atoi(v) : 0, &ctx) != B200_OK)
+    errx(EXIT_FAILURE, "b200 ingest: %s", b200_last_error());
+  struct csr *A = tcalloc(struct csr, 1);
+  A->base = base;
+  A->offs = tcalloc(unsigned, nnz + 1);
+  A->cols = tcalloc(unsigned, nnz);
+  A->vals = tcalloc(double, nnz);
+  if (!A->offs || !A->cols || !A->vals)
+    err(EXIT_FAILURE, "Unable to allocate the CSR arrays");
+  uint32_t nrows = 0;
+  uint64_t m = 0, nhost = 0;
+  int rc = b200_text_to_csr(ctx, body, len, nnz, &nrows, &m, A->offs, A->cols,
+                            A->vals, &nhost);
+  b200_ctx_destroy(ctx);
+  if (rc == B200_EINVAL) { /* not strict: let the tokeniser judge the file */
+    lsbench_matrix_free(A);
+    return NULL;
+  }
+  if (rc != B200_OK)
+    errx(EXIT_FAILURE, "b200 ingest: %s", b200_last_error());
+  A->nrows = nrows;
+  unsigned *o = (unsigned *)realloc(A->offs, ((size_t)nrows + 1) * sizeof(unsigned));
+  unsigned *c = (unsigned *)realloc(A->cols, (m ? m : 1) * sizeof(unsigned));
+  double *d = (double *)realloc(A->vals, (m ? m : 1) * sizeof(double));
+  A->offs = o ? o : A->offs, A->cols = c ? c : A->cols, A->vals = d ? d : A->vals;
+  return A;
+}
+#endif
+
 struct csr *lsbench_matrix_read(const char *fname) {
   struct csr *S = synthetic(fname);
   if (S)
@@ -219,6 +256,24 @@ struct csr *lsbench_matrix_read(const char *fname) {
     errx(EXIT_FAILURE, "Number of nnz values in the file are zero.");
   p = q + 1;
   size_t nnz = nnz_l;
+
+#if defined(LSBENCH_B200)
+  {
+    /* LSBENCH_B200_INGEST: lines found and parsed on the GPU when the body is
+     * one strict record per line; otherwise the tokeniser below */
+    const char *ing = getenv("LSBENCH_B200_INGEST");
+    if (ing && *ing && strcmp(ing, "0") != 0) {
+      struct csr *D = device_text_ingest(p, (size_t)size - (size_t)(p - text), nnz,
+                                         (unsigned)base_l);
+      if (D) {
+        free(text);
+        if (use_cache)
+          cache_store(fname, D);
+        return D;
+      }
+    }
+  }
+#endif
 
   /* the records in file order (src/lsbench-csr.c:49-53) */
   uint32_t *rows = tcalloc(uint32_t, nnz), *cols = tcalloc(uint32_t, nnz);

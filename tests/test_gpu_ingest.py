@@ -161,3 +161,61 @@ def test_driver_with_device_ingest(tmp_path):
         lines = p.stdout.strip().splitlines()
         outs.append(lines[3].split(",")[:5])       # gpus, iterations, status, relres, true_relres
     assert outs[0] == outs[1], outs
+
+
+# --------------------------------------------------------------------------- text on the device
+def body_of(path):
+    """(nnz, base, bytes after the header line)"""
+    raw = open(path, "rb").read()
+    nl = raw.index(b"\n")
+    nnz, base = (int(t) for t in raw[:nl].split())
+    return nnz, base, raw[nl + 1:]
+
+
+@pytest.mark.parametrize("name", orc.TOY + orc.NEK)
+def test_text_is_parsed_on_the_device(abi, ctx, name):
+    """lines found and numbers parsed on the GPU (parse.cuh: strict, exact),
+    then sort / fold / compress: the reference's files come out bit for bit"""
+    path = orc.matrix_path(name)
+    nnz, base, body = body_of(path)
+    nr, offs, cols, vals, nhost = abi.text_to_csr(ctx, body, nnz)
+    assert_same_csr((nr, offs, cols, vals), orc.matrix_read(path))
+    assert nhost <= 1e-4 * nnz + 1          # fixed-point 15-digit values: the exact fast path
+
+
+def test_text_with_values_for_the_host(abi, ctx, tmp_path):
+    """shuffled, duplicated records written with 17 significant digits: most
+    values are off the exact fast path and are parsed by strtod on the host;
+    the result is still the readers' CSR, bit for bit"""
+    base, r, c, v = read_records(orc.matrix_path("xn3b_A_18"))
+    r, c, v = hostile(base, r, c, v, seed=21)
+    f = str(tmp_path / "hostile.txt")
+    write_records(f, base, r, c, v)
+    nnz, base2, body = body_of(f)
+    nr, offs, cols, vals, nhost = abi.text_to_csr(ctx, body, nnz)
+    want = orc.matrix_read(f)
+    assert_same_csr((nr, offs, cols, vals), want)
+    assert 0 < nhost <= nnz
+    ref = orc.ref_matrix_read(f)
+    if ref is not None:
+        assert_same_csr((nr, offs, cols, vals), ref)
+
+
+@pytest.mark.parametrize("body,nnz", [
+    (b"1 1 2.5\n\n2 2 1.0\n", 2),       # a blank line: fscanf would skip it, a line parser must not guess
+    (b" 1 1 2.5\n2 2 1.0\n", 2),        # leading blank
+    (b"1 1 2.5 \n2 2 1.0\n", 2),        # trailing blank: the reference requires the newline right there
+    (b"1 1 2.5\n2 2\n", 2),             # a field missing
+    (b"1 1 2.5\n", 2),                  # fewer lines than records
+    (b"1 1 abc\n2 2 1\n", 2),
+])
+def test_text_that_is_not_one_strict_record_per_line_is_refused(abi, ctx, body, nnz):
+    with pytest.raises(abi.B200Error) as e:
+        abi.text_to_csr(ctx, body, nnz)
+    assert e.value.code == 1      # B200_EINVAL
+
+
+def test_text_extra_lines_after_the_records_are_ignored(abi, ctx):
+    nr, offs, cols, vals, nhost = abi.text_to_csr(ctx, b"3 1 4\n1 2 -0.5\n1 2 1e-3\ngarbage\n", 3)
+    assert (nr, offs.tolist(), cols.tolist()) == (2, [0, 1, 2], [2, 1])
+    assert vals.tolist() == [-0.5 + 1e-3, 4.0]
