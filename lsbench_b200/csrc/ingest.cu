@@ -356,17 +356,14 @@ static int text_to_plain(b200_ctx *c, const char *body, uint64_t len, uint64_t n
   if (n_host)
     *n_host = nask;
   if (nask) {
-    std::vector<uint64_t> list(nask), nl(2 * nask);
+    std::vector<uint64_t> list(nask), hpos(nnz);
     CU_TRY(cudaMemcpy(list.data(), d_list, nask * 8, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(hpos.data(), d_pos, nnz * 8, cudaMemcpyDeviceToHost));
     std::vector<uint32_t> pr(nask), pc(nask);
     std::vector<double> pv(nask);
     for (uint64_t k = 0; k < nask; k++) {
-      uint64_t b = 0, e = 0;  // [b, e]: the line, e at its newline
-      if (list[k]) {
-        CU_TRY(cudaMemcpy(&b, d_pos + list[k] - 1, 8, cudaMemcpyDeviceToHost));
-        b += 1;
-      }
-      CU_TRY(cudaMemcpy(&e, d_pos + list[k], 8, cudaMemcpyDeviceToHost));
+      // [b, e]: the line, e at its newline
+      const uint64_t b = list[k] ? hpos[list[k] - 1] + 1 : 0, e = hpos[list[k]];
       // libc on this one line; the value must end exactly at the newline
       const std::string line(body + b, body + e + 1);
       const char *p0 = line.c_str(), *last = p0 + line.size() - 1;
