@@ -14,9 +14,15 @@
 //              doubles and ONE correctly rounded IEEE multiply or divide gives
 //              the correctly rounded result (Clinger's fast path) -- the same
 //              double strtod returns.  The Nek files ("0.217534912180770")
-//              are entirely on this path.  Anything else -- more digits, a
-//              larger exponent, inf / nan / hex floats, stray characters, a
-//              missing newline -- is not guessed at.
+//              are entirely on this path.  Beyond it, for |q| <= 27 (every
+//              "%.17g" value between 1e-27 and 1e46), w x 10^q is rounded
+//              with EXACT integer arithmetic: a 154-bit product, or a binary
+//              long division by 10^|q| < 2^90 with the remainder as sticky
+//              bit, then round-half-even to 53 bits -- no tables, no
+//              heuristics, so again what a correctly rounding strtod gives.
+//              Anything else -- more digits, a larger exponent, inf / nan /
+//              hex floats, stray characters, a missing newline -- is not
+//              guessed at.
 #pragma once
 #include <stdint.h>
 
@@ -52,6 +58,81 @@ B2_PARSE_HD double b2_pow10_exact(int k) {  // 10^k, 0 <= k <= 22: exact in fp64
                         1e8,  1e9,  1e10, 1e11, 1e12, 1e13, 1e14, 1e15,
                         1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
   return t[k];
+}
+
+typedef unsigned __int128 b2_u128;
+
+B2_PARSE_HD int b2_bitlen64(uint64_t v) {
+  int n = 0;
+  while (v)
+    n++, v >>= 1;
+  return n;
+}
+B2_PARSE_HD int b2_bitlen128(b2_u128 v) {
+  const uint64_t hi = (uint64_t)(v >> 64);
+  return hi ? 64 + b2_bitlen64(hi) : b2_bitlen64((uint64_t)v);
+}
+
+// m (up to 128 bits, m != 0) x 2^e2, plus "there were non-zero bits below"
+// (sticky): round half to even to 53 bits and assemble the double.  The
+// callers keep the result in the normal range.
+B2_PARSE_HD double b2_round_pack(b2_u128 m, int e2, bool sticky, bool neg) {
+  const int L = b2_bitlen128(m);
+  if (L > 53) {
+    const int drop = L - 53;
+    const b2_u128 one = 1;
+    const b2_u128 rest = m & ((one << drop) - 1), half = one << (drop - 1);
+    m >>= drop, e2 += drop;
+    const bool up = rest > half || (rest == half && (sticky || (m & 1)));
+    if (up) {
+      m += 1;
+      if (m >> 53)
+        m >>= 1, e2 += 1;
+    }
+  } else if (L < 53) {
+    m <<= (53 - L), e2 -= (53 - L);  // exact: nothing was dropped
+  }
+  const uint64_t mant = (uint64_t)m;  // bit 52 set
+  const uint64_t bits = ((uint64_t)neg << 63) | ((uint64_t)(e2 + 52 + 1023) << 52) |
+                        (mant & ((1ull << 52) - 1));
+  double d;
+#ifdef __CUDA_ARCH__
+  d = __longlong_as_double((long long)bits);
+#else
+  __builtin_memcpy(&d, &bits, 8);
+#endif
+  return d;
+}
+
+// w x 10^q, 1 <= w < 2^64, |q| <= 27, correctly rounded, by exact integer
+// arithmetic (10^27 < 2^90).
+B2_PARSE_HD double b2_exact_decimal(uint64_t w, int q, bool neg) {
+  b2_u128 p10 = 1;
+  for (int i = 0; i < (q < 0 ? -q : q); i++)
+    p10 *= 10u;
+  if (q >= 0) {
+    // 64-bit x 90-bit product, up to 154 bits: mid holds bits 64.., low bits 0..63
+    const b2_u128 lo64 = (b2_u128)(uint64_t)p10 * w;
+    const b2_u128 mid = (p10 >> 64) * w + (lo64 >> 64);
+    const uint64_t low = (uint64_t)lo64;
+    if ((mid >> 64) == 0)  // the product fits 128 bits
+      return b2_round_pack((mid << 64) | low, 0, false, neg);
+    return b2_round_pack(mid, 64, low != 0, neg);  // >= 65 bits kept, low 64 are sticky
+  }
+  // w / 10^n: binary long division of w x 2^s by p10 with s such that the
+  // quotient has at least 55 bits; a non-zero remainder is the sticky bit
+  const int bw = b2_bitlen64(w), bd = b2_bitlen128(p10);
+  int s = 55 + bd - bw;
+  if (s < 0)
+    s = 0;
+  b2_u128 rem = 0, quo = 0;
+  for (int i = bw - 1; i >= -s; i--) {
+    rem = (rem << 1) | (i >= 0 ? (b2_u128)((w >> i) & 1u) : (b2_u128)0);
+    quo <<= 1;
+    if (rem >= p10)
+      rem -= p10, quo |= 1u;
+  }
+  return b2_round_pack(quo, -s, rem != 0, neg);
 }
 
 // floating-point field at p; advances p past it
@@ -109,11 +190,15 @@ B2_PARSE_HD bool b2_parse_f64(const char *&p, const char *end, double &out) {
     out = neg ? -0.0 : 0.0;
     return true;
   }
-  if (w > (1ull << 53) || q < -22 || q > 22)
+  if (w <= (1ull << 53) && q >= -22 && q <= 22) {
+    const double m = (double)w;  // exact
+    const double r = q < 0 ? m / b2_pow10_exact(-q) : m * b2_pow10_exact(q);
+    out = neg ? -r : r;
+    return true;
+  }
+  if (q < -27 || q > 27)
     return false;
-  const double m = (double)w;  // exact
-  const double r = q < 0 ? m / b2_pow10_exact(-q) : m * b2_pow10_exact(q);
-  out = neg ? -r : r;
+  out = b2_exact_decimal(w, q, neg);
   return true;
 }
 

@@ -183,19 +183,27 @@ def test_text_is_parsed_on_the_device(abi, ctx, name):
     assert nhost <= 1e-4 * nnz + 1          # fixed-point 15-digit values: the exact fast path
 
 
-def test_text_with_values_for_the_host(abi, ctx, tmp_path):
-    """shuffled, duplicated records written with 17 significant digits: most
-    values are off the exact fast path and are parsed by strtod on the host;
-    the result is still the readers' CSR, bit for bit"""
+def test_text_with_17_digit_values(abi, ctx, tmp_path):
+    """shuffled, duplicated records written with 17 significant digits: off
+    Clinger's fast path, rounded on the device with exact integer arithmetic
+    (parse.cuh b2_exact_decimal); a few records carry values only the host's
+    strtod is trusted with.  The result is the readers' CSR, bit for bit"""
     base, r, c, v = read_records(orc.matrix_path("xn3b_A_18"))
     r, c, v = hostile(base, r, c, v, seed=21)
     f = str(tmp_path / "hostile.txt")
     write_records(f, base, r, c, v)
+    # values outside what the device takes: tiny / huge exponents, 25 digits, inf
+    extra = ["7 7 1.5e-300\n", "7 8 -2.25e+200\n", "8 8 0.1234567890123456789012345\n",
+             "9 9 1e-40\n", "9 10 inf\n"]
+    raw = open(f).read().split("\n", 1)
+    nnz0 = int(raw[0].split()[0])
+    with open(f, "w") as g:
+        g.write("%d %d\n" % (nnz0 + len(extra), base) + raw[1] + "".join(extra))
     nnz, base2, body = body_of(f)
     nr, offs, cols, vals, nhost = abi.text_to_csr(ctx, body, nnz)
     want = orc.matrix_read(f)
     assert_same_csr((nr, offs, cols, vals), want)
-    assert 0 < nhost <= nnz
+    assert nhost == len(extra)
     ref = orc.ref_matrix_read(f)
     if ref is not None:
         assert_same_csr((nr, offs, cols, vals), ref)

@@ -41,3 +41,29 @@ def test_random_records_in_many_formats(checker):
     rc, acc, tot, bad = run(checker, "--random", "1000000")
     assert rc == 0 and bad == 0
     assert 0.5 * tot < acc < tot      # %.17g and large exponents must be handed back
+
+
+def test_values_next_to_rounding_boundaries(checker, tmp_path):
+    """17-19 digit decimals at and one decimal ulp either side of the midpoint of
+    two adjacent doubles: the exact integer path (product / long division with a
+    sticky bit, round half to even) must agree with strtod on every accepted one."""
+    import random
+    from decimal import Decimal, getcontext
+    getcontext().prec = 60
+    random.seed(7)
+    lines = []
+    for _ in range(40000):
+        e = random.randint(-60, 100)
+        m = random.getrandbits(52) | (1 << 52)
+        mid = (Decimal(m) + Decimal(m + 1)) / 2 * (Decimal(2) ** (e - 52))
+        nd = random.choice([17, 18, 19])
+        s = format(mid, ".%de" % (nd - 1))
+        d = Decimal(s)
+        step = Decimal(1).scaleb(d.adjusted() - (nd - 1))
+        for v in (d, d + step, d - step):
+            lines.append("1 2 %s\n" % format(v, ".%de" % (nd - 1)))
+    f = tmp_path / "halfway.txt"
+    f.write_text("%d 1\n" % len(lines) + "".join(lines))
+    rc, acc, tot, bad = run(checker, str(f))
+    assert rc == 0 and bad == 0 and tot == len(lines)
+    assert acc > 0.7 * tot            # exponents within +-27 after scaling: most are taken
