@@ -257,11 +257,10 @@ k_spmv_long(uint32_t nrows, const uint32_t *__restrict__ ids,
 }
 
 // ---------------------------------------------------------------------------
-static int persistent_grid(b200_ctx *c, const void *kernel, uint64_t work_ctas,
-                           int threads = SPMV_THREADS, size_t smem = 0) {
+static int persistent_grid(b200_ctx *c, const void *kernel, uint64_t work_ctas) {
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel,
-                                                    threads, smem) != cudaSuccess ||
+                                                    SPMV_THREADS, 0) != cudaSuccess ||
       per_sm < 1)
     per_sm = 4;
   uint64_t g = (uint64_t)c->sm_count * per_sm;

@@ -1,5 +1,10 @@
+"""Per-phase clock64 profile of the on-chip PCG kernel (csrc/small.cu):
+   B200_SMALL_PROFILE=1 python tools/smallprof.py
+prints cycles per iteration for SpMV, the two all-reduce waits, the update and
+the window update, as seen by thread 0 of CTA 0."""
 import sys, os
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, orc
 from lsbench_b200 import abi
 ctx = abi.Context(0)
