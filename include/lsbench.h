@@ -15,31 +15,29 @@
 extern "C" {
 #endif
 
-/* Solver ids.  0..5 are the reference's (src/lsbench.h:8-16); 6 is new. */
+/* Solver, precision and ordering ids: the reference's names and values
+ * (src/lsbench.h:8-29), so code written against either header compiles
+ * against the other; LSBENCH_SOLVER_B200 is the one addition.
+ *
+ *   id  --solver     backend
+ *   -1  (none)       unknown string (the reference falls back to CHOLMOD, src/lsbench.c:31-33)
+ *    0  cusolver     cuSOLVER-Sp sparse Cholesky      not built in this tree
+ *    1  hypre        BoomerAMG                        not built
+ *    2  amgx         AmgX classical AMG (fp32)        not built
+ *    3  cholmod      CHOLMOD direct solve             not built (stand-in: tests/cholmod_standin.c)
+ *    4  paralmond    parAlmond AMG                    not built
+ *    5  ginkgo       BiCGSTAB + Jacobi                not built
+ *    6  b200         fp64 SELL SpMV + fused Jacobi-PCG, sm_100a   this tree
+ *
+ * Precision: only FP64 is accepted (src/lsbench.c:140-141).  Ordering: parsed
+ * and printed; the b200 backend renumbers only inside its coarse-grid kernel. */
 typedef enum {
-  LSBENCH_SOLVER_NONE = -1,
-  LSBENCH_SOLVER_CUSOLVER = 0,
-  LSBENCH_SOLVER_HYPRE = 1,
-  LSBENCH_SOLVER_AMGX = 2,
-  LSBENCH_SOLVER_CHOLMOD = 3,
-  LSBENCH_SOLVER_PARALMOND = 4,
-  LSBENCH_SOLVER_GINKGO = 5,
-  LSBENCH_SOLVER_B200 = 6 /* fp64 SELL SpMV + fused Jacobi-PCG, sm_100a */
+  LSBENCH_SOLVER_NONE = -1, LSBENCH_SOLVER_CUSOLVER, LSBENCH_SOLVER_HYPRE, LSBENCH_SOLVER_AMGX,
+  LSBENCH_SOLVER_CHOLMOD, LSBENCH_SOLVER_PARALMOND, LSBENCH_SOLVER_GINKGO, LSBENCH_SOLVER_B200
 } lsbench_solver_t;
-
-/* src/lsbench.h:18-22.  Only FP64 is accepted (src/lsbench.c:140-141). */
+typedef enum { LSBENCH_PRECISION_FP64, LSBENCH_PRECISION_FP32, LSBENCH_PRECISION_FP16 } lsbench_precision_t;
 typedef enum {
-  LSBENCH_PRECISION_FP64 = 0,
-  LSBENCH_PRECISION_FP32 = 1,
-  LSBENCH_PRECISION_FP16 = 2
-} lsbench_precision_t;
-
-/* src/lsbench.h:24-29.  The b200 backend does not reorder. */
-typedef enum {
-  LSBENCH_ORDERING_NONE = -1,
-  LSBENCH_ORDERING_RCM = 0,
-  LSBENCH_ORDERING_AMD = 1,
-  LSBENCH_ORDERING_METIS = 2
+  LSBENCH_ORDERING_NONE = -1, LSBENCH_ORDERING_RCM, LSBENCH_ORDERING_AMD, LSBENCH_ORDERING_METIS
 } lsbench_ordering_t;
 
 /* ---- matrix ------------------------------------------------------------ */

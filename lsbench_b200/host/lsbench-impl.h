@@ -43,24 +43,21 @@ struct csr {
 /* Backend convention (src/lsbench-impl.h:42-68): X_init / X_finalize return 1
  * if already (un)initialised, X_bench returns 1 if the backend is not usable,
  * 0 on success; x has nrows zeros on entry, r is read-only. */
+#define LSBENCH_BENCH_FN(name)                                                 \
+  int name##_bench(double *x, struct csr *A, const double *r,                  \
+                   const struct lsbench *cb)
 int b200_init(void);
 int b200_finalize(void);
-int b200_bench(double *x, struct csr *A, const double *r,
-               const struct lsbench *cb);
+LSBENCH_BENCH_FN(b200);
 
-/* The reference's third-party wrappers: not built in this tree. */
-int cusparse_bench(double *x, struct csr *A, const double *r,
-                   const struct lsbench *cb);
-int hypre_bench(double *x, struct csr *A, const double *r,
-                const struct lsbench *cb);
-int amgx_bench(double *x, struct csr *A, const double *r,
-               const struct lsbench *cb);
-int cholmod_bench(double *x, struct csr *A, const double *r,
-                  const struct lsbench *cb);
-int paralmond_bench(double *x, struct csr *A, const double *r,
-                    const struct lsbench *cb);
-int ginkgo_bench(double *x, struct csr *A, const double *r,
-                 const struct lsbench *cb);
+/* The reference's third-party wrappers are not built in this tree; their
+ * bench entry points exist (lsbench.c) and report "not built". */
+LSBENCH_BENCH_FN(cusparse);
+LSBENCH_BENCH_FN(hypre);
+LSBENCH_BENCH_FN(amgx);
+LSBENCH_BENCH_FN(cholmod);
+LSBENCH_BENCH_FN(paralmond);
+LSBENCH_BENCH_FN(ginkgo);
 
 #ifdef __cplusplus
 }

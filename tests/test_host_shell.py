@@ -67,10 +67,26 @@ def test_public_api_is_the_reference_api(host):
               "lsbench_init", "lsbench_get_matrix_name", "lsbench_bench", "lsbench_finalize",
               "b200_init", "b200_bench", "b200_finalize"):
         assert hasattr(L, f), f
-    hdr = open(os.path.join(ROOT, "include", "lsbench.h")).read()
-    for name, val in (("CUSOLVER", 0), ("HYPRE", 1), ("AMGX", 2), ("CHOLMOD", 3),
-                      ("PARALMOND", 4), ("GINKGO", 5), ("B200", 6)):
-        assert "LSBENCH_SOLVER_%s = %d" % (name, val) in hdr
+    # the enumerators carry the reference's values (src/lsbench.h:8-29): ask the compiler
+    want = {"LSBENCH_SOLVER_NONE": -1, "LSBENCH_SOLVER_CUSOLVER": 0, "LSBENCH_SOLVER_HYPRE": 1,
+            "LSBENCH_SOLVER_AMGX": 2, "LSBENCH_SOLVER_CHOLMOD": 3, "LSBENCH_SOLVER_PARALMOND": 4,
+            "LSBENCH_SOLVER_GINKGO": 5, "LSBENCH_SOLVER_B200": 6,
+            "LSBENCH_PRECISION_FP64": 0, "LSBENCH_PRECISION_FP32": 1, "LSBENCH_PRECISION_FP16": 2,
+            "LSBENCH_ORDERING_NONE": -1, "LSBENCH_ORDERING_RCM": 0, "LSBENCH_ORDERING_AMD": 1,
+            "LSBENCH_ORDERING_METIS": 2}
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "enums.c")
+        with open(src, "w") as f:
+            f.write('#include "lsbench.h"\n#include <stdio.h>\nint main(void) {\n'
+                    + "".join('  printf("%s %%d\\n", (int)%s);\n' % (k, k) for k in want)
+                    + "  return 0;\n}\n")
+        exe = os.path.join(d, "enums")
+        cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+        subprocess.run([cc, "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
+        out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    got = {l.split()[0]: int(l.split()[1]) for l in out.splitlines()}
+    assert got == want
 
 
 @pytest.mark.parametrize("name", orc.TOY + orc.NEK)
