@@ -43,7 +43,8 @@
 extern "C" {
 #endif
 
-#define B200_ABI_VERSION 1
+/* 2: b200_mat_info grew (index compression), ingest and row-block entry points */
+#define B200_ABI_VERSION 2
 
 enum {
   B200_OK = 0,
