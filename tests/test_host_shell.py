@@ -265,3 +265,50 @@ def test_binary_cache_real_matrix(host, name, tmp_path, monkeypatch):
         L.lsbench_matrix_free(p)
         for k, v in got.items():
             assert READER[name][k] == v, k
+
+
+def _random_coo_text(rng):
+    """a COO file the reference's fscanf grammar accepts (src/lsbench-csr.c:37,50):
+    any white space before a field, the newline right after the value; records in
+    any order, with duplicates and absent row ids"""
+    base = int(rng.integers(0, 2))
+    nrec = int(rng.integers(1, 60))
+    rows = rng.integers(base, base + 12, nrec) * int(rng.integers(1, 4))
+    cols = rng.integers(base, base + 15, nrec)
+    fmts = ["%.17g", "%.6f", "%.3e", "%d", "%+.10e", "%.15f"]
+    out = ["%d %d\n" % (nrec, base)]
+    for r, c in zip(rows, cols):
+        v = float(rng.standard_normal() * 10.0 ** int(rng.integers(-6, 7)))
+        f = fmts[int(rng.integers(0, len(fmts)))]
+        val = f % (int(v) if f == "%d" else v)
+        ws = lambda: rng.choice([" ", "  ", "\t", " \t "])
+        lead = rng.choice(["", "", "", " ", "\n", "\n\n  ", "\t"])
+        out.append("%s%d%s%d%s%s\n" % (lead, r, ws(), c, ws(), val))
+    return "".join(out)
+
+
+def test_reader_fuzz_against_the_reference_and_the_oracle(host, tmp_path):
+    """300 generated files: this tree's reader, the CPU oracle and -- when
+    oracle/_ref is built -- the reference's own reader give the same CSR, bit for
+    bit (duplicates are summed in file order by all three)."""
+    L, _ = host
+    rng = np.random.default_rng(2024)
+    f = str(tmp_path / "fuzz.txt")
+    have_ref = os.path.exists(orc.REF_LIB)
+    for _ in range(300):
+        text = _random_coo_text(rng)
+        with open(f, "w") as g:
+            g.write(text)
+        want = orc.matrix_read(f)
+        assert want is not None, text
+        p = L.lsbench_matrix_read(f.encode())
+        a = p.contents
+        nnz = a.offs[a.nrows]
+        got = (a.nrows, a.base, np.ctypeslib.as_array(a.offs, (a.nrows + 1,)).copy(),
+               np.ctypeslib.as_array(a.cols, (nnz,)).copy(), np.ctypeslib.as_array(a.vals, (nnz,)).copy())
+        L.lsbench_matrix_free(p)
+        refs = [want] + ([orc.ref_matrix_read(f)] if have_ref else [])
+        for w in refs:
+            assert (got[0], got[1]) == (w.nrows, w.base), text
+            assert np.array_equal(got[2], w.offs) and np.array_equal(got[3], w.cols), text
+            assert got[4].tobytes() == w.vals.tobytes(), text
