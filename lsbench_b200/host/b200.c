@@ -20,6 +20,17 @@
  * and one GPU per block (piece 5 of the design); the interface to the harness
  * stays the single synchronous call.
  *
+ * --ordering (the reference honours it only in
+ * src/cusparse.c:66-85): with LSBENCH_B200_ORDERING=cli the harness's
+ * cb->ordering is applied before the conversion, LSBENCH_B200_ORDERING=rcm
+ * forces RCM; the default leaves the file's numbering alone, because the
+ * harness cannot express "none" (calloc zero is RCM, src/lsbench.c:95).  RCM
+ * is implemented below (reverse Cuthill-McKee from a George-Liu
+ * pseudo-peripheral vertex, on the operator that is solved); AMD and METIS
+ * are fill-reducing orderings for a factorisation and do nothing for a
+ * Krylov method's gathers, so they are reported and not applied.  The solve
+ * runs on P A P^T with P b and the caller gets x back in its own numbering.
+ *
  * Differences from the reference backends, on purpose: elapsed is wall time
  * (CLOCK_MONOTONIC) instead of clock() CPU time; extra lines after the CSV row
  * report iterations and residuals; nothing touches CUDA before b200_bench, so
@@ -47,10 +58,11 @@ struct settings {
   int ngpus, device, maxit;
   double tol;
   unsigned flags;
+  int ordering; /* 0 off, 1 take cb->ordering, 2 RCM */
 };
 
 static struct settings read_settings(void) {
-  struct settings s = {1, 0, 10000, 1e-10, B200_MAT_SYM_UPPER};
+  struct settings s = {1, 0, 10000, 1e-10, B200_MAT_SYM_UPPER, 0};
   const char *v;
   if ((v = getenv("LSBENCH_B200_NGPUS")) && atoi(v) > 0)
     s.ngpus = atoi(v);
@@ -64,7 +76,309 @@ static struct settings read_settings(void) {
    * (src/cusparse.c:55-63); the default mirrors the upper triangle. */
   if ((v = getenv("LSBENCH_B200_OPERATOR")) && strcmp(v, "full") == 0)
     s.flags = 0;
+  if ((v = getenv("LSBENCH_B200_ORDERING"))) {
+    if (strcmp(v, "cli") == 0)
+      s.ordering = 1;
+    else if (strcmp(v, "rcm") == 0 || strcmp(v, "RCM") == 0)
+      s.ordering = 2;
+    else if (strcmp(v, "none") != 0 && strcmp(v, "") != 0)
+      errx(EXIT_FAILURE, "b200: LSBENCH_B200_ORDERING=%s (none, cli or rcm)", v);
+  }
   return s;
+}
+
+/* ---- ordering ------------------------------------------------------------
+ * The operator that is solved, as a 0-based host CSR with ascending columns:
+ * the upper triangle mirrored (src/cholmod-impl.h:5-21) or the matrix as
+ * stored.  Built on the host only when an ordering is applied: P A P^T has a
+ * different upper triangle than A, so the mirror has to come first. */
+struct op_csr {
+  unsigned n;
+  unsigned *offs, *cols;
+  double *vals;
+};
+
+static void op_free(struct op_csr *S) {
+  tfree(S->offs), tfree(S->cols), tfree(S->vals);
+  S->offs = S->cols = NULL, S->vals = NULL;
+}
+
+static void op_alloc(struct op_csr *S, unsigned n, size_t nnz) {
+  S->n = n;
+  S->offs = tcalloc(unsigned, (size_t)n + 1);
+  S->cols = tcalloc(unsigned, nnz ? nnz : 1);
+  S->vals = tcalloc(double, nnz ? nnz : 1);
+  if (!S->offs || !S->cols || !S->vals)
+    err(EXIT_FAILURE, "b200: unable to allocate the reordered operator");
+}
+
+/* one row by column: Shell sort (Ciura gaps), a single pass when the row is
+ * already ordered; v may be NULL (adjacency lists) */
+static void row_sort(unsigned *c, double *v, unsigned len) {
+  static const unsigned gaps[] = {1750, 701, 301, 132, 57, 23, 10, 4, 1};
+  unsigned g0 = 1750;
+  while ((unsigned long long)g0 * 9 / 4 < len)
+    g0 = (unsigned)((unsigned long long)g0 * 9 / 4);
+  for (unsigned gi = 0, gap = g0; gap >= 1;) {
+    for (unsigned i = gap; i < len; i++) {
+      unsigned ck = c[i], j = i;
+      double vk = v ? v[i] : 0.0;
+      for (; j >= gap && c[j - gap] > ck; j -= gap) {
+        c[j] = c[j - gap];
+        if (v)
+          v[j] = v[j - gap];
+      }
+      c[j] = ck;
+      if (v)
+        v[j] = vk;
+    }
+    if (gap == 1)
+      break;
+    if (gap > 1750) {
+      gap = (unsigned)((unsigned long long)gap * 4 / 9);
+      if (gap <= 1750)
+        gap = 1750;
+    } else {
+      while (gaps[gi] >= gap)
+        gi++;
+      gap = gaps[gi];
+    }
+  }
+}
+
+static struct op_csr op_build(const struct csr *A, int sym_upper) {
+  const unsigned n = A->nrows, base = A->base;
+  struct op_csr S = {n, NULL, NULL, NULL};
+  unsigned *cnt = tcalloc(unsigned, (size_t)n + 1);
+  if (!cnt)
+    err(EXIT_FAILURE, "b200: unable to allocate the reordered operator");
+  for (unsigned i = 0; i < n; i++)
+    for (unsigned k = A->offs[i]; k < A->offs[i + 1]; k++) {
+      unsigned c = A->cols[k] - base;
+      if (c >= n)
+        errx(EXIT_FAILURE, "b200: column %u of row %u is outside the matrix", c, i);
+      if (!sym_upper)
+        cnt[i]++;
+      else if (c >= i)
+        cnt[i]++, cnt[c] += c > i;
+    }
+  size_t nnz = 0;
+  for (unsigned i = 0; i < n; i++)
+    nnz += cnt[i];
+  if (nnz > 0xffffffffu)
+    errx(EXIT_FAILURE, "b200: the mirrored operator has more than 2^32 entries");
+  op_alloc(&S, n, nnz);
+  for (unsigned i = 0; i < n; i++)
+    S.offs[i + 1] = S.offs[i] + cnt[i], cnt[i] = S.offs[i];
+  for (unsigned i = 0; i < n; i++)
+    for (unsigned k = A->offs[i]; k < A->offs[i + 1]; k++) {
+      unsigned c = A->cols[k] - base;
+      if (sym_upper && c < i)
+        continue;
+      S.cols[cnt[i]] = c, S.vals[cnt[i]++] = A->vals[k];
+      if (sym_upper && c > i)
+        S.cols[cnt[c]] = i, S.vals[cnt[c]++] = A->vals[k];
+    }
+  tfree(cnt);
+  for (unsigned i = 0; i < n; i++)
+    row_sort(S.cols + S.offs[i], S.vals + S.offs[i], S.offs[i + 1] - S.offs[i]);
+  return S;
+}
+
+/* Reverse Cuthill-McKee on the pattern of S + S^T.  perm[new] = old.
+ * Deterministic: every tie is broken by the smaller original index.  One
+ * breadth-first numbering per connected component, started from a
+ * pseudo-peripheral vertex (George & Liu: from the lowest-degree vertex, move
+ * to the lowest-degree vertex of the last level while the level count grows),
+ * neighbours taken in order of increasing degree; the whole order reversed. */
+struct rcm_work {
+  unsigned n;
+  unsigned *aoff, *adj, *deg; /* symmetric pattern without the diagonal */
+  unsigned *level;            /* scratch of the breadth-first passes */
+  unsigned *queue;
+  unsigned stamp;
+};
+
+static const unsigned *rcm_deg;
+static int rcm_by_degree(const void *a, const void *b) {
+  unsigned x = *(const unsigned *)a, y = *(const unsigned *)b;
+  if (rcm_deg[x] != rcm_deg[y])
+    return rcm_deg[x] < rcm_deg[y] ? -1 : 1;
+  return x < y ? -1 : x > y;
+}
+
+/* breadth-first levels of root's component inside `mark` (vertices with
+ * mark[v] == free_mark are free); returns the number of levels, *last_lo the
+ * queue position where the last level starts, *count the component size. */
+static unsigned rcm_levels(struct rcm_work *w, const unsigned *mark, unsigned free_mark,
+                           unsigned root, unsigned *last_lo, unsigned *count) {
+  unsigned st = ++w->stamp, head = 0, tail = 0, levels = 0, lo = 0;
+  w->queue[tail++] = root, w->level[root] = st;
+  while (head < tail) {
+    unsigned end = tail;
+    lo = head, levels++;
+    for (; head < end; head++) {
+      unsigned u = w->queue[head];
+      for (unsigned k = w->aoff[u]; k < w->aoff[u + 1]; k++) {
+        unsigned v = w->adj[k];
+        if (mark[v] == free_mark && w->level[v] != st)
+          w->level[v] = st, w->queue[tail++] = v;
+      }
+    }
+  }
+  *last_lo = lo, *count = tail;
+  return levels;
+}
+
+/* exported (not static) so tests/ can hold them against scipy without a GPU */
+int b200_host_rcm(unsigned n, const unsigned *offs, const unsigned *cols, unsigned *perm);
+struct csr *b200_host_reordered_operator(const struct csr *A, int sym_upper, unsigned *perm);
+
+int b200_host_rcm(unsigned n, const unsigned *offs, const unsigned *cols, unsigned *perm) {
+  if (n == 0)
+    return 0;
+  struct rcm_work w;
+  memset(&w, 0, sizeof w);
+  w.n = n;
+  w.aoff = tcalloc(unsigned, (size_t)n + 1);
+  w.deg = tcalloc(unsigned, n);
+  w.level = tcalloc(unsigned, n);
+  w.queue = tcalloc(unsigned, n);
+  unsigned *mark = tcalloc(unsigned, n); /* 0 free, 1 numbered */
+  if (!w.aoff || !w.deg || !w.level || !w.queue || !mark)
+    return 1;
+  /* pattern of S + S^T without the diagonal: count, fill, sort, unique */
+  for (unsigned i = 0; i < n; i++)
+    for (unsigned k = offs[i]; k < offs[i + 1]; k++)
+      if (cols[k] != i && cols[k] < n)
+        w.aoff[i + 1]++, w.aoff[cols[k] + 1]++;
+  for (unsigned i = 0; i < n; i++)
+    w.aoff[i + 1] += w.aoff[i];
+  w.adj = tcalloc(unsigned, w.aoff[n] ? w.aoff[n] : 1);
+  unsigned *cur = tcalloc(unsigned, n);
+  if (!w.adj || !cur)
+    return 1;
+  for (unsigned i = 0; i < n; i++)
+    cur[i] = w.aoff[i];
+  for (unsigned i = 0; i < n; i++)
+    for (unsigned k = offs[i]; k < offs[i + 1]; k++)
+      if (cols[k] != i && cols[k] < n)
+        w.adj[cur[i]++] = cols[k], w.adj[cur[cols[k]]++] = i;
+  {
+    /* sort each list by index and drop the doubles, compacting in place */
+    unsigned out = 0;
+    for (unsigned i = 0; i < n; i++) {
+      unsigned b = w.aoff[i], e = w.aoff[i + 1], start = out;
+      row_sort(w.adj + b, NULL, e - b);
+      for (unsigned a = b; a < e; a++)
+        if (a == b || w.adj[a] != w.adj[a - 1])
+          w.adj[out++] = w.adj[a];
+      w.aoff[i] = start;
+      w.deg[i] = out - start;
+    }
+    w.aoff[n] = out;
+  }
+  tfree(cur);
+
+  unsigned *byd = tcalloc(unsigned, n);
+  if (!byd)
+    return 1;
+  for (unsigned i = 0; i < n; i++)
+    byd[i] = i;
+  rcm_deg = w.deg;
+  qsort(byd, n, sizeof(unsigned), rcm_by_degree);
+
+  unsigned done = 0;
+  for (unsigned b = 0; b < n; b++) {
+    unsigned root = byd[b];
+    if (mark[root])
+      continue;
+    /* pseudo-peripheral vertex of root's component */
+    unsigned lo, cnt, levels = rcm_levels(&w, mark, 0, root, &lo, &cnt);
+    for (;;) {
+      unsigned cand = w.queue[lo];
+      for (unsigned k = lo + 1; k < cnt; k++) {
+        unsigned v = w.queue[k];
+        if (w.deg[v] < w.deg[cand] || (w.deg[v] == w.deg[cand] && v < cand))
+          cand = v;
+      }
+      unsigned lo2, cnt2, l2 = rcm_levels(&w, mark, 0, cand, &lo2, &cnt2);
+      if (l2 <= levels)
+        break;
+      root = cand, levels = l2, lo = lo2, cnt = cnt2;
+      /* queue now holds cand's levels: lo, cnt describe them */
+    }
+    /* Cuthill-McKee numbering from root */
+    unsigned head = done, tail = done;
+    perm[tail++] = root, mark[root] = 1;
+    while (head < tail) {
+      unsigned u = perm[head++], first = tail;
+      for (unsigned k = w.aoff[u]; k < w.aoff[u + 1]; k++) {
+        unsigned v = w.adj[k];
+        if (!mark[v])
+          mark[v] = 1, perm[tail++] = v;
+      }
+      if (tail - first > 1)
+        qsort(perm + first, tail - first, sizeof(unsigned), rcm_by_degree);
+    }
+    done = tail;
+  }
+  for (unsigned i = 0, j = n - 1; i < j; i++, j--) {
+    unsigned t = perm[i];
+    perm[i] = perm[j], perm[j] = t;
+  }
+  tfree(w.aoff), tfree(w.adj), tfree(w.deg), tfree(w.level), tfree(w.queue);
+  tfree(mark), tfree(byd);
+  return 0;
+}
+
+/* B = P S P^T with perm[new] = old, columns ascending inside every row */
+static struct op_csr op_permute(const struct op_csr *S, const unsigned *perm) {
+  const unsigned n = S->n;
+  struct op_csr B = {n, NULL, NULL, NULL};
+  unsigned *inv = tcalloc(unsigned, n ? n : 1);
+  if (!inv)
+    err(EXIT_FAILURE, "b200: unable to allocate the reordered operator");
+  for (unsigned i = 0; i < n; i++)
+    inv[perm[i]] = i;
+  op_alloc(&B, n, S->offs[n]);
+  for (unsigned i = 0; i < n; i++) {
+    unsigned o = perm[i], len = S->offs[o + 1] - S->offs[o];
+    B.offs[i + 1] = B.offs[i] + len;
+    for (unsigned k = 0; k < len; k++) {
+      B.cols[B.offs[i] + k] = inv[S->cols[S->offs[o] + k]];
+      B.vals[B.offs[i] + k] = S->vals[S->offs[o] + k];
+    }
+    row_sort(B.cols + B.offs[i], B.vals + B.offs[i], len);
+  }
+  tfree(inv);
+  return B;
+}
+
+static unsigned op_bandwidth(unsigned n, const unsigned *offs, const unsigned *cols) {
+  unsigned bw = 0;
+  for (unsigned i = 0; i < n; i++)
+    for (unsigned k = offs[i]; k < offs[i + 1]; k++) {
+      unsigned d = cols[k] > i ? cols[k] - i : i - cols[k];
+      bw = d > bw ? d : bw;
+    }
+  return bw;
+}
+
+/* The operator that is solved (mirrored upper triangle, or A as stored), RCM
+ * ordered: a 0-based `struct csr` the caller frees with lsbench_matrix_free,
+ * perm[new] = old (n entries, caller-owned). */
+struct csr *b200_host_reordered_operator(const struct csr *A, int sym_upper, unsigned *perm) {
+  struct op_csr S = op_build(A, sym_upper);
+  if (b200_host_rcm(A->nrows, S.offs, S.cols, perm) != 0)
+    err(EXIT_FAILURE, "b200: RCM ordering");
+  struct op_csr B = op_permute(&S, perm);
+  op_free(&S);
+  struct csr *R = tcalloc(struct csr, 1);
+  if (!R)
+    err(EXIT_FAILURE, "b200: unable to allocate the reordered operator");
+  R->nrows = A->nrows, R->base = 0, R->offs = B.offs, R->cols = B.cols, R->vals = B.vals;
+  return R;
 }
 
 struct shared {
@@ -190,6 +504,36 @@ int b200_bench(double *x, struct csr *A, const double *r,
   memset(&sh, 0, sizeof sh);
   sh.cfg = read_settings();
   sh.A = A, sh.r = r, sh.x = x, sh.cb = cb;
+
+  /* --ordering: solve P A P^T (P x) = P b, hand x back in the caller's order */
+  unsigned *perm = NULL;
+  struct csr *Ap = NULL;
+  double *rp = NULL, *xp = NULL;
+  int want = sh.cfg.ordering == 2   ? (int)LSBENCH_ORDERING_RCM
+             : sh.cfg.ordering == 1 ? (int)cb->ordering
+                                    : (int)LSBENCH_ORDERING_NONE;
+  if (want != LSBENCH_ORDERING_NONE && A->offs == NULL) {
+    warnx("b200: generated operators keep their natural ordering");
+    want = LSBENCH_ORDERING_NONE;
+  }
+  if (want == LSBENCH_ORDERING_AMD || want == LSBENCH_ORDERING_METIS) {
+    warnx("b200: ordering %s reduces the fill of a factorisation; a Krylov "
+          "solve has none, not applied", want == LSBENCH_ORDERING_AMD ? "AMD" : "METIS");
+    want = LSBENCH_ORDERING_NONE;
+  }
+  if (want == LSBENCH_ORDERING_RCM) {
+    const unsigned n = A->nrows;
+    perm = tcalloc(unsigned, n ? n : 1);
+    rp = tcalloc(double, n ? n : 1), xp = tcalloc(double, n ? n : 1);
+    if (!perm || !rp || !xp)
+      err(EXIT_FAILURE, "b200: unable to allocate the reordered vectors");
+    Ap = b200_host_reordered_operator(A, (sh.cfg.flags & B200_MAT_SYM_UPPER) != 0, perm);
+    for (unsigned i = 0; i < n; i++)
+      rp[i] = r[perm[i]];
+    sh.A = Ap, sh.r = rp, sh.x = xp;
+    sh.cfg.flags &= ~(unsigned)B200_MAT_SYM_UPPER; /* already mirrored */
+  }
+
   int ndev = 0;
   chk_b200(b200_device_count(&ndev));
   if (sh.cfg.device + sh.cfg.ngpus > ndev)
@@ -213,6 +557,11 @@ int b200_bench(double *x, struct csr *A, const double *r,
   tfree(w), tfree(th);
   pthread_barrier_destroy(&sh.bar);
   pthread_mutex_destroy(&sh.lock);
+  if (perm) {
+    for (unsigned i = 0; i < A->nrows; i++)
+      x[perm[i]] = xp[i];
+    tfree(rp), tfree(xp);
+  }
 
   /* nnz as the other backends print it: stored entries of the input CSR
    * (src/cusparse.c:169); for a generated matrix, the generated count */
@@ -242,7 +591,17 @@ int b200_bench(double *x, struct csr *A, const double *r,
            (unsigned long long)sh.info.long_rows,
            (unsigned long long)sh.info.nnz_padded,
            (double)sh.info.device_bytes / 1e6);
+    if (perm) {
+      struct op_csr S = op_build(A, (read_settings().flags & B200_MAT_SYM_UPPER) != 0);
+      printf("b200: ordering=rcm bandwidth %u -> %u\n",
+             op_bandwidth(S.n, S.offs, S.cols),
+             op_bandwidth(Ap->nrows, Ap->offs, Ap->cols));
+      op_free(&S);
+    }
   }
+  if (Ap)
+    lsbench_matrix_free(Ap);
+  tfree(perm);
   fflush(stdout);
   return 0;
 }

@@ -100,3 +100,29 @@ def test_driver_synthetic_and_multi_gpu(bh, tmp_path):
         assert int(ext2[0]) == 2 and int(ext2[2]) == 0 and row2[2] == row[2]
         x2 = np.fromfile(out)
         assert np.linalg.norm(x2 - x1) / np.linalg.norm(x1) <= 1e-9
+
+
+@pytest.mark.parametrize("name,env", [("xn3b_A_10", {"LSBENCH_B200_ORDERING": "rcm"}),
+                                      ("xn3b_A_18", {"LSBENCH_B200_ORDERING": "cli"}),
+                                      ("tj7a_A_18", {"LSBENCH_B200_ORDERING": "rcm", "LSBENCH_B200_OPERATOR": "full"})])
+def test_driver_applies_the_ordering(bh, name, env, tmp_path):
+    """with LSBENCH_B200_ORDERING the solve runs on P A P^T (RCM
+    computed on the host, src/cusparse.c:66-85 being the reference's precedent) and
+    x comes back in the caller's numbering: same answer as without, to the bar"""
+    A = orc.matrix_read(orc.matrix_path(name))
+    out = str(tmp_path / "x.bin")
+    r = subprocess.run([bh.DRIVER, "--solver", "b200", "--matrix", orc.matrix_path(name),
+                        "--trials=2", "--verbose=1", "--ordering=RCM", "--dump-x", out],
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ, **env))
+    assert r.returncode == 0, r.stderr
+    row, ext = parse(r.stdout)
+    assert row[1:6] == [str(A.nrows), str(A.nnz), "2", "6", "0"]
+    assert int(ext[2]) == 0 and float(ext[4]) <= 1.05e-10
+    assert "b200: ordering=rcm bandwidth" in r.stdout
+    x = np.fromfile(out)
+    full = env.get("LSBENCH_B200_OPERATOR") == "full"
+    M = orc.op_full(A) if full else orc.op_upper_mirror(A)
+    assert orc.true_relres(M, orc.rhs(M.n), x) <= 1.05e-10
+    if not full:
+        g = DIRECT[name]
+        assert np.linalg.norm(x - g) / np.linalg.norm(g) <= 1e-8

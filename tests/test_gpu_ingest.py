@@ -227,3 +227,38 @@ def test_text_extra_lines_after_the_records_are_ignored(abi, ctx):
     nr, offs, cols, vals, nhost = abi.text_to_csr(ctx, b"3 1 4\n1 2 -0.5\n1 2 1e-3\ngarbage\n", 3)
     assert (nr, offs.tolist(), cols.tolist()) == (2, [0, 1, 2], [2, 1])
     assert vals.tolist() == [-0.5 + 1e-3, 4.0]
+
+
+def test_harness_reader_fuzz_with_device_ingest(tmp_path, monkeypatch):
+    """generated files, strict (one record per line -> parsed on the device) and
+    loose (white space the fscanf grammar allows -> refused by the device parser,
+    tokenised on the host, sorted / folded on the device): the harness reader with
+    LSBENCH_B200_INGEST=1 returns the oracle reader's CSR bit for bit"""
+    import ctypes as C
+    from lsbench_b200 import build_host
+    from test_host_shell import Csr, _random_coo_text
+    build_host.build()
+    L = C.CDLL(build_host.LIB)
+    L.lsbench_matrix_read.restype = C.POINTER(Csr)
+    L.lsbench_matrix_read.argtypes = [C.c_char_p]
+    L.lsbench_matrix_free.argtypes = [C.POINTER(Csr)]
+    monkeypatch.setenv("LSBENCH_B200_INGEST", "1")
+    rng = np.random.default_rng(99)
+    f = str(tmp_path / "fuzz.txt")
+    for k in range(80):
+        text = _random_coo_text(rng)
+        if k % 2 == 0:   # make it strict: one record per line, single blanks
+            head, *recs = [l for l in text.split("\n") if l.strip()]
+            text = head + "\n" + "".join(" ".join(r.split()) + "\n" for r in recs)
+        with open(f, "w") as g:
+            g.write(text)
+        want = orc.matrix_read(f)
+        p = L.lsbench_matrix_read(f.encode())
+        a = p.contents
+        nnz = a.offs[a.nrows]
+        got = (a.nrows, np.ctypeslib.as_array(a.offs, (a.nrows + 1,)).copy(),
+               np.ctypeslib.as_array(a.cols, (nnz,)).copy(), np.ctypeslib.as_array(a.vals, (nnz,)).copy())
+        base = int(a.base)
+        L.lsbench_matrix_free(p)
+        assert base == want.base
+        assert_same_csr(got, want)

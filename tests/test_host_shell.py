@@ -312,3 +312,97 @@ def test_reader_fuzz_against_the_reference_and_the_oracle(host, tmp_path):
             assert (got[0], got[1]) == (w.nrows, w.base), text
             assert np.array_equal(got[2], w.offs) and np.array_equal(got[3], w.cols), text
             assert got[4].tobytes() == w.vals.tobytes(), text
+
+
+# ---- --ordering: host-side RCM, no GPU needed ---------------------
+
+def _order_fns(L):
+    L.b200_host_rcm.restype = C.c_int
+    L.b200_host_rcm.argtypes = [C.c_uint, C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
+    L.b200_host_reordered_operator.restype = C.POINTER(Csr)
+    L.b200_host_reordered_operator.argtypes = [C.POINTER(Csr), C.c_int, C.POINTER(C.c_uint)]
+
+
+def _bandwidth(S):
+    S = S.tocoo()
+    return int(np.abs(S.row.astype(np.int64) - S.col).max()) if S.nnz else 0
+
+
+def _rcm(L, S):
+    S = S.tocsr()
+    S.sort_indices()
+    offs = np.ascontiguousarray(S.indptr, dtype=np.uint32)
+    cols = np.ascontiguousarray(S.indices, dtype=np.uint32)
+    perm = np.zeros(max(S.shape[0], 1), dtype=np.uint32)
+    p = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint))
+    assert L.b200_host_rcm(S.shape[0], p(offs), p(cols), p(perm)) == 0
+    return perm[:S.shape[0]]
+
+
+@pytest.mark.parametrize("name", ["tj7a_A_12", "tj7a_A_15", "tj7a_A_18", "xn3b_A_10", "xn3b_A_12",
+                                  "xn3b_A_15", "xn3b_A_18"])
+def test_rcm_is_a_permutation_and_as_narrow_as_scipy(host, name):
+    """RCM of the operator that is solved: a permutation, deterministic, and a
+    bandwidth comparable with scipy's reverse_cuthill_mckee (measured here, file
+    numbering -> this code / scipy: xn3b_A_10 2343 -> 1053 / 1053, xn3b_A_12
+    1975 -> 961 / 724, xn3b_A_18 2123 -> 568 / 772; the tj7a files are already
+    numbered better than either, 277 -> 443 / 444)"""
+    from scipy.sparse.csgraph import reverse_cuthill_mckee
+    L, _ = host
+    _order_fns(L)
+    S = orc.op_upper_mirror(orc.matrix_read(orc.matrix_path(name))).scipy()
+    perm = _rcm(L, S)
+    assert np.array_equal(np.sort(perm), np.arange(S.shape[0]))
+    assert np.array_equal(perm, _rcm(L, S))
+    mine = _bandwidth(S[perm][:, perm])
+    sp = reverse_cuthill_mckee(S.tocsr(), symmetric_mode=True)
+    theirs = _bandwidth(S[sp][:, sp])
+    assert mine <= 1.4 * theirs, (mine, theirs, _bandwidth(S))
+    if name.startswith("xn3b"):
+        assert mine < 0.5 * _bandwidth(S)
+
+
+def test_rcm_edge_shapes(host):
+    """one row; a diagonal matrix (n components); two components; an
+    unsymmetric pattern (ordered on S + S^T); a path numbered at random comes
+    back with bandwidth 1"""
+    import scipy.sparse as sp
+    L, _ = host
+    _order_fns(L)
+    assert _rcm(L, sp.identity(1, format="csr")).tolist() == [0]
+    assert np.array_equal(np.sort(_rcm(L, sp.identity(7, format="csr"))), np.arange(7))
+    two = sp.block_diag([sp.diags([1.0, 1.0], [0, 1], shape=(4, 4)), sp.diags([1.0, 1.0], [0, 1], shape=(3, 3))]).tocsr()
+    p = _rcm(L, two)
+    assert np.array_equal(np.sort(p), np.arange(7)) and _bandwidth((two + two.T).tocsr()[p][:, p]) == 1
+    rng = np.random.default_rng(5)
+    n = 200
+    q = rng.permutation(n)
+    path = sp.diags([1.0, 2.0], [-1, 0], shape=(n, n)).tocsr()[q][:, q]   # lower bidiagonal, shuffled
+    p = _rcm(L, path)
+    assert _bandwidth(path[p][:, p]) == 1
+
+
+@pytest.mark.parametrize("name,sym", [("xn3b_A_15", 1), ("xn3b_A_15", 0), ("I1_05x05", 1), ("A1_02x02", 0)])
+def test_reordered_operator_is_P_S_Pt(host, name, sym):
+    """what b200_bench hands to the conversion under an ordering: the operator
+    that is solved (upper triangle mirrored like src/cholmod-impl.h:5-21, or the
+    matrix as stored) with rows and columns renumbered, values bit for bit,
+    columns ascending"""
+    L, _ = host
+    _order_fns(L)
+    A = orc.matrix_read(orc.matrix_path(name))
+    S = (orc.op_upper_mirror(A) if sym else orc.op_full(A)).scipy().tocsr()
+    a = L.lsbench_matrix_read(orc.matrix_path(name).encode())
+    perm = np.zeros(A.nrows, dtype=np.uint32)
+    b = L.b200_host_reordered_operator(a, sym, perm.ctypes.data_as(C.POINTER(C.c_uint)))
+    B = b.contents
+    n, nnz = B.nrows, B.offs[B.nrows]
+    got = (int(B.base), np.ctypeslib.as_array(B.offs, (n + 1,)).copy(),
+           np.ctypeslib.as_array(B.cols, (nnz,)).copy(), np.ctypeslib.as_array(B.vals, (nnz,)).copy())
+    L.lsbench_matrix_free(b)
+    L.lsbench_matrix_free(a)
+    assert np.array_equal(np.sort(perm), np.arange(n))
+    want = S[perm][:, perm].tocsr()
+    want.sort_indices()
+    assert got[0] == 0 and np.array_equal(got[1], want.indptr) and np.array_equal(got[2], want.indices)
+    assert got[3].tobytes() == want.data.tobytes()
