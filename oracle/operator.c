@@ -14,6 +14,18 @@
  *
  * orc_op_full restates what the other backends are handed (cols - base, all
  * stored entries): src/cusparse.c:55-63, src/amgx.c:41.
+ *
+ * orc_op_perm_lower_mirror restates what the reference's cuSOLVER backend
+ * actually solves, src/cusparse.c:66-99 + :181-197: the matrix is renumbered
+ * with the ordering Q (B = Q A Q^T, :66-99) and handed to
+ * cusolverSpDcsrlsvchol, a Cholesky solver that reads ONE triangle of what it
+ * is given -- the lower one of B.  On a file that is not exactly symmetric
+ * that is a_ij = a_ji = the file value at (i, j) where i is the vertex
+ * numbered LATER by Q: an operator that depends on the ordering.  Pinned by
+ * the reference's own output: tests/golden/cusolver_x.npz holds the x its
+ * cusparse_bench returned on a B200 and the Q cuSOLVER produced, and the
+ * direct solve of this operator reproduces that x to 1e-13 (the upper-mirror
+ * and as-stored operators are 1e-6 ... 3e-5 away).
  */
 #include "oracle.h"
 #include <stdlib.h>
@@ -91,6 +103,55 @@ orc_op *orc_op_upper_mirror(const orc_csr *A) {
     }
   }
   free(fill), free(cnt), free(ustart);
+  return M;
+}
+
+/* q[new] = old, as cusolverSpXcsrsym*Host return it (src/cusparse.c:66-85).
+ * The result is in the caller's numbering. */
+orc_op *orc_op_perm_lower_mirror(const orc_csr *A, const int32_t *q) {
+  uint64_t n = A->nrows;
+  uint32_t *pos = (uint32_t *)malloc((n ? n : 1) * sizeof(uint32_t));
+  uint64_t *cnt = (uint64_t *)calloc(n + 1, sizeof(uint64_t));
+  for (uint64_t i = 0; i < n; i++)
+    pos[q[i]] = (uint32_t)i;
+  /* entry (i, c) is read iff it lies in the lower triangle of B: pos[i] >= pos[c] */
+  for (uint64_t i = 0; i < n; i++)
+    for (uint32_t j = A->offs[i]; j < A->offs[i + 1]; j++) {
+      uint64_t c = A->cols[j] - A->base;
+      if (c < n && pos[i] >= pos[c]) {
+        cnt[i]++;
+        if (c != i)
+          cnt[c]++;
+      }
+    }
+  uint64_t nnz = 0;
+  for (uint64_t i = 0; i < n; i++)
+    nnz += cnt[i];
+  orc_op *M = op_alloc(n, nnz);
+  for (uint64_t i = 0; i < n; i++)
+    M->offs[i + 1] = M->offs[i] + cnt[i];
+  uint64_t *fill = (uint64_t *)malloc((n + 1) * sizeof(uint64_t));
+  memcpy(fill, M->offs, (n + 1) * sizeof(uint64_t));
+  for (uint64_t i = 0; i < n; i++)
+    for (uint32_t j = A->offs[i]; j < A->offs[i + 1]; j++) {
+      uint64_t c = A->cols[j] - A->base;
+      if (c < n && pos[i] >= pos[c]) {
+        M->cols[fill[i]] = (uint32_t)c, M->vals[fill[i]++] = A->vals[j];
+        if (c != i)
+          M->cols[fill[c]] = (uint32_t)i, M->vals[fill[c]++] = A->vals[j];
+      }
+    }
+  /* rows in ascending column order (insertion sort: rows are short) */
+  for (uint64_t i = 0; i < n; i++)
+    for (uint64_t a = M->offs[i] + 1; a < M->offs[i + 1]; a++) {
+      uint32_t ck = M->cols[a];
+      double vk = M->vals[a];
+      uint64_t b = a;
+      for (; b > M->offs[i] && M->cols[b - 1] > ck; b--)
+        M->cols[b] = M->cols[b - 1], M->vals[b] = M->vals[b - 1];
+      M->cols[b] = ck, M->vals[b] = vk;
+    }
+  free(fill), free(cnt), free(pos);
   return M;
 }
 

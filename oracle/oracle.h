@@ -54,6 +54,8 @@ void orc_matrix_free(orc_csr *A);
 orc_op *orc_op_upper_mirror(const orc_csr *A);
 /* As stored (what cusolver / ginkgo / amgx are handed): cols - base. */
 orc_op *orc_op_full(const orc_csr *A);
+/* what src/cusparse.c solves: lower triangle of Q A Q^T mirrored; q[new] = old */
+orc_op *orc_op_perm_lower_mirror(const orc_csr *A, const int32_t *q);
 void orc_op_free(orc_op *M);
 uint64_t orc_op_nnz(const orc_op *M);
 

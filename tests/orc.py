@@ -57,6 +57,8 @@ def lib():
         for f in ("orc_op_upper_mirror", "orc_op_full"):
             getattr(L, f).restype = C.POINTER(_Op)
             getattr(L, f).argtypes = [C.POINTER(_Csr)]
+        L.orc_op_perm_lower_mirror.restype = C.POINTER(_Op)
+        L.orc_op_perm_lower_mirror.argtypes = [C.POINTER(_Csr), C.POINTER(C.c_int32)]
         L.orc_op_free.argtypes = [C.POINTER(_Op)]
         L.orc_spmv.argtypes = [C.POINTER(_Op)] + [C.c_void_p] * 3
         L.orc_spmv_omp.argtypes = [C.POINTER(_Op)] + [C.c_void_p] * 2
@@ -215,6 +217,13 @@ def op_upper_mirror(A):
 def op_full(A):
     s = A.as_struct()
     return _take_op(lib().orc_op_full(C.byref(s)))
+
+
+def op_perm_lower_mirror(A, q):
+    """the operator the reference's cuSOLVER backend solves (oracle/operator.c)"""
+    s = A.as_struct()
+    q = np.ascontiguousarray(q, dtype=np.int32)
+    return _take_op(lib().orc_op_perm_lower_mirror(C.byref(s), q.ctypes.data_as(C.POINTER(C.c_int32))))
 
 
 def rhs(n):

@@ -153,6 +153,49 @@ def test_direct_and_pcg_against_superlu(name):
     assert np.linalg.norm(xp - xg) / np.linalg.norm(xg) < 1e-8  # the parity bar
 
 
+CUSOLVER = np.load(os.path.join(GOLD, "cusolver_x.npz"))
+
+
+@pytest.mark.parametrize("name", orc.NEK + ["I1_05x05"])
+def test_oracle_against_the_references_own_cusolver_output(name):
+    """tests/golden/cusolver_x.npz: x as the reference's `--solver cusolver`
+    backend (src/cusparse.c, compiled from the reference's sources, run on a B200
+    by tests/golden/make_cusolver_golden.py) returned it, and the RCM permutation
+    cuSOLVER produced for it.  The oracle's operator restatement for that backend
+    (lower triangle of Q A Q^T mirrored, oracle/operator.c) + the oracle's direct
+    solve reproduce that x to 1e-11, the oracle's PCG to the 1e-8 parity bar; the
+    CHOLMOD operator and the matrix as stored are a measurably different problem
+    (the reference's two direct backends do not solve the same system)."""
+    A = orc.matrix_read(orc.matrix_path(name))
+    xref, q = CUSOLVER[name], CUSOLVER[name + "__rcm"]
+    assert np.array_equal(np.sort(q), np.arange(A.nrows))
+    M = orc.op_perm_lower_mirror(A, q)
+    S = M.scipy()
+    assert abs(S - S.T).max() == 0.0
+    b = orc.rhs(M.n)
+    F = orc.Ldlt(M, 1)
+    assert F.spd
+    x = F.solve(b)
+    assert np.linalg.norm(x - xref) / np.linalg.norm(xref) < 1e-11
+    assert orc.true_relres(M, b, xref) < 1e-11          # the reference's x solves THIS operator
+    xp, it, rel, rc = orc.pcg(M, b, tol=1e-10)
+    assert rc == 0 and np.linalg.norm(xp - xref) / np.linalg.norm(xref) < 1e-8
+    if name != "I1_05x05":
+        for other in (orc.op_upper_mirror(A), orc.op_full(A)):
+            assert orc.true_relres(other, b, xref) > 1e-7
+        assert np.linalg.norm(DIRECT[name] - xref) / np.linalg.norm(xref) > 1e-7
+
+
+def test_perm_lower_mirror_picks_the_later_numbered_vertex(tmp_path):
+    """2x2, a_01 = 3, a_10 = 7: with the identity ordering the lower triangle
+    (7) is read, with the reversed ordering the upper one (3)"""
+    f = tmp_path / "m.txt"
+    f.write_text("4 0\n0 0 4\n0 1 3\n1 0 7\n1 1 5\n")
+    A = orc.matrix_read(str(f))
+    assert orc.op_perm_lower_mirror(A, [0, 1]).scipy().toarray().tolist() == [[4, 7], [7, 5]]
+    assert orc.op_perm_lower_mirror(A, [1, 0]).scipy().toarray().tolist() == [[4, 3], [3, 5]]
+
+
 def test_full_operator_is_a_different_problem():
     # SURVEY 0: solving the as-stored (value-asymmetric) matrix moves x by ~1e-7,
     # i.e. outside the 1e-8 bar -- the reason the operator must be the mirror.
