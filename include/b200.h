@@ -43,8 +43,9 @@
 extern "C" {
 #endif
 
-/* 2: b200_mat_info grew (index compression), ingest and row-block entry points */
-#define B200_ABI_VERSION 2
+/* 2: b200_mat_info grew (index compression), ingest and row-block entry points
+ * 3: b200_mat_info.values_f32, b200_pcg_result.outer_iters, new flags */
+#define B200_ABI_VERSION 3
 
 enum {
   B200_OK = 0,
@@ -100,7 +101,14 @@ enum {
   B200_MAT_FORCE_VECTOR = 1u << 1, /* kernel sweep: no SELL bin */
   B200_MAT_FORCE_SELL = 1u << 2,   /* kernel sweep: everything in SELL */
   B200_MAT_NO_SORT = 1u << 3,      /* SELL without the length-sort window */
-  B200_MAT_NO_COMPRESS = 1u << 4   /* keep one explicit u32 column per entry */
+  B200_MAT_NO_COMPRESS = 1u << 4,  /* keep one explicit u32 column per entry */
+  /* SURVEY 8f row 4 (--precision FP32): store the SELL values as fp32.  If every
+   * value is exactly representable (any stencil) that is lossless: the fp64
+   * copy is dropped, products and PCG iterates keep their bits, the value
+   * stream halves.  Otherwise both copies stay resident and b200_pcg_solve
+   * runs iterative refinement: inner PCG on the fp32-valued operator (fp64
+   * vectors), residual b - A x with the fp64 values, to the same fp64 bar. */
+  B200_MAT_VALUES_F32 = 1u << 5
 };
 
 /* Host CSR exactly as lsbench_matrix_read leaves it: offs 0-based, cols
@@ -169,6 +177,10 @@ typedef struct {
    * permutation) one SpMV actually reads -- compare with 12 nnz + 4 (n+1) */
   uint64_t sell_uniform_slices;
   uint64_t matrix_stream_bytes;
+  /* B200_MAT_VALUES_F32: 0 off, 1 lossless (fp64 copy dropped), 2 rounded
+   * (both copies resident, PCG = iterative refinement) */
+  uint32_t values_f32;
+  uint32_t reserved0;
 } b200_mat_info;
 int b200_mat_get_info(const b200_mat *M, b200_mat_info *info);
 
@@ -202,7 +214,11 @@ typedef struct {
 enum {
   B200_PCG_TIME_KERNELS = 1u << 0, /* per-class CUDA-event timing */
   B200_PCG_NO_GRAPH = 1u << 1,
-  B200_PCG_NO_SMALL = 1u << 2      /* never take the on-chip small-matrix path */
+  B200_PCG_NO_SMALL = 1u << 2,     /* never take the on-chip small-matrix path */
+  /* Chronopoulos-Gear CG -- both dot products of an iteration
+   * in one place (one reduction / one all-reduce point per iteration), two
+   * kernels per iteration instead of three, same HBM bytes.  Streaming path. */
+  B200_PCG_SINGLE_REDUCTION = 1u << 3
 };
 
 typedef struct {
@@ -215,6 +231,8 @@ typedef struct {
   float spmv_ms, update_ms, pupdate_ms; /* B200_PCG_TIME_KERNELS only */
   int32_t kernel_launches;
   int32_t path;        /* 0 = streaming kernels, 1 = on-chip small-matrix */
+  int32_t outer_iters; /* refinement passes (values_f32 == 2), else 0 */
+  int32_t reserved0;
 } b200_pcg_result;
 
 /* x: in x0, out solution (n_local).  b: n_local.  Device pointers. */

@@ -20,12 +20,14 @@ MAT_FORCE_VECTOR = 1 << 1
 MAT_FORCE_SELL = 1 << 2
 MAT_NO_SORT = 1 << 3
 MAT_NO_COMPRESS = 1 << 4
+MAT_VALUES_F32 = 1 << 5
 
 GEN_POISSON7, GEN_POISSON27, GEN_POWERLAW = 1, 2, 3
 
 PCG_TIME_KERNELS = 1 << 0
 PCG_NO_GRAPH = 1 << 1
 PCG_NO_SMALL = 1 << 2
+PCG_SINGLE_REDUCTION = 1 << 3
 
 # every symbol include/b200.h declares (tests check the library exports them)
 SYMBOLS = [
@@ -58,7 +60,7 @@ class MatInfo(C.Structure):
         ("hist", C.c_uint64 * HIST_BINS), ("max_row_len", C.c_uint64),
         ("pattern_symmetric", C.c_uint32), ("sell_perm", C.c_uint32),
         ("device_bytes", C.c_uint64), ("sell_uniform_slices", C.c_uint64),
-        ("matrix_stream_bytes", C.c_uint64)]
+        ("matrix_stream_bytes", C.c_uint64), ("values_f32", C.c_uint32), ("reserved0", C.c_uint32)]
 
 
 class PcgOpts(C.Structure):
@@ -72,7 +74,7 @@ class PcgResult(C.Structure):
                 ("bnorm", C.c_double), ("solve_ms", C.c_float),
                 ("spmv_ms", C.c_float), ("update_ms", C.c_float),
                 ("pupdate_ms", C.c_float), ("kernel_launches", C.c_int32),
-                ("path", C.c_int32)]
+                ("path", C.c_int32), ("outer_iters", C.c_int32), ("reserved0", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

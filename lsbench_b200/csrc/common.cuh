@@ -121,6 +121,10 @@ struct PcgState {
   double true_rr;
   int iter, done, status, maxit;
   unsigned ticket[4];
+  // single-reduction CG (pcg.cu k_sr_update): alpha of the iteration by parity,
+  // iterations finished before the chunk being replayed / after it
+  double sr_alpha[2];
+  int sr_base, sr_next;
 };
 
 struct b200_mat {
@@ -132,6 +136,14 @@ struct b200_mat {
   uint32_t *sell_off = nullptr;   // sell_slices+1, in units of 32 entries
   uint32_t *sell_cols = nullptr;
   double *sell_vals = nullptr;
+  // B200_MAT_VALUES_F32: the SELL values as fp32 in the same layout.  When
+  // every value survived the rounding (vals32_exact) the fp64 stream is freed
+  // and all products read this one -- same fp64 arithmetic, same bits, half the
+  // value bytes; otherwise both stay and the PCG runs as iterative refinement
+  // (inner iterations on the fp32-valued operator, residuals on the fp64 one).
+  float *sell_vals32 = nullptr;
+  bool vals32_exact = false;
+  bool spmv_use32 = false;        // which value stream launch_spmv multiplies with
   uint32_t *sell_perm = nullptr;  // nullptr == identity (row = 32 s + lane)
   // index compression (nullptr == off): sell_meta[s] = {o, w | uniform << 31,
   // column offset, 0} (uint4 per slice), the deltas of the uniform slices;
@@ -159,6 +171,8 @@ struct b200_mat {
   // --- solver workspace (lazily allocated) ----------------------------------
   double *w_r = nullptr, *w_p = nullptr, *w_q = nullptr;  // p has halo room
   double *w_x = nullptr;          // iterate (graph-stable pointer)
+  double *w_pp = nullptr, *w_s = nullptr;   // single-reduction CG: p and s = A p
+  double *w_d = nullptr, *w_rhs = nullptr;  // refinement: correction and residual
   double *stage_b = nullptr, *stage_x = nullptr;  // b200_pcg_solve_host staging
   int grid_ew = 0;                // element-wise kernels
   unsigned partial_stride = 0;
@@ -173,6 +187,7 @@ struct b200_mat {
   int graph_chunk = 0;
   int graph_kernels = 0;         // kernel nodes in the captured chunk
   void *graph_stream = nullptr;
+  bool graph_sr = false;         // the chunk was captured in the single-reduction form
 };
 
 // ---- helpers implemented across the .cu files --------------------------------
@@ -352,6 +367,9 @@ __device__ __forceinline__ double ld_stream(const double *p) {
   return __ldcs(p);
 }
 __device__ __forceinline__ uint32_t ld_stream(const uint32_t *p) {
+  return __ldcs(p);
+}
+__device__ __forceinline__ float ld_stream(const float *p) {
   return __ldcs(p);
 }
 #endif

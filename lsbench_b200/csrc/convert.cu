@@ -465,6 +465,22 @@ __global__ void k_inv_diag(uint64_t n, const uint64_t *offs,
   dinv[i] = d != 0.0 ? 1.0 / d : 1.0;
 }
 
+// B200_MAT_VALUES_F32: the SELL value stream rounded to fp32; *inexact is set
+// when some value did not survive the rounding (NaN counts as not surviving)
+__global__ void k_vals_to_f32(const double *__restrict__ v, float *__restrict__ o,
+                              uint64_t n, unsigned *inexact) {
+  bool bad = false;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const double d = v[i];
+    const float f = (float)d;
+    o[i] = f;
+    bad |= !((double)f == d);
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0)
+    atomicOr(inexact, 1u);
+}
+
 int build_layout(b200_ctx *c, PlainCsr *A, uint64_t n_global,
                  uint64_t row_begin, uint32_t flags, b200_mat **out) {
   // NOTE: *out may already carry halo / partition fields; create if null.
@@ -654,6 +670,27 @@ int build_layout(b200_ctx *c, PlainCsr *A, uint64_t n_global,
       M->device_bytes += (sell_padded_rows + 1) * 4;
       ids[0] = nullptr;
     }
+    // ---- fp32 value stream ------------------------------------
+    if ((flags & B200_MAT_VALUES_F32) && padded) {
+      unsigned *d_bad, h_bad = 0;
+      CU_TRY(cudaMalloc(&d_bad, 4));
+      CU_TRY(cudaMemsetAsync(d_bad, 0, 4, s));
+      B_TRY(dev_alloc(M, (void **)&M->sell_vals32, padded * 4));
+      uint64_t g = (padded + T256 - 1) / T256;
+      if (g > (uint64_t)c->sm_count * 16)
+        g = (uint64_t)c->sm_count * 16;
+      k_vals_to_f32<<<(unsigned)g, T256, 0, s>>>(M->sell_vals, M->sell_vals32, padded, d_bad);
+      CU_TRY(cudaGetLastError());
+      CU_TRY(cudaMemcpyAsync(&h_bad, d_bad, 4, cudaMemcpyDeviceToHost, s));
+      CU_TRY(cudaStreamSynchronize(s));
+      cudaFree(d_bad);
+      M->vals32_exact = h_bad == 0;
+      if (M->vals32_exact) {  // lossless: the fp64 copy is not needed any more
+        cudaFree(M->sell_vals);
+        M->sell_vals = nullptr;
+        M->device_bytes -= padded * 8;
+      }
+    }
   }
 
   // ---- vector and long bins: one shared row-major store ------------------------
@@ -771,7 +808,8 @@ extern "C" int b200_mat_destroy(b200_mat *M) {
   small_free(M);
   halo_free(M);
   if (M->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)M->graph_exec);
-  void *ptrs[] = {M->sell_off, M->sell_cols, M->sell_vals, M->sell_perm,
+  void *ptrs[] = {M->sell_off, M->sell_cols, M->sell_vals, M->sell_vals32, M->sell_perm,
+                  M->w_pp, M->w_s, M->w_d, M->w_rhs,
                   M->sell_meta, M->sell_dcols,
                   M->vec_row_ids, M->long_row_ids, M->vec_off, M->long_off,
                   M->vl_cols, M->vl_vals, M->dinv, M->row_len, M->w_r, M->w_p,
@@ -800,10 +838,11 @@ extern "C" int b200_mat_get_info(const b200_mat *M, b200_mat_info *o) {
   o->sell_perm = M->sell_perm != nullptr;
   o->device_bytes = M->device_bytes;
   o->sell_uniform_slices = M->sell_uniform_slices;
-  // what one SpMV streams from the matrix: values, columns / deltas, slice and
-  // row offsets, the row permutation
+  o->values_f32 = M->sell_vals32 ? (M->vals32_exact ? 1u : 2u) : 0u;
+  // what one SpMV (of the PCG iteration) streams from the matrix: values,
+  // columns / deltas, slice and row offsets, the row permutation
   o->matrix_stream_bytes =
-      8 * (M->sell_entries + M->vl_entries) +
+      (M->sell_vals32 ? 4 : 8) * M->sell_entries + 8 * M->vl_entries +
       4 * (M->sell_col_entries + M->sell_delta_entries + M->vl_entries) +
       (M->sell_meta ? 16 : 4) * (uint64_t)(M->sell_slices + 1) +
       (M->sell_perm ? 4 * (uint64_t)M->sell_slices * B2_SLICE : 0) +
@@ -826,6 +865,7 @@ __global__ void k_export_sell(uint32_t nslices, const uint32_t *list, uint64_t n
                               const uint32_t *len, const uint32_t *sell_off,
                               const uint4 *meta, const uint32_t *scols,
                               const int32_t *dcols, const double *svals,
+                              const float *svals32,
                               const uint64_t *ooffs, uint32_t *ocols, double *ovals) {
   uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (s >= nslices)
@@ -840,12 +880,13 @@ __global__ void k_export_sell(uint32_t nslices, const uint32_t *list, uint64_t n
   if (meta && (m.y >> 31)) {  // uniform slice: column = row + delta
     const int32_t *dp = dcols + c;
     for (uint32_t k = 0; k < len[row]; k++, src += B2_SLICE)
-      ocols[dst + k] = row + (uint32_t)dp[k], ovals[dst + k] = svals[src];
+      ocols[dst + k] = row + (uint32_t)dp[k],
+                 ovals[dst + k] = svals ? svals[src] : (double)svals32[src];
     return;
   }
   uint64_t csrc = meta ? (uint64_t)c * B2_SLICE + lane : src;
   for (uint32_t k = 0; k < len[row]; k++, src += B2_SLICE, csrc += B2_SLICE)
-    ocols[dst + k] = scols[csrc], ovals[dst + k] = svals[src];
+    ocols[dst + k] = scols[csrc], ovals[dst + k] = svals ? svals[src] : (double)svals32[src];
 }
 
 __global__ void k_export_vl(uint32_t nrows, const uint32_t *ids,
@@ -892,7 +933,8 @@ extern "C" int b200_mat_export(const b200_mat *M, uint64_t *offs,
     if (M->sell_slices)
       k_export_sell<<<nblk((uint64_t)M->sell_slices * 32), T256, 0, s>>>(
           M->sell_slices, M->sell_perm, n, M->row_len, M->sell_off,
-          (const uint4 *)M->sell_meta, M->sell_cols, M->sell_dcols, M->sell_vals, ooffs, oc, ov);
+          (const uint4 *)M->sell_meta, M->sell_cols, M->sell_dcols, M->sell_vals,
+          M->sell_vals32, ooffs, oc, ov);
     if (M->vec_rows)
       k_export_vl<<<nblk((uint64_t)M->vec_rows * 32), T256, 0, s>>>(
           M->vec_rows, M->vec_row_ids, M->row_len, M->vec_off, M->vl_cols,

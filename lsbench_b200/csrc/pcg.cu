@@ -18,6 +18,16 @@
 // iterations queued past convergence return at their first instruction.
 // Every reduction has a fixed order (common.cuh grid_sum_finish), hence
 // bit-identical iterates and iteration counts run to run.
+//
+// the Chronopoulos-Gear form of
+// the same method -- two kernels per iteration, one place where sums are needed:
+//   K1' w = A u            + u.w                  (u = D^-1 r)
+//   K2' p = u + b p; s = w + b s; x += a p; r -= a s; u = D^-1 r  + r.u, r.r
+// with a = (r.u) / (u.w - b (r.u) / a_prev), the same 104 n vector bytes.
+//
+// SURVEY 8(f) row 4, matrices converted with B200_MAT_VALUES_F32 whose values do
+// not all survive the rounding: iterative refinement (pcg_refine below) -- inner
+// iterations stream the fp32 values, the residual b - A x the fp64 ones.
 #include "common.cuh"
 
 #define EW_THREADS 256
@@ -166,6 +176,125 @@ k_pcg_pupdate(uint64_t n, const double *__restrict__ r,
     p[i] = fma(beta, p[i], dinv[i] * r[i]);
 }
 
+// ---- single-reduction CG ----------------------------------------------------------
+__global__ void k_sr_start(PcgState *st) {
+  // first pass: beta = gamma / inf = 0, alpha = gamma / (delta - 0 * gamma / 1)
+  st->red[2] = __longlong_as_double(0x7ff0000000000000ll);
+  st->sr_alpha[0] = 1.0, st->sr_alpha[1] = 1.0;
+  st->sr_base = 0, st->sr_next = 0;
+}
+
+// head of every chunk of queued iterations (one per graph replay): the kernels
+// of the chunk know their index inside it, this is where the chunk starts
+__global__ void k_sr_chunk_begin(PcgState *st, int chunk) {
+  st->sr_base = st->sr_next;
+  st->sr_next += chunk;
+}
+
+// K2'.  idx: position of the iteration inside its chunk (chunks are even, so
+// idx & 1 is the parity of the iteration).  Everything a CTA reads to decide
+// and to form alpha / beta was written by earlier kernels; thread 0 of CTA 0
+// writes only what this kernel does not read.
+__global__ void __launch_bounds__(EW_THREADS)
+k_sr_update(uint64_t n, double *__restrict__ x, double *__restrict__ r,
+            double *__restrict__ p, double *__restrict__ sv,
+            const double *__restrict__ w, double *__restrict__ u,
+            const double *__restrict__ dinv, double *partials, unsigned stride,
+            PcgState *st, int idx, double *out) {
+  if (st->done)
+    return;
+  __shared__ double red[EW_WARPS];
+  const int par = idx & 1;
+  const int it = st->sr_base + idx;  // iterations finished before this one
+  const double gamma = st->red[par * 2], rr = st->red[par * 2 + 1];
+  const double gamma_prev = st->red[(par ^ 1) * 2];
+  const double delta = st->pq, alpha_prev = st->sr_alpha[par ^ 1];
+  const bool first = blockIdx.x == 0 && threadIdx.x == 0;
+  if (rr <= st->thr2) {
+    if (first)
+      st->done = 1, st->status = 0;
+    return;
+  }
+  if (!(rr == rr)) {
+    if (first)
+      st->done = 1, st->status = 2;
+    return;
+  }
+  if (it >= st->maxit) {
+    if (first)
+      st->done = 1;  // status stays 1
+    return;
+  }
+  const double beta = gamma / gamma_prev;
+  const double den = delta - beta * gamma / alpha_prev;  // = p.Ap
+  if (!(den > 0.0)) {  // not SPD, or NaN crept in
+    if (first)
+      st->done = 1, st->status = 2;
+    return;
+  }
+  const double alpha = gamma / den;
+  if (first)
+    st->sr_alpha[par] = alpha, st->iter = it + 1;
+  double s[2] = {0.0, 0.0};
+  const uint64_t stride_e = (uint64_t)gridDim.x * EW_THREADS;
+  uint64_t i = blockIdx.x * (uint64_t)EW_THREADS + threadIdx.x;
+  for (; i + stride_e < n; i += 2 * stride_e) {
+    const uint64_t j = i + stride_e;
+    double ri = r[i], di = __ldcs(dinv + i), pi = p[i], si = sv[i], wi = __ldcs(w + i), xi = x[i];
+    double rj = r[j], dj = __ldcs(dinv + j), pj = p[j], sj = sv[j], wj = __ldcs(w + j), xj = x[j];
+    pi = fma(beta, pi, di * ri), si = fma(beta, si, wi);
+    pj = fma(beta, pj, dj * rj), sj = fma(beta, sj, wj);
+    xi = fma(alpha, pi, xi), ri = fma(-alpha, si, ri);
+    xj = fma(alpha, pj, xj), rj = fma(-alpha, sj, rj);
+    const double ui = di * ri, uj = dj * rj;
+    p[i] = pi, sv[i] = si, x[i] = xi, r[i] = ri, u[i] = ui;
+    p[j] = pj, sv[j] = sj, x[j] = xj, r[j] = rj, u[j] = uj;
+    s[0] = fma(ri, ui, s[0]), s[1] = fma(ri, ri, s[1]);
+    s[0] = fma(rj, uj, s[0]), s[1] = fma(rj, rj, s[1]);
+  }
+  if (i < n) {
+    double ri = r[i], di = dinv[i], pi = p[i], si = sv[i], wi = w[i], xi = x[i];
+    pi = fma(beta, pi, di * ri), si = fma(beta, si, wi);
+    xi = fma(alpha, pi, xi), ri = fma(-alpha, si, ri);
+    const double ui = di * ri;
+    p[i] = pi, sv[i] = si, x[i] = xi, r[i] = ri, u[i] = ui;
+    s[0] = fma(ri, ui, s[0]), s[1] = fma(ri, ri, s[1]);
+  }
+  double bs[2];
+  bs[0] = block_sum<EW_WARPS>(s[0], red);
+  bs[1] = block_sum<EW_WARPS>(s[1], red);
+  grid_sum_finish<2, EW_WARPS>(bs, partials, stride, blockIdx.x, gridDim.x,
+                               &st->ticket[2], out, red);
+}
+
+// ---- refinement (B200_MAT_VALUES_F32, rounded values) ---------------------------------
+// rhs = b - q (q = A x with the fp64 values); sums ||rhs||^2 and ||b||^2
+__global__ void __launch_bounds__(EW_THREADS)
+k_refine_resid(uint64_t n, const double *__restrict__ b, const double *__restrict__ q,
+               double *__restrict__ rhs, double *partials, unsigned stride,
+               PcgState *st, double *out) {
+  __shared__ double red[EW_WARPS];
+  double s[2] = {0.0, 0.0};
+  for (uint64_t i = blockIdx.x * (uint64_t)EW_THREADS + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * EW_THREADS) {
+    const double bi = b[i], d = bi - q[i];
+    rhs[i] = d;
+    s[0] = fma(d, d, s[0]), s[1] = fma(bi, bi, s[1]);
+  }
+  double bs[2];
+  bs[0] = block_sum<EW_WARPS>(s[0], red);
+  bs[1] = block_sum<EW_WARPS>(s[1], red);
+  grid_sum_finish<2, EW_WARPS>(bs, partials, stride, blockIdx.x, gridDim.x,
+                               &st->ticket[3], out, red);
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+k_add_into(uint64_t n, double *__restrict__ x, const double *__restrict__ d) {
+  for (uint64_t i = blockIdx.x * (uint64_t)EW_THREADS + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * EW_THREADS)
+    x[i] += d[i];
+}
+
 // ||b - A x||^2 for the exit check (q = A x)
 __global__ void __launch_bounds__(EW_THREADS)
 k_true_resid(uint64_t n, const double *__restrict__ b, const double *__restrict__ q,
@@ -264,9 +393,43 @@ static int queue_iteration(b200_mat *M, int par, cudaEvent_t *ev = nullptr) {
   return B200_OK;
 }
 
+// One single-reduction iteration: K2' then K1'.  On several ranks the sums go
+// through the NCCL all-reduce (the peer-memory mailboxes are sequenced for the
+// three-kernel iteration; a single exchange point per iteration is what this
+// form allows next).
+static int queue_iteration_sr(b200_mat *M, int idx, cudaEvent_t *ev = nullptr) {
+  b200_ctx *c = M->ctx;
+  cudaStream_t s = c->stream;
+  PcgState *st = M->state;
+  const int nx = ((idx & 1) ^ 1) * 2;
+  if (ev) CU_TRY(cudaEventRecord(ev[0], s));  // ev: before K2', between, after K1'
+  k_sr_update<<<M->grid_ew, EW_THREADS, 0, s>>>(
+      M->n_local, M->w_x, M->w_r, M->w_pp, M->w_s, M->w_q, M->w_p, M->dinv, M->partials,
+      M->partial_stride, st, idx, sum_target(M, &st->red[nx], &st->loc[nx]));
+  B_TRY(reduce_ranks(M, &st->red[nx], &st->loc[nx], 2));
+  if (ev) CU_TRY(cudaEventRecord(ev[1], s));
+  B_TRY(spmv_full_internal(M, M->w_p, M->w_q, true, nullptr));  // K1'
+  B_TRY(reduce_ranks(M, &st->pq, &st->pq_loc, 1));
+  if (ev) CU_TRY(cudaEventRecord(ev[2], s));
+  c->launches += 1;
+  CU_TRY(cudaGetLastError());
+  return B200_OK;
+}
+
+static int queue_chunk(b200_mat *M, int chunk, bool sr) {
+  if (sr) {
+    k_sr_chunk_begin<<<1, 1, 0, M->ctx->stream>>>(M->state, chunk);
+    M->ctx->launches += 1;
+  }
+  for (int i = 0; i < chunk; i++)
+    B_TRY(sr ? queue_iteration_sr(M, i) : queue_iteration(M, i & 1));
+  return B200_OK;
+}
+
 // One graph = `chunk` (even) iterations; replayed until the device says done.
-static int ensure_graph(b200_mat *M, int chunk) {
-  if (M->graph_exec && M->graph_chunk == chunk && M->graph_stream == (void *)M->ctx->stream)
+static int ensure_graph(b200_mat *M, int chunk, bool sr) {
+  if (M->graph_exec && M->graph_chunk == chunk && M->graph_stream == (void *)M->ctx->stream &&
+      M->graph_sr == sr)
     return B200_OK;
   if (M->graph_exec) {
     cudaGraphExecDestroy((cudaGraphExec_t)M->graph_exec);
@@ -277,8 +440,7 @@ static int ensure_graph(b200_mat *M, int chunk) {
   CU_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
   int rc = B200_OK;
   const uint64_t before = M->ctx->launches;
-  for (int i = 0; i < chunk && rc == B200_OK; i++)
-    rc = queue_iteration(M, i & 1);
+  rc = queue_chunk(M, chunk, sr);
   cudaError_t e = cudaStreamEndCapture(s, &g);
   M->graph_kernels = (int)(M->ctx->launches - before);
   M->ctx->launches = before;  // captured, not launched
@@ -289,27 +451,23 @@ static int ensure_graph(b200_mat *M, int chunk) {
   CU_TRY(cudaGraphInstantiate(&ge, g, 0));
   cudaGraphDestroy(g);
   M->graph_exec = ge, M->graph_chunk = chunk, M->graph_stream = (void *)s;
+  M->graph_sr = sr;
   return B200_OK;
 }
 
-extern "C" int b200_pcg_solve(b200_mat *M, const double *d_b, double *d_x,
-                              const b200_pcg_opts *o, b200_pcg_result *res) {
-  if (!M || !d_b || !d_x || !o || !res)
-    B_FAIL(B200_EINVAL, "b200_pcg_solve: null argument");
-  if (!(o->tol > 0.0) || o->maxit < 0)
-    B_FAIL(B200_EINVAL, "b200_pcg_solve: tol=%g maxit=%d", o->tol, o->maxit);
+// The streaming solve: start-up, chunks of queued iterations, exit residual.
+static int pcg_stream(b200_mat *M, const double *d_b, double *d_x,
+                      const b200_pcg_opts *o, b200_pcg_result *res) {
   b200_ctx *c = M->ctx;
-  CU_TRY(cudaSetDevice(c->device));
-  memset(res, 0, sizeof *res);
-  if (!(o->flags & B200_PCG_NO_SMALL) && c->nranks == 1) {
-    B_TRY(small_try_build(M));
-    if (M->small)
-      return small_solve(M, d_b, d_x, o, res);
-  }
   B_TRY(ensure_workspace(M));
   cudaStream_t s = c->stream;
   const uint64_t n = M->n_local;
   const bool timing = o->flags & B200_PCG_TIME_KERNELS;
+  const bool sr = o->flags & B200_PCG_SINGLE_REDUCTION;
+  if (sr && !M->w_pp) {
+    B_TRY(dev_alloc(M, (void **)&M->w_pp, (n + 2) * 8));
+    B_TRY(dev_alloc(M, (void **)&M->w_s, (n + 2) * 8));
+  }
   int chunk = o->check_every > 0 ? o->check_every : 32;
   chunk = (chunk + 1) & ~1;  // even: the parity pattern repeats per chunk
   // (multi-rank: plain launches; the NCCL calls stay outside any capture)
@@ -328,6 +486,15 @@ extern "C" int b200_pcg_solve(b200_mat *M, const double *d_b, double *d_x,
   B_TRY(reduce_ranks(M, &M->state->red[4], &M->state->loc[4], 3));
   k_pcg_start<<<1, 1, 0, s>>>(M->state, o->tol, o->maxit);
   c->launches += 2;
+  if (sr) {
+    // w_p holds u = D^-1 r; p = s = 0; w = A u with u.w
+    k_sr_start<<<1, 1, 0, s>>>(M->state);
+    CU_TRY(cudaMemsetAsync(M->w_pp, 0, n * 8, s));
+    CU_TRY(cudaMemsetAsync(M->w_s, 0, n * 8, s));
+    B_TRY(spmv_full_internal(M, M->w_p, M->w_q, true, nullptr));
+    B_TRY(reduce_ranks(M, &M->state->pq, &M->state->pq_loc, 1));
+    c->launches += 1;
+  }
   CU_TRY(cudaGetLastError());
 
   // ---- iterations ---------------------------------------------------------------
@@ -339,14 +506,30 @@ extern "C" int b200_pcg_solve(b200_mat *M, const double *d_b, double *d_x,
     CU_TRY(cudaMemcpyAsync((void *)flag, &M->state->iter, 16, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaEventRecord(c->ev_poll, s));
     CU_TRY(cudaEventSynchronize(c->ev_poll));
-    if (flag[1] || queued >= o->maxit)
+    // (single-reduction: the stopping test of iteration k sits at the head of
+    // iteration k + 1, so one more than maxit may have to be queued)
+    if (flag[1] || queued >= o->maxit + (sr ? 1 : 0))
       break;
     if (timing && timed_iters == 0) {
       // per-class device time over one chunk, events on the launch stream
       cudaEvent_t ev[4];
       for (auto &e : ev)
         CU_TRY(cudaEventCreate(&e));
+      if (sr) {
+        k_sr_chunk_begin<<<1, 1, 0, s>>>(M->state, chunk);
+        c->launches += 1;
+      }
       for (int i = 0; i < chunk; i++) {
+        if (sr) {
+          B_TRY(queue_iteration_sr(M, i, ev));
+          CU_TRY(cudaEventSynchronize(ev[2]));
+          float t;
+          CU_TRY(cudaEventElapsedTime(&t, ev[0], ev[1]));
+          t_cls[1] += t;
+          CU_TRY(cudaEventElapsedTime(&t, ev[1], ev[2]));
+          t_cls[0] += t;
+          continue;
+        }
         B_TRY(queue_iteration(M, i & 1, ev));
         CU_TRY(cudaEventSynchronize(ev[3]));
         for (int k = 0; k < 3; k++) {
@@ -359,12 +542,11 @@ extern "C" int b200_pcg_solve(b200_mat *M, const double *d_b, double *d_x,
       for (auto &e : ev)
         cudaEventDestroy(e);
     } else if (use_graph) {
-      B_TRY(ensure_graph(M, chunk));
+      B_TRY(ensure_graph(M, chunk, sr));
       CU_TRY(cudaGraphLaunch((cudaGraphExec_t)M->graph_exec, s));
       c->launches += M->graph_kernels;
     } else {
-      for (int i = 0; i < chunk; i++)
-        B_TRY(queue_iteration(M, i & 1));
+      B_TRY(queue_chunk(M, chunk, sr));
     }
     queued += chunk;
   }
@@ -386,6 +568,8 @@ extern "C" int b200_pcg_solve(b200_mat *M, const double *d_b, double *d_x,
 
   const int parity = h.iter & 1;  // {rz, rr} of the last finished iteration
   double rr = h.iter == 0 ? h.red[1] : h.red[parity * 2 + 1];
+  if (sr && h.status == 1 && rr <= h.thr2)
+    h.status = 0;  // the last queued iteration converged; no later kernel said so
   res->iters = h.iter, res->status = h.status;
   res->bnorm = sqrt(h.bb);
   res->relres = h.bb > 0 ? sqrt(rr / h.bb) : sqrt(rr);
@@ -404,6 +588,110 @@ extern "C" int b200_pcg_solve(b200_mat *M, const double *d_b, double *d_x,
     B_FAIL(B200_ENCCL, "b200_pcg_solve: a rank's partial sums did not arrive over peer "
                        "memory (iteration %d)", h.iter);
   return B200_OK;
+}
+
+// SURVEY 8(f) row 4.  A B200_MAT_VALUES_F32 matrix whose values do not all
+// survive the rounding keeps both value streams; the solve is iterative
+// refinement to the same fp64 bar:
+//   repeat  r = b - A x            fp64 values (spmv_use32 = false)
+//           stop if ||r|| <= tol ||b||
+//           solve A32 d = r        streaming PCG on the fp32 values, fp64 vectors,
+//                                  to max(eta, tol ||b|| / (2 ||r||)), eta = 1e-4
+//           x += d
+// (tests hold it against a CPU statement of the same loop).
+static int pcg_refine(b200_mat *M, const double *d_b, double *d_x,
+                      const b200_pcg_opts *o, b200_pcg_result *res) {
+  b200_ctx *c = M->ctx;
+  B_TRY(ensure_workspace(M));
+  cudaStream_t s = c->stream;
+  const uint64_t n = M->n_local;
+  if (!M->w_d) {
+    B_TRY(dev_alloc(M, (void **)&M->w_d, (n + 2) * 8));
+    B_TRY(dev_alloc(M, (void **)&M->w_rhs, (n + 2) * 8));
+  }
+  const double eta = 1e-4;
+  cudaEvent_t e0, e1;
+  CU_TRY(cudaEventCreate(&e0));
+  CU_TRY(cudaEventCreate(&e1));
+  CU_TRY(cudaEventRecord(e0, s));
+  const uint64_t launches0 = c->launches;
+  int total = 0, passes = 0, status = 1, rc = B200_OK;
+  double rr = 0, bb = 0;
+  for (;;) {
+    M->spmv_use32 = false;
+    CU_TRY(cudaMemcpyAsync(M->w_p, d_x, n * 8, cudaMemcpyDeviceToDevice, s));
+    B_TRY(spmv_full_internal(M, M->w_p, M->w_q, false));
+    k_refine_resid<<<M->grid_ew, EW_THREADS, 0, s>>>(
+        n, d_b, M->w_q, M->w_rhs, M->partials, M->partial_stride, M->state,
+        sum_target(M, &M->state->red[4], &M->state->loc[4]));
+    B_TRY(reduce_ranks(M, &M->state->red[4], &M->state->loc[4], 2));
+    c->launches += 1;
+    double h[2];
+    CU_TRY(cudaMemcpyAsync(h, &M->state->red[4], 16, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    rr = h[0], bb = h[1];
+    if (rr <= o->tol * o->tol * bb) {
+      status = 0;
+      break;
+    }
+    if (!(rr == rr)) {
+      status = 2;
+      break;
+    }
+    if (total >= o->maxit || passes >= 40)
+      break;
+    double t = 0.5 * o->tol * sqrt(bb / rr);
+    b200_pcg_opts in = *o;
+    in.tol = t < eta ? eta : t;
+    in.maxit = o->maxit - total;
+    in.flags &= ~(uint32_t)B200_PCG_TIME_KERNELS;
+    b200_pcg_result ir;
+    memset(&ir, 0, sizeof ir);
+    CU_TRY(cudaMemsetAsync(M->w_d, 0, n * 8, s));
+    M->spmv_use32 = true;
+    rc = pcg_stream(M, M->w_rhs, M->w_d, &in, &ir);
+    M->spmv_use32 = false;
+    total += ir.iters, passes++;
+    if (rc != B200_OK)
+      break;
+    k_add_into<<<M->grid_ew, EW_THREADS, 0, s>>>(n, d_x, M->w_d);
+    c->launches += 1;
+    CU_TRY(cudaGetLastError());
+  }
+  CU_TRY(cudaEventRecord(e1, s));
+  CU_TRY(cudaEventSynchronize(e1));
+  CU_TRY(cudaEventElapsedTime(&res->solve_ms, e0, e1));
+  cudaEventDestroy(e0), cudaEventDestroy(e1);
+  res->iters = total, res->outer_iters = passes;
+  res->status = rc == B200_ENOTSPD ? 2 : status;
+  res->bnorm = sqrt(bb);
+  res->relres = res->true_relres = bb > 0 ? sqrt(rr / bb) : sqrt(rr);
+  res->kernel_launches = (int32_t)(c->launches - launches0);
+  res->path = 0;
+  if (rc != B200_OK)
+    return rc;
+  if (status == 2)
+    B_FAIL(B200_ENOTSPD, "b200_pcg_solve: NaN residual in refinement pass %d", passes);
+  return B200_OK;
+}
+
+extern "C" int b200_pcg_solve(b200_mat *M, const double *d_b, double *d_x,
+                              const b200_pcg_opts *o, b200_pcg_result *res) {
+  if (!M || !d_b || !d_x || !o || !res)
+    B_FAIL(B200_EINVAL, "b200_pcg_solve: null argument");
+  if (!(o->tol > 0.0) || o->maxit < 0)
+    B_FAIL(B200_EINVAL, "b200_pcg_solve: tol=%g maxit=%d", o->tol, o->maxit);
+  b200_ctx *c = M->ctx;
+  CU_TRY(cudaSetDevice(c->device));
+  memset(res, 0, sizeof *res);
+  if (!(o->flags & (B200_PCG_NO_SMALL | B200_PCG_SINGLE_REDUCTION)) && c->nranks == 1) {
+    B_TRY(small_try_build(M));
+    if (M->small)
+      return small_solve(M, d_b, d_x, o, res);
+  }
+  if (M->sell_vals32 && M->sell_vals)  // rounded fp32 values: refinement
+    return pcg_refine(M, d_b, d_x, o, res);
+  return pcg_stream(M, d_b, d_x, o, res);
 }
 
 extern "C" int b200_pcg_solve_host(b200_mat *M, const double *h_b, double *h_x,

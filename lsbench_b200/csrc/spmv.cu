@@ -48,10 +48,45 @@ __device__ __forceinline__ double sell_chunk(const double *vp, const double *__r
   return sum;
 }
 
-template <bool DOT>
+// The same for fp32-stored values (B200_MAT_VALUES_F32): a chunk is 16 entries
+// so that a warp keeps as many value bytes in flight as with fp64 (16 x 128 B);
+// the gathers and the fma chain run in two halves of 8, in row order, on the
+// values widened to fp64 -- when the stored fp32 equals the original fp64 the
+// result has the same bits as the fp64 kernel's.
+template <bool FULL, typename ColF>
+__device__ __forceinline__ double sell_chunk(const float *vp, const double *__restrict__ x,
+                                             uint32_t k, uint32_t rem, double sum, ColF colf) {
+  constexpr int N = FULL ? 16 : 15;
+  float a[16];
+#pragma unroll
+  for (int j = 0; j < N; j++)
+    a[j] = (FULL || j < rem) ? ld_stream(vp + (size_t)(k + j) * B2_SLICE) : 0.0f;
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    uint32_t c[8];
+    double xv[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      c[j] = (h * 8 + j < N && (FULL || h * 8 + j < rem)) ? colf(h * 8 + j) : 0u;
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      xv[j] = (h * 8 + j < N && (FULL || h * 8 + j < rem)) ? __ldg(x + c[j]) : 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      if (h * 8 + j < N && (FULL || h * 8 + j < rem))
+        sum = fma((double)a[h * 8 + j], xv[j], sum);
+  }
+  return sum;
+}
+
+// entries per full chunk of the value type
+template <typename VT> struct ChunkOf { static constexpr uint32_t n = 8; };
+template <> struct ChunkOf<float> { static constexpr uint32_t n = 16; };
+
+template <bool DOT, typename VT>
 __global__ void __launch_bounds__(SPMV_THREADS, 4)
 k_spmv_sell(const uint32_t *__restrict__ sell_off,
-            const uint32_t *__restrict__ cols, const double *__restrict__ vals,
+            const uint32_t *__restrict__ cols, const VT *__restrict__ vals,
             const uint32_t *__restrict__ perm, const double *__restrict__ x,
             double *__restrict__ y, uint32_t b0, uint32_t e0, uint32_t b1,
             uint32_t e1, uint32_t n_rows, double *partials, unsigned slot_base,
@@ -59,6 +94,7 @@ k_spmv_sell(const uint32_t *__restrict__ sell_off,
   if (DOT && st->done)
     return;
   __shared__ double red[SPMV_WARPS];
+  constexpr uint32_t CH = ChunkOf<VT>::n;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t n0 = e0 - b0, nv = n0 + (e1 - b1);
   const uint32_t stride = gridDim.x * SPMV_WARPS;
@@ -69,11 +105,11 @@ k_spmv_sell(const uint32_t *__restrict__ sell_off,
     const uint32_t w = __ldg(sell_off + s + 1) - o;
     const size_t base = (size_t)o * B2_SLICE + lane;
     const uint32_t *cp = cols + base;
-    const double *vp = vals + base;
+    const VT *vp = vals + base;
     double sum = 0.0;
     uint32_t k = 0;
-    for (; k + 8 <= w; k += 8)
-      sum = sell_chunk<true>(vp, x, k, 8, sum, [&](int j) {
+    for (; k + CH <= w; k += CH)
+      sum = sell_chunk<true>(vp, x, k, CH, sum, [&](int j) {
         return ld_stream(cp + (size_t)(k + j) * B2_SLICE);
       });
     if (k < w)
@@ -113,12 +149,14 @@ k_spmv_sell(const uint32_t *__restrict__ sell_off,
 //
 // Compiled for 5 CTAs per SM (48 registers, 40 warps): the uniform path needs no
 // column registers, and the extra warps are worth 6 % (27-point 512^3: 6.07 ->
-// 5.73 ms in PCG; 6 CTAs/SM spills and loses again).
+// 5.73 ms in PCG; 6 CTAs/SM spills and loses again).  The fp32-value
+// instantiation holds 16 values per chunk and is compiled for 4 CTAs per SM
+// (64 registers; at 48 it spills 112 bytes in the loop).
 #define SELLC_MINB 5
-template <bool DOT>
-__global__ void __launch_bounds__(SPMV_THREADS, SELLC_MINB)
+template <bool DOT, typename VT>
+__global__ void __launch_bounds__(SPMV_THREADS, sizeof(VT) == 8 ? SELLC_MINB : 4)
 k_spmv_sellc(const uint4 *__restrict__ meta, const uint32_t *__restrict__ cols,
-             const int32_t *__restrict__ dcols, const double *__restrict__ vals,
+             const int32_t *__restrict__ dcols, const VT *__restrict__ vals,
              const uint32_t *__restrict__ perm, const double *__restrict__ x,
              double *__restrict__ y, uint32_t b0, uint32_t e0, uint32_t b1,
              uint32_t e1, uint32_t n_rows, double *partials, unsigned slot_base,
@@ -126,6 +164,7 @@ k_spmv_sellc(const uint4 *__restrict__ meta, const uint32_t *__restrict__ cols,
   if (DOT && st->done)
     return;
   __shared__ double red[SPMV_WARPS];
+  constexpr uint32_t CH = ChunkOf<VT>::n;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t n0 = e0 - b0, nv = n0 + (e1 - b1);
   const uint32_t stride = gridDim.x * SPMV_WARPS;
@@ -134,15 +173,15 @@ k_spmv_sellc(const uint4 *__restrict__ meta, const uint32_t *__restrict__ cols,
     const uint32_t s = v < n0 ? b0 + v : b1 + (v - n0);
     const uint4 m = __ldg(meta + s);
     const uint32_t o = m.x, w = m.y & 0x7fffffffu;
-    const double *vp = vals + (size_t)o * B2_SLICE + lane;
+    const VT *vp = vals + (size_t)o * B2_SLICE + lane;
     const uint32_t pos = s * B2_SLICE + lane;
     const uint32_t row = perm ? __ldg(perm + pos) : pos;
     double sum = 0.0;
     uint32_t k = 0;
     if (m.y >> 31) {
       const int32_t *dp = dcols + m.z;
-      for (; k + 8 <= w; k += 8)
-        sum = sell_chunk<true>(vp, x, k, 8, sum, [&](int j) {
+      for (; k + CH <= w; k += CH)
+        sum = sell_chunk<true>(vp, x, k, CH, sum, [&](int j) {
           return row + (uint32_t)__ldg(dp + k + j);
         });
       if (k < w)
@@ -151,8 +190,8 @@ k_spmv_sellc(const uint4 *__restrict__ meta, const uint32_t *__restrict__ cols,
         });
     } else {
       const uint32_t *cp = cols + (size_t)m.z * B2_SLICE + lane;
-      for (; k + 8 <= w; k += 8)
-        sum = sell_chunk<true>(vp, x, k, 8, sum, [&](int j) {
+      for (; k + CH <= w; k += CH)
+        sum = sell_chunk<true>(vp, x, k, CH, sum, [&](int j) {
           return ld_stream(cp + (size_t)(k + j) * B2_SLICE);
         });
       if (k < w)
@@ -298,10 +337,15 @@ static SpmvPlan compute_plan(b200_mat *M, int phase) {
     P.b0 = 0, P.e0 = ib, P.b1 = ie, P.e1 = ns;
   uint32_t nv = (P.e0 - P.b0) + (P.e1 - P.b1);
   if (nv)
-    P.g_sell = persistent_grid(c,
-                               M->sell_meta ? (const void *)k_spmv_sellc<true>
-                                            : (const void *)k_spmv_sell<true>,
-                               (nv + SPMV_WARPS - 1) / SPMV_WARPS);
+    // one grid per matrix (fixed count of dot partials = fixed summation
+    // order): sized for the fp32-value instantiation when that stream exists
+    P.g_sell = persistent_grid(
+        c,
+        M->sell_vals32 ? (M->sell_meta ? (const void *)k_spmv_sellc<true, float>
+                                       : (const void *)k_spmv_sell<true, float>)
+                       : (M->sell_meta ? (const void *)k_spmv_sellc<true, double>
+                                       : (const void *)k_spmv_sell<true, double>),
+        (nv + SPMV_WARPS - 1) / SPMV_WARPS);
   if (others && M->vec_rows)
     P.g_vec = persistent_grid(c, (const void *)k_spmv_vec<true>,
                               (M->vec_rows + SPMV_WARPS - 1) / SPMV_WARPS);
@@ -348,18 +392,27 @@ int launch_spmv(b200_mat *M, const double *x, double *y, bool dot, int phase,
       DOTV ? slot_base : 0u, DOTV ? total : 0u, DOTV ? M->state : nullptr,        \
       DOTV ? dot_out : nullptr, xr
     const uint4 *meta = (const uint4 *)M->sell_meta;
-    if (dot && meta)
-      k_spmv_sellc<true><<<P.g_sell, SPMV_THREADS, 0, s>>>(
-          meta, M->sell_cols, M->sell_dcols, M->sell_vals, B2_SELL_ARGS(true));
-    else if (meta)
-      k_spmv_sellc<false><<<P.g_sell, SPMV_THREADS, 0, s>>>(
-          meta, M->sell_cols, M->sell_dcols, M->sell_vals, B2_SELL_ARGS(false));
-    else if (dot)
-      k_spmv_sell<true><<<P.g_sell, SPMV_THREADS, 0, s>>>(
-          M->sell_off, M->sell_cols, M->sell_vals, B2_SELL_ARGS(true));
+    const bool f32 = M->sell_vals32 && (M->spmv_use32 || !M->sell_vals);
+#define B2_SELL_LAUNCH(VT, VALS)                                                  \
+  do {                                                                            \
+    if (dot && meta)                                                              \
+      k_spmv_sellc<true, VT><<<P.g_sell, SPMV_THREADS, 0, s>>>(                   \
+          meta, M->sell_cols, M->sell_dcols, VALS, B2_SELL_ARGS(true));           \
+    else if (meta)                                                                \
+      k_spmv_sellc<false, VT><<<P.g_sell, SPMV_THREADS, 0, s>>>(                  \
+          meta, M->sell_cols, M->sell_dcols, VALS, B2_SELL_ARGS(false));          \
+    else if (dot)                                                                 \
+      k_spmv_sell<true, VT><<<P.g_sell, SPMV_THREADS, 0, s>>>(                    \
+          M->sell_off, M->sell_cols, VALS, B2_SELL_ARGS(true));                   \
+    else                                                                          \
+      k_spmv_sell<false, VT><<<P.g_sell, SPMV_THREADS, 0, s>>>(                   \
+          M->sell_off, M->sell_cols, VALS, B2_SELL_ARGS(false));                  \
+  } while (0)
+    if (f32)
+      B2_SELL_LAUNCH(float, M->sell_vals32);
     else
-      k_spmv_sell<false><<<P.g_sell, SPMV_THREADS, 0, s>>>(
-          M->sell_off, M->sell_cols, M->sell_vals, B2_SELL_ARGS(false));
+      B2_SELL_LAUNCH(double, M->sell_vals);
+#undef B2_SELL_LAUNCH
 #undef B2_SELL_ARGS
     slot_base += P.g_sell;
   }

@@ -59,10 +59,11 @@ struct settings {
   double tol;
   unsigned flags;
   int ordering; /* 0 off, 1 take cb->ordering, 2 RCM */
+  unsigned pcg_flags;
 };
 
 static struct settings read_settings(void) {
-  struct settings s = {1, 0, 10000, 1e-10, B200_MAT_SYM_UPPER, 0};
+  struct settings s = {1, 0, 10000, 1e-10, B200_MAT_SYM_UPPER, 0, 0};
   const char *v;
   if ((v = getenv("LSBENCH_B200_NGPUS")) && atoi(v) > 0)
     s.ngpus = atoi(v);
@@ -76,6 +77,9 @@ static struct settings read_settings(void) {
    * (src/cusparse.c:55-63); the default mirrors the upper triangle. */
   if ((v = getenv("LSBENCH_B200_OPERATOR")) && strcmp(v, "full") == 0)
     s.flags = 0;
+  /* "sr": single-reduction (Chronopoulos-Gear) CG on the streaming kernels */
+  if ((v = getenv("LSBENCH_B200_PCG")) && strcmp(v, "sr") == 0)
+    s.pcg_flags |= B200_PCG_SINGLE_REDUCTION;
   if ((v = getenv("LSBENCH_B200_ORDERING"))) {
     if (strcmp(v, "cli") == 0)
       s.ordering = 1;
@@ -444,7 +448,7 @@ static void *run_rank(void *arg) {
   chk_b200(b200_malloc(ctx, bytes, (void **)&d_x));
   chk_b200(b200_memcpy_h2d(ctx, d_r, sh->r + info.row_begin, bytes));
 
-  b200_pcg_opts opts = {cfg->tol, cfg->maxit, 0, 0};
+  b200_pcg_opts opts = {cfg->tol, cfg->maxit, 0, cfg->pcg_flags};
   b200_pcg_result res;
   memset(&res, 0, sizeof res);
 
@@ -503,6 +507,8 @@ int b200_bench(double *x, struct csr *A, const double *r,
   struct shared sh;
   memset(&sh, 0, sizeof sh);
   sh.cfg = read_settings();
+  if (cb->precision == LSBENCH_PRECISION_FP32) /* --precision FP32 */
+    sh.cfg.flags |= B200_MAT_VALUES_F32;
   sh.A = A, sh.r = r, sh.x = x, sh.cb = cb;
 
   /* --ordering: solve P A P^T (P x) = P b, hand x back in the caller's order */
@@ -591,6 +597,10 @@ int b200_bench(double *x, struct csr *A, const double *r,
            (unsigned long long)sh.info.long_rows,
            (unsigned long long)sh.info.nnz_padded,
            (double)sh.info.device_bytes / 1e6);
+    if (sh.info.values_f32)
+      printf("b200: precision=fp32 values %s, refinement passes %d\n",
+             sh.info.values_f32 == 1 ? "lossless (fp64 copy dropped)" : "rounded (fp64 copy kept)",
+             sh.last.outer_iters);
     if (perm) {
       struct op_csr S = op_build(A, (read_settings().flags & B200_MAT_SYM_UPPER) != 0);
       printf("b200: ordering=rcm bandwidth %u -> %u\n",

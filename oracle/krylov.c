@@ -167,3 +167,135 @@ int orc_pcg_omp(const orc_op *M, const double *b, double *x, double tol,
                 int maxit, int *iters, double *relres) {
   PCG_BODY(OMP_FOR, OMP_RED1, OMP_RED2, orc_spmv_omp)
 }
+
+/* ---- single-reduction CG (Chronopoulos & Gear 1989) ------
+ * The same Krylov method with the two dot products of an iteration moved next
+ * to each other, so a multi-GPU or on-chip solve pays one reduction per
+ * iteration instead of two.  u = D^-1 r, w = A u; p and s = A p follow by
+ * recurrence:
+ *   r = b - A x0; u = D^-1 r; w = A u; gamma = r.u; delta = w.u; p = s = 0
+ *   loop: stop if ||r|| <= tol ||b||
+ *         beta = gamma / gamma_prev            (0 in the first pass)
+ *         alpha = gamma / (delta - beta gamma / alpha_prev)     (= gamma / p.Ap)
+ *         p = u + beta p; s = w + beta s; x += alpha p; r -= alpha s
+ *         u = D^-1 r; gamma' = r.u; rr = r.r;  w = A u; delta = w.u
+ * What csrc/pcg.cu runs with B200_PCG_SINGLE_REDUCTION. */
+int orc_pcg_sr(const orc_op *M, const double *b, double *x, double tol,
+               int maxit, int *iters, double *relres) {
+  int64_t n = (int64_t)M->n;
+  double *dinv = inv_diag(M);
+  double *r = (double *)calloc(5 * (size_t)n + 1, sizeof(double));
+  double *u = r + n, *w = u + n, *p = w + n, *s = p + n;
+  double bb = 0, gamma = 0, rr = 0, delta = 0;
+  orc_spmv(M, x, w, NULL);
+  for (int64_t i = 0; i < n; i++) {
+    r[i] = b[i] - w[i];
+    u[i] = dinv[i] * r[i];
+    bb += b[i] * b[i], gamma += r[i] * u[i], rr += r[i] * r[i];
+  }
+  orc_spmv(M, u, w, NULL);
+  for (int64_t i = 0; i < n; i++)
+    delta += w[i] * u[i];
+  double bnorm = sqrt(bb), thr = tol * bnorm;
+  double gamma_prev = INFINITY, alpha_prev = 1.0;
+  int it = 0, rc = 1;
+  while (it < maxit || sqrt(rr) <= thr) {
+    if (sqrt(rr) <= thr) {
+      rc = 0;
+      break;
+    }
+    double beta = gamma / gamma_prev;
+    double den = delta - beta * gamma / alpha_prev;
+    if (!(den > 0.0)) {
+      rc = 2;
+      break;
+    }
+    double alpha = gamma / den, gn = 0;
+    rr = 0;
+    for (int64_t i = 0; i < n; i++) {
+      p[i] = u[i] + beta * p[i];
+      s[i] = w[i] + beta * s[i];
+      x[i] += alpha * p[i];
+      double ri = r[i] - alpha * s[i];
+      r[i] = ri, u[i] = dinv[i] * ri;
+      gn += ri * u[i], rr += ri * ri;
+    }
+    it++;
+    gamma_prev = gamma, gamma = gn, alpha_prev = alpha;
+    orc_spmv(M, u, w, NULL);
+    delta = 0;
+    for (int64_t i = 0; i < n; i++)
+      delta += w[i] * u[i];
+  }
+  if (iters)
+    *iters = it;
+  if (relres)
+    *relres = bnorm > 0 ? sqrt(rr) / bnorm : sqrt(rr);
+  free(r), free(dinv);
+  return rc;
+}
+
+/* ---- fp32-stored operator + fp64 refinement --------------
+ * What b200_pcg_solve does on a B200_MAT_VALUES_F32 matrix whose values do not
+ * all survive the rounding to fp32: A32 = fl32(A); repeat { r = b - A x in
+ * fp64 with the fp64 values; stop if ||r|| <= tol ||b||; solve A32 d = r by
+ * Jacobi-PCG (fp64 vectors) to max(eta, tol ||b|| / (2 ||r||)); x += d }.
+ * When every value survives, A32 == A and this is orc_pcg. */
+int orc_pcg_refine32(const orc_op *M, const double *b, double *x, double tol,
+                     int maxit, double eta, int *iters, int *outer, double *relres) {
+  int64_t n = (int64_t)M->n;
+  uint64_t nnz = M->offs[n];
+  orc_op M32 = *M;
+  M32.vals = (double *)malloc((nnz ? nnz : 1) * sizeof(double));
+  int exact = 1;
+  for (uint64_t k = 0; k < nnz; k++) {
+    M32.vals[k] = (double)(float)M->vals[k];
+    exact &= M32.vals[k] == M->vals[k];
+  }
+  if (exact) { /* lossless storage: the product runs the plain solve */
+    free(M32.vals);
+    if (outer)
+      *outer = 0;
+    return orc_pcg(M, b, x, tol, maxit, iters, relres);
+  }
+  double *r = (double *)malloc(2 * (size_t)n * sizeof(double) + 8), *d = r + n;
+  double bb = 0, rr = 0;
+  for (int64_t i = 0; i < n; i++)
+    bb += b[i] * b[i];
+  int total = 0, passes = 0, rc = 1;
+  for (;;) {
+    orc_spmv(M, x, r, NULL);
+    rr = 0;
+    for (int64_t i = 0; i < n; i++) {
+      r[i] = b[i] - r[i];
+      rr += r[i] * r[i];
+    }
+    if (rr <= tol * tol * bb) {
+      rc = 0;
+      break;
+    }
+    if (total >= maxit || passes >= 40)
+      break;
+    double t = 0.5 * tol * sqrt(bb / rr);
+    if (t < eta)
+      t = eta;
+    memset(d, 0, (size_t)n * sizeof(double));
+    int it = 0;
+    int irc = orc_pcg(&M32, r, d, t, maxit - total, &it, NULL);
+    total += it, passes++;
+    if (irc == 2) {
+      rc = 2;
+      break;
+    }
+    for (int64_t i = 0; i < n; i++)
+      x[i] += d[i];
+  }
+  if (iters)
+    *iters = total;
+  if (outer)
+    *outer = passes;
+  if (relres)
+    *relres = bb > 0 ? sqrt(rr / bb) : sqrt(rr);
+  free(M32.vals), free(r);
+  return rc;
+}

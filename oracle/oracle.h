@@ -75,6 +75,13 @@ int orc_pcg(const orc_op *M, const double *b, double *x, double tol,
             int maxit, int *iters, double *relres);
 int orc_pcg_omp(const orc_op *M, const double *b, double *x, double tol,
                 int maxit, int *iters, double *relres);
+/* Single-reduction CG (Chronopoulos-Gear), same contract. */
+int orc_pcg_sr(const orc_op *M, const double *b, double *x, double tol,
+               int maxit, int *iters, double *relres);
+/* fp32-stored operator + fp64 iterative refinement; iters =
+ * inner iterations in total, outer = refinement passes, relres = true one. */
+int orc_pcg_refine32(const orc_op *M, const double *b, double *x, double tol,
+                     int maxit, double eta, int *iters, int *outer, double *relres);
 /* ||b - M x||_2 / ||b||_2 with a long-double accumulator. */
 double orc_true_relres(const orc_op *M, const double *b, const double *x);
 

@@ -68,6 +68,12 @@ def lib():
             getattr(L, f).argtypes = [C.POINTER(_Op), C.c_void_p, C.c_void_p,
                                       C.c_double, C.c_int,
                                       C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        L.orc_pcg_sr.restype = C.c_int
+        L.orc_pcg_sr.argtypes = L.orc_pcg.argtypes
+        L.orc_pcg_refine32.restype = C.c_int
+        L.orc_pcg_refine32.argtypes = [C.POINTER(_Op), C.c_void_p, C.c_void_p, C.c_double, C.c_int,
+                                       C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                       C.POINTER(C.c_double)]
         L.orc_true_relres.restype = C.c_double
         L.orc_true_relres.argtypes = [C.POINTER(_Op), C.c_void_p, C.c_void_p]
         L.orc_ldlt_factor.restype = C.c_void_p
@@ -257,6 +263,28 @@ def pcg(M, b, x0=None, tol=1e-10, maxit=10000, omp=False):
     rc = f(C.byref(s), b.ctypes.data, x.ctypes.data, tol, maxit,
            C.byref(it), C.byref(rel))
     return x, it.value, rel.value, rc
+
+
+def pcg_sr(M, b, x0=None, tol=1e-10, maxit=10000):
+    """single-reduction (Chronopoulos-Gear) Jacobi-PCG, oracle/krylov.c"""
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.zeros(M.n) if x0 is None else np.array(x0, dtype=np.float64)
+    it, rel = C.c_int(0), C.c_double(0)
+    s = M.as_struct()
+    rc = lib().orc_pcg_sr(C.byref(s), b.ctypes.data, x.ctypes.data, tol, maxit,
+                          C.byref(it), C.byref(rel))
+    return x, it.value, rel.value, rc
+
+
+def pcg_refine32(M, b, x0=None, tol=1e-10, maxit=10000, eta=1e-4):
+    """fp32-stored operator + fp64 refinement, oracle/krylov.c"""
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.zeros(M.n) if x0 is None else np.array(x0, dtype=np.float64)
+    it, outer, rel = C.c_int(0), C.c_int(0), C.c_double(0)
+    s = M.as_struct()
+    rc = lib().orc_pcg_refine32(C.byref(s), b.ctypes.data, x.ctypes.data, tol, maxit, eta,
+                                C.byref(it), C.byref(outer), C.byref(rel))
+    return x, it.value, outer.value, rel.value, rc
 
 
 def true_relres(M, b, x):

@@ -30,14 +30,26 @@ def test_library_exports_every_declared_symbol(abi):
     L = ctypes.CDLL(abi.LIB_PATH)
     for s in declared_symbols():
         assert hasattr(L, s), s
-    assert abi.load().b200_abi_version() == 2
+    assert abi.load().b200_abi_version() == 3
 
 
-def test_struct_sizes_match_header(abi):
-    # b200_mat_info: 16 u64 + 24 u64 hist + u64 + 2 u32 + 3 u64
-    assert ctypes.sizeof(abi.MatInfo) == 8 * (16 + 24 + 1) + 8 + 8 * 3
-    assert ctypes.sizeof(abi.PcgOpts) == 24
-    assert ctypes.sizeof(abi.PcgResult) == 56
+def test_struct_sizes_match_header(abi, tmp_path):
+    """sizes and the offsets of the newest members, as the C compiler sees
+    include/b200.h, against the ctypes mirror"""
+    import subprocess
+    src = tmp_path / "sizes.c"
+    src.write_text(
+        '#include "b200.h"\n#include <stdio.h>\n#include <stddef.h>\n'
+        'int main(void) { printf("%zu %zu %zu %zu %zu\\n", sizeof(b200_mat_info), sizeof(b200_pcg_opts),'
+        ' sizeof(b200_pcg_result), offsetof(b200_mat_info, values_f32), offsetof(b200_pcg_result, outer_iters));'
+        ' return 0; }\n')
+    exe = tmp_path / "sizes"
+    subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert got == [ctypes.sizeof(abi.MatInfo), ctypes.sizeof(abi.PcgOpts), ctypes.sizeof(abi.PcgResult),
+                   abi.MatInfo.values_f32.offset, abi.PcgResult.outer_iters.offset]
+    # b200_mat_info: 16 u64 + 24 u64 hist + u64 + 2 u32 + 3 u64 + 2 u32
+    assert got[:3] == [8 * (16 + 24 + 1) + 8 + 8 * 3 + 8, 24, 64]
 
 
 def test_product_does_not_reach_into_the_oracle():
