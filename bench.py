@@ -193,6 +193,9 @@ def main():
     ap.add_argument("--no-uncompressed-leg", action="store_true",
                     help="skip the extra NO_COMPRESS solve reported beside the headline")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--variants", action="store_true",
+                    help="also time the opt-in variants beside the headline: fp32-stored values "
+                         "(B200_MAT_VALUES_F32, lossless on the stencils) and single-reduction CG")
     args = ap.parse_args()
     CPU_SAMPLE["n"], CPU_SAMPLE["its"] = args.cpu_sample_n or None, args.cpu_sample_its
     if args.impl == "reference":
@@ -354,6 +357,36 @@ def main():
                 "spmv_frac_of_measured": spmv_bytes / (ru.spmv_ms * 1e-3) / 1e9 / peak if ru.spmv_ms > 0 else None,
                 "note": "B200_MAT_NO_COMPRESS: 12 B/nnz streams, the layout the algorithmic-byte count describes"}
             Mu.close()
+        if args.variants:
+            # opt-in variants, reported beside the headline, never as it
+            def leg(mat_flags, pcg_flags, note):
+                Mv = abi.Matrix.generate(ctx, gen, size, flags=mat_flags)
+                iv = Mv.info()
+                d_x.zero_()
+                Mv.pcg(d_b, d_x, tol=TOL, maxit=MAXIT, flags=pcg_flags)
+                torch.cuda.synchronize()
+                d_x.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                rv, _ = Mv.pcg(d_b, d_x, tol=TOL, maxit=MAXIT, flags=pcg_flags)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                sv = e0.elapsed_time(e1) / 1e3
+                out_v = {"value": sv, "unit": UNIT, "iterations": rv.iters, "status": rv.status,
+                         "true_relres": rv.true_relres, "outer_iters": rv.outer_iters,
+                         "ms_per_iteration": sv * 1e3 / max(rv.iters, 1),
+                         "kernel_ms": {"spmv_dot": rv.spmv_ms, "update": rv.update_ms, "pupdate": rv.pupdate_ms},
+                         "values_f32": iv.values_f32, "matrix_stream_bytes": iv.matrix_stream_bytes,
+                         "note": note}
+                Mv.close()
+                return out_v
+            extra["variants"] = {
+                "values_f32": leg(mflags | abi.MAT_VALUES_F32, flags,
+                                  "SELL values stored as fp32 (exact for this operator): fp64 arithmetic, same bits"),
+                "single_reduction": leg(mflags, flags | abi.PCG_SINGLE_REDUCTION,
+                                        "Chronopoulos-Gear CG: two kernels and one reduction point per iteration"),
+                "values_f32+single_reduction": leg(mflags | abi.MAT_VALUES_F32,
+                                                   flags | abi.PCG_SINGLE_REDUCTION, "both")}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_pcg_sample(kind, size, iters)

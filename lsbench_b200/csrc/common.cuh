@@ -175,6 +175,7 @@ struct b200_mat {
   double *w_d = nullptr, *w_rhs = nullptr;  // refinement: correction and residual
   double *stage_b = nullptr, *stage_x = nullptr;  // b200_pcg_solve_host staging
   int grid_ew = 0;                // element-wise kernels
+  int grid_sr = 0;                // single-reduction update kernel
   unsigned partial_stride = 0;
   double *x_ext = nullptr;        // spmv staging: n_local + n_halo
   double *partials = nullptr;     // per-CTA partial sums, 4 lanes of them

@@ -403,7 +403,7 @@ static int queue_iteration_sr(b200_mat *M, int idx, cudaEvent_t *ev = nullptr) {
   PcgState *st = M->state;
   const int nx = ((idx & 1) ^ 1) * 2;
   if (ev) CU_TRY(cudaEventRecord(ev[0], s));  // ev: before K2', between, after K1'
-  k_sr_update<<<M->grid_ew, EW_THREADS, 0, s>>>(
+  k_sr_update<<<M->grid_sr, EW_THREADS, 0, s>>>(
       M->n_local, M->w_x, M->w_r, M->w_pp, M->w_s, M->w_q, M->w_p, M->dinv, M->partials,
       M->partial_stride, st, idx, sum_target(M, &st->red[nx], &st->loc[nx]));
   B_TRY(reduce_ranks(M, &st->red[nx], &st->loc[nx], 2));
@@ -467,6 +467,15 @@ static int pcg_stream(b200_mat *M, const double *d_b, double *d_x,
   if (sr && !M->w_pp) {
     B_TRY(dev_alloc(M, (void **)&M->w_pp, (n + 2) * 8));
     B_TRY(dev_alloc(M, (void **)&M->w_s, (n + 2) * 8));
+    // K2' holds more registers than K2 / K3: its own one-wave grid
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sr_update, EW_THREADS, 0) !=
+            cudaSuccess || per_sm < 1)
+      per_sm = 4;
+    uint64_t g = (uint64_t)c->sm_count * per_sm, need = (n + EW_THREADS - 1) / EW_THREADS;
+    g = g > need ? need : g;
+    g = g > (uint64_t)M->grid_ew ? (uint64_t)M->grid_ew : g;  // never more partial slots than sized for
+    M->grid_sr = g < 1 ? 1 : (int)g;
   }
   int chunk = o->check_every > 0 ? o->check_every : 32;
   chunk = (chunk + 1) & ~1;  // even: the parity pattern repeats per chunk

@@ -1,0 +1,189 @@
+"""GPU parity of the SURVEY 8(f) rows 2 and 4 variants, through the C ABI:
+
+  B200_MAT_VALUES_F32        SELL values stored as fp32 -- lossless on the
+                             stencils (same bits as the fp64-stored matrix),
+                             fp64 refinement otherwise (same fp64 bars)
+  B200_PCG_SINGLE_REDUCTION  Chronopoulos-Gear CG on the streaming kernels
+
+Oracles: oracle/krylov.c orc_pcg_sr / orc_pcg_refine32, the SuperLU direct
+solves (tests/golden/direct.npz), and the default fp64 path of the same library.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import orc
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+DIRECT = np.load(os.path.join(GOLD, "direct.npz"))
+
+
+@pytest.fixture(scope="module")
+def abi():
+    from lsbench_b200 import abi as m
+    m.load()
+    return m
+
+
+@pytest.fixture(scope="module")
+def ctx(abi):
+    c = abi.Context(0)
+    yield c
+    c.close()
+
+
+def op_to_csr(M):
+    return orc.HostCsr(M.n, 0, M.offs.astype(np.uint32), M.cols, M.vals)
+
+
+def make(abi, ctx, A, flags=0):
+    return abi.Matrix.from_csr(ctx, A.nrows, A.base, A.offs, A.cols, A.vals, flags)
+
+
+# ------------------------------------------------------------------ fp32-stored values
+@pytest.mark.parametrize("gen,N", [("poisson7", 40), ("poisson27", 33), ("poisson27", 64)])
+@pytest.mark.parametrize("compress", [True, False])
+def test_f32_values_are_lossless_on_stencils(abi, ctx, gen, N, compress):
+    """every stencil value is an fp32 number: the fp64 copy is dropped
+    (values_f32 == 1), the export returns the same CSR bit for bit, SpMV has the
+    bits of the oracle's fma product, and the PCG takes the same number of
+    iterations to the same solution as the fp64-stored matrix"""
+    M = getattr(orc, "gen_" + gen)(N)
+    A = op_to_csr(M)
+    base = 0 if compress else abi.MAT_NO_COMPRESS
+    M64 = make(abi, ctx, A, base)
+    M32 = make(abi, ctx, A, base | abi.MAT_VALUES_F32)
+    i64, i32 = M64.info(), M32.info()
+    assert (i64.values_f32, i32.values_f32) == (0, 1)
+    assert i32.matrix_stream_bytes == i64.matrix_stream_bytes - 4 * i64.nnz_padded
+    assert i32.device_bytes < i64.device_bytes
+    offs, cols, vals = M32.export()
+    assert np.array_equal(offs, M.offs) and np.array_equal(cols, M.cols)
+    assert vals.tobytes() == M.vals.tobytes()
+    x = np.random.default_rng(3).standard_normal(M.n)
+    y32, y64 = M32.spmv_host(x), M64.spmv_host(x)
+    assert y32.tobytes() == y64.tobytes() == orc.spmv_fma(M, x).tobytes()
+    b = orc.rhs(M.n)
+    xa, ra, _ = M64.pcg_host(b, flags=abi.PCG_NO_SMALL)
+    xb, rb, _ = M32.pcg_host(b, flags=abi.PCG_NO_SMALL)
+    assert (rb.status, rb.outer_iters) == (0, 0) and abs(rb.iters - ra.iters) <= 1
+    assert np.linalg.norm(xb - xa) / np.linalg.norm(xa) <= 1e-10
+    assert orc.true_relres(M, b, xb) <= 1.05e-10
+    # run to run: identical bits
+    xc, rc_, _ = M32.pcg_host(b, flags=abi.PCG_NO_SMALL)
+    assert rc_.iters == rb.iters and xc.tobytes() == xb.tobytes()
+    M64.close(), M32.close()
+
+
+def test_f32_values_odd_widths(abi, ctx):
+    """rows of every length 1..40 (chunks of 16 + a tail of 0..15) with exactly
+    representable values: bit-identical to the oracle's fma product"""
+    rng = np.random.default_rng(11)
+    n = 4000
+    lens = (np.arange(n) % 40) + 1
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    cols = np.concatenate([np.sort(rng.choice(n, l, replace=False)) for l in lens]).astype(np.uint32)
+    vals = rng.integers(-1000, 1000, int(offs[-1])).astype(np.float64) / 64.0
+    M = orc.Op(n, offs, cols, vals)
+    for flags in (abi.MAT_VALUES_F32, abi.MAT_VALUES_F32 | abi.MAT_NO_SORT):
+        Md = make(abi, ctx, op_to_csr(M), flags)
+        assert Md.info().values_f32 == 1
+        x = rng.standard_normal(n)
+        assert Md.spmv_host(x).tobytes() == orc.spmv_fma(M, x).tobytes()
+        Md.close()
+
+
+@pytest.mark.parametrize("name", ["tj7a_A_18", "xn3b_A_10"])
+def test_f32_values_rounded_then_refined(abi, ctx, name):
+    """the Nek values do not survive the rounding: both streams stay
+    (values_f32 == 2), b200_spmv still multiplies with the fp64 operator, and the
+    solve is iterative refinement to the same bars -- true residual <= 1e-10 and x
+    within 1e-8 of the direct solution -- with the oracle's pass count"""
+    A = orc.matrix_read(orc.matrix_path(name))
+    M = orc.op_upper_mirror(A)
+    Md = make(abi, ctx, A, abi.MAT_SYM_UPPER | abi.MAT_VALUES_F32)
+    assert Md.info().values_f32 == 2
+    offs, cols, vals = Md.export()
+    assert vals.tobytes() == M.vals.tobytes()
+    x = np.random.default_rng(2).standard_normal(M.n)
+    assert Md.spmv_host(x).tobytes() == orc.spmv_fma(M, x).tobytes()
+    b = orc.rhs(M.n)
+    xs, res, rc = Md.pcg_host(b, flags=abi.PCG_NO_SMALL)
+    xo, ito, outo, relo, rco = orc.pcg_refine32(M, b)
+    assert rc == 0 and res.status == 0 and res.true_relres <= 1e-10
+    assert abs(res.outer_iters - outo) <= 1 and abs(res.iters - ito) <= 0.15 * ito, (res.iters, ito, res.outer_iters, outo)
+    assert orc.true_relres(M, b, xs) <= 1.05e-10
+    xg = DIRECT[name]
+    assert np.linalg.norm(xs - xg) / np.linalg.norm(xg) <= 1e-8
+    x2, r2, _ = Md.pcg_host(b, flags=abi.PCG_NO_SMALL)
+    assert r2.iters == res.iters and x2.tobytes() == xs.tobytes()
+    Md.close()
+
+
+# ------------------------------------------------------------------ single-reduction CG
+@pytest.mark.parametrize("name", orc.NEK)
+def test_single_reduction_pcg_nek(abi, ctx, name):
+    A = orc.matrix_read(orc.matrix_path(name))
+    M = orc.op_upper_mirror(A)
+    Md = make(abi, ctx, A, abi.MAT_SYM_UPPER)
+    b = orc.rhs(M.n)
+    x, r, rc = Md.pcg_host(b, flags=abi.PCG_SINGLE_REDUCTION)
+    assert rc == 0 and r.status == 0 and r.path == 0 and r.relres <= 1e-10
+    assert orc.true_relres(M, b, x) <= 1.05e-10
+    xg = DIRECT[name]
+    assert np.linalg.norm(x - xg) / np.linalg.norm(xg) <= 1e-8
+    _, it_cpu, _, _ = orc.pcg_sr(M, b)
+    assert abs(r.iters - it_cpu) <= 3, (r.iters, it_cpu)
+    # bit-for-bit reproducible; graph replay, plain launches and the timed path agree
+    x2, r2, _ = Md.pcg_host(b, flags=abi.PCG_SINGLE_REDUCTION | abi.PCG_NO_GRAPH, check_every=6)
+    x3, r3, _ = Md.pcg_host(b, flags=abi.PCG_SINGLE_REDUCTION | abi.PCG_TIME_KERNELS)
+    assert r2.iters == r.iters == r3.iters and x2.tobytes() == x.tobytes() == x3.tobytes()
+    assert r3.spmv_ms > 0 and r3.update_ms > 0 and r3.pupdate_ms == 0
+    # two kernels per iteration instead of three
+    _, r4, _ = Md.pcg_host(b, flags=abi.PCG_NO_SMALL)
+    assert r.kernel_launches < 0.75 * r4.kernel_launches
+    Md.close()
+
+
+def test_single_reduction_pcg_edges(abi, ctx):
+    M = orc.gen_poisson7(16)
+    Md = make(abi, ctx, op_to_csr(M))
+    b = orc.rhs(M.n)
+    SR = abi.PCG_SINGLE_REDUCTION
+    xs, rs, _ = Md.pcg_host(b, flags=SR)
+    assert rs.status == 0 and orc.true_relres(M, b, xs) <= 1.05e-10
+    x, r, rc = Md.pcg_host(b, x0=xs, tol=1e-9, flags=SR)          # starting at the solution
+    assert (r.iters, r.status) == (0, 0)
+    x, r, rc = Md.pcg_host(b, maxit=5, flags=SR)                  # stops at maxit, says so
+    xc, itc, _, rcc = orc.pcg_sr(M, b, maxit=5)
+    assert (r.iters, r.status) == (5, 1) == (itc, rcc)
+    assert np.linalg.norm(x - xc) / np.linalg.norm(xc) < 1e-12
+    x, r, rc = Md.pcg_host(b, maxit=32, check_every=32, flags=SR)  # maxit on a chunk boundary
+    assert (r.iters, r.status) == (32, 1)
+    x, r, rc = Md.pcg_host(b, maxit=rs.iters, flags=SR)           # converges exactly at maxit
+    assert (r.iters, r.status) == (rs.iters, 0) and x.tobytes() == xs.tobytes()
+    Md.close()
+    A = orc.matrix_read(orc.matrix_path("A0_02x02"))              # indefinite: breakdown is reported
+    Md = make(abi, ctx, A)
+    x, r, rc = Md.pcg_host(np.array([1.0, -1.0]), flags=SR)
+    assert (rc, r.status) in ((5, 2), (0, 0))
+    Md.close()
+
+
+def test_single_reduction_with_f32_values_large_enough_to_leave_l2(abi, ctx):
+    """27-point 160^3 (4.1 M rows, 0.9 GB of matrix): both variants together
+    against the default path -- same solution, iteration counts within 1"""
+    M0 = abi.Matrix.generate(ctx, abi.GEN_POISSON27, 160, 1, 0)
+    M1 = abi.Matrix.generate(ctx, abi.GEN_POISSON27, 160, 1, abi.MAT_VALUES_F32)
+    assert M1.info().values_f32 == 1
+    n = M0.info().n_local
+    b = orc.rhs(n)
+    x0, r0, _ = M0.pcg_host(b)
+    x1, r1, _ = M1.pcg_host(b, flags=abi.PCG_SINGLE_REDUCTION)
+    assert r0.status == r1.status == 0 and abs(r0.iters - r1.iters) <= 1
+    assert np.linalg.norm(x1 - x0) / np.linalg.norm(x0) <= 1e-9
+    print("27-pt 160^3: default %.3f ms/it, f32 values + single reduction %.3f ms/it (%d / %d its)"
+          % (r0.solve_ms / r0.iters, r1.solve_ms / r1.iters, r0.iters, r1.iters))
+    M0.close(), M1.close()

@@ -258,3 +258,66 @@ def test_pcg_iteration_counts_poisson():
         xo, ito, relo, rco = orc.pcg(M, orc.rhs(M.n), omp=True)
         assert rco == 0 and abs(ito - it) <= 1
         assert np.linalg.norm(xo - x) / np.linalg.norm(x) < 1e-9
+
+
+# ---- the restatements the new GPU variants are held against
+@pytest.mark.parametrize("name", orc.NEK)
+def test_single_reduction_cg_is_the_same_method(name):
+    """Chronopoulos-Gear CG (oracle/krylov.c orc_pcg_sr): same iteration count
+    as the two-reduction form (+-2), same solution to the parity bar, residual
+    bar met; direct solve as the judge"""
+    A = orc.matrix_read(orc.matrix_path(name))
+    M = orc.op_upper_mirror(A)
+    b = orc.rhs(M.n)
+    x0, it0, _, _ = orc.pcg(M, b)
+    x1, it1, rel1, rc1 = orc.pcg_sr(M, b)
+    assert rc1 == 0 and rel1 <= 1e-10 and abs(it1 - it0) <= 2
+    assert orc.true_relres(M, b, x1) <= 1.05e-10
+    xg = DIRECT[name]
+    assert np.linalg.norm(x1 - xg) / np.linalg.norm(xg) < 1e-8
+
+
+def test_single_reduction_cg_edges():
+    M = orc.gen_poisson7(16)
+    b = orc.rhs(M.n)
+    x, it, rel, rc = orc.pcg_sr(M, b, maxit=5)            # stops at maxit, says so
+    xs, its, _, rcs = orc.pcg(M, b, maxit=5)
+    assert (it, rc) == (5, 1) == (its, rcs) and np.linalg.norm(x - xs) / np.linalg.norm(xs) < 1e-12
+    xf, itf, _, rcf = orc.pcg_sr(M, b)
+    x, it, rel, rc = orc.pcg_sr(M, b, x0=xf, tol=1e-9)    # starting at the solution
+    assert (it, rc) == (0, 0)
+    A = orc.matrix_read(orc.matrix_path("I1_05x05"))      # diagonal: one iteration, exact
+    x, it, rel, rc = orc.pcg_sr(orc.op_upper_mirror(A), orc.rhs(5))
+    assert (it, rc) == (1, 0)
+    np.testing.assert_allclose(x, [0, 1 / 2, 2 / 3, 3 / 4, 4 / 5], rtol=1e-15)
+    A = orc.matrix_read(orc.matrix_path("A0_02x02"))      # indefinite: breakdown, not garbage
+    assert orc.pcg_sr(orc.op_full(A), np.array([1.0, -1.0]))[3] in (0, 2)
+
+
+@pytest.mark.parametrize("name", ["tj7a_A_18", "xn3b_A_18"])
+def test_fp32_operator_with_fp64_refinement_meets_the_fp64_bar(name):
+    """values rounded to fp32 (they do not survive: the Nek values carry 17
+    digits) + refinement with the fp64 operator: the TRUE residual reaches 1e-10
+    and x is the direct solution to the parity bar, in 3 passes and about 1.3 -
+    1.6 x the iterations of the fp64 solve -- the honest price of the restart"""
+    A = orc.matrix_read(orc.matrix_path(name))
+    M = orc.op_upper_mirror(A)
+    assert not np.array_equal(M.vals.astype(np.float32).astype(np.float64), M.vals)
+    b = orc.rhs(M.n)
+    _, it0, _, _ = orc.pcg(M, b)
+    x, it, outer, rel, rc = orc.pcg_refine32(M, b)
+    assert rc == 0 and rel <= 1e-10 and 2 <= outer <= 5 and it0 < it < 2 * it0
+    assert orc.true_relres(M, b, x) <= 1.05e-10
+    xg = DIRECT[name]
+    assert np.linalg.norm(x - xg) / np.linalg.norm(xg) < 1e-8
+
+
+def test_fp32_storage_is_lossless_on_the_stencils():
+    """every value of the Poisson operators is an fp32 number: the fp32-stored
+    solve IS the fp64 solve (same iterates, zero refinement passes)"""
+    for M in (orc.gen_poisson7(12), orc.gen_poisson27(10)):
+        assert np.array_equal(M.vals.astype(np.float32).astype(np.float64), M.vals)
+        b = orc.rhs(M.n)
+        x0, it0, _, _ = orc.pcg(M, b)
+        x, it, outer, rel, rc = orc.pcg_refine32(M, b)
+        assert (it, outer, rc) == (it0, 0, 0) and x.tobytes() == x0.tobytes()
