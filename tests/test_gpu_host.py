@@ -126,3 +126,30 @@ def test_driver_applies_the_ordering(bh, name, env, tmp_path):
     if not full:
         g = DIRECT[name]
         assert np.linalg.norm(x - g) / np.linalg.norm(g) <= 1e-8
+
+
+def test_driver_precision_fp32_and_single_reduction(bh, tmp_path):
+    """--precision FP32 (fp32-stored operator: rounded on a Nek file -> refinement
+    passes, lossless on a stencil) and LSBENCH_B200_PCG=sr through the harness:
+    the same bars as the default run"""
+    name = "xn3b_A_18"
+    A = orc.matrix_read(orc.matrix_path(name))
+    out = str(tmp_path / "x.bin")
+    r = subprocess.run([bh.DRIVER, "--solver", "b200", "--matrix", orc.matrix_path(name), "--trials=2",
+                        "--precision=FP32", "--verbose=1", "--dump-x", out],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    row, ext = parse(r.stdout)
+    assert int(ext[2]) == 0 and float(ext[4]) <= 1.05e-10
+    assert "precision=fp32 values rounded" in r.stdout
+    x, g = np.fromfile(out), DIRECT[name]
+    assert np.linalg.norm(x - g) / np.linalg.norm(g) <= 1e-8
+    r = subprocess.run([bh.DRIVER, "--solver", "b200", "--matrix", "poisson27:40", "--trials=2",
+                        "--precision=FP32", "--verbose=1", "--dump-x", out],
+                       capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, LSBENCH_B200_PCG="sr"))
+    assert r.returncode == 0, r.stderr
+    row, ext = parse(r.stdout)
+    assert int(ext[2]) == 0 and "precision=fp32 values lossless" in r.stdout
+    M = orc.gen_poisson27(40)
+    assert orc.true_relres(M, orc.rhs(M.n), np.fromfile(out)) <= 1.05e-10

@@ -146,6 +146,13 @@ def test_cli_defaults_and_both_option_forms(host):
     L.lsbench_finalize(cb)
 
 
+def test_fp32_is_accepted_for_b200_only(host):
+    L, _ = host
+    cb = init(L, "--matrix", "m", "--solver", "b200", "--precision=fp32")
+    assert (cb.contents.solver, cb.contents.precision) == (6, 1)
+    L.lsbench_finalize(cb)
+
+
 def test_driver_cli_errors(host):
     _, bh = host
     r = subprocess.run([bh.DRIVER, "--help"], capture_output=True, text=True)
@@ -155,6 +162,13 @@ def test_driver_cli_errors(host):
     r = subprocess.run([bh.DRIVER, "--matrix", "x", "--precision=FP32"],
                        capture_output=True, text=True)
     assert r.returncode == 1 and "FP64" in r.stderr
+    # FP32 has a meaning for b200 only (fp32-stored operator); FP16 for nobody
+    for words in (["--solver", "cholmod", "--precision=FP32"], ["--solver", "b200", "--precision=FP16"]):
+        r = subprocess.run([bh.DRIVER, "--matrix", "x"] + words, capture_output=True, text=True)
+        assert r.returncode == 1 and "Precisions other than FP64 are not implemented yet." in r.stderr
+    r = subprocess.run([bh.DRIVER, "--matrix", "/nonexistent.txt", "--solver", "b200", "--precision=FP32"],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "Unable to open file" in r.stderr   # got past the precision check
     r = subprocess.run([bh.DRIVER, "--matrix", "/nonexistent.txt", "--solver", "b200"],
                        capture_output=True, text=True)
     assert r.returncode == 1 and "Unable to open file" in r.stderr
