@@ -212,6 +212,8 @@ k_spmv_sellc(const uint4 *__restrict__ meta, const uint32_t *__restrict__ cols,
   }
 }
 
+#include "sellc32p.cuh"
+
 template <bool DOT>
 __global__ void __launch_bounds__(SPMV_THREADS, 4)
 k_spmv_vec(uint32_t nrows, const uint32_t *__restrict__ ids,
@@ -308,6 +310,25 @@ static int persistent_grid(b200_ctx *c, const void *kernel, uint64_t work_ctas) 
   return g < 1 ? 1 : (int)g;
 }
 
+// B200_SPMV_PIPE=1 selects k_spmv_sellc32p where it applies: fp32 value stream,
+// index-compressed layout, no slice wider than 32.  Returns the WMAX to
+// instantiate, 0 for the plain kernels.
+static int pipe_wmax(const b200_mat *M) {
+  static const int on = [] {
+    const char *v = getenv("B200_SPMV_PIPE");
+    return v && *v && strcmp(v, "0") != 0 ? 1 : 0;
+  }();
+  if (!on || !M->sell_vals32 || !M->sell_meta || M->sell_max_width > 32)
+    return 0;
+  return M->sell_max_width > 16 ? 32 : (M->sell_max_width > 8 ? 16 : 8);
+}
+
+static const void *pipe_kernel(int wmax) {
+  return wmax == 32   ? (const void *)k_spmv_sellc32p<true, 32>
+         : wmax == 16 ? (const void *)k_spmv_sellc32p<true, 16>
+                      : (const void *)k_spmv_sellc32p<true, 8>;
+}
+
 static SpmvPlan compute_plan(b200_mat *M, int phase) {
   SpmvPlan P = {0, 0, 0, 0, 0, 0, 0};
   b200_ctx *c = M->ctx;
@@ -341,7 +362,8 @@ static SpmvPlan compute_plan(b200_mat *M, int phase) {
     // order): sized for the fp32-value instantiation when that stream exists
     P.g_sell = persistent_grid(
         c,
-        M->sell_vals32 ? (M->sell_meta ? (const void *)k_spmv_sellc<true, float>
+        pipe_wmax(M)   ? pipe_kernel(pipe_wmax(M))
+        : M->sell_vals32 ? (M->sell_meta ? (const void *)k_spmv_sellc<true, float>
                                        : (const void *)k_spmv_sell<true, float>)
                        : (M->sell_meta ? (const void *)k_spmv_sellc<true, double>
                                        : (const void *)k_spmv_sell<true, double>),
@@ -408,10 +430,27 @@ int launch_spmv(b200_mat *M, const double *x, double *y, bool dot, int phase,
       k_spmv_sell<false, VT><<<P.g_sell, SPMV_THREADS, 0, s>>>(                   \
           M->sell_off, M->sell_cols, VALS, B2_SELL_ARGS(false));                  \
   } while (0)
-    if (f32)
+    const int pw = f32 ? pipe_wmax(M) : 0;
+#define B2_PIPE_LAUNCH(W)                                                         \
+  do {                                                                            \
+    if (dot)                                                                      \
+      k_spmv_sellc32p<true, W><<<P.g_sell, SPMV_THREADS, 0, s>>>(                 \
+          meta, M->sell_cols, M->sell_dcols, M->sell_vals32, B2_SELL_ARGS(true)); \
+    else                                                                          \
+      k_spmv_sellc32p<false, W><<<P.g_sell, SPMV_THREADS, 0, s>>>(                \
+          meta, M->sell_cols, M->sell_dcols, M->sell_vals32, B2_SELL_ARGS(false));\
+  } while (0)
+    if (pw == 32)
+      B2_PIPE_LAUNCH(32);
+    else if (pw == 16)
+      B2_PIPE_LAUNCH(16);
+    else if (pw == 8)
+      B2_PIPE_LAUNCH(8);
+    else if (f32)
       B2_SELL_LAUNCH(float, M->sell_vals32);
     else
       B2_SELL_LAUNCH(double, M->sell_vals);
+#undef B2_PIPE_LAUNCH
 #undef B2_SELL_LAUNCH
 #undef B2_SELL_ARGS
     slot_base += P.g_sell;

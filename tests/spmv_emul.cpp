@@ -1,0 +1,69 @@
+// spmv_emul.cpp -- TEST INFRASTRUCTURE.  Compiles the body of the pipelined
+// fp32-value SELL kernel (lsbench_b200/csrc/sellc32p.cuh) for the host, with
+// one-line stand-ins for the CUDA built-ins, and runs it thread by thread over a
+// launch grid.  Without the fused dot product a thread talks to no other thread,
+// so running the threads one after another is exactly what the GPU computes.
+// The caller (tests/test_spmv_emul.py) builds the index-compressed SELL layout
+// of DESIGN.md section 2 with numpy and compares y with a CSR product bit for bit.
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+
+struct uint4 {
+  unsigned x, y, z, w;
+};
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) {
+  return uint4{x, y, z, w};
+}
+struct Dim {
+  unsigned x;
+};
+static Dim threadIdx, blockIdx, gridDim;
+#define __global__
+#define __launch_bounds__(...)
+#define __shared__ static
+#define B2_SLICE 32
+#define SPMV_THREADS 256
+#define SPMV_WARPS (SPMV_THREADS / 32)
+template <typename T> static inline T __ldg(const T *p) { return *p; }
+template <typename T> static inline T ld_stream(const T *p) { return *p; }
+struct PcgState {
+  int done;
+  unsigned ticket[4];
+};
+struct XrArgs {};
+template <int N> static double block_sum(double v, double *) { return v; }
+template <int NV, int NW>
+static void grid_sum_finish(const double (&)[NV], double *, unsigned, unsigned, unsigned,
+                            unsigned *, double *, double *, const XrArgs &) {}
+
+#include "sellc32p.cuh"
+
+template <int WMAX>
+static void run(unsigned grid, const uint4 *meta, const uint32_t *cols, const int32_t *dcols,
+                const float *vals, const uint32_t *perm, const double *x, double *y,
+                uint32_t b0, uint32_t e0, uint32_t b1, uint32_t e1, uint32_t n_rows) {
+  gridDim.x = grid;
+  for (unsigned b = 0; b < grid; b++)
+    for (unsigned t = 0; t < SPMV_THREADS; t++) {
+      blockIdx.x = b, threadIdx.x = t;
+      k_spmv_sellc32p<false, WMAX>(meta, cols, dcols, vals, perm, x, y, b0, e0, b1, e1, n_rows,
+                                   nullptr, 0, 0, nullptr, nullptr, XrArgs{});
+    }
+}
+
+extern "C" int emul_sellc32p(int wmax, unsigned grid, const uint4 *meta, const uint32_t *cols,
+                             const int32_t *dcols, const float *vals, const uint32_t *perm,
+                             const double *x, double *y, uint32_t b0, uint32_t e0, uint32_t b1,
+                             uint32_t e1, uint32_t n_rows) {
+  if (wmax == 8)
+    run<8>(grid, meta, cols, dcols, vals, perm, x, y, b0, e0, b1, e1, n_rows);
+  else if (wmax == 16)
+    run<16>(grid, meta, cols, dcols, vals, perm, x, y, b0, e0, b1, e1, n_rows);
+  else if (wmax == 32)
+    run<32>(grid, meta, cols, dcols, vals, perm, x, y, b0, e0, b1, e1, n_rows);
+  else
+    return 1;
+  return 0;
+}
