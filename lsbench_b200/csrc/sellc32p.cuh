@@ -17,10 +17,21 @@
 // warp has a full slice of the value stream (w x 128 B) in flight all the time
 // and pays no DRAM latency on its critical path.  Same fma chain per row, so
 // the same bits.
-template <bool DOT, int WMAX>
-__global__ void __launch_bounds__(SPMV_THREADS, WMAX > 16 ? 2 : (WMAX > 8 ? 3 : 4))
+//
+// The same idea carries to fp64 values when the CTA is small enough to give a
+// thread the registers (2 x 27 doubles): THREADS = 128, three CTAs per SM -- 12
+// warps, each with 6.9 KB of values in flight, which is more than the 65 KB per
+// SM that 6.4 TB/s x 1.5 us asks for (B200_SPMV_PIPE=2; same caveat).
+template <typename VT, int WMAX> struct PipeCfg {
+  static constexpr int threads = sizeof(VT) == 8 && WMAX > 16 ? 128 : 256;
+  static constexpr int min_blocks =
+      sizeof(VT) == 8 ? (WMAX > 16 ? 3 : (WMAX > 8 ? 2 : 3)) : (WMAX > 16 ? 2 : (WMAX > 8 ? 3 : 4));
+};
+
+template <bool DOT, int WMAX, typename VT>
+__global__ void __launch_bounds__(PipeCfg<VT, WMAX>::threads, PipeCfg<VT, WMAX>::min_blocks)
 k_spmv_sellc32p(const uint4 *__restrict__ meta, const uint32_t *__restrict__ cols,
-                const int32_t *__restrict__ dcols, const float *__restrict__ vals,
+                const int32_t *__restrict__ dcols, const VT *__restrict__ vals,
                 const uint32_t *__restrict__ perm, const double *__restrict__ x,
                 double *__restrict__ y, uint32_t b0, uint32_t e0, uint32_t b1,
                 uint32_t e1, uint32_t n_rows, double *partials, unsigned slot_base,
@@ -29,38 +40,39 @@ k_spmv_sellc32p(const uint4 *__restrict__ meta, const uint32_t *__restrict__ col
     if (st->done)
       return;
   }
-  __shared__ double red[SPMV_WARPS];
+  constexpr int WARPS = PipeCfg<VT, WMAX>::threads / 32;
+  __shared__ double red[WARPS];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t n0 = e0 - b0, nv = n0 + (e1 - b1);
-  const uint32_t stride = gridDim.x * SPMV_WARPS;
+  const uint32_t stride = gridDim.x * WARPS;
   double dot = 0.0;
-  uint32_t v = blockIdx.x * SPMV_WARPS + warp;
-  float a[WMAX];
+  uint32_t v = blockIdx.x * WARPS + warp;
+  VT a[WMAX];
   uint4 m = make_uint4(0u, 0u, 0u, 0u);
   if (v < nv) {
     m = __ldg(meta + (v < n0 ? b0 + v : b1 + (v - n0)));
-    const float *vp = vals + (size_t)m.x * B2_SLICE + lane;
+    const VT *vp = vals + (size_t)m.x * B2_SLICE + lane;
     const uint32_t w = m.y & 0x7fffffffu;
 #pragma unroll
     for (int k = 0; k < WMAX; k++)
-      a[k] = k < w ? ld_stream(vp + (size_t)k * B2_SLICE) : 0.0f;
+      a[k] = k < w ? ld_stream(vp + (size_t)k * B2_SLICE) : VT(0);
   }
   while (v < nv) {
     // ---- request the next slice's values -------------------------------------------
     const uint32_t vn = v + stride;
-    float an[WMAX];
+    VT an[WMAX];
     uint4 mn = m;
     if (vn < nv) {
       mn = __ldg(meta + (vn < n0 ? b0 + vn : b1 + (vn - n0)));
-      const float *vp = vals + (size_t)mn.x * B2_SLICE + lane;
+      const VT *vp = vals + (size_t)mn.x * B2_SLICE + lane;
       const uint32_t wn = mn.y & 0x7fffffffu;
 #pragma unroll
       for (int k = 0; k < WMAX; k++)
-        an[k] = k < wn ? ld_stream(vp + (size_t)k * B2_SLICE) : 0.0f;
+        an[k] = k < wn ? ld_stream(vp + (size_t)k * B2_SLICE) : VT(0);
     } else {
 #pragma unroll
       for (int k = 0; k < WMAX; k++)
-        an[k] = 0.0f;
+        an[k] = VT(0);
     }
     // ---- the current slice: gathers and the fma chain, 8 entries at a time ------------
     const uint32_t s = v < n0 ? b0 + v : b1 + (v - n0);
@@ -102,8 +114,8 @@ k_spmv_sellc32p(const uint4 *__restrict__ meta, const uint32_t *__restrict__ col
       a[k] = an[k];
   }
   if constexpr (DOT) {
-    double b[1] = {block_sum<SPMV_WARPS>(dot, red)};
-    grid_sum_finish<1, SPMV_WARPS>(b, partials, 0, slot_base + blockIdx.x,
+    double b[1] = {block_sum<WARPS>(dot, red)};
+    grid_sum_finish<1, WARPS>(b, partials, 0, slot_base + blockIdx.x,
                                    total_slots, &st->ticket[0], dot_out, red, xr);
   }
 }

@@ -298,10 +298,11 @@ k_spmv_long(uint32_t nrows, const uint32_t *__restrict__ ids,
 }
 
 // ---------------------------------------------------------------------------
-static int persistent_grid(b200_ctx *c, const void *kernel, uint64_t work_ctas) {
+static int persistent_grid(b200_ctx *c, const void *kernel, uint64_t work_ctas,
+                           int threads = SPMV_THREADS) {
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel,
-                                                    SPMV_THREADS, 0) != cudaSuccess ||
+                                                    threads, 0) != cudaSuccess ||
       per_sm < 1)
     per_sm = 4;
   uint64_t g = (uint64_t)c->sm_count * per_sm;
@@ -310,23 +311,40 @@ static int persistent_grid(b200_ctx *c, const void *kernel, uint64_t work_ctas) 
   return g < 1 ? 1 : (int)g;
 }
 
-// B200_SPMV_PIPE=1 selects k_spmv_sellc32p where it applies: fp32 value stream,
-// index-compressed layout, no slice wider than 32.  Returns the WMAX to
-// instantiate, 0 for the plain kernels.
+// B200_SPMV_PIPE selects the software-pipelined kernel (sellc32p.cuh) where it
+// applies -- index-compressed layout, no slice wider than 32, ONE value stream
+// resident: 1 = matrices with fp32-stored values, 2 = fp64-stored ones as well.
+// Returns the WMAX to instantiate, 0 for the plain kernels.
 static int pipe_wmax(const b200_mat *M) {
-  static const int on = [] {
+  static const int level = [] {
     const char *v = getenv("B200_SPMV_PIPE");
-    return v && *v && strcmp(v, "0") != 0 ? 1 : 0;
+    return v ? atoi(v) : 0;
   }();
-  if (!on || !M->sell_vals32 || !M->sell_meta || M->sell_max_width > 32)
+  if (level < 1 || !M->sell_meta || M->sell_max_width > 32 || M->sell_max_width == 0)
+    return 0;
+  if (M->sell_vals32 && M->sell_vals)  // refinement mode alternates the streams
+    return 0;
+  if (!M->sell_vals32 && level < 2)
     return 0;
   return M->sell_max_width > 16 ? 32 : (M->sell_max_width > 8 ? 16 : 8);
 }
 
-static const void *pipe_kernel(int wmax) {
-  return wmax == 32   ? (const void *)k_spmv_sellc32p<true, 32>
-         : wmax == 16 ? (const void *)k_spmv_sellc32p<true, 16>
-                      : (const void *)k_spmv_sellc32p<true, 8>;
+template <typename VT>
+static const void *pipe_kernel_of(int wmax) {
+  return wmax == 32   ? (const void *)k_spmv_sellc32p<true, 32, VT>
+         : wmax == 16 ? (const void *)k_spmv_sellc32p<true, 16, VT>
+                      : (const void *)k_spmv_sellc32p<true, 8, VT>;
+}
+template <typename VT>
+static int pipe_threads_of(int wmax) {
+  return wmax == 32 ? PipeCfg<VT, 32>::threads : wmax == 16 ? PipeCfg<VT, 16>::threads
+                                                            : PipeCfg<VT, 8>::threads;
+}
+static const void *pipe_kernel(const b200_mat *M, int wmax) {
+  return M->sell_vals32 ? pipe_kernel_of<float>(wmax) : pipe_kernel_of<double>(wmax);
+}
+static int pipe_threads(const b200_mat *M, int wmax) {
+  return M->sell_vals32 ? pipe_threads_of<float>(wmax) : pipe_threads_of<double>(wmax);
 }
 
 static SpmvPlan compute_plan(b200_mat *M, int phase) {
@@ -357,17 +375,23 @@ static SpmvPlan compute_plan(b200_mat *M, int phase) {
   else
     P.b0 = 0, P.e0 = ib, P.b1 = ie, P.e1 = ns;
   uint32_t nv = (P.e0 - P.b0) + (P.e1 - P.b1);
-  if (nv)
+  if (nv) {
     // one grid per matrix (fixed count of dot partials = fixed summation
-    // order): sized for the fp32-value instantiation when that stream exists
-    P.g_sell = persistent_grid(
-        c,
-        pipe_wmax(M)   ? pipe_kernel(pipe_wmax(M))
-        : M->sell_vals32 ? (M->sell_meta ? (const void *)k_spmv_sellc<true, float>
-                                       : (const void *)k_spmv_sell<true, float>)
-                       : (M->sell_meta ? (const void *)k_spmv_sellc<true, double>
-                                       : (const void *)k_spmv_sell<true, double>),
-        (nv + SPMV_WARPS - 1) / SPMV_WARPS);
+    // order): sized for the instantiation that will run
+    const int pw = pipe_wmax(M);
+    if (pw) {
+      const int th = pipe_threads(M, pw);
+      P.g_sell = persistent_grid(c, pipe_kernel(M, pw), (nv + th / 32 - 1) / (th / 32), th);
+    } else {
+      P.g_sell = persistent_grid(
+          c,
+          M->sell_vals32 ? (M->sell_meta ? (const void *)k_spmv_sellc<true, float>
+                                         : (const void *)k_spmv_sell<true, float>)
+                         : (M->sell_meta ? (const void *)k_spmv_sellc<true, double>
+                                         : (const void *)k_spmv_sell<true, double>),
+          (nv + SPMV_WARPS - 1) / SPMV_WARPS);
+    }
+  }
   if (others && M->vec_rows)
     P.g_vec = persistent_grid(c, (const void *)k_spmv_vec<true>,
                               (M->vec_rows + SPMV_WARPS - 1) / SPMV_WARPS);
@@ -430,26 +454,34 @@ int launch_spmv(b200_mat *M, const double *x, double *y, bool dot, int phase,
       k_spmv_sell<false, VT><<<P.g_sell, SPMV_THREADS, 0, s>>>(                   \
           M->sell_off, M->sell_cols, VALS, B2_SELL_ARGS(false));                  \
   } while (0)
-    const int pw = f32 ? pipe_wmax(M) : 0;
-#define B2_PIPE_LAUNCH(W)                                                         \
+    const int pw = pipe_wmax(M);
+#define B2_PIPE_LAUNCH(W, VT, VALS)                                               \
   do {                                                                            \
     if (dot)                                                                      \
-      k_spmv_sellc32p<true, W><<<P.g_sell, SPMV_THREADS, 0, s>>>(                 \
-          meta, M->sell_cols, M->sell_dcols, M->sell_vals32, B2_SELL_ARGS(true)); \
+      k_spmv_sellc32p<true, W, VT><<<P.g_sell, PipeCfg<VT, W>::threads, 0, s>>>(  \
+          meta, M->sell_cols, M->sell_dcols, VALS, B2_SELL_ARGS(true));           \
     else                                                                          \
-      k_spmv_sellc32p<false, W><<<P.g_sell, SPMV_THREADS, 0, s>>>(                \
-          meta, M->sell_cols, M->sell_dcols, M->sell_vals32, B2_SELL_ARGS(false));\
+      k_spmv_sellc32p<false, W, VT><<<P.g_sell, PipeCfg<VT, W>::threads, 0, s>>>( \
+          meta, M->sell_cols, M->sell_dcols, VALS, B2_SELL_ARGS(false));          \
   } while (0)
-    if (pw == 32)
-      B2_PIPE_LAUNCH(32);
-    else if (pw == 16)
-      B2_PIPE_LAUNCH(16);
-    else if (pw == 8)
-      B2_PIPE_LAUNCH(8);
+#define B2_PIPE_ANY(VT, VALS)                                                     \
+  do {                                                                            \
+    if (pw == 32)                                                                 \
+      B2_PIPE_LAUNCH(32, VT, VALS);                                               \
+    else if (pw == 16)                                                            \
+      B2_PIPE_LAUNCH(16, VT, VALS);                                               \
+    else                                                                          \
+      B2_PIPE_LAUNCH(8, VT, VALS);                                                \
+  } while (0)
+    if (pw && f32)
+      B2_PIPE_ANY(float, M->sell_vals32);
+    else if (pw)
+      B2_PIPE_ANY(double, M->sell_vals);
     else if (f32)
       B2_SELL_LAUNCH(float, M->sell_vals32);
     else
       B2_SELL_LAUNCH(double, M->sell_vals);
+#undef B2_PIPE_ANY
 #undef B2_PIPE_LAUNCH
 #undef B2_SELL_LAUNCH
 #undef B2_SELL_ARGS

@@ -40,30 +40,41 @@ static void grid_sum_finish(const double (&)[NV], double *, unsigned, unsigned, 
 
 #include "sellc32p.cuh"
 
-template <int WMAX>
+template <int WMAX, typename VT>
 static void run(unsigned grid, const uint4 *meta, const uint32_t *cols, const int32_t *dcols,
-                const float *vals, const uint32_t *perm, const double *x, double *y,
+                const VT *vals, const uint32_t *perm, const double *x, double *y,
                 uint32_t b0, uint32_t e0, uint32_t b1, uint32_t e1, uint32_t n_rows) {
   gridDim.x = grid;
   for (unsigned b = 0; b < grid; b++)
-    for (unsigned t = 0; t < SPMV_THREADS; t++) {
+    for (unsigned t = 0; t < (unsigned)PipeCfg<VT, WMAX>::threads; t++) {
       blockIdx.x = b, threadIdx.x = t;
-      k_spmv_sellc32p<false, WMAX>(meta, cols, dcols, vals, perm, x, y, b0, e0, b1, e1, n_rows,
-                                   nullptr, 0, 0, nullptr, nullptr, XrArgs{});
+      k_spmv_sellc32p<false, WMAX, VT>(meta, cols, dcols, vals, perm, x, y, b0, e0, b1, e1, n_rows,
+                                       nullptr, 0, 0, nullptr, nullptr, XrArgs{});
     }
 }
 
-extern "C" int emul_sellc32p(int wmax, unsigned grid, const uint4 *meta, const uint32_t *cols,
-                             const int32_t *dcols, const float *vals, const uint32_t *perm,
-                             const double *x, double *y, uint32_t b0, uint32_t e0, uint32_t b1,
-                             uint32_t e1, uint32_t n_rows) {
+template <typename VT>
+static int run_any(int wmax, unsigned grid, const uint4 *meta, const uint32_t *cols,
+                   const int32_t *dcols, const VT *vals, const uint32_t *perm, const double *x,
+                   double *y, uint32_t b0, uint32_t e0, uint32_t b1, uint32_t e1, uint32_t n_rows) {
   if (wmax == 8)
-    run<8>(grid, meta, cols, dcols, vals, perm, x, y, b0, e0, b1, e1, n_rows);
+    run<8, VT>(grid, meta, cols, dcols, vals, perm, x, y, b0, e0, b1, e1, n_rows);
   else if (wmax == 16)
-    run<16>(grid, meta, cols, dcols, vals, perm, x, y, b0, e0, b1, e1, n_rows);
+    run<16, VT>(grid, meta, cols, dcols, vals, perm, x, y, b0, e0, b1, e1, n_rows);
   else if (wmax == 32)
-    run<32>(grid, meta, cols, dcols, vals, perm, x, y, b0, e0, b1, e1, n_rows);
+    run<32, VT>(grid, meta, cols, dcols, vals, perm, x, y, b0, e0, b1, e1, n_rows);
   else
     return 1;
   return 0;
+}
+
+// vals: float[] when f64 == 0, double[] otherwise
+extern "C" int emul_sellc32p(int wmax, int f64, unsigned grid, const uint4 *meta,
+                             const uint32_t *cols, const int32_t *dcols, const void *vals,
+                             const uint32_t *perm, const double *x, double *y, uint32_t b0,
+                             uint32_t e0, uint32_t b1, uint32_t e1, uint32_t n_rows) {
+  return f64 ? run_any<double>(wmax, grid, meta, cols, dcols, (const double *)vals, perm, x, y, b0,
+                               e0, b1, e1, n_rows)
+             : run_any<float>(wmax, grid, meta, cols, dcols, (const float *)vals, perm, x, y, b0,
+                              e0, b1, e1, n_rows);
 }

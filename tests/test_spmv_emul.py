@@ -26,7 +26,7 @@ def emul(tmp_path_factory):
                     os.path.join(ROOT, "tests", "spmv_emul.cpp"), "-o", so], check=True)
     L = C.CDLL(so)
     L.emul_sellc32p.restype = C.c_int
-    L.emul_sellc32p.argtypes = [C.c_int, C.c_uint] + [C.c_void_p] * 7 + [C.c_uint32] * 5
+    L.emul_sellc32p.argtypes = [C.c_int, C.c_int, C.c_uint] + [C.c_void_p] * 7 + [C.c_uint32] * 5
     return L
 
 
@@ -72,12 +72,18 @@ def sellc_layout(M, perm=None):
 
 
 def run(emul, Lay, n, x, wmax, grid, ranges=None):
-    y = np.full(n, np.nan)
+    """both instantiations: fp32-stored values (256-thread CTAs) and fp64-stored
+    ones (128-thread CTAs when wmax = 32); the answers must not differ"""
     b0, e0, b1, e1 = ranges or (0, Lay["ns"], 0, 0)
     p = lambda a: None if a is None else a.ctypes.data
-    assert emul.emul_sellc32p(wmax, grid, p(Lay["meta"]), p(Lay["ecols"]), p(Lay["dcols"]), p(Lay["vals"]),
-                              p(Lay["list"]), p(x), p(y), b0, e0, b1, e1, n) == 0
-    return y
+    ys = []
+    for f64, vals in ((0, Lay["vals"]), (1, Lay["vals"].astype(np.float64))):
+        y = np.full(n, np.nan)
+        assert emul.emul_sellc32p(wmax, f64, grid, p(Lay["meta"]), p(Lay["ecols"]), p(Lay["dcols"]), p(vals),
+                                  p(Lay["list"]), p(x), p(y), b0, e0, b1, e1, n) == 0
+        ys.append(y)
+    assert ys[0].tobytes() == ys[1].tobytes()
+    return ys[0]
 
 
 @pytest.mark.parametrize("gen,N,wmax", [("poisson27", 8, 32), ("poisson7", 12, 8), ("poisson7", 12, 16),

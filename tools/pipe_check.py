@@ -2,6 +2,9 @@
 (csrc/sellc32p.cuh) on a GPU -- parity first, then time, beside the plain kernels.
 
     B200_SPMV_PIPE=1 python tools/pipe_check.py [N]        27-point N^3, default 192
+    B200_SPMV_PIPE=2 python tools/pipe_check.py [N]        fp64-stored values pipelined as well
+                                                           (128-thread CTAs); compare with the
+                                                           "f64" line of a B200_SPMV_PIPE=1 run
 
 Parity: SpMV bits against the oracle's fma product on a 27-point 40^3 and a 7-point
 48^3 grid and on ragged rows; PCG iteration count and solution against the fp64-stored
@@ -54,7 +57,15 @@ for fl in (abi.MAT_VALUES_F32, abi.MAT_VALUES_F32 | abi.MAT_NO_SORT):
 print("parity: ok")
 
 out = {"workload": "poisson27:%d" % N, "B200_SPMV_PIPE": os.environ.get("B200_SPMV_PIPE")}
-for mname, mflags in (("f64", 0), ("f32_pipelined", abi.MAT_VALUES_F32)):
+LEVEL = int(os.environ["B200_SPMV_PIPE"])
+if LEVEL >= 2:   # fp64-stored values through the pipelined kernel: bits first
+    for M in (orc.gen_poisson27(40), orc.gen_poisson7(48)):
+        Md = abi.Matrix.from_csr(ctx, *csr(M), 0)
+        x = rng.standard_normal(M.n)
+        assert Md.spmv_host(x).tobytes() == orc.spmv_fma(M, x).tobytes(), "fp64 pipelined SpMV bits differ"
+        Md.close()
+    print("parity (fp64 values, pipelined): ok")
+for mname, mflags in (("f64_pipelined" if LEVEL >= 2 else "f64", 0), ("f32_pipelined", abi.MAT_VALUES_F32)):
     Md = abi.Matrix.generate(ctx, abi.GEN_POISSON27, N, 1, mflags)
     i = Md.info()
     n = i.n_local
