@@ -203,11 +203,11 @@ struct rcm_work {
   unsigned stamp;
 };
 
-static const unsigned *rcm_deg;
-static int rcm_by_degree(const void *a, const void *b) {
+static int rcm_by_degree(const void *a, const void *b, void *deg_) {
+  const unsigned *deg = (const unsigned *)deg_;
   unsigned x = *(const unsigned *)a, y = *(const unsigned *)b;
-  if (rcm_deg[x] != rcm_deg[y])
-    return rcm_deg[x] < rcm_deg[y] ? -1 : 1;
+  if (deg[x] != deg[y])
+    return deg[x] < deg[y] ? -1 : 1;
   return x < y ? -1 : x > y;
 }
 
@@ -289,8 +289,7 @@ int b200_host_rcm(unsigned n, const unsigned *offs, const unsigned *cols, unsign
     return 1;
   for (unsigned i = 0; i < n; i++)
     byd[i] = i;
-  rcm_deg = w.deg;
-  qsort(byd, n, sizeof(unsigned), rcm_by_degree);
+  qsort_r(byd, n, sizeof(unsigned), rcm_by_degree, w.deg);
 
   unsigned done = 0;
   for (unsigned b = 0; b < n; b++) {
@@ -323,7 +322,7 @@ int b200_host_rcm(unsigned n, const unsigned *offs, const unsigned *cols, unsign
           mark[v] = 1, perm[tail++] = v;
       }
       if (tail - first > 1)
-        qsort(perm + first, tail - first, sizeof(unsigned), rcm_by_degree);
+        qsort_r(perm + first, tail - first, sizeof(unsigned), rcm_by_degree, w.deg);
     }
     done = tail;
   }
