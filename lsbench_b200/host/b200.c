@@ -427,14 +427,15 @@ static void *run_rank(void *arg) {
 
   /* csr_init: host CSR -> backend layout, untimed (src/cusparse.c:174) */
   b200_mat *M = NULL;
+#ifdef LSBENCH_HAS_SYNTHETIC /* this tree's extension of struct csr (lsbench-impl.h) */
   if (A->offs == NULL) {
     unsigned gflags = cfg->flags & ~(unsigned)B200_MAT_SYM_UPPER;
     chk_b200(b200_mat_generate(ctx, A->gen_kind, A->gen_size, A->gen_seed,
                                gflags, &M));
-  } else {
+  } else
+#endif
     chk_b200(b200_mat_from_csr(ctx, A->nrows, A->base, A->offs, A->cols,
                                A->vals, cfg->flags, &M));
-  }
   b200_mat_info info;
   chk_b200(b200_mat_get_info(M, &info));
   pthread_mutex_lock(&sh->lock);
@@ -572,8 +573,10 @@ int b200_bench(double *x, struct csr *A, const double *r,
    * (src/cusparse.c:169); for a generated matrix, the generated count */
   unsigned m = A->nrows;
   unsigned long long nnz_in = A->offs ? A->offs[m] : sh.nnz;
+#ifdef LSBENCH_HAS_SYNTHETIC
   if (!A->offs)
     A->gen_nnz = sh.nnz;
+#endif
   printf("===matrix,n,nnz,trials,solver,ordering,elapsed===\n");
   printf("%s,%u,%llu,%u,%u,%d,%.15lf\n", cb->matrix, m, nnz_in, cb->trials,
          cb->solver, cb->ordering, sh.elapsed);

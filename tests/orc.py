@@ -8,6 +8,7 @@ import ctypes as C
 import lzma
 import os
 import subprocess
+import sys
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -29,6 +30,10 @@ def build_oracle():
     if os.path.isdir("/root/reference/src"):
         subprocess.run(["make", "-s", "-C", ORACLE_DIR, "ref"], check=True)
         subprocess.run(["make", "-s", "-C", ORACLE_DIR, "ref-cusolver"], check=True)
+        if os.path.exists(os.path.join(ROOT, "lsbench_b200", "libb200.so")):
+            # the drop-in for real: the reference tree + the five registration edits + b200.c
+            subprocess.run([sys.executable, os.path.join(ORACLE_DIR, "dropin.py")], check=True,
+                           stdout=subprocess.DEVNULL)
 
 
 class _Csr(C.Structure):

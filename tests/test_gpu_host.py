@@ -153,3 +153,26 @@ def test_driver_precision_fp32_and_single_reduction(bh, tmp_path):
     assert int(ext[2]) == 0 and "precision=fp32 values lossless" in r.stdout
     M = orc.gen_poisson27(40)
     assert orc.true_relres(M, orc.rhs(M.n), np.fromfile(out)) <= 1.05e-10
+
+
+def test_stock_lsbench_tree_with_b200_dropped_in(bh):
+    """oracle/_ref/driver_ref_b200: the REFERENCE's lsbench.c / lsbench-csr.c /
+    bin/driver.c with the five registration edits and this repository's b200.c
+    (built by oracle/dropin.py where the reference tree is mounted).  The stock
+    harness runs the b200 backend on a B200: the reference's CSV row, convergence
+    to 1e-10, and the same iteration count as this tree's own driver."""
+    drop = os.path.join(ROOT, "oracle", "_ref", "driver_ref_b200")
+    if not os.path.exists(drop):
+        pytest.skip("oracle/_ref/driver_ref_b200 was not built (no reference tree at build time)")
+    name = "tj7a_A_18"
+    A = orc.matrix_read(orc.matrix_path(name))
+    runs = []
+    for exe in (drop, bh.DRIVER):
+        r = subprocess.run([exe, "--solver", "b200", "--matrix", orc.matrix_path(name), "--trials=2"],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        runs.append(parse(r.stdout))
+    (row, ext), (row0, ext0) = runs
+    assert row[1:6] == [str(A.nrows), str(A.nnz), "2", "6", "0"] == row0[1:6]
+    assert int(ext[2]) == 0 and float(ext[4]) <= 1.05e-10
+    assert ext[1] == ext0[1] and ext[3] == ext0[3]      # iterations and residual: the same solve

@@ -10,6 +10,7 @@ import hashlib
 import json
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -420,3 +421,34 @@ def test_reordered_operator_is_P_S_Pt(host, name, sym):
     want.sort_indices()
     assert got[0] == 0 and np.array_equal(got[1], want.indptr) and np.array_equal(got[2], want.indices)
     assert got[3].tobytes() == want.data.tobytes()
+
+
+# ---- the drop-in, done for real: --solver b200 inside the stock lsbench tree ---------------
+DROPIN = os.path.join(ROOT, "oracle", "_ref", "driver_ref_b200")
+
+
+def test_b200_drops_into_the_stock_lsbench_tree(host):
+    """oracle/dropin.py copies the reference tree to a scratch directory, applies
+    the five registration edits of INTEGRATION.md, adds this repository's b200.c
+    (unchanged) and builds the reference's own sources with -DLSBENCH_B200: the
+    stock `driver` then knows `--solver b200`, fails loudly when there is no GPU
+    (no fallback), and its other backends behave as before"""
+    if not os.path.isdir("/root/reference/src"):
+        if not os.path.exists(DROPIN):
+            pytest.skip("no reference tree and no prebuilt oracle/_ref/driver_ref_b200")
+    else:
+        subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "dropin.py")], check=True,
+                       capture_output=True)
+    m = orc.matrix_path("I1_05x05")
+    r = subprocess.run([DROPIN, "--solver", "cholmod", "--matrix", m, "--trials=2"], capture_output=True, text=True)
+    assert r.returncode == 0                        # the stock stub: returns without a solve
+    r = subprocess.run([DROPIN, "--solver", "b200", "--matrix", m, "--trials=2"], capture_output=True, text=True)
+    from lsbench_b200 import abi
+    try:
+        have_gpu = abi.device_count() > 0
+    except abi.B200Error:
+        have_gpu = False
+    if have_gpu:
+        assert r.returncode == 0 and "===b200:" in r.stdout
+    else:
+        assert r.returncode == 1 and "b200 error" in r.stderr and "cuda error" in r.stderr
