@@ -1,0 +1,199 @@
+// sell_kernels.cuh -- the SELL-32 SpMV kernels (included by spmv.cu, which holds
+// the launch logic and the description of the layout).  In a header of their own
+// so that tests/ can also compile the kernel bodies for the host, with one-line
+// stand-ins for the CUDA built-ins, and run them thread by thread against a CSR
+// product without a GPU (tests/spmv_emul.cpp, tests/test_spmv_emul.py).
+#pragma once
+
+#define SPMV_THREADS 256
+#define SPMV_WARPS (SPMV_THREADS / 32)
+
+// One k-chunk of up to 8 entries of a slice: columns -> values -> gathers ->
+// fma in row order.  `colf(j)` yields the column of entry k + j.
+template <bool FULL, typename ColF>
+__device__ __forceinline__ double sell_chunk(const double *vp, const double *__restrict__ x,
+                                             uint32_t k, uint32_t rem, double sum, ColF colf) {
+  constexpr int N = FULL ? 8 : 7;
+  uint32_t c[8];
+  double a[8], xv[8];
+#pragma unroll
+  for (int j = 0; j < N; j++)
+    c[j] = (FULL || j < rem) ? colf(j) : 0u;
+#pragma unroll
+  for (int j = 0; j < N; j++)
+    a[j] = (FULL || j < rem) ? ld_stream(vp + (size_t)(k + j) * B2_SLICE) : 0.0;
+#pragma unroll
+  for (int j = 0; j < N; j++)
+    xv[j] = (FULL || j < rem) ? __ldg(x + c[j]) : 0.0;
+#pragma unroll
+  for (int j = 0; j < N; j++)
+    if (FULL || j < rem)
+      sum = fma(a[j], xv[j], sum);
+  return sum;
+}
+
+// The same for fp32-stored values (B200_MAT_VALUES_F32): a chunk is 16 entries
+// so that a warp keeps as many value bytes in flight as with fp64 (16 x 128 B);
+// the gathers and the fma chain run in two halves of 8, in row order, on the
+// values widened to fp64 -- when the stored fp32 equals the original fp64 the
+// result has the same bits as the fp64 kernel's.
+template <bool FULL, typename ColF>
+__device__ __forceinline__ double sell_chunk(const float *vp, const double *__restrict__ x,
+                                             uint32_t k, uint32_t rem, double sum, ColF colf) {
+  constexpr int N = FULL ? 16 : 15;
+  float a[16];
+#pragma unroll
+  for (int j = 0; j < N; j++)
+    a[j] = (FULL || j < rem) ? ld_stream(vp + (size_t)(k + j) * B2_SLICE) : 0.0f;
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    uint32_t c[8];
+    double xv[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      c[j] = (h * 8 + j < N && (FULL || h * 8 + j < rem)) ? colf(h * 8 + j) : 0u;
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      xv[j] = (h * 8 + j < N && (FULL || h * 8 + j < rem)) ? __ldg(x + c[j]) : 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      if (h * 8 + j < N && (FULL || h * 8 + j < rem))
+        sum = fma((double)a[h * 8 + j], xv[j], sum);
+  }
+  return sum;
+}
+
+// entries per full chunk of the value type
+template <typename VT> struct ChunkOf { static constexpr uint32_t n = 8; };
+template <> struct ChunkOf<float> { static constexpr uint32_t n = 16; };
+
+template <bool DOT, typename VT>
+__global__ void __launch_bounds__(SPMV_THREADS, 4)
+k_spmv_sell(const uint32_t *__restrict__ sell_off,
+            const uint32_t *__restrict__ cols, const VT *__restrict__ vals,
+            const uint32_t *__restrict__ perm, const double *__restrict__ x,
+            double *__restrict__ y, uint32_t b0, uint32_t e0, uint32_t b1,
+            uint32_t e1, uint32_t n_rows, double *partials, unsigned slot_base,
+            unsigned total_slots, PcgState *st, double *dot_out, const XrArgs xr) {
+  if (DOT && st->done)
+    return;
+  __shared__ double red[SPMV_WARPS];
+  constexpr uint32_t CH = ChunkOf<VT>::n;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t n0 = e0 - b0, nv = n0 + (e1 - b1);
+  const uint32_t stride = gridDim.x * SPMV_WARPS;
+  double dot = 0.0;
+  for (uint32_t v = blockIdx.x * SPMV_WARPS + warp; v < nv; v += stride) {
+    const uint32_t s = v < n0 ? b0 + v : b1 + (v - n0);
+    const uint32_t o = __ldg(sell_off + s);
+    const uint32_t w = __ldg(sell_off + s + 1) - o;
+    const size_t base = (size_t)o * B2_SLICE + lane;
+    const uint32_t *cp = cols + base;
+    const VT *vp = vals + base;
+    double sum = 0.0;
+    uint32_t k = 0;
+    for (; k + CH <= w; k += CH)
+      sum = sell_chunk<true>(vp, x, k, CH, sum, [&](int j) {
+        return ld_stream(cp + (size_t)(k + j) * B2_SLICE);
+      });
+    if (k < w)
+      sum = sell_chunk<false>(vp, x, k, w - k, sum, [&](int j) {
+        return ld_stream(cp + (size_t)(k + j) * B2_SLICE);
+      });
+    const uint32_t pos = s * B2_SLICE + lane;
+    const uint32_t row = perm ? __ldg(perm + pos) : pos;
+    if (row < n_rows) {
+      y[row] = sum;
+      if (DOT)
+        dot = fma(sum, __ldg(x + row), dot);
+    }
+  }
+  if (DOT) {
+    double b[1] = {block_sum<SPMV_WARPS>(dot, red)};
+    grid_sum_finish<1, SPMV_WARPS>(b, partials, 0, slot_base + blockIdx.x,
+                                   total_slots, &st->ticket[0], dot_out, red, xr);
+  }
+}
+
+// Index-compressed SELL (convert.cu, step 6).  A slice whose 32 rows all have
+// the slice's width and whose k-th column is `row + d_k` with the same d_k in
+// every lane (the interior of any stencil or banded operator, in any numbering
+// that keeps neighbouring rows together) stores its w deltas once -- 4 w bytes
+// instead of 128 w -- and its gathers become one coalesced warp access each.
+// Other slices keep explicit columns.  meta[s] = {o, w | uniform << 31, c, 0}:
+// o as in sell_off; c = offset into dcols (entries) for a uniform slice, into
+// cols (units of 32 entries) otherwise.  Values and the order of the additions
+// are untouched, so the result is bit-identical to the uncompressed kernel.
+//
+// Measured alternatives that lost to this plain loop on 27-point 512^3 (5.99 ms
+// in PCG): deltas prefetched one slice ahead and broadcast by shuffle (6.38),
+// next-chunk values prefetched into registers (8.0-8.4), a bulk-copy
+// (cp.async.bulk + mbarrier) ring of value tiles in shared memory (10.3), and
+// balanced 9+9+9 chunks instead of 8+8+8+3 (6.25).
+//
+// Compiled for 5 CTAs per SM (48 registers, 40 warps): the uniform path needs no
+// column registers, and the extra warps are worth 6 % (27-point 512^3: 6.07 ->
+// 5.73 ms in PCG; 6 CTAs/SM spills and loses again).  The fp32-value
+// instantiation holds 16 values per chunk and is compiled for 4 CTAs per SM
+// (64 registers; at 48 it spills 112 bytes in the loop).
+#define SELLC_MINB 5
+template <bool DOT, typename VT>
+__global__ void __launch_bounds__(SPMV_THREADS, sizeof(VT) == 8 ? SELLC_MINB : 4)
+k_spmv_sellc(const uint4 *__restrict__ meta, const uint32_t *__restrict__ cols,
+             const int32_t *__restrict__ dcols, const VT *__restrict__ vals,
+             const uint32_t *__restrict__ perm, const double *__restrict__ x,
+             double *__restrict__ y, uint32_t b0, uint32_t e0, uint32_t b1,
+             uint32_t e1, uint32_t n_rows, double *partials, unsigned slot_base,
+             unsigned total_slots, PcgState *st, double *dot_out, const XrArgs xr) {
+  if (DOT && st->done)
+    return;
+  __shared__ double red[SPMV_WARPS];
+  constexpr uint32_t CH = ChunkOf<VT>::n;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t n0 = e0 - b0, nv = n0 + (e1 - b1);
+  const uint32_t stride = gridDim.x * SPMV_WARPS;
+  double dot = 0.0;
+  for (uint32_t v = blockIdx.x * SPMV_WARPS + warp; v < nv; v += stride) {
+    const uint32_t s = v < n0 ? b0 + v : b1 + (v - n0);
+    const uint4 m = __ldg(meta + s);
+    const uint32_t o = m.x, w = m.y & 0x7fffffffu;
+    const VT *vp = vals + (size_t)o * B2_SLICE + lane;
+    const uint32_t pos = s * B2_SLICE + lane;
+    const uint32_t row = perm ? __ldg(perm + pos) : pos;
+    double sum = 0.0;
+    uint32_t k = 0;
+    if (m.y >> 31) {
+      const int32_t *dp = dcols + m.z;
+      for (; k + CH <= w; k += CH)
+        sum = sell_chunk<true>(vp, x, k, CH, sum, [&](int j) {
+          return row + (uint32_t)__ldg(dp + k + j);
+        });
+      if (k < w)
+        sum = sell_chunk<false>(vp, x, k, w - k, sum, [&](int j) {
+          return row + (uint32_t)__ldg(dp + k + j);
+        });
+    } else {
+      const uint32_t *cp = cols + (size_t)m.z * B2_SLICE + lane;
+      for (; k + CH <= w; k += CH)
+        sum = sell_chunk<true>(vp, x, k, CH, sum, [&](int j) {
+          return ld_stream(cp + (size_t)(k + j) * B2_SLICE);
+        });
+      if (k < w)
+        sum = sell_chunk<false>(vp, x, k, w - k, sum, [&](int j) {
+          return ld_stream(cp + (size_t)(k + j) * B2_SLICE);
+        });
+    }
+    if (row < n_rows) {
+      y[row] = sum;
+      if (DOT)
+        dot = fma(sum, __ldg(x + row), dot);
+    }
+  }
+  if (DOT) {
+    double b[1] = {block_sum<SPMV_WARPS>(dot, red)};
+    grid_sum_finish<1, SPMV_WARPS>(b, partials, 0, slot_base + blockIdx.x,
+                                   total_slots, &st->ticket[0], dot_out, red, xr);
+  }
+}
+
+#include "sellc32p.cuh"

@@ -1,6 +1,7 @@
-// spmv_emul.cpp -- TEST INFRASTRUCTURE.  Compiles the body of the pipelined
-// fp32-value SELL kernel (lsbench_b200/csrc/sellc32p.cuh) for the host, with
-// one-line stand-ins for the CUDA built-ins, and runs it thread by thread over a
+// spmv_emul.cpp -- TEST INFRASTRUCTURE.  Compiles the bodies of the SELL SpMV
+// kernels (lsbench_b200/csrc/sell_kernels.cuh: k_spmv_sell, k_spmv_sellc, and
+// the pipelined k_spmv_sellc32p of sellc32p.cuh) for the host, with one-line
+// stand-ins for the CUDA built-ins, and runs them thread by thread over a
 // launch grid.  Without the fused dot product a thread talks to no other thread,
 // so running the threads one after another is exactly what the GPU computes.
 // The caller (tests/test_spmv_emul.py) builds the index-compressed SELL layout
@@ -21,11 +22,11 @@ struct Dim {
 };
 static Dim threadIdx, blockIdx, gridDim;
 #define __global__
+#define __device__
+#define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __shared__ static
 #define B2_SLICE 32
-#define SPMV_THREADS 256
-#define SPMV_WARPS (SPMV_THREADS / 32)
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 template <typename T> static inline T ld_stream(const T *p) { return *p; }
 struct PcgState {
@@ -38,7 +39,7 @@ template <int NV, int NW>
 static void grid_sum_finish(const double (&)[NV], double *, unsigned, unsigned, unsigned,
                             unsigned *, double *, double *, const XrArgs &) {}
 
-#include "sellc32p.cuh"
+#include "sell_kernels.cuh"
 
 template <int WMAX, typename VT>
 static void run(unsigned grid, const uint4 *meta, const uint32_t *cols, const int32_t *dcols,
@@ -77,4 +78,52 @@ extern "C" int emul_sellc32p(int wmax, int f64, unsigned grid, const uint4 *meta
                                e0, b1, e1, n_rows)
              : run_any<float>(wmax, grid, meta, cols, dcols, (const float *)vals, perm, x, y, b0,
                               e0, b1, e1, n_rows);
+}
+
+// ---- the default kernels: k_spmv_sellc (index-compressed) and k_spmv_sell ----------
+template <typename VT>
+static void run_sellc(unsigned grid, const uint4 *meta, const uint32_t *cols, const int32_t *dcols,
+                      const VT *vals, const uint32_t *perm, const double *x, double *y,
+                      uint32_t b0, uint32_t e0, uint32_t b1, uint32_t e1, uint32_t n_rows) {
+  gridDim.x = grid;
+  for (unsigned b = 0; b < grid; b++)
+    for (unsigned t = 0; t < SPMV_THREADS; t++) {
+      blockIdx.x = b, threadIdx.x = t;
+      k_spmv_sellc<false, VT>(meta, cols, dcols, vals, perm, x, y, b0, e0, b1, e1, n_rows, nullptr,
+                              0, 0, nullptr, nullptr, XrArgs{});
+    }
+}
+
+extern "C" int emul_sellc(int f64, unsigned grid, const uint4 *meta, const uint32_t *cols,
+                          const int32_t *dcols, const void *vals, const uint32_t *perm,
+                          const double *x, double *y, uint32_t b0, uint32_t e0, uint32_t b1,
+                          uint32_t e1, uint32_t n_rows) {
+  if (f64)
+    run_sellc<double>(grid, meta, cols, dcols, (const double *)vals, perm, x, y, b0, e0, b1, e1, n_rows);
+  else
+    run_sellc<float>(grid, meta, cols, dcols, (const float *)vals, perm, x, y, b0, e0, b1, e1, n_rows);
+  return 0;
+}
+
+template <typename VT>
+static void run_sell(unsigned grid, const uint32_t *sell_off, const uint32_t *cols, const VT *vals,
+                     const uint32_t *perm, const double *x, double *y, uint32_t b0, uint32_t e0,
+                     uint32_t b1, uint32_t e1, uint32_t n_rows) {
+  gridDim.x = grid;
+  for (unsigned b = 0; b < grid; b++)
+    for (unsigned t = 0; t < SPMV_THREADS; t++) {
+      blockIdx.x = b, threadIdx.x = t;
+      k_spmv_sell<false, VT>(sell_off, cols, vals, perm, x, y, b0, e0, b1, e1, n_rows, nullptr, 0, 0,
+                             nullptr, nullptr, XrArgs{});
+    }
+}
+
+extern "C" int emul_sell(int f64, unsigned grid, const uint32_t *sell_off, const uint32_t *cols,
+                         const void *vals, const uint32_t *perm, const double *x, double *y,
+                         uint32_t b0, uint32_t e0, uint32_t b1, uint32_t e1, uint32_t n_rows) {
+  if (f64)
+    run_sell<double>(grid, sell_off, cols, (const double *)vals, perm, x, y, b0, e0, b1, e1, n_rows);
+  else
+    run_sell<float>(grid, sell_off, cols, (const float *)vals, perm, x, y, b0, e0, b1, e1, n_rows);
+  return 0;
 }

@@ -1,8 +1,10 @@
-"""The software-pipelined fp32-value SELL kernel (lsbench_b200/csrc/sellc32p.cuh,
-B200_SPMV_PIPE=1 -- written at the end of round 1, not yet timed on hardware),
-compiled for the HOST by tests/spmv_emul.cpp and run thread by thread over a
-launch grid: its indexing and the order of its additions against the oracle's
-fma CSR product, bit for bit.  The index-compressed SELL layout (DESIGN.md
+"""The SELL SpMV kernels of the product, compiled for the HOST by
+tests/spmv_emul.cpp and run thread by thread over a launch grid: indexing and
+the order of the additions against the oracle's fma CSR product, bit for bit,
+without a GPU.  Covered: the default kernels k_spmv_sellc / k_spmv_sell
+(lsbench_b200/csrc/sell_kernels.cuh; fp64 and fp32 value streams) and the
+software-pipelined k_spmv_sellc32p (sellc32p.cuh, B200_SPMV_PIPE -- written at the
+end of round 1, not yet timed on hardware).  The index-compressed SELL layout (DESIGN.md
 section 2, csrc/convert.cu k_sell_fill / k_slice_uniform / k_compact_cols) is
 restated here with numpy."""
 import ctypes as C
@@ -27,6 +29,8 @@ def emul(tmp_path_factory):
     L = C.CDLL(so)
     L.emul_sellc32p.restype = C.c_int
     L.emul_sellc32p.argtypes = [C.c_int, C.c_int, C.c_uint] + [C.c_void_p] * 7 + [C.c_uint32] * 5
+    L.emul_sellc.argtypes = [C.c_int, C.c_uint] + [C.c_void_p] * 7 + [C.c_uint32] * 5
+    L.emul_sell.argtypes = [C.c_int, C.c_uint] + [C.c_void_p] * 6 + [C.c_uint32] * 5
     return L
 
 
@@ -38,7 +42,7 @@ def sellc_layout(M, perm=None):
     lst = np.full(ns * 32 + 1, NONE, dtype=np.uint32)
     lst[:n] = np.arange(n) if perm is None else perm
     meta = np.zeros((ns + 1, 4), dtype=np.uint32)
-    vals, ecols, dcols = [], [], []
+    vals, ecols, dcols, allcols, sell_off = [], [], [], [], [0]
     o = 0
     for s in range(ns):
         rows = lst[32 * s:32 * s + 32]
@@ -63,26 +67,40 @@ def sellc_layout(M, perm=None):
             meta[s] = (o, w, len(ecols) // 32, 0)
             ecols += Cc.reshape(-1).tolist()
         vals += V.reshape(-1).tolist()
+        allcols += Cc.reshape(-1).tolist()
         o += w
+        sell_off.append(o)
     return dict(ns=ns, meta=meta, list=None if perm is None else lst,
                 vals=np.array(vals + [0.0], dtype=np.float32),
                 ecols=np.array(ecols + [0], dtype=np.uint32),
                 dcols=np.array(dcols + [0] * 40, dtype=np.int32),
+                allcols=np.array(allcols + [0], dtype=np.uint32), sell_off=np.array(sell_off, dtype=np.uint32),
                 uniform=int((meta[:ns, 1] >> 31).sum()), wmax=int((meta[:ns, 1] & 0x7FFFFFFF).max()))
 
 
 def run(emul, Lay, n, x, wmax, grid, ranges=None):
-    """both instantiations: fp32-stored values (256-thread CTAs) and fp64-stored
-    ones (128-thread CTAs when wmax = 32); the answers must not differ"""
+    """every kernel on the same layout -- pipelined (fp32 values: 256-thread CTAs;
+    fp64 values: 128-thread CTAs when wmax = 32), k_spmv_sellc and k_spmv_sell with
+    both value types; the answers must not differ"""
     b0, e0, b1, e1 = ranges or (0, Lay["ns"], 0, 0)
     p = lambda a: None if a is None else a.ctypes.data
     ys = []
-    for f64, vals in ((0, Lay["vals"]), (1, Lay["vals"].astype(np.float64))):
+    for f64, vals in ((0, Lay["vals"]), (1, Lay["vals"].astype(np.float64))) if wmax else ():
         y = np.full(n, np.nan)
         assert emul.emul_sellc32p(wmax, f64, grid, p(Lay["meta"]), p(Lay["ecols"]), p(Lay["dcols"]), p(vals),
                                   p(Lay["list"]), p(x), p(y), b0, e0, b1, e1, n) == 0
         ys.append(y)
-    assert ys[0].tobytes() == ys[1].tobytes()
+    # the default kernels on the same layout: index-compressed and explicit columns
+    for f64, vals in ((0, Lay["vals"]), (1, Lay["vals"].astype(np.float64))):
+        y = np.full(n, np.nan)
+        assert emul.emul_sellc(f64, grid, p(Lay["meta"]), p(Lay["ecols"]), p(Lay["dcols"]), p(vals),
+                               p(Lay["list"]), p(x), p(y), b0, e0, b1, e1, n) == 0
+        ys.append(y)
+        y = np.full(n, np.nan)
+        assert emul.emul_sell(f64, grid, p(Lay["sell_off"]), p(Lay["allcols"]), p(vals),
+                              p(Lay["list"]), p(x), p(y), b0, e0, b1, e1, n) == 0
+        ys.append(y)
+    assert all(y.tobytes() == ys[0].tobytes() for y in ys)
     return ys[0]
 
 
@@ -159,3 +177,23 @@ def test_pipelined_kernel_banded_rows_compress_in_any_numbering(emul):
     assert 0 < Lay["uniform"] < Lay["ns"]            # the wrap-around slices are not uniform
     x = np.random.default_rng(3).standard_normal(n)
     assert run(emul, Lay, n, x, 16, 2).tobytes() == orc.spmv_fma(M, x).tobytes()
+
+
+def test_default_kernels_on_wide_ragged_rows(emul):
+    """rows of every length 1..70: full chunks of 8 (fp64 values) and 16 (fp32
+    values) plus every tail length, in explicit slices, for k_spmv_sellc and
+    k_spmv_sell (the pipelined kernel is for slices of at most 32 entries)"""
+    rng = np.random.default_rng(17)
+    n = 70 * 12 + 5
+    lens = (np.arange(n) % 70) + 1
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    cols = np.concatenate([np.sort(rng.choice(n, l, replace=False)) for l in lens]).astype(np.uint32)
+    vals = rng.integers(-1000, 1000, int(offs[-1])).astype(np.float64) / 64.0
+    M = orc.Op(n, offs, cols, vals)
+    x = rng.standard_normal(n)
+    want = orc.spmv_fma(M, x)
+    for perm in (None, np.argsort(-lens, kind="stable").astype(np.uint32)):
+        Lay = sellc_layout(M, perm)
+        assert Lay["wmax"] == 70
+        for grid in (1, 6):
+            assert run(emul, Lay, n, x, None, grid).tobytes() == want.tobytes()
