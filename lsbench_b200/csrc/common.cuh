@@ -212,7 +212,10 @@ int small_solve(b200_mat *M, const double *d_b, double *d_x,
                 const b200_pcg_opts *o, b200_pcg_result *res);
 
 // ---- device-side helpers -----------------------------------------------------
-#ifdef __CUDACC__
+// (B2_SIMT_EMUL: tests/simt_emul.hpp compiles them for the host, one host thread
+// per CUDA thread, to run the kernels of pcg_kernels.cuh / sell_kernels.cuh
+// without a GPU)
+#if defined(__CUDACC__) || defined(B2_SIMT_EMUL)
 __device__ __forceinline__ double warp_sum(double v) {
   // fixed butterfly: the same tree for every run
 #pragma unroll
@@ -240,6 +243,7 @@ __device__ __forceinline__ double block_sum(double v, double *smem /*NWARPS*/) {
 }
 
 // ---- peer-memory all-reduce, device side --------------------------------------
+#ifndef B2_SIMT_EMUL
 __device__ __forceinline__ void st_relaxed_sys(double *p, double v) {
   asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
@@ -256,6 +260,21 @@ __device__ __forceinline__ double ld_relaxed_sys(const double *p) {
   asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
   return v;
 }
+
+#else  // host emulation: one process, ordinary memory
+static inline void st_relaxed_sys(double *p, double v) { __atomic_store(p, &v, __ATOMIC_RELAXED); }
+static inline void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
+  __atomic_store_n(p, v, __ATOMIC_RELEASE);
+}
+static inline unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  return __atomic_load_n(p, __ATOMIC_ACQUIRE);
+}
+static inline double ld_relaxed_sys(const double *p) {
+  double v;
+  __atomic_load(p, &v, __ATOMIC_RELAXED);
+  return v;
+}
+#endif
 
 // One CTA, after its __syncthreads: thread r < nranks stores the NV values and
 // then the sequence number into rank r's mailbox slot [kind][me].

@@ -1,0 +1,286 @@
+// pcg_kernels.cuh -- the element-wise kernels of the Jacobi-PCG (included by
+// pcg.cu, which holds the solver logic and the description of the method).  In a
+// header of their own so that tests/ can also compile the kernel bodies for the
+// host and run them on a small SIMT emulator (tests/simt_emul.hpp: one host
+// thread per CUDA thread, barriers for __syncthreads and the warp shuffles), the
+// fixed-order reductions included.
+#pragma once
+
+#define EW_THREADS 256
+#define EW_WARPS (EW_THREADS / 32)
+
+// r = b - q (q = A x0), p = D^-1 r; partial sums of r.z, r.r, b.b
+__global__ void __launch_bounds__(EW_THREADS)
+k_pcg_init(uint64_t n, const double *__restrict__ b, const double *__restrict__ q,
+           const double *__restrict__ dinv, double *__restrict__ r,
+           double *__restrict__ p, double *partials, unsigned stride,
+           PcgState *st, double *out) {
+  __shared__ double red[EW_WARPS];
+  double s[3] = {0.0, 0.0, 0.0};
+  for (uint64_t i = blockIdx.x * (uint64_t)EW_THREADS + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * EW_THREADS) {
+    double bi = b[i], ri = bi - q[i], zi = dinv[i] * ri;
+    r[i] = ri, p[i] = zi;
+    s[0] = fma(ri, zi, s[0]), s[1] = fma(ri, ri, s[1]), s[2] = fma(bi, bi, s[2]);
+  }
+  double bs[3];
+#pragma unroll
+  for (int v = 0; v < 3; v++)
+    bs[v] = block_sum<EW_WARPS>(s[v], red);
+  grid_sum_finish<3, EW_WARPS>(bs, partials, stride, blockIdx.x, gridDim.x,
+                               &st->ticket[1], out, red);
+}
+
+__global__ void k_pcg_start(PcgState *st, double tol, int maxit) {
+  st->red[0] = st->red[4], st->red[1] = st->red[5];
+  st->bb = st->red[6];
+  st->tol = tol, st->thr2 = tol * tol * st->bb;
+  st->iter = 0, st->maxit = maxit, st->status = 1, st->done = 0;
+  st->pq = 0.0;
+  if (st->red[5] <= st->thr2)
+    st->done = 1, st->status = 0;  // x0 already solves it
+  else if (maxit <= 0)
+    st->done = 1;
+}
+
+// K2.  xin: where p.q comes from when the ranks all-reduce over peer memory
+// (common.cuh xr_wait_sum); xout: where this kernel's {r.z, r.r} go.
+__global__ void __launch_bounds__(EW_THREADS)
+k_pcg_update(uint64_t n, double *__restrict__ x, double *__restrict__ r,
+             const double *__restrict__ p, const double *__restrict__ q,
+             const double *__restrict__ dinv, double *partials, unsigned stride,
+             PcgState *st, int par, double *out, const XrArgs xin, const XrArgs xout) {
+  if (st->done)
+    return;
+  __shared__ double red[EW_WARPS];
+  __shared__ double xr_s[B2_XR_MAX_RANKS + 1];
+  double pq = st->pq;
+  const double rz = st->red[par * 2];
+  if (xin.peers) {
+    double t[1];
+    if (!xr_wait_sum<1>(xin, t, xr_s)) {  // a peer never delivered: stop, do not hang
+      if (blockIdx.x == 0 && threadIdx.x == 0)
+        st->done = 1, st->status = 3;
+      return;
+    }
+    pq = t[0];
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+      st->pq = pq;
+  }
+  if (!(pq > 0.0)) {  // not SPD, or NaN crept in: SURVEY 5 breakdown guard
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+      st->done = 1, st->status = 2;
+    return;
+  }
+  const double alpha = rz / pq;
+  double s[2] = {0.0, 0.0};
+  const uint64_t stride_e = (uint64_t)gridDim.x * EW_THREADS;
+  uint64_t i = blockIdx.x * (uint64_t)EW_THREADS + threadIdx.x;
+  // two elements in flight per thread
+  for (; i + stride_e < n; i += 2 * stride_e) {
+    const uint64_t j = i + stride_e;
+    double xi = x[i], pi = __ldcs(p + i), ri = r[i], qi = __ldcs(q + i), di = __ldcs(dinv + i);
+    double xj = x[j], pj = __ldcs(p + j), rj = r[j], qj = __ldcs(q + j), dj = __ldcs(dinv + j);
+    xi = fma(alpha, pi, xi), ri = fma(-alpha, qi, ri);
+    xj = fma(alpha, pj, xj), rj = fma(-alpha, qj, rj);
+    x[i] = xi, r[i] = ri, x[j] = xj, r[j] = rj;
+    s[0] = fma(ri, di * ri, s[0]), s[1] = fma(ri, ri, s[1]);
+    s[0] = fma(rj, dj * rj, s[0]), s[1] = fma(rj, rj, s[1]);
+  }
+  if (i < n) {
+    double xi = x[i], pi = p[i], ri = r[i], qi = q[i], di = dinv[i];
+    xi = fma(alpha, pi, xi), ri = fma(-alpha, qi, ri);
+    x[i] = xi, r[i] = ri;
+    s[0] = fma(ri, di * ri, s[0]), s[1] = fma(ri, ri, s[1]);
+  }
+  double bs[2];
+  bs[0] = block_sum<EW_WARPS>(s[0], red);
+  bs[1] = block_sum<EW_WARPS>(s[1], red);
+  grid_sum_finish<2, EW_WARPS>(bs, partials, stride, blockIdx.x, gridDim.x,
+                               &st->ticket[2], out, red, xout);
+}
+
+// K3 (also owns the convergence decision and the iteration counter).  xin: the
+// {r.z, r.r} of all ranks over peer memory, when that path is on.
+__global__ void __launch_bounds__(EW_THREADS)
+k_pcg_pupdate(uint64_t n, const double *__restrict__ r,
+              const double *__restrict__ dinv, double *__restrict__ p,
+              PcgState *st, int par, const XrArgs xin) {
+  if (st->done)
+    return;
+  __shared__ double xr_s[2 * B2_XR_MAX_RANKS + 1];
+  double rzn = st->red[(par ^ 1) * 2], rr = st->red[(par ^ 1) * 2 + 1];
+  if (xin.peers) {
+    double t[2];
+    if (!xr_wait_sum<2>(xin, t, xr_s)) {
+      if (blockIdx.x == 0 && threadIdx.x == 0)
+        st->done = 1, st->status = 3;
+      return;
+    }
+    rzn = t[0], rr = t[1];
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+      st->red[(par ^ 1) * 2] = rzn, st->red[(par ^ 1) * 2 + 1] = rr;
+  }
+  const double rz = st->red[par * 2];
+  const bool conv = rr <= st->thr2;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int it = st->iter + 1;
+    st->iter = it;
+    if (conv)
+      st->done = 1, st->status = 0;
+    else if (!(rr == rr))
+      st->done = 1, st->status = 2;
+    else if (it >= st->maxit)
+      st->done = 1, st->status = 1;
+  }
+  if (conv)
+    return;
+  const double beta = rzn / rz;
+  const uint64_t stride_e = (uint64_t)gridDim.x * EW_THREADS;
+  uint64_t i = blockIdx.x * (uint64_t)EW_THREADS + threadIdx.x;
+  for (; i + stride_e < n; i += 2 * stride_e) {
+    const uint64_t j = i + stride_e;
+    double ri = __ldcs(r + i), di = __ldcs(dinv + i), pi = p[i];
+    double rj = __ldcs(r + j), dj = __ldcs(dinv + j), pj = p[j];
+    p[i] = fma(beta, pi, di * ri);
+    p[j] = fma(beta, pj, dj * rj);
+  }
+  if (i < n)
+    p[i] = fma(beta, p[i], dinv[i] * r[i]);
+}
+
+// ---- single-reduction CG ----------------------------------------------------------
+__global__ void k_sr_start(PcgState *st) {
+  // first pass: beta = gamma / inf = 0, alpha = gamma / (delta - 0 * gamma / 1)
+  st->red[2] = __longlong_as_double(0x7ff0000000000000ll);
+  st->sr_alpha[0] = 1.0, st->sr_alpha[1] = 1.0;
+  st->sr_base = 0, st->sr_next = 0;
+}
+
+// head of every chunk of queued iterations (one per graph replay): the kernels
+// of the chunk know their index inside it, this is where the chunk starts
+__global__ void k_sr_chunk_begin(PcgState *st, int chunk) {
+  st->sr_base = st->sr_next;
+  st->sr_next += chunk;
+}
+
+// K2'.  idx: position of the iteration inside its chunk (chunks are even, so
+// idx & 1 is the parity of the iteration).  Everything a CTA reads to decide
+// and to form alpha / beta was written by earlier kernels; thread 0 of CTA 0
+// writes only what this kernel does not read.
+__global__ void __launch_bounds__(EW_THREADS)
+k_sr_update(uint64_t n, double *__restrict__ x, double *__restrict__ r,
+            double *__restrict__ p, double *__restrict__ sv,
+            const double *__restrict__ w, double *__restrict__ u,
+            const double *__restrict__ dinv, double *partials, unsigned stride,
+            PcgState *st, int idx, double *out) {
+  if (st->done)
+    return;
+  __shared__ double red[EW_WARPS];
+  const int par = idx & 1;
+  const int it = st->sr_base + idx;  // iterations finished before this one
+  const double gamma = st->red[par * 2], rr = st->red[par * 2 + 1];
+  const double gamma_prev = st->red[(par ^ 1) * 2];
+  const double delta = st->pq, alpha_prev = st->sr_alpha[par ^ 1];
+  const bool first = blockIdx.x == 0 && threadIdx.x == 0;
+  if (rr <= st->thr2) {
+    if (first)
+      st->done = 1, st->status = 0;
+    return;
+  }
+  if (!(rr == rr)) {
+    if (first)
+      st->done = 1, st->status = 2;
+    return;
+  }
+  if (it >= st->maxit) {
+    if (first)
+      st->done = 1;  // status stays 1
+    return;
+  }
+  const double beta = gamma / gamma_prev;
+  const double den = delta - beta * gamma / alpha_prev;  // = p.Ap
+  if (!(den > 0.0)) {  // not SPD, or NaN crept in
+    if (first)
+      st->done = 1, st->status = 2;
+    return;
+  }
+  const double alpha = gamma / den;
+  if (first)
+    st->sr_alpha[par] = alpha, st->iter = it + 1;
+  double s[2] = {0.0, 0.0};
+  const uint64_t stride_e = (uint64_t)gridDim.x * EW_THREADS;
+  uint64_t i = blockIdx.x * (uint64_t)EW_THREADS + threadIdx.x;
+  for (; i + stride_e < n; i += 2 * stride_e) {
+    const uint64_t j = i + stride_e;
+    double ri = r[i], di = __ldcs(dinv + i), pi = p[i], si = sv[i], wi = __ldcs(w + i), xi = x[i];
+    double rj = r[j], dj = __ldcs(dinv + j), pj = p[j], sj = sv[j], wj = __ldcs(w + j), xj = x[j];
+    pi = fma(beta, pi, di * ri), si = fma(beta, si, wi);
+    pj = fma(beta, pj, dj * rj), sj = fma(beta, sj, wj);
+    xi = fma(alpha, pi, xi), ri = fma(-alpha, si, ri);
+    xj = fma(alpha, pj, xj), rj = fma(-alpha, sj, rj);
+    const double ui = di * ri, uj = dj * rj;
+    p[i] = pi, sv[i] = si, x[i] = xi, r[i] = ri, u[i] = ui;
+    p[j] = pj, sv[j] = sj, x[j] = xj, r[j] = rj, u[j] = uj;
+    s[0] = fma(ri, ui, s[0]), s[1] = fma(ri, ri, s[1]);
+    s[0] = fma(rj, uj, s[0]), s[1] = fma(rj, rj, s[1]);
+  }
+  if (i < n) {
+    double ri = r[i], di = dinv[i], pi = p[i], si = sv[i], wi = w[i], xi = x[i];
+    pi = fma(beta, pi, di * ri), si = fma(beta, si, wi);
+    xi = fma(alpha, pi, xi), ri = fma(-alpha, si, ri);
+    const double ui = di * ri;
+    p[i] = pi, sv[i] = si, x[i] = xi, r[i] = ri, u[i] = ui;
+    s[0] = fma(ri, ui, s[0]), s[1] = fma(ri, ri, s[1]);
+  }
+  double bs[2];
+  bs[0] = block_sum<EW_WARPS>(s[0], red);
+  bs[1] = block_sum<EW_WARPS>(s[1], red);
+  grid_sum_finish<2, EW_WARPS>(bs, partials, stride, blockIdx.x, gridDim.x,
+                               &st->ticket[2], out, red);
+}
+
+// ---- refinement (B200_MAT_VALUES_F32, rounded values) ---------------------------------
+// rhs = b - q (q = A x with the fp64 values); sums ||rhs||^2 and ||b||^2
+__global__ void __launch_bounds__(EW_THREADS)
+k_refine_resid(uint64_t n, const double *__restrict__ b, const double *__restrict__ q,
+               double *__restrict__ rhs, double *partials, unsigned stride,
+               PcgState *st, double *out) {
+  __shared__ double red[EW_WARPS];
+  double s[2] = {0.0, 0.0};
+  for (uint64_t i = blockIdx.x * (uint64_t)EW_THREADS + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * EW_THREADS) {
+    const double bi = b[i], d = bi - q[i];
+    rhs[i] = d;
+    s[0] = fma(d, d, s[0]), s[1] = fma(bi, bi, s[1]);
+  }
+  double bs[2];
+  bs[0] = block_sum<EW_WARPS>(s[0], red);
+  bs[1] = block_sum<EW_WARPS>(s[1], red);
+  grid_sum_finish<2, EW_WARPS>(bs, partials, stride, blockIdx.x, gridDim.x,
+                               &st->ticket[3], out, red);
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+k_add_into(uint64_t n, double *__restrict__ x, const double *__restrict__ d) {
+  for (uint64_t i = blockIdx.x * (uint64_t)EW_THREADS + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * EW_THREADS)
+    x[i] += d[i];
+}
+
+// ||b - A x||^2 for the exit check (q = A x)
+__global__ void __launch_bounds__(EW_THREADS)
+k_true_resid(uint64_t n, const double *__restrict__ b, const double *__restrict__ q,
+             double *partials, unsigned stride, PcgState *st, double *out) {
+  __shared__ double red[EW_WARPS];
+  double s = 0.0;
+  for (uint64_t i = blockIdx.x * (uint64_t)EW_THREADS + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * EW_THREADS) {
+    double d = b[i] - q[i];
+    s = fma(d, d, s);
+  }
+  double bs[1] = {block_sum<EW_WARPS>(s, red)};
+  grid_sum_finish<1, EW_WARPS>(bs, partials, stride, blockIdx.x, gridDim.x,
+                               &st->ticket[3], out, red);
+}
+
