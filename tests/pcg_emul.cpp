@@ -1,0 +1,100 @@
+// pcg_emul.cpp -- TEST INFRASTRUCTURE.  The product's Jacobi-PCG kernels
+// (lsbench_b200/csrc/pcg_kernels.cuh) and its SELL SpMV with the fused dot
+// product (sell_kernels.cuh), compiled for the host and run on the SIMT
+// emulator of simt_emul.hpp.  The loop around them restates what pcg.cu queues
+// (start-up, K1 K2 K3 per iteration, or K2' K1' in the single-reduction form);
+// the arithmetic -- every fma, every reduction tree -- is the product's.
+//   g++ -std=c++20 -O1 -DB2_SIMT_EMUL -I include -I lsbench_b200/csrc -I $CUDA/include
+#include <cuda_runtime.h>  // first: its own declarations of threadIdx etc. stay untouched
+#include "simt_emul.hpp"   // then the emulator's spellings ...
+#include "common.cuh"      // ... for the device helpers (B2_SIMT_EMUL) and the kernels
+#include "sell_kernels.cuh"
+#include "pcg_kernels.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+struct Layout {  // the index-compressed SELL layout, built by the caller (numpy)
+  uint32_t n, ns;
+  const uint4 *meta;
+  const uint32_t *cols;
+  const int32_t *dcols;
+  const double *vals;
+  const uint32_t *perm;
+  const double *dinv;
+};
+
+static const XrArgs NOXR = {nullptr, nullptr, 1, 0, 0, 0ull};
+
+static void spmv(const Layout &L, unsigned grid, const double *x, double *y, bool dot,
+                 double *partials, PcgState *st) {
+  if (dot)
+    simt::launch(grid, SPMV_THREADS, [&] {
+      k_spmv_sellc<true, double>(L.meta, L.cols, L.dcols, L.vals, L.perm, x, y, 0, L.ns, 0, 0, L.n,
+                                 partials, 0, grid, st, &st->pq, NOXR);
+    });
+  else
+    simt::launch(grid, SPMV_THREADS, [&] {
+      k_spmv_sellc<false, double>(L.meta, L.cols, L.dcols, L.vals, L.perm, x, y, 0, L.ns, 0, 0, L.n,
+                                  nullptr, 0, 0, nullptr, nullptr, NOXR);
+    });
+}
+
+// returns 0; out: iters, status, relres (recurrence), x
+extern "C" int emul_pcg(uint32_t n, uint32_t ns, const uint4 *meta, const uint32_t *cols,
+                        const int32_t *dcols, const double *vals, const uint32_t *perm,
+                        const double *dinv, const double *b, double *x, double tol, int maxit,
+                        int single_reduction, unsigned grid_spmv, unsigned grid_ew, int *iters,
+                        int *status, double *relres) {
+  Layout L{n, ns, meta, cols, dcols, vals, perm, dinv};
+  std::vector<double> r(n + 2), p(n + 2), q(n + 2), pp(n + 2, 0.0), sv(n + 2, 0.0);
+  const unsigned stride = 148 * 32 * 3 + 64;
+  std::vector<double> partials((size_t)stride * 3, 0.0);
+  PcgState st;
+  std::memset(&st, 0, sizeof st);
+  // ---- start-up (pcg.cu pcg_stream) ---------------------------------------------------
+  std::copy(x, x + n, p.begin());
+  spmv(L, grid_spmv, p.data(), q.data(), false, nullptr, nullptr);
+  simt::launch(grid_ew, EW_THREADS, [&] {
+    k_pcg_init(n, b, q.data(), dinv, r.data(), p.data(), partials.data(), stride, &st, &st.red[4]);
+  });
+  simt::launch(1, 1, [&] { k_pcg_start(&st, tol, maxit); });
+  if (single_reduction) {
+    simt::launch(1, 1, [&] { k_sr_start(&st); });
+    spmv(L, grid_spmv, p.data(), q.data(), true, partials.data(), &st);
+  }
+  // ---- iterations, in chunks as the product queues them -----------------------------------
+  const int chunk = 8;
+  int queued = 0;
+  while (!st.done && queued < maxit + (single_reduction ? 1 : 0)) {
+    if (single_reduction)
+      simt::launch(1, 1, [&] { k_sr_chunk_begin(&st, chunk); });
+    for (int i = 0; i < chunk; i++) {
+      const int par = i & 1, nx = (par ^ 1) * 2;
+      if (single_reduction) {
+        simt::launch(grid_ew, EW_THREADS, [&] {
+          k_sr_update(n, x, r.data(), pp.data(), sv.data(), q.data(), p.data(), dinv,
+                      partials.data(), stride, &st, i, &st.red[nx]);
+        });
+        spmv(L, grid_spmv, p.data(), q.data(), true, partials.data(), &st);
+      } else {
+        spmv(L, grid_spmv, p.data(), q.data(), true, partials.data(), &st);
+        simt::launch(grid_ew, EW_THREADS, [&] {
+          k_pcg_update(n, x, r.data(), p.data(), q.data(), dinv, partials.data(), stride, &st, par,
+                       &st.red[nx], NOXR, NOXR);
+        });
+        simt::launch(grid_ew, EW_THREADS, [&] {
+          k_pcg_pupdate(n, r.data(), dinv, p.data(), &st, par, NOXR);
+        });
+      }
+    }
+    queued += chunk;
+  }
+  const int parity = st.iter & 1;
+  double rr = st.iter == 0 ? st.red[1] : st.red[parity * 2 + 1];
+  if (single_reduction && st.status == 1 && rr <= st.thr2)
+    st.status = 0;
+  *iters = st.iter, *status = st.status;
+  *relres = st.bb > 0 ? std::sqrt(rr / st.bb) : std::sqrt(rr);
+  return 0;
+}

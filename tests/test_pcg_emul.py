@@ -1,0 +1,85 @@
+"""The product's Jacobi-PCG kernels (lsbench_b200/csrc/pcg_kernels.cuh) and its
+SELL SpMV with the fused dot product, compiled for the host and run on the SIMT
+emulator of tests/simt_emul.hpp -- one host thread per CUDA thread, barriers for
+__syncthreads and the warp shuffles, the grid-wide fixed-order reductions
+included.  The solve they produce is held against the oracle: same iteration
+count, same solution, the stopping rules, bit-reproducibility, for the
+three-kernel iteration and for the single-reduction form.  No GPU needed."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import orc
+from test_spmv_emul import sellc_layout
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def emul(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("emul") / "libpcg_emul.so")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    if not os.path.exists(os.path.join(cuda, "include", "cuda_runtime.h")):
+        pytest.skip("no CUDA headers")
+    subprocess.run(["/usr/bin/g++", "-std=c++20", "-O1", "-w", "-DB2_SIMT_EMUL", "-shared", "-fPIC", "-pthread",
+                    "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "lsbench_b200", "csrc"),
+                    "-I", os.path.join(cuda, "include"), "-I", os.path.join(ROOT, "tests"),
+                    os.path.join(ROOT, "tests", "pcg_emul.cpp"), "-o", so], check=True)
+    L = C.CDLL(so)
+    L.emul_pcg.restype = C.c_int
+    L.emul_pcg.argtypes = ([C.c_uint32, C.c_uint32] + [C.c_void_p] * 8 + [C.c_double, C.c_int, C.c_int,
+                           C.c_uint, C.c_uint] + [C.POINTER(C.c_int)] * 2 + [C.POINTER(C.c_double)])
+    return L
+
+
+def solve(emul, M, b, x0=None, tol=1e-10, maxit=10000, sr=False):
+    Lay = sellc_layout(M)
+    vals = Lay["vals"].astype(np.float64)
+    assert np.array_equal(vals[:-1].astype(np.float32), Lay["vals"][:-1])
+    S = M.scipy()
+    d = S.diagonal()
+    dinv = np.where(d != 0, 1.0 / np.where(d != 0, d, 1.0), 1.0)
+    x = np.zeros(M.n) if x0 is None else np.array(x0, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    it, st, rel = C.c_int(0), C.c_int(0), C.c_double(0)
+    p = lambda a: None if a is None else a.ctypes.data
+    grid_spmv = (Lay["ns"] + 7) // 8
+    grid_ew = (M.n + 255) // 256
+    assert emul.emul_pcg(M.n, Lay["ns"], p(Lay["meta"]), p(Lay["ecols"]), p(Lay["dcols"]), p(vals), None,
+                         p(dinv), p(b), p(x), tol, maxit, int(sr), grid_spmv, grid_ew,
+                         C.byref(it), C.byref(st), C.byref(rel)) == 0
+    return x, it.value, st.value, rel.value
+
+
+@pytest.mark.parametrize("sr", [False, True])
+def test_product_pcg_kernels_on_the_emulator(emul, sr):
+    M = orc.gen_poisson7(8)                       # 512 rows: 2 CTAs per kernel
+    b = orc.rhs(M.n)
+    x, it, st, rel = solve(emul, M, b, sr=sr)
+    xo, ito, relo, rco = (orc.pcg_sr if sr else orc.pcg)(M, b)
+    assert st == 0 and rco == 0 and abs(it - ito) <= 1 and rel <= 1e-10
+    assert np.linalg.norm(x - xo) / np.linalg.norm(xo) <= 1e-10
+    assert orc.true_relres(M, b, x) <= 1.05e-10
+    # bit-reproducible: every reduction has a fixed order
+    x2, it2, _, _ = solve(emul, M, b, sr=sr)
+    assert it2 == it and x2.tobytes() == x.tobytes()
+
+
+@pytest.mark.parametrize("sr", [False, True])
+def test_product_pcg_stopping_rules_on_the_emulator(emul, sr):
+    M = orc.gen_poisson27(6)                      # 216 rows, one CTA
+    b = orc.rhs(M.n)
+    xs, its, st, _ = solve(emul, M, b, sr=sr)
+    assert st == 0
+    x, it, st, _ = solve(emul, M, b, maxit=5, sr=sr)          # stops at maxit, says so
+    xo, ito, _, rco = (orc.pcg_sr if sr else orc.pcg)(M, b, maxit=5)
+    assert (it, st) == (5, 1) == (ito, rco) and np.linalg.norm(x - xo) / np.linalg.norm(xo) < 1e-12
+    x, it, st, _ = solve(emul, M, b, x0=xs, tol=1e-9, sr=sr)  # starting at the solution
+    assert (it, st) == (0, 0)
+    x, it, st, _ = solve(emul, M, b, maxit=8, sr=sr)          # maxit on a chunk boundary
+    assert (it, st) == (8, 1)
+    x, it, st, _ = solve(emul, M, b, maxit=its, sr=sr)        # converges exactly at maxit
+    assert (it, st) == (its, 0) and x.tobytes() == xs.tobytes()
