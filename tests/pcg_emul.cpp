@@ -22,22 +22,56 @@ struct Layout {  // the index-compressed SELL layout, built by the caller (numpy
   const double *vals;
   const uint32_t *perm;
   const double *dinv;
+  const float *vals32;  // the same values as fp32 (exact), for the fp32-value kernels
+  int kernel;           // 0 k_spmv_sellc fp64 | 1 k_spmv_sellc fp32 | 2 pipelined fp64 | 3 pipelined fp32
+  int wmax;             // 8, 16 or 32 for the pipelined kernels
 };
 
 static const XrArgs NOXR = {nullptr, nullptr, 1, 0, 0, 0ull};
 
+template <bool DOT, typename VT, int W>
+static void pipe_launch(const Layout &L, const VT *vals, const double *x, double *y,
+                        double *partials, PcgState *st) {
+  constexpr unsigned th = PipeCfg<VT, W>::threads;
+  const unsigned grid = (L.ns + th / 32 - 1) / (th / 32);
+  simt::launch(grid, th, [&] {
+    k_spmv_sellc32p<DOT, W, VT>(L.meta, L.cols, L.dcols, vals, L.perm, x, y, 0, L.ns, 0, 0, L.n,
+                                DOT ? partials : nullptr, 0, DOT ? grid : 0u, DOT ? st : nullptr,
+                                DOT ? &st->pq : nullptr, NOXR);
+  });
+}
+template <bool DOT, typename VT>
+static void pipe_any(const Layout &L, const VT *vals, const double *x, double *y, double *partials,
+                     PcgState *st) {
+  if (L.wmax == 32)
+    pipe_launch<DOT, VT, 32>(L, vals, x, y, partials, st);
+  else if (L.wmax == 16)
+    pipe_launch<DOT, VT, 16>(L, vals, x, y, partials, st);
+  else
+    pipe_launch<DOT, VT, 8>(L, vals, x, y, partials, st);
+}
+template <bool DOT, typename VT>
+static void plain_launch(const Layout &L, const VT *vals, unsigned grid, const double *x, double *y,
+                         double *partials, PcgState *st) {
+  simt::launch(grid, SPMV_THREADS, [&] {
+    k_spmv_sellc<DOT, VT>(L.meta, L.cols, L.dcols, vals, L.perm, x, y, 0, L.ns, 0, 0, L.n,
+                          DOT ? partials : nullptr, 0, DOT ? grid : 0u, DOT ? st : nullptr,
+                          DOT ? &st->pq : nullptr, NOXR);
+  });
+}
+
 static void spmv(const Layout &L, unsigned grid, const double *x, double *y, bool dot,
                  double *partials, PcgState *st) {
-  if (dot)
-    simt::launch(grid, SPMV_THREADS, [&] {
-      k_spmv_sellc<true, double>(L.meta, L.cols, L.dcols, L.vals, L.perm, x, y, 0, L.ns, 0, 0, L.n,
-                                 partials, 0, grid, st, &st->pq, NOXR);
-    });
-  else
-    simt::launch(grid, SPMV_THREADS, [&] {
-      k_spmv_sellc<false, double>(L.meta, L.cols, L.dcols, L.vals, L.perm, x, y, 0, L.ns, 0, 0, L.n,
-                                  nullptr, 0, 0, nullptr, nullptr, NOXR);
-    });
+  switch (L.kernel * 2 + (dot ? 1 : 0)) {
+  case 0: plain_launch<false, double>(L, L.vals, grid, x, y, partials, st); break;
+  case 1: plain_launch<true, double>(L, L.vals, grid, x, y, partials, st); break;
+  case 2: plain_launch<false, float>(L, L.vals32, grid, x, y, partials, st); break;
+  case 3: plain_launch<true, float>(L, L.vals32, grid, x, y, partials, st); break;
+  case 4: pipe_any<false, double>(L, L.vals, x, y, partials, st); break;
+  case 5: pipe_any<true, double>(L, L.vals, x, y, partials, st); break;
+  case 6: pipe_any<false, float>(L, L.vals32, x, y, partials, st); break;
+  default: pipe_any<true, float>(L, L.vals32, x, y, partials, st); break;
+  }
 }
 
 // returns 0; out: iters, status, relres (recurrence), x
@@ -45,8 +79,8 @@ extern "C" int emul_pcg(uint32_t n, uint32_t ns, const uint4 *meta, const uint32
                         const int32_t *dcols, const double *vals, const uint32_t *perm,
                         const double *dinv, const double *b, double *x, double tol, int maxit,
                         int single_reduction, unsigned grid_spmv, unsigned grid_ew, int *iters,
-                        int *status, double *relres) {
-  Layout L{n, ns, meta, cols, dcols, vals, perm, dinv};
+                        int *status, double *relres, const float *vals32, int kernel, int wmax) {
+  Layout L{n, ns, meta, cols, dcols, vals, perm, dinv, vals32, kernel, wmax};
   std::vector<double> r(n + 2), p(n + 2), q(n + 2), pp(n + 2, 0.0), sv(n + 2, 0.0);
   const unsigned stride = 148 * 32 * 3 + 64;
   std::vector<double> partials((size_t)stride * 3, 0.0);
