@@ -197,3 +197,88 @@ k_spmv_sellc(const uint4 *__restrict__ meta, const uint32_t *__restrict__ cols,
 }
 
 #include "sellc32p.cuh"
+
+// ---- the row-major bins: one warp per row, one CTA per row ----------------------------
+template <bool DOT>
+__global__ void __launch_bounds__(SPMV_THREADS, 4)
+k_spmv_vec(uint32_t nrows, const uint32_t *__restrict__ ids,
+           const uint64_t *__restrict__ off, const uint32_t *__restrict__ cols,
+           const double *__restrict__ vals, const double *__restrict__ x,
+           double *__restrict__ y, double *partials, unsigned slot_base,
+           unsigned total_slots, PcgState *st, double *dot_out, const XrArgs xr) {
+  if (DOT && st->done)
+    return;
+  __shared__ double red[SPMV_WARPS];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t stride = gridDim.x * SPMV_WARPS;
+  double dot = 0.0;
+  for (uint32_t r = blockIdx.x * SPMV_WARPS + warp; r < nrows; r += stride) {
+    const uint64_t s = __ldg(off + r), e = __ldg(off + r + 1);
+    double sum = 0.0;
+    for (uint64_t k = s + lane * 4; k < e; k += 128) {
+      const uint4 c = __ldcs(reinterpret_cast<const uint4 *>(cols + k));
+      const double2 v01 = __ldcs(reinterpret_cast<const double2 *>(vals + k));
+      const double2 v23 = __ldcs(reinterpret_cast<const double2 *>(vals + k + 2));
+      const double x0 = __ldg(x + c.x), x1 = __ldg(x + c.y),
+                   x2 = __ldg(x + c.z), x3 = __ldg(x + c.w);
+      sum = fma(v01.x, x0, sum);
+      sum = fma(v01.y, x1, sum);
+      sum = fma(v23.x, x2, sum);
+      sum = fma(v23.y, x3, sum);
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) {
+      const uint32_t row = __ldg(ids + r);
+      y[row] = sum;
+      if (DOT)
+        dot = fma(sum, __ldg(x + row), dot);
+    }
+  }
+  if (DOT) {
+    double b[1] = {block_sum<SPMV_WARPS>(dot, red)};
+    grid_sum_finish<1, SPMV_WARPS>(b, partials, 0, slot_base + blockIdx.x,
+                                   total_slots, &st->ticket[0], dot_out, red, xr);
+  }
+}
+
+template <bool DOT>
+__global__ void __launch_bounds__(SPMV_THREADS, 4)
+k_spmv_long(uint32_t nrows, const uint32_t *__restrict__ ids,
+            const uint64_t *__restrict__ off, const uint32_t *__restrict__ cols,
+            const double *__restrict__ vals, const double *__restrict__ x,
+            double *__restrict__ y, double *partials, unsigned slot_base,
+            unsigned total_slots, PcgState *st, double *dot_out, const XrArgs xr) {
+  if (DOT && st->done)
+    return;
+  __shared__ double red[SPMV_WARPS];
+  double dot = 0.0;
+  for (uint32_t r = blockIdx.x; r < nrows; r += gridDim.x) {
+    const uint64_t s = __ldg(off + r), e = __ldg(off + r + 1);
+    double sum = 0.0;
+    for (uint64_t k = s + threadIdx.x * 4; k < e; k += SPMV_THREADS * 4) {
+      const uint4 c = __ldcs(reinterpret_cast<const uint4 *>(cols + k));
+      const double2 v01 = __ldcs(reinterpret_cast<const double2 *>(vals + k));
+      const double2 v23 = __ldcs(reinterpret_cast<const double2 *>(vals + k + 2));
+      const double x0 = __ldg(x + c.x), x1 = __ldg(x + c.y),
+                   x2 = __ldg(x + c.z), x3 = __ldg(x + c.w);
+      sum = fma(v01.x, x0, sum);
+      sum = fma(v01.y, x1, sum);
+      sum = fma(v23.x, x2, sum);
+      sum = fma(v23.y, x3, sum);
+    }
+    sum = block_sum<SPMV_WARPS>(sum, red);
+    if (threadIdx.x == 0) {
+      const uint32_t row = __ldg(ids + r);
+      y[row] = sum;
+      if (DOT)
+        dot = fma(sum, __ldg(x + row), dot);
+    }
+  }
+  if (DOT) {
+    // only thread 0 carries a value; block_sum keeps the protocol uniform
+    double b[1] = {block_sum<SPMV_WARPS>(dot, red)};
+    grid_sum_finish<1, SPMV_WARPS>(b, partials, 0, slot_base + blockIdx.x,
+                                   total_slots, &st->ticket[0], dot_out, red, xr);
+  }
+}
+

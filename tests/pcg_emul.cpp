@@ -132,3 +132,27 @@ extern "C" int emul_pcg(uint32_t n, uint32_t ns, const uint4 *meta, const uint32
   *relres = st.bb > 0 ? std::sqrt(rr / st.bb) : std::sqrt(rr);
   return 0;
 }
+
+// ---- the row-major bins (power-law tail): k_spmv_vec, one warp per row, and
+// k_spmv_long, one CTA per row; rows padded to multiples of 4 entries -------------
+extern "C" int emul_rowmajor(int long_kernel, unsigned grid, uint32_t nrows, const uint32_t *ids,
+                             const uint64_t *off, const uint32_t *cols, const double *vals,
+                             const double *x, double *y, int dot, double *dot_out) {
+  const unsigned stride = 148 * 32 * 3 + 64;
+  std::vector<double> partials((size_t)stride * 3, 0.0);
+  PcgState st;
+  std::memset(&st, 0, sizeof st);
+  simt::launch(grid, SPMV_THREADS, [&] {
+    if (long_kernel && dot)
+      k_spmv_long<true>(nrows, ids, off, cols, vals, x, y, partials.data(), 0, grid, &st, &st.pq, NOXR);
+    else if (long_kernel)
+      k_spmv_long<false>(nrows, ids, off, cols, vals, x, y, nullptr, 0, 0, nullptr, nullptr, NOXR);
+    else if (dot)
+      k_spmv_vec<true>(nrows, ids, off, cols, vals, x, y, partials.data(), 0, grid, &st, &st.pq, NOXR);
+    else
+      k_spmv_vec<false>(nrows, ids, off, cols, vals, x, y, nullptr, 0, 0, nullptr, nullptr, NOXR);
+  });
+  if (dot)
+    *dot_out = st.pq;
+  return 0;
+}

@@ -27,8 +27,15 @@ static Dim threadIdx, blockIdx, gridDim;
 #define __launch_bounds__(...)
 #define __shared__ static
 #define B2_SLICE 32
+struct double2 {
+  double x, y;
+};
 template <typename T> static inline T __ldg(const T *p) { return *p; }
+template <typename T> static inline T __ldcs(const T *p) { return *p; }
 template <typename T> static inline T ld_stream(const T *p) { return *p; }
+// (the row-major kernels of the same header reduce over a warp: they compile here
+// and run on the SIMT emulator of pcg_emul.cpp, not thread by thread)
+static inline double warp_sum(double v) { return v; }
 struct PcgState {
   int done;
   unsigned ticket[4];

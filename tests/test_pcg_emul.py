@@ -143,3 +143,42 @@ def test_product_kernels_solve_a_nek_matrix_on_the_emulator(emul, name, sr):
     assert orc.true_relres(M, b, x) <= 1.05e-10
     g = np.load(os.path.join(ROOT, "tests", "golden", "direct.npz"))[name]
     assert np.linalg.norm(x - g) / np.linalg.norm(g) <= 1e-8
+
+
+@pytest.mark.parametrize("long_kernel", [0, 1])
+def test_row_major_kernels_on_the_emulator(emul, long_kernel):
+    """the bins of the power-law tail (BASELINE.json config 5): k_spmv_vec (one
+    warp per row, 128-bit loads, butterfly reduction) and k_spmv_long (one CTA per
+    row) on rows of 257 ... 1500 entries padded to multiples of 4 -- within the
+    1e-13 bar of the CSR product (another summation tree, so not bit for bit), the
+    fused dot product included"""
+    emul.emul_rowmajor.argtypes = [C.c_int, C.c_uint, C.c_uint32] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p]
+    rng = np.random.default_rng(23)
+    n, nrows = 6000, 37
+    lens = rng.integers(257, 1500, nrows)
+    ids = rng.choice(n, nrows, replace=False).astype(np.uint32)
+    pad = (lens + 3) // 4 * 4
+    off = np.concatenate([[0], np.cumsum(pad)]).astype(np.uint64)
+    o = off.astype(np.int64)
+    lens = lens.astype(np.int64)
+    cols = np.zeros(int(off[-1]) + 4, dtype=np.uint32)
+    vals = np.zeros(int(off[-1]) + 4)
+    for r in range(nrows):
+        c = np.sort(rng.choice(n, lens[r], replace=False))
+        cols[o[r]:o[r] + lens[r]] = c
+        cols[o[r] + lens[r]:o[r + 1]] = ids[r]            # padding: own row, value 0
+        vals[o[r]:o[r] + lens[r]] = rng.uniform(-1, 1, lens[r])
+    x = rng.standard_normal(n)
+    want = np.array([vals[o[r]:o[r + 1]] @ x[cols[o[r]:o[r + 1]]] for r in range(nrows)])
+    scale = np.array([np.abs(vals[o[r]:o[r + 1]] * x[cols[o[r]:o[r + 1]]]).sum() for r in range(nrows)])
+    p = lambda a: a.ctypes.data
+    for dot in (0, 1):
+        for grid in (1, 5):
+            y = np.full(n, np.nan)
+            d = np.zeros(1)
+            assert emul.emul_rowmajor(long_kernel, grid, nrows, p(ids), p(off), p(cols), p(vals), p(x), p(y),
+                                      dot, p(d)) == 0
+            assert np.all(np.abs(y[ids] - want) <= 1e-13 * scale)
+            assert np.isnan(np.delete(y, ids)).all()          # nothing else is written
+            if dot:
+                assert abs(d[0] - y[ids] @ x[ids]) <= 1e-12 * np.abs(y[ids] * x[ids]).sum()
