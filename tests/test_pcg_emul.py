@@ -182,3 +182,19 @@ def test_row_major_kernels_on_the_emulator(emul, long_kernel):
             assert np.isnan(np.delete(y, ids)).all()          # nothing else is written
             if dot:
                 assert abs(d[0] - y[ids] @ x[ids]) <= 1e-12 * np.abs(y[ids] * x[ids]).sum()
+
+
+@pytest.mark.parametrize("sr", [False, True])
+def test_breakdown_is_reported_by_the_product_kernels(emul, sr):
+    """[[1, 2], [2, 1]] x = [1, -1]: p.Ap = -2 in the first iteration -- the
+    guard of K2 (pq <= 0) / K2' (delta - beta gamma / alpha_prev <= 0) sets status
+    2 and leaves x alone; NaN in b does the same instead of spinning to maxit"""
+    M = orc.Op(2, np.array([0, 2, 4], dtype=np.uint64), np.array([0, 1, 0, 1], dtype=np.uint32),
+               np.array([1.0, 2.0, 2.0, 1.0]))
+    x, it, st, _ = solve(emul, M, np.array([1.0, -1.0]), sr=sr)
+    assert (it, st) == (0, 2) and x.tolist() == [0.0, 0.0]
+    M = orc.gen_poisson7(4)
+    b = orc.rhs(M.n)
+    b[5] = np.nan
+    x, it, st, _ = solve(emul, M, b, sr=sr, maxit=50)
+    assert st == 2 and it <= 1
