@@ -156,3 +156,54 @@ extern "C" int emul_rowmajor(int long_kernel, unsigned grid, uint32_t nrows, con
     *dot_out = st.pq;
   return 0;
 }
+
+// ---- the two-launch form of the overlapped multi-GPU SpMV: interior slices, then
+// boundary slices, ONE fused dot product (the partial slots and the ticket span
+// both launches; the last CTA of the second launch adds all of them) -----------------
+template <typename VT, int W>
+static void two_phase_pipe(const Layout &L, const VT *vals, const double *x, double *y, uint32_t ib,
+                           uint32_t ie, double *partials, PcgState *st) {
+  constexpr unsigned th = PipeCfg<VT, W>::threads, wp = th / 32;
+  const unsigned g1 = (ie - ib + wp - 1) / wp, g2 = (ib + (L.ns - ie) + wp - 1) / wp;
+  simt::launch(g1, th, [&] {
+    k_spmv_sellc32p<true, W, VT>(L.meta, L.cols, L.dcols, vals, L.perm, x, y, ib, ie, 0, 0, L.n, partials,
+                                 0, g1 + g2, st, &st->pq, NOXR);
+  });
+  simt::launch(g2, th, [&] {
+    k_spmv_sellc32p<true, W, VT>(L.meta, L.cols, L.dcols, vals, L.perm, x, y, 0, ib, ie, L.ns, L.n,
+                                 partials, g1, g1 + g2, st, &st->pq, NOXR);
+  });
+}
+
+extern "C" int emul_spmv_two_phase(uint32_t n, uint32_t ns, const uint4 *meta, const uint32_t *cols,
+                                   const int32_t *dcols, const double *vals, const float *vals32,
+                                   int kernel, int wmax, uint32_t ib, uint32_t ie, const double *x,
+                                   double *y, double *dot_out) {
+  Layout L{n, ns, meta, cols, dcols, vals, nullptr, nullptr, vals32, kernel, wmax};
+  const unsigned stride = 148 * 32 * 3 + 64;
+  std::vector<double> partials((size_t)stride * 3, 0.0);
+  PcgState st;
+  std::memset(&st, 0, sizeof st);
+  if (kernel == 2 && wmax == 32)
+    two_phase_pipe<double, 32>(L, vals, x, y, ib, ie, partials.data(), &st);
+  else if (kernel == 2)
+    two_phase_pipe<double, 8>(L, vals, x, y, ib, ie, partials.data(), &st);
+  else if (kernel == 3 && wmax == 32)
+    two_phase_pipe<float, 32>(L, vals32, x, y, ib, ie, partials.data(), &st);
+  else if (kernel == 3)
+    two_phase_pipe<float, 8>(L, vals32, x, y, ib, ie, partials.data(), &st);
+  else {
+    const unsigned g1 = (ie - ib + SPMV_WARPS - 1) / SPMV_WARPS,
+                   g2 = (ib + (ns - ie) + SPMV_WARPS - 1) / SPMV_WARPS;
+    simt::launch(g1, SPMV_THREADS, [&] {
+      k_spmv_sellc<true, double>(meta, cols, dcols, vals, nullptr, x, y, ib, ie, 0, 0, n, partials.data(),
+                                 0, g1 + g2, &st, &st.pq, NOXR);
+    });
+    simt::launch(g2, SPMV_THREADS, [&] {
+      k_spmv_sellc<true, double>(meta, cols, dcols, vals, nullptr, x, y, 0, ib, ie, ns, n, partials.data(),
+                                 g1, g1 + g2, &st, &st.pq, NOXR);
+    });
+  }
+  *dot_out = st.pq;
+  return st.ticket[0] == 0 ? 0 : 1;  // the last CTA must have reset the ticket
+}

@@ -198,3 +198,28 @@ def test_breakdown_is_reported_by_the_product_kernels(emul, sr):
     b[5] = np.nan
     x, it, st, _ = solve(emul, M, b, sr=sr, maxit=50)
     assert st == 2 and it <= 1
+
+
+@pytest.mark.parametrize("gen,N", [("poisson27", 10), ("poisson7", 12)])
+def test_two_launch_spmv_with_one_fused_dot(emul, gen, N):
+    """what the overlapped multi-GPU SpMV launches: interior slices while the halo
+    is in flight, boundary slices after it, ONE p.Ap -- the partial slots and the
+    ticket span both launches.  Default and pipelined kernels: y with the bits of
+    the CSR product, x.y to rounding, the ticket back at zero"""
+    emul.emul_spmv_two_phase.argtypes = ([C.c_uint32, C.c_uint32] + [C.c_void_p] * 5 + [C.c_int, C.c_int,
+                                         C.c_uint32, C.c_uint32] + [C.c_void_p] * 3)
+    M = getattr(orc, "gen_" + gen)(N)
+    Lay = sellc_layout(M)
+    vals = Lay["vals"].astype(np.float64)
+    x = np.random.default_rng(9).standard_normal(M.n)
+    want = orc.spmv_fma(M, x)
+    ns = Lay["ns"]
+    wmax = 32 if Lay["wmax"] > 8 else 8
+    p = lambda a: a.ctypes.data
+    for kernel in (0, 2, 3):
+        for ib, ie in ((ns // 4, 3 * ns // 4), (0, ns - 1), (1, ns)):
+            y, d = np.full(M.n, np.nan), np.zeros(1)
+            assert emul.emul_spmv_two_phase(M.n, ns, p(Lay["meta"]), p(Lay["ecols"]), p(Lay["dcols"]), p(vals),
+                                            p(Lay["vals"]), kernel, wmax, ib, ie, p(x), p(y), p(d)) == 0
+            assert y.tobytes() == want.tobytes()
+            assert abs(d[0] - x @ want) <= 1e-12 * np.abs(x * want).sum()
