@@ -140,6 +140,13 @@ def test_product_kernels_solve_a_nek_matrix_on_the_emulator(emul, name, sr):
                          C.byref(it), C.byref(st), C.byref(rel), None, 0, 32) == 0
     _, ito, _, _ = (orc.pcg_sr if sr else orc.pcg)(M, b)
     assert st.value == 0 and abs(it.value - ito) <= 3 and rel.value <= 1e-10
+    if not sr:
+        # same kernels, same launch geometry (15 - 26 CTAs: fewer than the GPU holds at
+        # once), same fixed-order reductions: the emulator takes exactly the iterations
+        # the B200 took (tests/golden/gpu_iters.json, from profiles/r01_nek_table...)
+        import json
+        gpu = json.load(open(os.path.join(ROOT, "tests", "golden", "gpu_iters.json")))["stream_iters"]
+        assert it.value == gpu[name]
     assert orc.true_relres(M, b, x) <= 1.05e-10
     g = np.load(os.path.join(ROOT, "tests", "golden", "direct.npz"))[name]
     assert np.linalg.norm(x - g) / np.linalg.norm(g) <= 1e-8
