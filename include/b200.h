@@ -108,7 +108,16 @@ enum {
    * stream halves.  Otherwise both copies stay resident and b200_pcg_solve
    * runs iterative refinement: inner PCG on the fp32-valued operator (fp64
    * vectors), residual b - A x with the fp64 values, to the same fp64 bar. */
-  B200_MAT_VALUES_F32 = 1u << 5
+  B200_MAT_VALUES_F32 = 1u << 5,
+  /* Column blocking for operators whose SpMV is bound by random gathers (the
+   * power-law matrix: 101 B of DRAM traffic per 8-byte gather): the columns are
+   * cut into ranges of B200_COL_BLOCK_MB (environment, default 48) megabytes of
+   * x, every range becomes a matrix of its own over all rows, and y = A x runs
+   * as y = A_0 x; y += A_1 x; ... so that the gathers of one pass stay inside
+   * one L2-sized piece of x.  Single rank, SpMV only (b200_pcg_solve refuses);
+   * row sums are formed block by block, i.e. equal to the CSR product to
+   * rounding, not bit for bit.  Ignored when one block would hold everything. */
+  B200_MAT_COL_BLOCK = 1u << 6
 };
 
 /* Host CSR exactly as lsbench_matrix_read leaves it: offs 0-based, cols
@@ -180,7 +189,7 @@ typedef struct {
   /* B200_MAT_VALUES_F32: 0 off, 1 lossless (fp64 copy dropped), 2 rounded
    * (both copies resident, PCG = iterative refinement) */
   uint32_t values_f32;
-  uint32_t reserved0;
+  uint32_t col_blocks;   /* B200_MAT_COL_BLOCK: number of column ranges, else 0 */
 } b200_mat_info;
 int b200_mat_get_info(const b200_mat *M, b200_mat_info *info);
 

@@ -21,6 +21,7 @@ MAT_FORCE_SELL = 1 << 2
 MAT_NO_SORT = 1 << 3
 MAT_NO_COMPRESS = 1 << 4
 MAT_VALUES_F32 = 1 << 5
+MAT_COL_BLOCK = 1 << 6
 
 GEN_POISSON7, GEN_POISSON27, GEN_POWERLAW = 1, 2, 3
 
@@ -60,7 +61,7 @@ class MatInfo(C.Structure):
         ("hist", C.c_uint64 * HIST_BINS), ("max_row_len", C.c_uint64),
         ("pattern_symmetric", C.c_uint32), ("sell_perm", C.c_uint32),
         ("device_bytes", C.c_uint64), ("sell_uniform_slices", C.c_uint64),
-        ("matrix_stream_bytes", C.c_uint64), ("values_f32", C.c_uint32), ("reserved0", C.c_uint32)]
+        ("matrix_stream_bytes", C.c_uint64), ("values_f32", C.c_uint32), ("col_blocks", C.c_uint32)]
 
 
 class PcgOpts(C.Structure):

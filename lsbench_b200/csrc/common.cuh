@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #define B200_SM_COUNT_FALLBACK 148
 #define B2_SLICE 32  // SELL slice height = one warp, one row per lane
@@ -182,6 +183,10 @@ struct b200_mat {
   PcgState *state = nullptr;
   SpmvPlan plan[3];              // phase 0 all, 1 interior, 2 boundary
   bool plan_ready = false;
+  // column-blocked operator (B200_MAT_COL_BLOCK): the column ranges as matrices of
+  // their own (all n rows, global column ids); this one then holds no entries
+  std::vector<b200_mat *> blocks;
+  uint64_t col_block_width = 0;
   void *small = nullptr;          // on-chip small-matrix plan (small.cu)
   bool small_tried = false;
   void *graph_exec = nullptr;     // cudaGraphExec_t of one iteration chunk
@@ -196,6 +201,8 @@ int dev_alloc(b200_mat *M, void **p, size_t bytes);  // tracks device_bytes
 int plain_free(PlainCsr *A);
 int build_layout(b200_ctx *ctx, PlainCsr *A, uint64_t n_global,
                  uint64_t row_begin, uint32_t flags, b200_mat **out);
+int build_layout_or_blocks(b200_ctx *ctx, PlainCsr *A, uint64_t n_global,
+                           uint64_t row_begin, uint32_t flags, b200_mat **out);
 int partition_and_renumber(b200_ctx *ctx, PlainCsr *A, uint64_t n_global,
                            uint64_t row_begin, b200_mat *M);
 int halo_setup(b200_mat *M);

@@ -748,6 +748,119 @@ int build_layout(b200_ctx *c, PlainCsr *A, uint64_t n_global,
   return B200_OK;
 }
 
+#include "colblock_kernels.cuh"
+
+// What build_layout is to one matrix, for a column-blocked one: M keeps the row
+// lengths, the histogram and D^-1 of the whole operator and no entries; every
+// column range becomes a child matrix over all rows.  Falls back to
+// build_layout when blocking does not apply.
+int build_layout_or_blocks(b200_ctx *c, PlainCsr *A, uint64_t n_global, uint64_t row_begin,
+                           uint32_t flags, b200_mat **out) {
+  uint64_t mb = 48;
+  if (const char *v = getenv("B200_COL_BLOCK_MB"))
+    if (atoll(v) > 0)
+      mb = (uint64_t)atoll(v);
+  const uint64_t width = (mb << 20) / 8 / 32 * 32;
+  const uint64_t nb64 = width ? (n_global + width - 1) / width : 1;
+  if (!(flags & B200_MAT_COL_BLOCK) || c->nranks > 1 || nb64 < 2 || A->n != n_global || A->nnz == 0)
+    return build_layout(c, A, n_global, row_begin, flags & ~(uint32_t)B200_MAT_COL_BLOCK, out);
+  if (nb64 > 64)
+    B_FAIL(B200_EINVAL, "B200_MAT_COL_BLOCK: %llu column blocks of %llu MB (at most 64)",
+           (unsigned long long)nb64, (unsigned long long)mb);
+  const uint32_t nb = (uint32_t)nb64;
+  cudaStream_t s = c->stream;
+  const uint64_t n = A->n;
+  b200_mat *M = *out ? *out : new b200_mat();
+  *out = M;
+  M->ctx = c, M->n_global = n_global, M->row_begin = row_begin;
+  M->n_local = n, M->nnz = A->nnz, M->flags = flags, M->col_block_width = width;
+  M->interior_begin = 0, M->interior_end = n;
+  // ---- what describes the whole operator: row lengths, histogram, D^-1 ---------------------
+  B_TRY(dev_alloc(M, (void **)&M->row_len, (n + 1) * 4));
+  B_TRY(dev_alloc(M, (void **)&M->dinv, (n + 1) * 8));
+  {
+    unsigned long long *d_hist, h_hist[B200_HIST_BINS + 2];
+    CU_TRY(cudaMalloc(&d_hist, (B200_HIST_BINS + 2) * 8));
+    CU_TRY(cudaMemsetAsync(d_hist, 0, (B200_HIST_BINS + 2) * 8, s));
+    k_row_len<<<nblk(n), T256, 0, s>>>(n, A->offs, M->row_len, d_hist, d_hist + B200_HIST_BINS);
+    k_inv_diag<<<nblk(n), T256, 0, s>>>(n, A->offs, A->cols, A->vals, M->dinv);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(h_hist, d_hist, sizeof h_hist, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    cudaFree(d_hist);
+    for (int b = 0; b < B200_HIST_BINS; b++)
+      M->hist[b] = h_hist[b];
+    M->max_row_len = h_hist[B200_HIST_BINS];
+  }
+  // ---- cut the rows ------------------------------------------------------------------------
+  {
+    unsigned *d_bad, h_bad = 0;
+    CU_TRY(cudaMalloc(&d_bad, 4));
+    CU_TRY(cudaMemsetAsync(d_bad, 0, 4, s));
+    k_rows_sorted<<<nblk(n), T256, 0, s>>>(n, A->offs, A->cols, d_bad);
+    CU_TRY(cudaMemcpyAsync(&h_bad, d_bad, 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    cudaFree(d_bad);
+    if (h_bad)
+      B_FAIL(B200_EINVAL, "B200_MAT_COL_BLOCK needs rows with ascending columns");
+  }
+  uint64_t *cnt = nullptr, *boffs = nullptr;
+  CU_TRY(cudaMalloc(&cnt, (size_t)nb * (n + 1) * 8));
+  CU_TRY(cudaMalloc(&boffs, (size_t)nb * (n + 1) * 8));
+  k_colblock_count<<<nblk(n + 1), T256, 0, s>>>(n, A->offs, A->cols, width, nb, cnt);
+  CU_TRY(cudaGetLastError());
+  std::vector<PlainCsr> sub(nb);
+  std::vector<uint32_t *> h_cols(nb, nullptr);
+  std::vector<double *> h_vals(nb, nullptr);
+  int rc = B200_OK;
+  for (uint32_t b = 0; b < nb && rc == B200_OK; b++) {
+    rc = exclusive_scan<uint64_t>(s, cnt + (size_t)b * (n + 1), boffs + (size_t)b * (n + 1), n + 1);
+    if (rc != B200_OK)
+      break;
+    sub[b].n = n;
+    if (cudaMemcpy(&sub[b].nnz, boffs + (size_t)b * (n + 1) + n, 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMalloc(&sub[b].offs, (n + 1) * 8) != cudaSuccess ||
+        cudaMalloc(&sub[b].cols, (sub[b].nnz ? sub[b].nnz : 1) * 4) != cudaSuccess ||
+        cudaMalloc(&sub[b].vals, (sub[b].nnz ? sub[b].nnz : 1) * 8) != cudaSuccess ||
+        cudaMemcpyAsync(sub[b].offs, boffs + (size_t)b * (n + 1), (n + 1) * 8,
+                        cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
+      b200_set_error("b200: column block %u: %s", b, cudaGetErrorString(cudaGetLastError()));
+      rc = B200_ENOMEM;
+    }
+    h_cols[b] = sub[b].cols, h_vals[b] = sub[b].vals;
+  }
+  uint32_t **d_cols = nullptr;
+  double **d_vals = nullptr;
+  if (rc == B200_OK) {
+    CU_TRY(cudaMalloc(&d_cols, nb * sizeof(uint32_t *)));
+    CU_TRY(cudaMalloc(&d_vals, nb * sizeof(double *)));
+    CU_TRY(cudaMemcpy(d_cols, h_cols.data(), nb * sizeof(uint32_t *), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(d_vals, h_vals.data(), nb * sizeof(double *), cudaMemcpyHostToDevice));
+    const uint64_t warps = n < (uint64_t)c->sm_count * 64 ? n : (uint64_t)c->sm_count * 64;
+    k_colblock_fill<<<(unsigned)((warps * 32 + T256 - 1) / T256), T256, 0, s>>>(
+        n, A->offs, A->cols, A->vals, nb, boffs, d_cols, d_vals);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(s));
+  }
+  cudaFree(cnt), cudaFree(boffs);
+  if (d_cols) cudaFree(d_cols);
+  if (d_vals) cudaFree(d_vals);
+  // ---- every range: a layout of its own ----------------------------------------------------------
+  const uint32_t child_flags = flags & ~(uint32_t)(B200_MAT_COL_BLOCK | B200_MAT_SYM_UPPER);
+  for (uint32_t b = 0; b < nb; b++) {
+    if (rc == B200_OK) {
+      b200_mat *child = nullptr;
+      rc = build_layout(c, &sub[b], n_global, row_begin, child_flags, &child);
+      if (child) {
+        M->blocks.push_back(child);
+        M->device_bytes += child->device_bytes;
+      }
+    }
+    plain_free(&sub[b]);
+  }
+  return rc;
+}
+
 // ---------------------------------------------------------------------------
 // C ABI
 // plain device CSR (0-based columns, global rows) -> matrix; consumes A
@@ -766,7 +879,7 @@ int mat_from_plain(b200_ctx *c, PlainCsr *A, uint32_t flags, b200_mat **out) {
   M->ctx = c;
   rc = partition_and_renumber(c, A, nrows, 0, M);
   if (rc == B200_OK)
-    rc = build_layout(c, A, nrows, M->row_begin, flags, &M);
+    rc = build_layout_or_blocks(c, A, nrows, M->row_begin, flags, &M);
   plain_free(A);
   if (rc == B200_OK && c->nranks > 1)
     rc = halo_setup(M);
@@ -805,6 +918,9 @@ extern "C" int b200_mat_destroy(b200_mat *M) {
   if (M->ctx)
     cudaSetDevice(M->ctx->device);
   cudaDeviceSynchronize();
+  for (b200_mat *child : M->blocks)
+    b200_mat_destroy(child);
+  M->blocks.clear();
   small_free(M);
   halo_free(M);
   if (M->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)M->graph_exec);
@@ -839,6 +955,19 @@ extern "C" int b200_mat_get_info(const b200_mat *M, b200_mat_info *o) {
   o->device_bytes = M->device_bytes;
   o->sell_uniform_slices = M->sell_uniform_slices;
   o->values_f32 = M->sell_vals32 ? (M->vals32_exact ? 1u : 2u) : 0u;
+  o->col_blocks = (uint32_t)M->blocks.size();
+  if (!M->blocks.empty()) {  // the sums over the column ranges
+    b200_mat_info ci;
+    for (const b200_mat *child : M->blocks) {
+      B_TRY(b200_mat_get_info(child, &ci));
+      o->nnz_padded += ci.nnz_padded, o->matrix_stream_bytes += ci.matrix_stream_bytes;
+      o->sell_rows += ci.sell_rows, o->sell_slices += ci.sell_slices;
+      o->vec_rows += ci.vec_rows, o->vec_nnz += ci.vec_nnz;
+      o->long_rows += ci.long_rows, o->long_nnz += ci.long_nnz;
+      o->values_f32 = ci.values_f32;
+    }
+    return B200_OK;
+  }
   // what one SpMV (of the PCG iteration) streams from the matrix: values,
   // columns / deltas, slice and row offsets, the row permutation
   o->matrix_stream_bytes =
@@ -925,7 +1054,25 @@ extern "C" int b200_mat_export(const b200_mat *M, uint64_t *offs,
   B_TRY(exclusive_scan<uint64_t>(s, l64, ooffs, n + 1));
   if (offs)
     CU_TRY(cudaMemcpy(offs, ooffs, (n + 1) * 8, cudaMemcpyDeviceToHost));
-  if (cols && vals) {
+  if (cols && vals && !M->blocks.empty()) {
+    // a row of the operator = its pieces in the column ranges, in range order
+    std::vector<uint64_t> ho(n + 1), at(n + 1);
+    CU_TRY(cudaMemcpy(ho.data(), ooffs, (n + 1) * 8, cudaMemcpyDeviceToHost));
+    at = ho;
+    for (const b200_mat *child : M->blocks) {
+      std::vector<uint64_t> co(n + 1);
+      std::vector<uint32_t> cc(child->nnz ? child->nnz : 1);
+      std::vector<double> cv(child->nnz ? child->nnz : 1);
+      B_TRY(b200_mat_export(child, co.data(), cc.data(), cv.data()));
+      for (uint64_t i = 0; i < n; i++)
+        for (uint64_t e = co[i]; e < co[i + 1]; e++)
+          cols[at[i]] = cc[e], vals[at[i]++] = cv[e];
+    }
+    for (uint64_t i = 0; i < n; i++)
+      if (at[i] != ho[i + 1])
+        B_FAIL(B200_EINVAL, "b200_mat_export: column blocks do not add up in row %llu",
+               (unsigned long long)i);
+  } else if (cols && vals) {
     uint32_t *oc;
     double *ov;
     CU_TRY(cudaMalloc(&oc, (M->nnz ? M->nnz : 1) * 4));

@@ -252,7 +252,7 @@ extern "C" int b200_mat_generate(b200_ctx *c, int kind, uint64_t size,
   M->ctx = c;
   int rc = partition_and_renumber(c, &A, n, r0, M);
   if (rc == B200_OK)
-    rc = build_layout(c, &A, n, r0, flags, &M);
+    rc = build_layout_or_blocks(c, &A, n, r0, flags, &M);
   plain_free(&A);
   if (rc == B200_OK && c->nranks > 1)
     rc = halo_setup(M);

@@ -417,6 +417,8 @@ extern "C" int b200_pcg_solve(b200_mat *M, const double *d_b, double *d_x,
   b200_ctx *c = M->ctx;
   CU_TRY(cudaSetDevice(c->device));
   memset(res, 0, sizeof *res);
+  if (!M->blocks.empty())
+    B_FAIL(B200_EINVAL, "b200_pcg_solve: a column-blocked matrix (B200_MAT_COL_BLOCK) is SpMV-only");
   if (!(o->flags & (B200_PCG_NO_SMALL | B200_PCG_SINGLE_REDUCTION)) && c->nranks == 1) {
     B_TRY(small_try_build(M));
     if (M->small)

@@ -1,3 +1,6 @@
+// ACC (column-blocked matrices, convert.cu): y += A x instead of y = A x, so the
+// column blocks of one operator can be multiplied one after another.
+//
 // sell_kernels.cuh -- the SELL-32 SpMV kernels (included by spmv.cu, which holds
 // the launch logic and the description of the layout).  In a header of their own
 // so that tests/ can also compile the kernel bodies for the host, with one-line
@@ -67,7 +70,7 @@ __device__ __forceinline__ double sell_chunk(const float *vp, const double *__re
 template <typename VT> struct ChunkOf { static constexpr uint32_t n = 8; };
 template <> struct ChunkOf<float> { static constexpr uint32_t n = 16; };
 
-template <bool DOT, typename VT>
+template <bool DOT, typename VT, bool ACC = false>
 __global__ void __launch_bounds__(SPMV_THREADS, 4)
 k_spmv_sell(const uint32_t *__restrict__ sell_off,
             const uint32_t *__restrict__ cols, const VT *__restrict__ vals,
@@ -103,7 +106,7 @@ k_spmv_sell(const uint32_t *__restrict__ sell_off,
     const uint32_t pos = s * B2_SLICE + lane;
     const uint32_t row = perm ? __ldg(perm + pos) : pos;
     if (row < n_rows) {
-      y[row] = sum;
+      y[row] = ACC ? y[row] + sum : sum;
       if (DOT)
         dot = fma(sum, __ldg(x + row), dot);
     }
@@ -137,7 +140,7 @@ k_spmv_sell(const uint32_t *__restrict__ sell_off,
 // instantiation holds 16 values per chunk and is compiled for 4 CTAs per SM
 // (64 registers; at 48 it spills 112 bytes in the loop).
 #define SELLC_MINB 5
-template <bool DOT, typename VT>
+template <bool DOT, typename VT, bool ACC = false>
 __global__ void __launch_bounds__(SPMV_THREADS, sizeof(VT) == 8 ? SELLC_MINB : 4)
 k_spmv_sellc(const uint4 *__restrict__ meta, const uint32_t *__restrict__ cols,
              const int32_t *__restrict__ dcols, const VT *__restrict__ vals,
@@ -184,7 +187,7 @@ k_spmv_sellc(const uint4 *__restrict__ meta, const uint32_t *__restrict__ cols,
         });
     }
     if (row < n_rows) {
-      y[row] = sum;
+      y[row] = ACC ? y[row] + sum : sum;
       if (DOT)
         dot = fma(sum, __ldg(x + row), dot);
     }
@@ -199,7 +202,7 @@ k_spmv_sellc(const uint4 *__restrict__ meta, const uint32_t *__restrict__ cols,
 #include "sellc32p.cuh"
 
 // ---- the row-major bins: one warp per row, one CTA per row ----------------------------
-template <bool DOT>
+template <bool DOT, bool ACC = false>
 __global__ void __launch_bounds__(SPMV_THREADS, 4)
 k_spmv_vec(uint32_t nrows, const uint32_t *__restrict__ ids,
            const uint64_t *__restrict__ off, const uint32_t *__restrict__ cols,
@@ -229,7 +232,7 @@ k_spmv_vec(uint32_t nrows, const uint32_t *__restrict__ ids,
     sum = warp_sum(sum);
     if (lane == 0) {
       const uint32_t row = __ldg(ids + r);
-      y[row] = sum;
+      y[row] = ACC ? y[row] + sum : sum;
       if (DOT)
         dot = fma(sum, __ldg(x + row), dot);
     }
@@ -241,7 +244,7 @@ k_spmv_vec(uint32_t nrows, const uint32_t *__restrict__ ids,
   }
 }
 
-template <bool DOT>
+template <bool DOT, bool ACC = false>
 __global__ void __launch_bounds__(SPMV_THREADS, 4)
 k_spmv_long(uint32_t nrows, const uint32_t *__restrict__ ids,
             const uint64_t *__restrict__ off, const uint32_t *__restrict__ cols,
@@ -269,7 +272,7 @@ k_spmv_long(uint32_t nrows, const uint32_t *__restrict__ ids,
     sum = block_sum<SPMV_WARPS>(sum, red);
     if (threadIdx.x == 0) {
       const uint32_t row = __ldg(ids + r);
-      y[row] = sum;
+      y[row] = ACC ? y[row] + sum : sum;
       if (DOT)
         dot = fma(sum, __ldg(x + row), dot);
     }

@@ -239,9 +239,65 @@ int launch_spmv(b200_mat *M, const double *x, double *y, bool dot, int phase,
   return B200_OK;
 }
 
+// y += A x on all bins (no fused dot, no phases): what the second and later
+// column blocks of a column-blocked matrix run (convert.cu build_col_blocked).
+static int launch_spmv_acc(b200_mat *M, const double *x, double *y) {
+  b200_ctx *c = M->ctx;
+  cudaStream_t s = c->stream;
+  const SpmvPlan P = plan_phase(M, 0);
+  const XrArgs xr = XrArgs{nullptr, nullptr, 1, 0, 0, 0ull};
+  const uint32_t n = (uint32_t)M->n_local;
+  if (P.g_sell) {
+    const uint4 *meta = (const uint4 *)M->sell_meta;
+    const bool f32 = M->sell_vals32 && (M->spmv_use32 || !M->sell_vals);
+#define B2_ACC_ARGS M->sell_perm, x, y, P.b0, P.e0, P.b1, P.e1, n, nullptr, 0u, 0u, nullptr, nullptr, xr
+    if (meta && f32)
+      k_spmv_sellc<false, float, true><<<P.g_sell, SPMV_THREADS, 0, s>>>(
+          meta, M->sell_cols, M->sell_dcols, M->sell_vals32, B2_ACC_ARGS);
+    else if (meta)
+      k_spmv_sellc<false, double, true><<<P.g_sell, SPMV_THREADS, 0, s>>>(
+          meta, M->sell_cols, M->sell_dcols, M->sell_vals, B2_ACC_ARGS);
+    else if (f32)
+      k_spmv_sell<false, float, true><<<P.g_sell, SPMV_THREADS, 0, s>>>(
+          M->sell_off, M->sell_cols, M->sell_vals32, B2_ACC_ARGS);
+    else
+      k_spmv_sell<false, double, true><<<P.g_sell, SPMV_THREADS, 0, s>>>(
+          M->sell_off, M->sell_cols, M->sell_vals, B2_ACC_ARGS);
+#undef B2_ACC_ARGS
+  }
+  if (P.g_vec)
+    k_spmv_vec<false, true><<<P.g_vec, SPMV_THREADS, 0, s>>>(
+        M->vec_rows, M->vec_row_ids, M->vec_off, M->vl_cols, M->vl_vals, x, y, nullptr, 0, 0,
+        nullptr, nullptr, xr);
+  if (P.g_long)
+    k_spmv_long<false, true><<<P.g_long, SPMV_THREADS, 0, s>>>(
+        M->long_rows, M->long_row_ids, M->long_off, M->vl_cols, M->vl_vals, x, y, nullptr, 0, 0,
+        nullptr, nullptr, xr);
+  c->launches += (P.g_sell > 0) + (P.g_vec > 0) + (P.g_long > 0);
+  CU_TRY(cudaGetLastError());
+  return B200_OK;
+}
+
+// A column-blocked operator: y = A_0 x, then y += A_b x block after block, so that
+// the random gathers of one pass stay inside one L2-sized range of x.
+static int spmv_col_blocked(b200_mat *M, const double *x, double *y) {
+  for (size_t b = 0; b < M->blocks.size(); b++) {
+    if (b == 0)
+      B_TRY(launch_spmv(M->blocks[b], x, y, false, 0, nullptr));
+    else
+      B_TRY(launch_spmv_acc(M->blocks[b], x, y));
+  }
+  return B200_OK;
+}
+
 // Full SpMV with halo exchange overlapped with the interior rows (piece 5).
 static int spmv_full(b200_mat *M, double *x_ext, double *y, bool dot,
                      const XrArgs *xr = nullptr) {
+  if (!M->blocks.empty()) {
+    if (dot)
+      B_FAIL(B200_EINVAL, "a column-blocked matrix is SpMV-only");
+    return spmv_col_blocked(M, x_ext, y);
+  }
   if (!M->halo.n_halo && M->ctx->nranks == 1)
     return launch_spmv(M, x_ext, y, dot, 0, nullptr);
   B_TRY(halo_exchange_begin(M, x_ext));
@@ -259,6 +315,8 @@ extern "C" int b200_spmv(b200_mat *M, const double *d_x, double *d_y) {
     B_FAIL(B200_EINVAL, "b200_spmv: null argument");
   b200_ctx *c = M->ctx;
   CU_TRY(cudaSetDevice(c->device));
+  if (!M->blocks.empty())
+    return spmv_col_blocked(M, d_x, d_y);
   if (c->nranks == 1)
     return launch_spmv(M, d_x, d_y, false, 0, nullptr);
   B_TRY(ensure_workspace(M));

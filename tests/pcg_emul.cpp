@@ -207,3 +207,38 @@ extern "C" int emul_spmv_two_phase(uint32_t n, uint32_t ns, const uint4 *meta, c
   *dot_out = st.pq;
   return st.ticket[0] == 0 ? 0 : 1;  // the last CTA must have reset the ticket
 }
+
+// ---- column blocking (csrc/colblock_kernels.cuh): cut a CSR into column ranges, then
+// y = A_0 x; y += A_1 x; ... with the ACC instantiations of the SELL kernel ---------------
+#include "colblock_kernels.cuh"
+
+extern "C" int emul_colblock_split(uint64_t n, const uint64_t *offs, const uint32_t *cols,
+                                   const double *vals, uint64_t width, uint32_t nb,
+                                   uint64_t *cnt /* nb x (n+1) */, uint64_t *boffs /* nb x (n+1) */,
+                                   uint32_t **ocols, double **ovals, int stage, unsigned *unsorted) {
+  if (stage == 0) {
+    simt::launch((unsigned)((n + 1 + 255) / 256), 256,
+                 [&] { k_colblock_count(n, offs, cols, width, nb, cnt); });
+    simt::launch((unsigned)((n + 255) / 256), 256, [&] { k_rows_sorted(n, offs, cols, unsorted); });
+  } else {
+    simt::launch(3, 256, [&] { k_colblock_fill(n, offs, cols, vals, nb, boffs, ocols, ovals); });
+  }
+  return 0;
+}
+
+// y (+)= A x with k_spmv_sell<false, double, ACC> on an explicit-column SELL layout
+extern "C" int emul_sell_acc(int acc, unsigned grid, uint32_t ns, const uint32_t *sell_off,
+                             const uint32_t *cols, const double *vals, const double *x, double *y,
+                             uint32_t n_rows) {
+  if (acc)
+    simt::launch(grid, SPMV_THREADS, [&] {
+      k_spmv_sell<false, double, true>(sell_off, cols, vals, nullptr, x, y, 0, ns, 0, 0, n_rows, nullptr,
+                                       0, 0, nullptr, nullptr, NOXR);
+    });
+  else
+    simt::launch(grid, SPMV_THREADS, [&] {
+      k_spmv_sell<false, double, false>(sell_off, cols, vals, nullptr, x, y, 0, ns, 0, 0, n_rows, nullptr,
+                                        0, 0, nullptr, nullptr, NOXR);
+    });
+  return 0;
+}

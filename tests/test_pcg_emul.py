@@ -230,3 +230,76 @@ def test_two_launch_spmv_with_one_fused_dot(emul, gen, N):
                                             p(Lay["vals"]), kernel, wmax, ib, ie, p(x), p(y), p(d)) == 0
             assert y.tobytes() == want.tobytes()
             assert abs(d[0] - x @ want) <= 1e-12 * np.abs(x * want).sum()
+
+
+def test_column_blocked_spmv_on_the_emulator(emul):
+    """B200_MAT_COL_BLOCK without a GPU: the product's kernels cut a power-law
+    operator (oracle generator, BASELINE.json config 5) into column ranges
+    (k_colblock_count / k_colblock_fill), every range becomes a SELL layout over all
+    rows, and y = A_0 x; y += A_1 x; ... runs through the accumulate instantiation
+    of the SELL kernel.  The pieces add up to the operator bit for bit; the product
+    is the CSR product to the 1e-13 bar (row sums are formed block by block)."""
+    emul.emul_colblock_split.argtypes = ([C.c_uint64] + [C.c_void_p] * 3 + [C.c_uint64, C.c_uint32]
+                                         + [C.c_void_p] * 4 + [C.c_int, C.c_void_p])
+    emul.emul_sell_acc.argtypes = [C.c_int, C.c_uint, C.c_uint32] + [C.c_void_p] * 5 + [C.c_uint32]
+    n = 3000
+    M = orc.gen_powerlaw(n, 2)
+    keep = M.rowlens() <= 200                      # the SELL bin (longer rows go to other kernels)
+    offs = M.offs.astype(np.int64)
+    sel = np.concatenate([np.arange(offs[i], offs[i + 1]) if keep[i] else [] for i in range(n)]).astype(np.int64)
+    lens = np.where(keep, M.rowlens(), 0)
+    M = orc.Op(n, np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64), M.cols[sel], M.vals[sel])
+    width, nb = 704, 5                             # 5 ranges of 704 columns (a multiple of 32)
+    assert (nb - 1) * width < n <= nb * width
+    p = lambda a: a.ctypes.data
+    cnt = np.zeros(nb * (n + 1), dtype=np.uint64)
+    bad = np.zeros(1, dtype=np.uint32)
+    emul.emul_colblock_split(n, p(M.offs), p(M.cols), p(M.vals), width, nb, p(cnt), None, None, None, 0, p(bad))
+    assert bad[0] == 0
+    cnt = cnt.reshape(nb, n + 1)
+    want_cnt = np.array([[np.sum((M.cols[offs2[0]:offs2[1]] // width) == b) for offs2 in
+                          zip(M.offs[:-1].astype(np.int64), M.offs[1:].astype(np.int64))] for b in range(nb)])
+    assert np.array_equal(cnt[:, :n], want_cnt) and not cnt[:, n].any()
+    boffs = np.concatenate([np.zeros((nb, 1), dtype=np.uint64), np.cumsum(cnt[:, :n], axis=1).astype(np.uint64)],
+                           axis=1)             # the exclusive scan the host code does with cub
+    boffs = np.ascontiguousarray(boffs)
+    ocols = [np.zeros(max(int(boffs[b, n]), 1), dtype=np.uint32) for b in range(nb)]
+    ovals = [np.zeros(max(int(boffs[b, n]), 1)) for b in range(nb)]
+    pc = (C.c_void_p * nb)(*[p(a) for a in ocols])
+    pv = (C.c_void_p * nb)(*[p(a) for a in ovals])
+    emul.emul_colblock_split(n, p(M.offs), p(M.cols), p(M.vals), width, nb, None, p(boffs), pc, pv, 1, None)
+    # the pieces, row by row and in range order, are the operator
+    S = M.scipy()
+    x = np.random.default_rng(6).standard_normal(n)
+    y = np.full(n, np.nan)
+    total = 0
+    for b in range(nb):
+        nnz_b = int(boffs[b, n])
+        Mb = orc.Op(n, boffs[b], ocols[b][:max(nnz_b, 1)], ovals[b][:max(nnz_b, 1)], ncols=n)
+        if nnz_b:
+            assert Mb.cols[:nnz_b].min() >= b * width and Mb.cols[:nnz_b].max() < (b + 1) * width
+        total += nnz_b
+        Lay = sellc_layout(Mb)
+        vals = np.zeros(Lay["allcols"].size)
+        o = 0
+        for s_ in range(Lay["ns"]):
+            w = int(Lay["sell_off"][s_ + 1] - Lay["sell_off"][s_])
+            for l in range(32):
+                r = 32 * s_ + l
+                if r < n:
+                    a, e = int(Mb.offs[r]), int(Mb.offs[r + 1])
+                    vals[32 * o + l:32 * (o + e - a) + l:32] = Mb.vals[a:e]
+            o += w
+        emul.emul_sell_acc(int(b > 0), 3, Lay["ns"], p(Lay["sell_off"]), p(Lay["allcols"]), p(vals), p(x), p(y), n)
+    assert total == M.nnz
+    ref, scale = orc.spmv(M, x, want_abs=True)
+    assert np.all(np.abs(y - ref) <= 1e-13 * np.maximum(scale, 1e-300))
+    # an unsorted row is noticed
+    cols2 = M.cols.copy()
+    i = int(np.argmax(M.rowlens() >= 2))
+    a = int(M.offs[i])
+    cols2[a], cols2[a + 1] = cols2[a + 1], cols2[a]
+    bad[:] = 0
+    scratch = np.zeros(nb * (n + 1), dtype=np.uint64)
+    emul.emul_colblock_split(n, p(M.offs), p(cols2), p(M.vals), width, nb, p(scratch), None, None, None, 0, p(bad))
+    assert bad[0] == 1

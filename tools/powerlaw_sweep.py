@@ -41,6 +41,9 @@ ctx = abi.Context(local, rank, world, nccl_id)
 
 SEL = [("auto", 0), ("sell_only", abi.MAT_FORCE_SELL), ("vector_only", abi.MAT_FORCE_VECTOR),
        ("auto_nosort", abi.MAT_NO_SORT)]
+if world == 1:
+    # column blocking (B200_MAT_COL_BLOCK; width from B200_COL_BLOCK_MB, default 48 MB of x)
+    SEL.insert(1, ("auto_colblock", abi.MAT_COL_BLOCK))
 for seed in seeds:
     for name, fl in (SEL if seed == seeds[0] else SEL[:1]):
         t0 = time.time()
@@ -72,7 +75,8 @@ for seed in seeds:
                           "sell_rows": i.sell_rows, "sell_sigma": i.sell_sigma,
                           "sell_max_width": i.sell_max_width, "vec_rows": i.vec_rows,
                           "vec_nnz": i.vec_nnz, "long_rows": i.long_rows, "long_nnz": i.long_nnz,
-                          "max_row_len": i.max_row_len, "n_halo": i.n_halo,
+                          "max_row_len": i.max_row_len, "n_halo": i.n_halo, "col_blocks": i.col_blocks,
+                          "matrix_stream_bytes": i.matrix_stream_bytes,
                           "hist": list(i.hist)},
                 "setup_s": time.time() - t0, "ms_per_spmv": ms_max,
                 "algorithmic_bytes_all_ranks": tot_bytes,

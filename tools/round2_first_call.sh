@@ -22,3 +22,5 @@ if grep -q "parity: ok" $OUT/r02a_pipe1.log; then
       python tools/pipe_check.py 256 > $OUT/r02a_pipe_ncu.log 2>&1
 fi
 ls -la $OUT | grep r02a
+# (4) column-blocked SpMV of the power-law operator (config 5): parity, then block widths
+timeout 300 python tools/colblock_check.py 50000000 > $OUT/r02a_colblock.log 2>&1; tail -7 $OUT/r02a_colblock.log | cut -c1-300
