@@ -90,6 +90,8 @@ k_spmv_sell(const uint32_t *__restrict__ sell_off,
     const uint32_t s = v < n0 ? b0 + v : b1 + (v - n0);
     const uint32_t o = __ldg(sell_off + s);
     const uint32_t w = __ldg(sell_off + s + 1) - o;
+    if (ACC && w == 0)  // nothing to add: leave y alone (no read-modify-write traffic)
+      continue;
     const size_t base = (size_t)o * B2_SLICE + lane;
     const uint32_t *cp = cols + base;
     const VT *vp = vals + base;
@@ -160,6 +162,8 @@ k_spmv_sellc(const uint4 *__restrict__ meta, const uint32_t *__restrict__ cols,
     const uint32_t s = v < n0 ? b0 + v : b1 + (v - n0);
     const uint4 m = __ldg(meta + s);
     const uint32_t o = m.x, w = m.y & 0x7fffffffu;
+    if (ACC && w == 0)  // nothing to add: leave y alone
+      continue;
     const VT *vp = vals + (size_t)o * B2_SLICE + lane;
     const uint32_t pos = s * B2_SLICE + lane;
     const uint32_t row = perm ? __ldg(perm + pos) : pos;
