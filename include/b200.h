@@ -232,7 +232,10 @@ enum {
 
 typedef struct {
   int32_t iters;
-  int32_t status;      /* 0 converged, 1 maxit, 2 breakdown (not SPD / NaN) */
+  int32_t status;      /* 0 converged, 1 maxit, 2 breakdown (not SPD / NaN),
+                          4 stagnated: the recurrence residual met the bar, b - A x
+                          did not, and iterating on from the true residual did not
+                          get there either (the bar is below what fp64 reaches) */
   double relres;       /* recurrence ||r|| / ||b|| at exit */
   double true_relres;  /* ||b - A x|| / ||b|| recomputed with one SpMV */
   double bnorm;
@@ -241,7 +244,8 @@ typedef struct {
   int32_t kernel_launches;
   int32_t path;        /* 0 = streaming kernels, 1 = on-chip small-matrix */
   int32_t outer_iters; /* refinement passes (values_f32 == 2), else 0 */
-  int32_t reserved0;
+  int32_t replacements; /* residual replacements: exit checks that found ||b - A x|| above
+                           the bar with the recurrence below it, after which the solve went on */
 } b200_pcg_result;
 
 /* x: in x0, out solution (n_local).  b: n_local.  Device pointers. */

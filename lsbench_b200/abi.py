@@ -75,7 +75,7 @@ class PcgResult(C.Structure):
                 ("bnorm", C.c_double), ("solve_ms", C.c_float),
                 ("spmv_ms", C.c_float), ("update_ms", C.c_float),
                 ("pupdate_ms", C.c_float), ("kernel_launches", C.c_int32),
-                ("path", C.c_int32), ("outer_iters", C.c_int32), ("reserved0", C.c_int32)]
+                ("path", C.c_int32), ("outer_iters", C.c_int32), ("replacements", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

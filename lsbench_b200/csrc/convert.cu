@@ -834,8 +834,11 @@ int build_layout_or_blocks(b200_ctx *c, PlainCsr *A, uint64_t n_global, uint64_t
   if (rc == B200_OK) {
     CU_TRY(cudaMalloc(&d_cols, nb * sizeof(uint32_t *)));
     CU_TRY(cudaMalloc(&d_vals, nb * sizeof(double *)));
-    CU_TRY(cudaMemcpy(d_cols, h_cols.data(), nb * sizeof(uint32_t *), cudaMemcpyHostToDevice));
-    CU_TRY(cudaMemcpy(d_vals, h_vals.data(), nb * sizeof(double *), cudaMemcpyHostToDevice));
+    // (in the stream that consumes them: a blocking copy on the legacy stream is not
+    // ordered with a non-blocking stream)
+    CU_TRY(cudaMemcpyAsync(d_cols, h_cols.data(), nb * sizeof(uint32_t *), cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(d_vals, h_vals.data(), nb * sizeof(double *), cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaStreamSynchronize(s));
     const uint64_t warps = n < (uint64_t)c->sm_count * 64 ? n : (uint64_t)c->sm_count * 64;
     k_colblock_fill<<<(unsigned)((warps * 32 + T256 - 1) / T256), T256, 0, s>>>(
         n, A->offs, A->cols, A->vals, nb, boffs, d_cols, d_vals);
@@ -929,7 +932,7 @@ extern "C" int b200_mat_destroy(b200_mat *M) {
                   M->sell_meta, M->sell_dcols,
                   M->vec_row_ids, M->long_row_ids, M->vec_off, M->long_off,
                   M->vl_cols, M->vl_vals, M->dinv, M->row_len, M->w_r, M->w_p,
-                  M->w_q, M->x_ext, M->partials, M->state, M->stage_b, M->stage_x};
+                  M->w_q, M->w_x, M->x_ext, M->partials, M->state, M->stage_b, M->stage_x};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   delete M;

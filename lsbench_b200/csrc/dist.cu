@@ -125,7 +125,7 @@ static int xr_setup(b200_ctx *c) {
   mine.pid = (long long)getpid(), mine.dev = c->device, mine.ok = want;
   if (want) {
     CU_TRY(cudaMalloc(&c->xr_mail, mail_bytes));
-    CU_TRY(cudaMemset(c->xr_mail, 0, mail_bytes));
+    CU_TRY(cudaMemsetAsync(c->xr_mail, 0, mail_bytes, s));
     mine.ptr = (unsigned long long)c->xr_mail;
     if (cudaIpcGetMemHandle(&mine.handle, c->xr_mail) != cudaSuccess)
       cudaGetLastError(), mine.ok = 0;
@@ -174,8 +174,9 @@ static int xr_setup(b200_ctx *c) {
   cudaFree(d_all);
   if (ok) {
     CU_TRY(cudaMalloc(&c->xr_peers, sizeof(double *) * B2_XR_MAX_RANKS));
-    CU_TRY(cudaMemcpy(c->xr_peers, peers.data(), sizeof(double *) * B2_XR_MAX_RANKS,
-                      cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpyAsync(c->xr_peers, peers.data(), sizeof(double *) * B2_XR_MAX_RANKS,
+                           cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaStreamSynchronize(s));
   }
   c->xr_on = ok != 0;
   if (getenv("B200_VERBOSE") && c->rank == 0)
@@ -389,8 +390,8 @@ int halo_setup(b200_mat *M) {
   free(h_g);
   uint64_t *d_need;
   CU_TRY(cudaMalloc(&d_need, (size_t)P * P * 8));
-  CU_TRY(cudaMemcpy(d_need + (size_t)me * P, need + (size_t)me * P, P * 8,
-                    cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpyAsync(d_need + (size_t)me * P, need + (size_t)me * P, P * 8,
+                         cudaMemcpyHostToDevice, s));
   NC_TRY(g_nccl.AllGather(d_need + (size_t)me * P, d_need, P, ncclUint64, comm, s));
   CU_TRY(cudaStreamSynchronize(s));
   CU_TRY(cudaMemcpy(need, d_need, (size_t)P * P * 8, cudaMemcpyDeviceToHost));

@@ -224,7 +224,8 @@ extern "C" int b200_mat_generate(b200_ctx *c, int kind, uint64_t size,
                    : (uint64_t)floor(pow((double)PL_LMIN / (double)L, 1.2) *
                                      9007199254740992.0);
     CU_TRY(cudaMalloc(&d_thr, (PL_LMAX + 1) * 8));
-    CU_TRY(cudaMemcpy(d_thr, thr, (PL_LMAX + 1) * 8, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpyAsync(d_thr, thr, (PL_LMAX + 1) * 8, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaStreamSynchronize(s));  // pageable source: landed before it is freed
     free(thr);
     k_pl_len<<<nblk(nloc + 1), T256, 0, s>>>(n, seed, r0, nloc, d_thr, len);
   } else {

@@ -406,7 +406,10 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
   // ---- iterations ----------------------------------------------------------------------
   if (PROF)
     t0 = clock64();
-  while (status == 1 && it < maxit) {
+  int replacements = 0, it_stop = maxit;
+  double t4[1];
+  for (;;) {  // iterate; check b - A x; go on from the true residual if it misses the bar
+  while (status == 1 && it < it_stop) {
     if (tid == 0)
       bar_arm(bar_a, C * 8);
     double a1[1], t1[1];
@@ -461,9 +464,8 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
     B2_TICK(4)
   }
 #undef B2_TICK
-  if (PROF && rank == 0 && tid == 0)
-    for (int i = 0; i < 6; i++)
-      prof[i] = pt[i];
+  if (status == 1 && it < maxit)
+    status = 4;  // the bounded tail after a replacement did not get there: stagnated
 
   // ---- x out, true residual ---------------------------------------------------------------
   cl.sync();  // the loop may end on barrier B; the next use below is B again
@@ -481,7 +483,7 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
     bar_arm(bar_a, C * 8);
   small_spmv<false>(me, R, goff, vals, cols, rowid, z_w, q_s);
   __syncthreads();
-  double a4[1] = {0.0}, t4[1];
+  double a4[1] = {0.0};
   for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
     uint32_t row = rowid[i];
     if (row != 0xffffffffu) {
@@ -492,9 +494,52 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
   send_partials<1>(C, rank, a4, wred, slots, 0, bar_a);
   bar_wait(bar_a, par_a), par_a ^= 1;
   read_totals<1>(C, slots, 0, t4);
+  // Residual replacement (pcg_kernels.cuh k_pcg_replace, same rule as the streaming
+  // path): the recurrence says converged, b - A x does not.  q_s holds A x: take
+  // r = b - q, push z = D^-1 r, form r.z and r.r, p = z + (r.z / r.z_old) p with
+  // the direction of the last iteration (rz still is r.z_old: the loop left
+  // before overwriting it), and iterate on.  Barrier order stays B | B A | B, A B ...
+  if (!(status == 0 && it > 0 && it < maxit && t4[0] > thr2 && replacements < 4))
+    break;
+  replacements++;
+  if (tid == 0)
+    bar_arm(bar_b, (2 * C + me.n_recv) * 8);
+  double a5[2] = {0.0, 0.0}, t5[2];
+  for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
+    uint32_t row = rowid[i];
+    if (row == 0xffffffffu)
+      continue;
+    const double ri = b[orig[i]] - q_s[i], zi = d_s[i] * ri;
+    r_s[i] = ri;
+    push(row, dmask[i], zi);
+    a5[0] = fma(ri, zi, a5[0]), a5[1] = fma(ri, ri, a5[1]);
+  }
+  send_partials<2>(C, rank, a5, wred, slots, 1, bar_b);
+  bar_wait(bar_b, par_b), par_b ^= 1;
+  read_totals<2>(C, slots, 1, t5);
+  rr = t5[1];
+  if (rr <= thr2)
+    break;  // (cannot happen: the same sums as t4; keeps the loop honest)
+  {
+    const double beta = t5[0] / rz;
+    rz = t5[0];
+    for (uint32_t i = tid; i < me.col_n; i += SM_THREADS)
+      p_w[i] = fma(beta, p_w[i], z_w[i]);
+    __syncthreads();
+  }
+  status = 1;
+  it_stop = it + (it / 8 > 8 ? it / 8 : 8);
+  it_stop = it_stop < maxit ? it_stop : maxit;
+  if (PROF)
+    t0 = clock64();
+  }  // for (;;)
+  if (PROF && rank == 0 && tid == 0)
+    for (int i = 0; i < 6; i++)
+      prof[i] = pt[i];
   if (rank == 0 && tid == 0) {
     st->iter = it, st->status = status, st->done = 1;
     st->bb = bb, st->red[1] = rr, st->pq = pq, st->true_rr = t4[0];
+    st->sr_next = replacements;
   }
   cl.sync();  // nobody leaves while a neighbour may still be storing into it
 }
@@ -767,7 +812,8 @@ int small_try_build(b200_mat *M) {
     }
     auto up = [&](void **d, const void *h, size_t bytes) -> int {
       CU_TRY(cudaMalloc(d, bytes ? bytes : 8));
-      CU_TRY(cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice));
+      CU_TRY(cudaMemcpyAsync(*d, h, bytes, cudaMemcpyHostToDevice, c->stream));
+      CU_TRY(cudaStreamSynchronize(c->stream));
       M->device_bytes += bytes;
       return B200_OK;
     };
@@ -819,6 +865,7 @@ int small_solve(b200_mat *M, const double *d_b, double *d_x,
   res->true_relres = h.bb > 0 ? sqrt(h.true_rr / h.bb) : sqrt(h.true_rr);
   res->kernel_launches = 1;
   res->path = 1;
+  res->replacements = h.sr_next;
   if (prof && h.iter > 0) {
     long long hp[6];
     CU_TRY(cudaMemcpy(hp, P->d_prof, sizeof hp, cudaMemcpyDeviceToHost));

@@ -588,7 +588,23 @@ int b200_bench(double *x, struct csr *A, const double *r,
          sh.last.status, sh.last.relres, sh.last.true_relres,
          cb->trials ? 1e3 * sh.elapsed / cb->trials : 0.0, sh.nnz,
          sh.last.path);
+  /* the CSV row above is printed whatever happened (the format is the harness's);
+   * a solve that did not reach the bar must not pass silently */
+  if (sh.last.status != 0)
+    warnx("b200: the last solve ended with status %d (%s) after %d iterations, "
+          "||b - A x|| / ||b|| = %.3e", sh.last.status,
+          sh.last.status == 1   ? "maxit reached"
+          : sh.last.status == 2 ? "breakdown: not SPD or NaN"
+          : sh.last.status == 4 ? "stagnated above the bar: below what fp64 reaches here"
+                                : "a rank did not answer",
+          sh.last.iters, sh.last.true_relres);
+  else if (sh.last.true_relres > sh.cfg.tol)
+    warnx("b200: recurrence residual %.3e met the bar %.1e but ||b - A x|| / ||b|| = %.3e "
+          "does not after %d residual replacement(s)", sh.last.relres, sh.cfg.tol,
+          sh.last.true_relres, sh.last.replacements);
   if (cb->verbose > 0) {
+    if (sh.last.replacements)
+      printf("b200: residual replacements=%d\n", sh.last.replacements);
     printf("b200: rows/rank0=%llu halo=%llu sell_slices=%llu sigma=%llu "
            "vec_rows=%llu long_rows=%llu padded_nnz=%llu device_MB=%.1f\n",
            (unsigned long long)sh.info.n_local,

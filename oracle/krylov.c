@@ -10,6 +10,8 @@
  *   loop: q = A p; alpha = rz / p.q; x += alpha p; r -= alpha q;
  *         z = D^-1 r; rz' = r.z; stop if ||r|| <= tol ||b||;
  *         beta = rz'/rz; p = z + beta p
+ *   exit: if the recurrence met the bar and ||b - A x|| does not (drift after
+ *         many iterations), r = b - A x, rz' = r.z, p = z + (rz'/rz) p, go on
  * Summation order differs from the GPU (plain left-to-right here), so
  * agreement is to rounding, not bit for bit; see tests for the tolerances.
  */
@@ -109,7 +111,9 @@ double orc_true_relres(const orc_op *M, const double *b, const double *x) {
   int it = 0, rc = 1;                                                          \
   if (sqrt(rr) <= thr)                                                         \
     rc = 0;                                                                    \
-  while (rc == 1 && it < maxit) {                                              \
+  int it_stop = maxit;                                                         \
+  for (int replaced = 0;;) {                                                   \
+  while (rc == 1 && it < it_stop) {                                            \
     double pq = 0;                                                             \
     SPMV(M, p, q);                                                             \
     PRAGMA_RED1(pq)                                                            \
@@ -138,6 +142,36 @@ double orc_true_relres(const orc_op *M, const double *b, const double *x) {
     PRAGMA_FOR                                                                 \
     for (int64_t i = 0; i < n; i++)                                            \
       p[i] = dinv[i] * r[i] + beta * p[i];                                     \
+  }                                                                            \
+  /* residual replacement: the recurrence met the bar; if b - A x does not,    \
+   * go on from the true residual with the last direction */                   \
+  if (rc == 1 && it < maxit)                                                   \
+    rc = 4; /* the bounded tail after a replacement: stagnated */              \
+  if (rc != 0 || it == 0 || it >= maxit || replaced >= 4)                      \
+    break;                                                                     \
+  SPMV(M, x, q);                                                               \
+  double trr = 0;                                                              \
+  PRAGMA_RED1(trr)                                                             \
+  for (int64_t i = 0; i < n; i++)                                              \
+    trr += (b[i] - q[i]) * (b[i] - q[i]);                                      \
+  if (!(trr > thr * thr))                                                      \
+    break;                                                                     \
+  replaced++;                                                                  \
+  double rzn = 0;                                                              \
+  PRAGMA_RED1(rzn)                                                             \
+  for (int64_t i = 0; i < n; i++) {                                            \
+    r[i] = b[i] - q[i];                                                        \
+    rzn += r[i] * (dinv[i] * r[i]);                                            \
+  }                                                                            \
+  rr = trr;                                                                    \
+  double beta = rzn / rz;                                                      \
+  rz = rzn;                                                                    \
+  PRAGMA_FOR                                                                   \
+  for (int64_t i = 0; i < n; i++)                                              \
+    p[i] = dinv[i] * r[i] + beta * p[i];                                       \
+  rc = 1;                                                                      \
+  it_stop = it + (it / 8 > 8 ? it / 8 : 8);                                    \
+  it_stop = it_stop < maxit ? it_stop : maxit;                                 \
   }                                                                            \
   if (iters)                                                                   \
     *iters = it;                                                               \

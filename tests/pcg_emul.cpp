@@ -79,7 +79,8 @@ extern "C" int emul_pcg(uint32_t n, uint32_t ns, const uint4 *meta, const uint32
                         const int32_t *dcols, const double *vals, const uint32_t *perm,
                         const double *dinv, const double *b, double *x, double tol, int maxit,
                         int single_reduction, unsigned grid_spmv, unsigned grid_ew, int *iters,
-                        int *status, double *relres, const float *vals32, int kernel, int wmax) {
+                        int *status, double *relres, const float *vals32, int kernel, int wmax,
+                        int *replacements, double *true_relres) {
   Layout L{n, ns, meta, cols, dcols, vals, perm, dinv, vals32, kernel, wmax};
   std::vector<double> r(n + 2), p(n + 2), q(n + 2), pp(n + 2, 0.0), sv(n + 2, 0.0);
   const unsigned stride = 148 * 32 * 3 + 64;
@@ -118,12 +119,59 @@ extern "C" int emul_pcg(uint32_t n, uint32_t ns, const uint4 *meta, const uint32
                        &st.red[nx], NOXR, NOXR);
         });
         simt::launch(grid_ew, EW_THREADS, [&] {
-          k_pcg_pupdate(n, r.data(), dinv, p.data(), &st, par, NOXR);
+          k_pcg_pupdate(n, r.data(), dinv, p.data(), &st, par, NOXR, 0);
         });
       }
     }
     queued += chunk;
   }
+  // ---- exit check and residual replacement (pcg.cu pcg_stream) --------------------------
+  std::vector<double> xe(n + 2);
+  int replaced = 0;
+  bool stagnated = false;
+  for (;;) {
+    std::copy(x, x + n, xe.begin());
+    spmv(L, grid_spmv, xe.data(), q.data(), false, nullptr, nullptr);
+    simt::launch(grid_ew, EW_THREADS, [&] {
+      k_true_resid(n, b, q.data(), partials.data(), stride, &st, &st.true_rr);
+    });
+    if (stagnated) {
+      st.status = 4;
+      break;
+    }
+    if (single_reduction || st.status != 0 || st.iter == 0 || !(st.true_rr > st.thr2) ||
+        st.iter >= maxit || replaced >= 4)
+      break;
+    replaced++;
+    const int par_last = (st.iter - 1) & 1, nx = (par_last ^ 1) * 2;
+    simt::launch(grid_ew, EW_THREADS, [&] {
+      k_pcg_replace(n, b, q.data(), dinv, r.data(), partials.data(), stride, &st, &st.red[nx]);
+    });
+    simt::launch(1, 1, [&] { k_pcg_resume(&st, nx); });
+    simt::launch(grid_ew, EW_THREADS, [&] {
+      k_pcg_pupdate(n, r.data(), dinv, p.data(), &st, par_last, NOXR, 1);
+    });
+    const int tail = st.iter + (st.iter / 8 > 8 ? st.iter / 8 : 8);
+    for (int it = st.iter; !st.done; it++) {
+      if (it >= tail && (it - st.iter) % 4 == 0) {  // the product looks every 4 iterations
+        stagnated = true;
+        break;
+      }
+      const int par = it & 1, nx2 = (par ^ 1) * 2;
+      spmv(L, grid_spmv, p.data(), q.data(), true, partials.data(), &st);
+      simt::launch(grid_ew, EW_THREADS, [&] {
+        k_pcg_update(n, x, r.data(), p.data(), q.data(), dinv, partials.data(), stride, &st, par,
+                     &st.red[nx2], NOXR, NOXR);
+      });
+      simt::launch(grid_ew, EW_THREADS, [&] {
+        k_pcg_pupdate(n, r.data(), dinv, p.data(), &st, par, NOXR, 0);
+      });
+    }
+  }
+  if (replacements)
+    *replacements = replaced;
+  if (true_relres)
+    *true_relres = st.bb > 0 ? std::sqrt(st.true_rr / st.bb) : std::sqrt(st.true_rr);
   const int parity = st.iter & 1;
   double rr = st.iter == 0 ? st.red[1] : st.red[parity * 2 + 1];
   if (single_reduction && st.status == 1 && rr <= st.thr2)

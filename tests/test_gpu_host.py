@@ -43,12 +43,12 @@ def test_driver_b200_matches_direct_solve(bh, name, tmp_path):
     # matrix,n,nnz,trials,solver,ordering,elapsed  (src/cusparse.c:207-209)
     assert row[1:6] == [str(A.nrows), str(A.nnz), "3", "6", "0"] and float(row[6]) > 0
     gpus, iters, status, relres, true_relres = int(ext[0]), int(ext[1]), int(ext[2]), float(ext[3]), float(ext[4])
-    assert (gpus, status) == (1, 0) and relres <= 1e-10 and true_relres <= 1.05e-10
+    assert (gpus, status) == (1, 0) and relres <= 1e-10 and true_relres <= 1e-10
     x = np.fromfile(out)
     g = DIRECT[name]
     assert np.linalg.norm(x - g) / np.linalg.norm(g) <= 1e-8
     M = orc.op_upper_mirror(A)
-    assert orc.true_relres(M, orc.rhs(M.n), x) <= 1.05e-10
+    assert orc.true_relres(M, orc.rhs(M.n), x) <= 1e-10
 
 
 def test_unmodified_reference_driver_runs_b200(bh):
@@ -59,7 +59,7 @@ def test_unmodified_reference_driver_runs_b200(bh):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr
     row, ext = parse(r.stdout)
-    assert row[1] == "3707" and int(ext[2]) == 0 and float(ext[4]) <= 1.05e-10
+    assert row[1] == "3707" and int(ext[2]) == 0 and float(ext[4]) <= 1e-10
 
 
 def test_driver_full_operator_switch(bh, tmp_path):
@@ -76,7 +76,7 @@ def test_driver_full_operator_switch(bh, tmp_path):
     d = np.linalg.norm(x - g) / np.linalg.norm(g)
     assert 1e-8 < d < 1e-5
     A = orc.matrix_read(orc.matrix_path(name))
-    assert orc.true_relres(orc.op_full(A), orc.rhs(A.nrows), x) <= 1.05e-10
+    assert orc.true_relres(orc.op_full(A), orc.rhs(A.nrows), x) <= 1e-10
 
 
 def test_driver_synthetic_and_multi_gpu(bh, tmp_path):
@@ -89,7 +89,7 @@ def test_driver_synthetic_and_multi_gpu(bh, tmp_path):
     M = orc.gen_poisson27(40)
     assert row[1:3] == [str(M.n), str(M.nnz)] and int(ext[2]) == 0
     x1 = np.fromfile(out)
-    assert orc.true_relres(M, orc.rhs(M.n), x1) <= 1.05e-10
+    assert orc.true_relres(M, orc.rhs(M.n), x1) <= 1e-10
     if abi.device_count() >= 2:
         env = dict(os.environ, LSBENCH_B200_NGPUS="2")
         r = subprocess.run([bh.DRIVER, "--solver", "b200", "--matrix", "poisson27:40",
@@ -117,12 +117,12 @@ def test_driver_applies_the_ordering(bh, name, env, tmp_path):
     assert r.returncode == 0, r.stderr
     row, ext = parse(r.stdout)
     assert row[1:6] == [str(A.nrows), str(A.nnz), "2", "6", "0"]
-    assert int(ext[2]) == 0 and float(ext[4]) <= 1.05e-10
+    assert int(ext[2]) == 0 and float(ext[4]) <= 1e-10
     assert "b200: ordering=rcm bandwidth" in r.stdout
     x = np.fromfile(out)
     full = env.get("LSBENCH_B200_OPERATOR") == "full"
     M = orc.op_full(A) if full else orc.op_upper_mirror(A)
-    assert orc.true_relres(M, orc.rhs(M.n), x) <= 1.05e-10
+    assert orc.true_relres(M, orc.rhs(M.n), x) <= 1e-10
     if not full:
         g = DIRECT[name]
         assert np.linalg.norm(x - g) / np.linalg.norm(g) <= 1e-8
@@ -140,7 +140,7 @@ def test_driver_precision_fp32_and_single_reduction(bh, tmp_path):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr
     row, ext = parse(r.stdout)
-    assert int(ext[2]) == 0 and float(ext[4]) <= 1.05e-10
+    assert int(ext[2]) == 0 and float(ext[4]) <= 1e-10
     assert "precision=fp32 values rounded" in r.stdout
     x, g = np.fromfile(out), DIRECT[name]
     assert np.linalg.norm(x - g) / np.linalg.norm(g) <= 1e-8
@@ -152,7 +152,7 @@ def test_driver_precision_fp32_and_single_reduction(bh, tmp_path):
     row, ext = parse(r.stdout)
     assert int(ext[2]) == 0 and "precision=fp32 values lossless" in r.stdout
     M = orc.gen_poisson27(40)
-    assert orc.true_relres(M, orc.rhs(M.n), np.fromfile(out)) <= 1.05e-10
+    assert orc.true_relres(M, orc.rhs(M.n), np.fromfile(out)) <= 1e-10
 
 
 def test_stock_lsbench_tree_with_b200_dropped_in(bh):
@@ -174,5 +174,5 @@ def test_stock_lsbench_tree_with_b200_dropped_in(bh):
         runs.append(parse(r.stdout))
     (row, ext), (row0, ext0) = runs
     assert row[1:6] == [str(A.nrows), str(A.nnz), "2", "6", "0"] == row0[1:6]
-    assert int(ext[2]) == 0 and float(ext[4]) <= 1.05e-10
+    assert int(ext[2]) == 0 and float(ext[4]) <= 1e-10
     assert ext[1] == ext0[1] and ext[3] == ext0[3]      # iterations and residual: the same solve

@@ -149,7 +149,7 @@ def test_direct_and_pcg_against_superlu(name):
         assert np.linalg.norm(xn - xg) / np.linalg.norm(xg) < 1e-10
     xp, it, rel, rc = orc.pcg(M, b, tol=1e-10)
     assert rc == 0 and rel <= 1e-10 and 200 < it < 400
-    assert orc.true_relres(M, b, xp) <= 1.05e-10
+    assert orc.true_relres(M, b, xp) <= 1e-10
     assert np.linalg.norm(xp - xg) / np.linalg.norm(xg) < 1e-8  # the parity bar
 
 
@@ -272,7 +272,7 @@ def test_single_reduction_cg_is_the_same_method(name):
     x0, it0, _, _ = orc.pcg(M, b)
     x1, it1, rel1, rc1 = orc.pcg_sr(M, b)
     assert rc1 == 0 and rel1 <= 1e-10 and abs(it1 - it0) <= 2
-    assert orc.true_relres(M, b, x1) <= 1.05e-10
+    assert orc.true_relres(M, b, x1) <= 1e-10
     xg = DIRECT[name]
     assert np.linalg.norm(x1 - xg) / np.linalg.norm(xg) < 1e-8
 
@@ -307,7 +307,7 @@ def test_fp32_operator_with_fp64_refinement_meets_the_fp64_bar(name):
     _, it0, _, _ = orc.pcg(M, b)
     x, it, outer, rel, rc = orc.pcg_refine32(M, b)
     assert rc == 0 and rel <= 1e-10 and 2 <= outer <= 5 and it0 < it < 2 * it0
-    assert orc.true_relres(M, b, x) <= 1.05e-10
+    assert orc.true_relres(M, b, x) <= 1e-10
     xg = DIRECT[name]
     assert np.linalg.norm(x - xg) / np.linalg.norm(xg) < 1e-8
 

@@ -24,3 +24,8 @@ fi
 ls -la $OUT | grep r02a
 # (4) column-blocked SpMV of the power-law operator (config 5): parity, then block widths
 timeout 300 python tools/colblock_check.py 50000000 > $OUT/r02a_colblock.log 2>&1; tail -7 $OUT/r02a_colblock.log | cut -c1-300
+# (5) the on-chip coarse-grid kernel: plain run, then one full-set capture
+timeout 120 python tools/smallprof.py > $OUT/r02a_small_plain.log 2>&1 && \
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'k_pcg_small' -s 1 -c 1 \
+    -o $OUT/r02a_pcg_small -f python tools/smallprof.py > $OUT/r02a_small_ncu.log 2>&1
+tail -3 $OUT/r02a_small_plain.log
