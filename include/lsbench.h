@@ -29,8 +29,12 @@ extern "C" {
  *    5  ginkgo       BiCGSTAB + Jacobi                not built
  *    6  b200         fp64 SELL SpMV + fused Jacobi-PCG, sm_100a   this tree
  *
- * Precision: only FP64 is accepted (src/lsbench.c:140-141).  Ordering: parsed
- * and printed; the b200 backend renumbers only inside its coarse-grid kernel. */
+ * Precision: FP64 and FP32 are accepted (FP32 = matrix values stored as fp32, fp64
+ * arithmetic and the same fp64 bars: lossless on stencils, iterative refinement
+ * otherwise); FP16 is rejected as in src/lsbench.c:140-141.  Ordering: parsed and
+ * printed; the b200 backend applies RCM when LSBENCH_B200_ORDERING says so (AMD and
+ * METIS only reduce the fill of a factorisation: reported, not applied) and
+ * renumbers on its own inside its coarse-grid kernel. */
 typedef enum {
   LSBENCH_SOLVER_NONE = -1, LSBENCH_SOLVER_CUSOLVER, LSBENCH_SOLVER_HYPRE, LSBENCH_SOLVER_AMGX,
   LSBENCH_SOLVER_CHOLMOD, LSBENCH_SOLVER_PARALMOND, LSBENCH_SOLVER_GINKGO, LSBENCH_SOLVER_B200

@@ -48,8 +48,8 @@ def _digest(paths, extra):
 def build(force=False, verbose=False):
     nvcc, cxx = _nvcc(), _host_cxx()
     os.makedirs(OBJ, exist_ok=True)
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "sellc32p.cuh"), os.path.join(CSRC, "sell_kernels.cuh"), os.path.join(CSRC, "pcg_kernels.cuh"), os.path.join(CSRC, "colblock_kernels.cuh"),
-               os.path.join(CSRC, "parse.cuh"), os.path.join(ROOT, "include", "b200.h")]
+    headers = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh"))
+    headers.append(os.path.join(ROOT, "include", "b200.h"))
     flags = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
              "-ccbin", cxx, "-I", os.path.join(ROOT, "include"), "-I", CSRC] + ARCH
     if verbose:

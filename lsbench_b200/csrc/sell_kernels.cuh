@@ -203,7 +203,9 @@ k_spmv_sellc(const uint4 *__restrict__ meta, const uint32_t *__restrict__ cols,
   }
 }
 
-#include "sellc32p.cuh"
+#ifndef B2_NO_TMA_KERNEL
+#include "sell_tma.cuh"
+#endif
 
 // ---- the row-major bins: one warp per row, one CTA per row ----------------------------
 template <bool DOT, bool ACC = false>

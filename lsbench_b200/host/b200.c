@@ -80,6 +80,9 @@ static struct settings read_settings(void) {
   /* "sr": single-reduction (Chronopoulos-Gear) CG on the streaming kernels */
   if ((v = getenv("LSBENCH_B200_PCG")) && strcmp(v, "sr") == 0)
     s.pcg_flags |= B200_PCG_SINGLE_REDUCTION;
+  /* "stream": never the on-chip coarse-grid kernel, always the streaming kernels */
+  if (v && strcmp(v, "stream") == 0)
+    s.pcg_flags |= B200_PCG_NO_SMALL;
   if ((v = getenv("LSBENCH_B200_ORDERING"))) {
     if (strcmp(v, "cli") == 0)
       s.ordering = 1;

@@ -15,8 +15,11 @@
  * Summation order differs from the GPU (plain left-to-right here), so
  * agreement is to rounding, not bit for bit; see tests for the tolerances.
  */
+#define _POSIX_C_SOURCE 200809L
 #include "oracle.h"
 #include <math.h>
+#include <time.h>
+#include <unistd.h>
 #include <stdlib.h>
 #include <string.h>
 #ifdef _OPENMP
@@ -29,6 +32,82 @@ int orc_num_threads(void) {
 #else
   return 1;
 #endif
+}
+
+int orc_set_threads(int nthreads) {
+#ifdef _OPENMP
+  if (nthreads <= 0)
+    nthreads = (int)sysconf(_SC_NPROCESSORS_ONLN);
+  if (nthreads < 1)
+    nthreads = 1;
+  omp_set_dynamic(0);
+  omp_set_num_threads(nthreads);
+  return nthreads;
+#else
+  (void)nthreads;
+  return 1;
+#endif
+}
+
+/* One Jacobi-PCG iteration's memory traffic and arithmetic on a row slab (see
+ * oracle.h): K1 q = A p + p.q, K2 x += a p, r -= a q + r.z, r.r, K3 p = z + b p
+ * -- the passes orc_pcg_omp makes, on rows [row0, row0 + M->n) of an operator
+ * with n_global columns.  alpha and beta are kept harmless (the slab alone is
+ * not a linear system); what is measured is time. */
+double orc_pcg_slab_seconds(const orc_op *M, uint64_t n_global, uint64_t row0, int its) {
+  const int64_t n = (int64_t)M->n;
+  if (row0 + M->n > n_global || its < 1)
+    return -1.0;
+  double *p = (double *)malloc(n_global * sizeof(double));
+  double *v = (double *)malloc(4 * (size_t)n * sizeof(double));
+  if (!p || !v) {
+    free(p), free(v);
+    return -1.0;
+  }
+  double *q = v, *r = q + n, *x = r + n, *dinv = x + n;
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < (int64_t)n_global; i++)
+    p[i] = 1.0 / (double)(1 + (i & 1023));
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; i++) {
+    double a = 1.0;
+    for (uint64_t k = M->offs[i]; k < M->offs[i + 1]; k++)
+      if (M->cols[k] == row0 + (uint64_t)i)
+        a = M->vals[k];
+    q[i] = 0.0, r[i] = (double)(row0 + i), x[i] = 0.0, dinv[i] = 1.0 / a;
+  }
+  struct timespec t0, t1;
+  double sink = 0.0;
+  for (int it = -1; it < its; it++) {
+    if (it == 0)
+      clock_gettime(CLOCK_MONOTONIC, &t0);
+    double pq = 0.0, rz = 0.0, rr = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : pq)
+    for (int64_t i = 0; i < n; i++) {
+      double s = 0.0;
+      for (uint64_t k = M->offs[i]; k < M->offs[i + 1]; k++)
+        s += M->vals[k] * p[M->cols[k]];
+      q[i] = s;
+      pq += s * p[row0 + i];
+    }
+    const double alpha = 1e-3 / (1.0 + fabs(pq));
+#pragma omp parallel for schedule(static) reduction(+ : rz, rr)
+    for (int64_t i = 0; i < n; i++) {
+      x[i] += alpha * p[row0 + i];
+      const double ri = r[i] - alpha * q[i];
+      r[i] = ri;
+      rz += ri * (dinv[i] * ri), rr += ri * ri;
+    }
+    const double beta = 0.5;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++)
+      p[row0 + i] = dinv[i] * r[i] + beta * p[row0 + i];
+    sink += rz + rr;
+  }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  const double dt = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+  free(p), free(v);
+  return sink == 12345.678 ? -dt : dt;  /* keeps the sums alive */
 }
 
 void orc_spmv(const orc_op *M, const double *x, double *y, double *yabs) {

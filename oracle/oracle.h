@@ -14,9 +14,14 @@
  * (SuiteSparse v7.0.1 is fetched at configure time).  What IS pinned:
  *   - orc_matrix_read against the reference's own lsbench_matrix_read,
  *     compiled from the reference sources into oracle/_ref (bit-exact CSR);
- *   - the direct solve against scipy SuperLU on the same operator and the
- *     analytic answer for I1_05x05 (tests/golden).
- * The CHOLMOD arithmetic itself stays "parity unpinned".
+ *   - the solve against THE REFERENCE'S OWN OUTPUT: x as its cuSOLVER backend
+ *     (src/cusparse.c, compiled from the reference sources by `make
+ *     ref-cusolver`, run on a B200) returned it for the seven Nek matrices
+ *     (tests/golden/cusolver_x.npz; orc_op_perm_lower_mirror is the operator
+ *     that backend solves), reproduced by the direct solve here to 1.5e-13;
+ *   - the direct solve against scipy SuperLU on CHOLMOD's operator and the
+ *     analytic answer for I1_05x05 (tests/golden/direct.npz).
+ * Only the CHOLMOD backend's own arithmetic stays "parity unpinned".
  */
 #ifndef ORACLE_H_
 #define ORACLE_H_
@@ -109,6 +114,18 @@ uint32_t orc_powerlaw_rowlen(uint64_t n, uint64_t seed, uint64_t row);
 void orc_powerlaw_table(uint64_t *thr);
 
 int orc_num_threads(void);
+/* OpenMP threads for the *_omp functions: nthreads <= 0 means every online
+ * core, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1). */
+int orc_set_threads(int nthreads);
+
+/* bench.py's CPU legs: `its` iterations of the Jacobi-PCG kernel sequence on a
+ * ROW SLAB of a larger operator -- M holds rows [row0, row0 + M->n) with
+ * global column ids (orc_gen_poisson27 with a row range), the vectors p, q,
+ * r, x live on the slab, p on all n_global columns.  Not a solve: the
+ * per-iteration cost of real rows of the real operator, OpenMP over all
+ * threads.  One untimed iteration first (pages, caches).  Returns the
+ * seconds the `its` timed iterations took (CLOCK_MONOTONIC), < 0 on error. */
+double orc_pcg_slab_seconds(const orc_op *M, uint64_t n_global, uint64_t row0, int its);
 
 #ifdef __cplusplus
 }

@@ -349,3 +349,19 @@ def powerlaw_table():
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+def set_threads(n=0):
+    """OpenMP threads of the *_omp legs; 0 = every online core, whatever
+    OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1)."""
+    return lib().orc_set_threads(int(n))
+
+
+def pcg_slab_seconds(M, n_global, row0, its):
+    """seconds for `its` Jacobi-PCG iterations' worth of passes over the row slab M
+    (oracle/krylov.c orc_pcg_slab_seconds): bench.py's CPU timing sample"""
+    s = M.as_struct()
+    f = lib().orc_pcg_slab_seconds
+    f.restype = C.c_double
+    f.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int]
+    return f(C.byref(s), n_global, row0, its)

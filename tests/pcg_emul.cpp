@@ -23,32 +23,33 @@ struct Layout {  // the index-compressed SELL layout, built by the caller (numpy
   const uint32_t *perm;
   const double *dinv;
   const float *vals32;  // the same values as fp32 (exact), for the fp32-value kernels
-  int kernel;           // 0 k_spmv_sellc fp64 | 1 k_spmv_sellc fp32 | 2 pipelined fp64 | 3 pipelined fp32
-  int wmax;             // 8, 16 or 32 for the pipelined kernels
+  int kernel;           // 0 k_spmv_sellc fp64 | 1 k_spmv_sellc fp32 | 2 bulk-copy-fed fp64 | 3 fp32
+  int wmax;             // ring depth (stages per warp) of the bulk-copy-fed kernel
 };
 
 static const XrArgs NOXR = {nullptr, nullptr, 1, 0, 0, 0ull};
 
-template <bool DOT, typename VT, int W>
-static void pipe_launch(const Layout &L, const VT *vals, const double *x, double *y,
-                        double *partials, PcgState *st) {
-  constexpr unsigned th = PipeCfg<VT, W>::threads;
-  const unsigned grid = (L.ns + th / 32 - 1) / (th / 32);
-  simt::launch(grid, th, [&] {
-    k_spmv_sellc32p<DOT, W, VT>(L.meta, L.cols, L.dcols, vals, L.perm, x, y, 0, L.ns, 0, 0, L.n,
-                                DOT ? partials : nullptr, 0, DOT ? grid : 0u, DOT ? st : nullptr,
-                                DOT ? &st->pq : nullptr, NOXR);
-  });
-}
+// the bulk-copy-fed kernel (sell_tma.cuh): L.wmax carries the ring depth, 8 warps per CTA,
+// as many CTAs as the slices need up to `grid`
 template <bool DOT, typename VT>
 static void pipe_any(const Layout &L, const VT *vals, const double *x, double *y, double *partials,
                      PcgState *st) {
-  if (L.wmax == 32)
-    pipe_launch<DOT, VT, 32>(L, vals, x, y, partials, st);
-  else if (L.wmax == 16)
-    pipe_launch<DOT, VT, 16>(L, vals, x, y, partials, st);
-  else
-    pipe_launch<DOT, VT, 8>(L, vals, x, y, partials, st);
+  constexpr int WARPS = 8;
+  const unsigned grid = std::min<unsigned>((L.ns + WARPS - 1) / WARPS, 5u);  // > 1 slice per warp
+  uint32_t wmaxw = 0;
+  for (uint32_t s_ = 0; s_ < L.ns; s_++)
+    wmaxw = std::max(wmaxw, L.meta[s_].y & 0x7fffffffu);
+  const uint32_t stage = (wmaxw * 32 * (uint32_t)sizeof(VT) + 127u) & ~127u;
+  simt::launch(grid, WARPS * 32, [&] {
+    if (wmaxw <= 8)
+      k_spmv_sellc_tma<DOT, VT, WARPS, 8>(L.meta, L.cols, L.dcols, vals, L.perm, x, y, 0, L.ns, 0, 0, L.n,
+                                          DOT ? partials : nullptr, 0, DOT ? grid : 0u, DOT ? st : nullptr,
+                                          DOT ? &st->pq : nullptr, NOXR, stage, L.wmax);
+    else
+      k_spmv_sellc_tma<DOT, VT, WARPS, 32>(L.meta, L.cols, L.dcols, vals, L.perm, x, y, 0, L.ns, 0, 0, L.n,
+                                           DOT ? partials : nullptr, 0, DOT ? grid : 0u, DOT ? st : nullptr,
+                                           DOT ? &st->pq : nullptr, NOXR, stage, L.wmax);
+  });
 }
 template <bool DOT, typename VT>
 static void plain_launch(const Layout &L, const VT *vals, unsigned grid, const double *x, double *y,
@@ -208,18 +209,23 @@ extern "C" int emul_rowmajor(int long_kernel, unsigned grid, uint32_t nrows, con
 // ---- the two-launch form of the overlapped multi-GPU SpMV: interior slices, then
 // boundary slices, ONE fused dot product (the partial slots and the ticket span
 // both launches; the last CTA of the second launch adds all of them) -----------------
-template <typename VT, int W>
+template <typename VT>
 static void two_phase_pipe(const Layout &L, const VT *vals, const double *x, double *y, uint32_t ib,
                            uint32_t ie, double *partials, PcgState *st) {
-  constexpr unsigned th = PipeCfg<VT, W>::threads, wp = th / 32;
-  const unsigned g1 = (ie - ib + wp - 1) / wp, g2 = (ib + (L.ns - ie) + wp - 1) / wp;
-  simt::launch(g1, th, [&] {
-    k_spmv_sellc32p<true, W, VT>(L.meta, L.cols, L.dcols, vals, L.perm, x, y, ib, ie, 0, 0, L.n, partials,
-                                 0, g1 + g2, st, &st->pq, NOXR);
+  constexpr int WARPS = 8;
+  const unsigned g1 = std::max(1u, std::min<unsigned>((ie - ib + WARPS - 1) / WARPS, 3u)),
+                 g2 = std::max(1u, std::min<unsigned>((ib + (L.ns - ie) + WARPS - 1) / WARPS, 3u));
+  uint32_t wmaxw = 0;
+  for (uint32_t s_ = 0; s_ < L.ns; s_++)
+    wmaxw = std::max(wmaxw, L.meta[s_].y & 0x7fffffffu);
+  const uint32_t stage = (wmaxw * 32 * (uint32_t)sizeof(VT) + 127u) & ~127u;
+  simt::launch(g1, WARPS * 32, [&] {
+    k_spmv_sellc_tma<true, VT, WARPS, 32>(L.meta, L.cols, L.dcols, vals, L.perm, x, y, ib, ie, 0, 0, L.n,
+                                          partials, 0, g1 + g2, st, &st->pq, NOXR, stage, L.wmax);
   });
-  simt::launch(g2, th, [&] {
-    k_spmv_sellc32p<true, W, VT>(L.meta, L.cols, L.dcols, vals, L.perm, x, y, 0, ib, ie, L.ns, L.n,
-                                 partials, g1, g1 + g2, st, &st->pq, NOXR);
+  simt::launch(g2, WARPS * 32, [&] {
+    k_spmv_sellc_tma<true, VT, WARPS, 32>(L.meta, L.cols, L.dcols, vals, L.perm, x, y, 0, ib, ie, L.ns,
+                                          L.n, partials, g1, g1 + g2, st, &st->pq, NOXR, stage, L.wmax);
   });
 }
 
@@ -232,14 +238,10 @@ extern "C" int emul_spmv_two_phase(uint32_t n, uint32_t ns, const uint4 *meta, c
   std::vector<double> partials((size_t)stride * 3, 0.0);
   PcgState st;
   std::memset(&st, 0, sizeof st);
-  if (kernel == 2 && wmax == 32)
-    two_phase_pipe<double, 32>(L, vals, x, y, ib, ie, partials.data(), &st);
-  else if (kernel == 2)
-    two_phase_pipe<double, 8>(L, vals, x, y, ib, ie, partials.data(), &st);
-  else if (kernel == 3 && wmax == 32)
-    two_phase_pipe<float, 32>(L, vals32, x, y, ib, ie, partials.data(), &st);
+  if (kernel == 2)
+    two_phase_pipe<double>(L, vals, x, y, ib, ie, partials.data(), &st);
   else if (kernel == 3)
-    two_phase_pipe<float, 8>(L, vals32, x, y, ib, ie, partials.data(), &st);
+    two_phase_pipe<float>(L, vals32, x, y, ib, ie, partials.data(), &st);
   else {
     const unsigned g1 = (ie - ib + SPMV_WARPS - 1) / SPMV_WARPS,
                    g2 = (ib + (ns - ie) + SPMV_WARPS - 1) / SPMV_WARPS;
@@ -254,6 +256,39 @@ extern "C" int emul_spmv_two_phase(uint32_t n, uint32_t ns, const uint4 *meta, c
   }
   *dot_out = st.pq;
   return st.ticket[0] == 0 ? 0 : 1;  // the last CTA must have reset the ticket
+}
+
+// y = A x with the bulk-copy-fed kernel alone (no dot): every path of it against a CSR
+// product -- uniform and explicit slices, ragged tails, permuted lists, the two-range form
+extern "C" int emul_sellc_tma(int f64, int stages, unsigned grid, const uint4 *meta,
+                              const uint32_t *cols, const int32_t *dcols, const void *vals,
+                              const uint32_t *perm, const double *x, double *y, uint32_t b0,
+                              uint32_t e0, uint32_t b1, uint32_t e1, uint32_t n_rows, uint32_t wmax) {
+  constexpr int WARPS = 8;
+  const uint32_t stage = (wmax * 32 * (f64 ? 8u : 4u) + 127u) & ~127u;
+  if (f64)
+    simt::launch(grid, WARPS * 32, [&] {
+      if (wmax <= 8)
+        k_spmv_sellc_tma<false, double, WARPS, 8>(meta, cols, dcols, (const double *)vals, perm, x, y, b0,
+                                                  e0, b1, e1, n_rows, nullptr, 0, 0, nullptr, nullptr, NOXR,
+                                                  stage, stages);
+      else
+        k_spmv_sellc_tma<false, double, WARPS, 32>(meta, cols, dcols, (const double *)vals, perm, x, y, b0,
+                                                   e0, b1, e1, n_rows, nullptr, 0, 0, nullptr, nullptr, NOXR,
+                                                   stage, stages);
+    });
+  else
+    simt::launch(grid, WARPS * 32, [&] {
+      if (wmax <= 8)
+        k_spmv_sellc_tma<false, float, WARPS, 8>(meta, cols, dcols, (const float *)vals, perm, x, y, b0, e0,
+                                                 b1, e1, n_rows, nullptr, 0, 0, nullptr, nullptr, NOXR,
+                                                 stage, stages);
+      else
+        k_spmv_sellc_tma<false, float, WARPS, 32>(meta, cols, dcols, (const float *)vals, perm, x, y, b0, e0,
+                                                  b1, e1, n_rows, nullptr, 0, 0, nullptr, nullptr, NOXR,
+                                                  stage, stages);
+    });
+  return 0;
 }
 
 // ---- column blocking (csrc/colblock_kernels.cuh): cut a CSR into column ranges, then

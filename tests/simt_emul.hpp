@@ -118,6 +118,21 @@ template <typename T> inline T shfl_xor(T v, int o) {
   return r;
 }
 
+// value of lane `src` (every lane of the warp calls it)
+template <typename T> inline T shfl_idx(T v, int src) {
+  static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+  const unsigned w = cur->t_idx.x >> 5, lane = cur->t_idx.x & 31;
+  unsigned long long raw = 0;
+  __builtin_memcpy(&raw, &v, sizeof(T));
+  blk->xch[w * 32 + lane] = raw;
+  arrive_and_wait(blk->warp[w]);
+  raw = blk->xch[w * 32 + ((unsigned)src & 31u)];
+  arrive_and_wait(blk->warp[w]);
+  T r;
+  __builtin_memcpy(&r, &raw, sizeof(T));
+  return r;
+}
+
 // launch(grid, threads, [&] { kernel(args...); })
 inline void launch(unsigned grid, unsigned threads, const std::function<void()> &body) {
   g_dim = Idx{grid, 1, 1}, b_dim = Idx{threads, 1, 1};
@@ -173,9 +188,12 @@ inline void launch(unsigned grid, unsigned threads, const std::function<void()> 
 #define blockDim simt::b_dim
 #define __launch_bounds__(...)
 static inline void __syncthreads() { simt::arrive_and_wait(simt::blk->cta); }
+static inline void __syncwarp() { simt::arrive_and_wait(simt::blk->warp[simt::cur->t_idx.x >> 5]); }
 static inline void __threadfence() {}
 static inline void __threadfence_system() {}
 static inline double __shfl_xor_sync(unsigned, double v, int o) { return simt::shfl_xor(v, o); }
+static inline unsigned __shfl_sync(unsigned, unsigned v, int src) { return simt::shfl_idx(v, src); }
+static inline int __shfl_sync(unsigned, int v, int src) { return simt::shfl_idx(v, src); }
 static inline unsigned atomicAdd(unsigned *p, unsigned v) {
   const unsigned old = *p;
   *p = old + v;

@@ -1,8 +1,8 @@
 // spmv_emul.cpp -- TEST INFRASTRUCTURE.  Compiles the bodies of the SELL SpMV
-// kernels (lsbench_b200/csrc/sell_kernels.cuh: k_spmv_sell, k_spmv_sellc, and
-// the pipelined k_spmv_sellc32p of sellc32p.cuh) for the host, with one-line
-// stand-ins for the CUDA built-ins, and runs them thread by thread over a
-// launch grid.  Without the fused dot product a thread talks to no other thread,
+// kernels (lsbench_b200/csrc/sell_kernels.cuh: k_spmv_sell, k_spmv_sellc) for the
+// host, with one-line stand-ins for the CUDA built-ins, and runs them thread by
+// thread over a launch grid.  (The bulk-copy-fed k_spmv_sellc_tma of sell_tma.cuh
+// has lanes that work together: it runs on the fiber emulator, pcg_emul.cpp.)  Without the fused dot product a thread talks to no other thread,
 // so running the threads one after another is exactly what the GPU computes.
 // The caller (tests/test_spmv_emul.py) builds the index-compressed SELL layout
 // of DESIGN.md section 2 with numpy and compares y with a CSR product bit for bit.
@@ -46,46 +46,8 @@ template <int NV, int NW>
 static void grid_sum_finish(const double (&)[NV], double *, unsigned, unsigned, unsigned,
                             unsigned *, double *, double *, const XrArgs &) {}
 
+#define B2_NO_TMA_KERNEL
 #include "sell_kernels.cuh"
-
-template <int WMAX, typename VT>
-static void run(unsigned grid, const uint4 *meta, const uint32_t *cols, const int32_t *dcols,
-                const VT *vals, const uint32_t *perm, const double *x, double *y,
-                uint32_t b0, uint32_t e0, uint32_t b1, uint32_t e1, uint32_t n_rows) {
-  gridDim.x = grid;
-  for (unsigned b = 0; b < grid; b++)
-    for (unsigned t = 0; t < (unsigned)PipeCfg<VT, WMAX>::threads; t++) {
-      blockIdx.x = b, threadIdx.x = t;
-      k_spmv_sellc32p<false, WMAX, VT>(meta, cols, dcols, vals, perm, x, y, b0, e0, b1, e1, n_rows,
-                                       nullptr, 0, 0, nullptr, nullptr, XrArgs{});
-    }
-}
-
-template <typename VT>
-static int run_any(int wmax, unsigned grid, const uint4 *meta, const uint32_t *cols,
-                   const int32_t *dcols, const VT *vals, const uint32_t *perm, const double *x,
-                   double *y, uint32_t b0, uint32_t e0, uint32_t b1, uint32_t e1, uint32_t n_rows) {
-  if (wmax == 8)
-    run<8, VT>(grid, meta, cols, dcols, vals, perm, x, y, b0, e0, b1, e1, n_rows);
-  else if (wmax == 16)
-    run<16, VT>(grid, meta, cols, dcols, vals, perm, x, y, b0, e0, b1, e1, n_rows);
-  else if (wmax == 32)
-    run<32, VT>(grid, meta, cols, dcols, vals, perm, x, y, b0, e0, b1, e1, n_rows);
-  else
-    return 1;
-  return 0;
-}
-
-// vals: float[] when f64 == 0, double[] otherwise
-extern "C" int emul_sellc32p(int wmax, int f64, unsigned grid, const uint4 *meta,
-                             const uint32_t *cols, const int32_t *dcols, const void *vals,
-                             const uint32_t *perm, const double *x, double *y, uint32_t b0,
-                             uint32_t e0, uint32_t b1, uint32_t e1, uint32_t n_rows) {
-  return f64 ? run_any<double>(wmax, grid, meta, cols, dcols, (const double *)vals, perm, x, y, b0,
-                               e0, b1, e1, n_rows)
-             : run_any<float>(wmax, grid, meta, cols, dcols, (const float *)vals, perm, x, y, b0,
-                              e0, b1, e1, n_rows);
-}
 
 // ---- the default kernels: k_spmv_sellc (index-compressed) and k_spmv_sell ----------
 template <typename VT>

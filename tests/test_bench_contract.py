@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def run(*extra, env=None):
     cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2",
-           "--warmup", "1", "--cpu-sample-n", "40", "--cpu-sample-its", "20"] + list(extra)
+           "--warmup", "1", "--workload", "poisson27:64", "--cpu-planes", "8", "--cpu-its", "2"] + list(extra)
     return subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
 
 
@@ -24,11 +24,26 @@ def test_reference_arm_prints_one_contract_line():
     assert d["impl"] == "reference" and d["metric"] == "pcg_time_to_1e-10" and d["unit"] == "s"
     assert d["higher_is_better"] is False and d["scaling"] == "strong" and d["dtype"] == "f64"
     assert d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 1 and d["vs_baseline"] is None
-    assert d["config"]["workload"] == "poisson27:512" and d["data"] == "synthetic"
+    assert d["config"]["workload"] == "poisson27:64" and d["data"] == "synthetic"
+    # the same config dict as the b200 arm prints (bench.config_of): what `same_config` compares
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.config_of("poisson27:64", d["config"]["iterations"])
+    assert d["config"]["n"] == 64 ** 3 and d["config"]["nnz"] == (3 * 64 - 2) ** 3
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["unit"] == "s" and "poisson27 40^3" in cb["sample"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["unit"] == "s"
+    assert "8 z-planes of the real poisson27 64^3 operator (32768 rows" in cb["sample"]
     assert cb["value"] == d["value"] > 0 and abs(d["ms_per_step"] - 1e3 * d["value"]) < 1e-6 * d["ms_per_step"]
     assert d["e2e"] == {"value": d["value"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_uses_every_core_under_torchrun():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm must not run single-threaded
+    (round 1: the N >= 2 reference legs timed out)"""
+    r = run(env=dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["cpu_baseline"]["cores"] == os.cpu_count()
 
 
 def test_reference_arm_other_ranks_stay_silent():

@@ -536,7 +536,40 @@ def test_full_size_config4_poisson27_512(abi, ctx):
     Au = Md.spmv_host(u)
     lin = Md.spmv_host(-1.5 * u + 1.0)
     assert np.max(np.abs(lin - (-1.5 * Au + y))) <= 1e-12 * np.max(np.abs(lin))
+    del u, Au, lin, y
+    # the headline solve itself (bench.py's step): b[i] = i, x0 = 0, to the 1e-10 bar ON THE
+    # TRUE RESIDUAL -- checked with a product of its own, not with the solver's word.  The
+    # recurrence residual alone stops at 1176 iterations with ||b - A x|| / ||b|| = 1.0246e-10
+    # (round 1); the residual replacement takes it below the bar one iteration later.
+    b = np.arange(n, dtype=np.float64)
+    x, r, rc = Md.pcg_host(b, tol=1e-10, maxit=20000, flags=abi.PCG_NO_SMALL)
+    assert rc == 0 and r.status == 0 and r.relres <= 1e-10 and r.true_relres <= 1e-10
+    assert r.replacements >= 1 and 1170 <= r.iters <= 1190
+    res = b - Md.spmv_host(x)
+    true = float(np.sqrt(np.sum(res.astype(np.longdouble) ** 2)) / np.sqrt(np.sum(b.astype(np.longdouble) ** 2)))
+    assert true <= 1e-10 and abs(true - r.true_relres) <= 1e-3 * true
     Md.close()
+
+
+def test_pcg_against_the_oracles_solve_at_27pt_128(abi, ctx):
+    """The streaming PCG against the CPU oracle's OpenMP PCG on the same system at a size
+    the oracle still solves in seconds (27-point 128^3: 2.1 M rows, 55 M nnz, ~290
+    iterations): x within 1e-8 (relative, 2-norm) -- the parity bar of north_star -- the
+    iteration counts within 2, both true residuals below 1e-10."""
+    N = 128
+    Mo = orc.gen_poisson27(N)
+    b = orc.rhs(Mo.n)
+    orc.set_threads(0)
+    xo, ito, relo, rco = orc.pcg(Mo, b, tol=1e-10, maxit=5000, omp=True)
+    assert rco == 0 and orc.true_relres(Mo, b, xo) <= 1e-10
+    for fl in (0, abi.MAT_NO_COMPRESS, abi.MAT_VALUES_F32):
+        Md = abi.Matrix.generate(ctx, abi.GEN_POISSON27, N, flags=fl)
+        x, r, rc = Md.pcg_host(b, tol=1e-10, maxit=5000, flags=abi.PCG_NO_SMALL)
+        assert rc == 0 and r.status == 0 and r.true_relres <= 1e-10
+        assert abs(r.iters - ito) <= 2
+        assert np.linalg.norm(x - xo) / np.linalg.norm(xo) <= 1e-8
+        assert orc.true_relres(Mo, b, x) <= 1e-10
+        Md.close()
 
 
 # --------------------------------------------------------------------------- ragged / edge shapes

@@ -56,7 +56,7 @@ def solve(emul, M, b, x0=None, tol=1e-10, maxit=10000, sr=False, kernel=0):
     assert emul.emul_pcg(M.n, Lay["ns"], p(Lay["meta"]), p(Lay["ecols"]), p(Lay["dcols"]), p(vals), None,
                          p(dinv), p(b), p(x), tol, maxit, int(sr), grid_spmv, grid_ew,
                          C.byref(it), C.byref(st), C.byref(rel), p(Lay["vals"]), kernel,
-                         32 if Lay["wmax"] > 16 else (16 if Lay["wmax"] > 8 else 8),
+                         3,
                          C.byref(rep), C.byref(trr)) == 0
     LAST["replacements"], LAST["true_relres"] = rep.value, trr.value
     return x, it.value, st.value, rel.value
@@ -254,7 +254,7 @@ def test_two_launch_spmv_with_one_fused_dot(emul, gen, N):
     x = np.random.default_rng(9).standard_normal(M.n)
     want = orc.spmv_fma(M, x)
     ns = Lay["ns"]
-    wmax = 32 if Lay["wmax"] > 8 else 8
+    wmax = 2      # ring depth of the bulk-copy-fed kernel
     p = lambda a: a.ctypes.data
     for kernel in (0, 2, 3):
         for ib, ie in ((ns // 4, 3 * ns // 4), (0, ns - 1), (1, ns)):

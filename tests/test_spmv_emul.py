@@ -2,9 +2,9 @@
 tests/spmv_emul.cpp and run thread by thread over a launch grid: indexing and
 the order of the additions against the oracle's fma CSR product, bit for bit,
 without a GPU.  Covered: the default kernels k_spmv_sellc / k_spmv_sell
-(lsbench_b200/csrc/sell_kernels.cuh; fp64 and fp32 value streams) and the
-software-pipelined k_spmv_sellc32p (sellc32p.cuh, B200_SPMV_PIPE -- written at the
-end of round 1, not yet timed on hardware).  The index-compressed SELL layout (DESIGN.md
+(lsbench_b200/csrc/sell_kernels.cuh; fp64 and fp32 value streams) thread by thread,
+and the bulk-copy-fed k_spmv_sellc_tma (sell_tma.cuh: lanes work together through a
+shared-memory ring) on the fiber emulator of pcg_emul.cpp.  The index-compressed SELL layout (DESIGN.md
 section 2, csrc/convert.cu k_sell_fill / k_slice_uniform / k_compact_cols) is
 restated here with numpy."""
 import ctypes as C
@@ -27,8 +27,15 @@ def emul(tmp_path_factory):
                     "-I", os.path.join(ROOT, "lsbench_b200", "csrc"),
                     os.path.join(ROOT, "tests", "spmv_emul.cpp"), "-o", so], check=True)
     L = C.CDLL(so)
-    L.emul_sellc32p.restype = C.c_int
-    L.emul_sellc32p.argtypes = [C.c_int, C.c_int, C.c_uint] + [C.c_void_p] * 7 + [C.c_uint32] * 5
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    so2 = str(tmp_path_factory.mktemp("emul") / "libpcg_emul.so")
+    subprocess.run(["/usr/bin/g++", "-std=c++20", "-O1", "-w", "-DB2_SIMT_EMUL", "-shared", "-fPIC",
+                    "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "lsbench_b200", "csrc"),
+                    "-I", os.path.join(cuda, "include"), "-I", os.path.join(ROOT, "tests"),
+                    os.path.join(ROOT, "tests", "pcg_emul.cpp"), "-o", so2], check=True)
+    L.fiber = C.CDLL(so2)
+    L.fiber.emul_sellc_tma.restype = C.c_int
+    L.fiber.emul_sellc_tma.argtypes = [C.c_int, C.c_int, C.c_uint] + [C.c_void_p] * 7 + [C.c_uint32] * 6
     L.emul_sellc.argtypes = [C.c_int, C.c_uint] + [C.c_void_p] * 7 + [C.c_uint32] * 5
     L.emul_sell.argtypes = [C.c_int, C.c_uint] + [C.c_void_p] * 6 + [C.c_uint32] * 5
     return L
@@ -79,17 +86,21 @@ def sellc_layout(M, perm=None):
 
 
 def run(emul, Lay, n, x, wmax, grid, ranges=None):
-    """every kernel on the same layout -- pipelined (fp32 values: 256-thread CTAs;
-    fp64 values: 128-thread CTAs when wmax = 32), k_spmv_sellc and k_spmv_sell with
-    both value types; the answers must not differ"""
+    """every kernel on the same layout -- bulk-copy-fed (wmax: ring depths 2 and 3,
+    at most 5 CTAs so that a warp walks several slices), k_spmv_sellc and k_spmv_sell,
+    each with both value types; the answers must not differ"""
     b0, e0, b1, e1 = ranges or (0, Lay["ns"], 0, 0)
     p = lambda a: None if a is None else a.ctypes.data
     ys = []
     for f64, vals in ((0, Lay["vals"]), (1, Lay["vals"].astype(np.float64))) if wmax else ():
-        y = np.full(n, np.nan)
-        assert emul.emul_sellc32p(wmax, f64, grid, p(Lay["meta"]), p(Lay["ecols"]), p(Lay["dcols"]), p(vals),
-                                  p(Lay["list"]), p(x), p(y), b0, e0, b1, e1, n) == 0
-        ys.append(y)
+        for stages in (2, 3):
+            if 8 * stages * ((Lay["wmax"] * 32 * (8 if f64 else 4) + 127) & ~127) > 168 * 1024:
+                continue   # the ring does not fit (spmv.cu tma_cfg): the product takes the plain kernel
+            y = np.full(n, np.nan)
+            assert emul.fiber.emul_sellc_tma(f64, stages, min(grid, 5), p(Lay["meta"]), p(Lay["ecols"]),
+                                             p(Lay["dcols"]), p(vals), p(Lay["list"]), p(x), p(y),
+                                             b0, e0, b1, e1, n, Lay["wmax"]) == 0
+            ys.append(y)
     # the default kernels on the same layout: index-compressed and explicit columns
     for f64, vals in ((0, Lay["vals"]), (1, Lay["vals"].astype(np.float64))):
         y = np.full(n, np.nan)
@@ -106,7 +117,7 @@ def run(emul, Lay, n, x, wmax, grid, ranges=None):
 
 @pytest.mark.parametrize("gen,N,wmax", [("poisson27", 8, 32), ("poisson7", 12, 8), ("poisson7", 12, 16),
                                         ("poisson27", 20, 32)])
-def test_pipelined_kernel_on_stencils(emul, gen, N, wmax):
+def test_sell_kernels_on_stencils(emul, gen, N, wmax):
     M = getattr(orc, "gen_" + gen)(N)
     assert np.array_equal(M.vals.astype(np.float32).astype(np.float64), M.vals)
     Lay = sellc_layout(M)
@@ -125,7 +136,7 @@ def test_pipelined_kernel_on_stencils(emul, gen, N, wmax):
 
 
 @pytest.mark.parametrize("gen,wmax", [("poisson27", 32), ("poisson7", 8)])
-def test_pipelined_kernel_uniform_slices_of_a_row_block(emul, gen, wmax):
+def test_sell_kernels_uniform_slices_of_a_row_block(emul, gen, wmax):
     """40 x-lines out of the middle of a 96^3 grid, as a rank of the row-block
     partition holds them (global column ids): the slice in the middle of every
     x-line is uniform (w deltas instead of 32 w columns), the two with a line end
@@ -141,7 +152,7 @@ def test_pipelined_kernel_uniform_slices_of_a_row_block(emul, gen, wmax):
         assert run(emul, Lay, M.n, x, wmax, grid).tobytes() == want.tobytes()
 
 
-def test_pipelined_kernel_ragged_rows_and_a_permuted_list(emul):
+def test_sell_kernels_ragged_rows_and_a_permuted_list(emul):
     """rows of every length 1..32 (explicit slices, every tail length), the last
     slice half empty, with the identity list and with a length-sorted list"""
     rng = np.random.default_rng(7)
@@ -160,7 +171,7 @@ def test_pipelined_kernel_ragged_rows_and_a_permuted_list(emul):
             assert run(emul, Lay, n, x, 32, grid).tobytes() == want.tobytes()
 
 
-def test_pipelined_kernel_banded_rows_compress_in_any_numbering(emul):
+def test_sell_kernels_banded_rows_compress_in_any_numbering(emul):
     """a banded operator of constant row length: every full slice is uniform,
     and the deltas may be negative"""
     n, half = 32 * 9, 5
@@ -182,7 +193,7 @@ def test_pipelined_kernel_banded_rows_compress_in_any_numbering(emul):
 def test_default_kernels_on_wide_ragged_rows(emul):
     """rows of every length 1..70: full chunks of 8 (fp64 values) and 16 (fp32
     values) plus every tail length, in explicit slices, for k_spmv_sellc and
-    k_spmv_sell (the pipelined kernel is for slices of at most 32 entries)"""
+    k_spmv_sell """
     rng = np.random.default_rng(17)
     n = 70 * 12 + 5
     lens = (np.arange(n) % 70) + 1
@@ -196,4 +207,4 @@ def test_default_kernels_on_wide_ragged_rows(emul):
         Lay = sellc_layout(M, perm)
         assert Lay["wmax"] == 70
         for grid in (1, 6):
-            assert run(emul, Lay, n, x, None, grid).tobytes() == want.tobytes()
+            assert run(emul, Lay, n, x, 1, grid).tobytes() == want.tobytes()
