@@ -49,14 +49,31 @@ struct NcclApi;
 // sequence number from all ranks in its own mailbox and adds the values in
 // rank order (xr_wait_sum) -- the same additions on every rank.  No collective
 // kernel, no extra launch: the reduction is fused into producer and consumer.
+//
+// Sequence numbers live on the device so that a chunk of iterations can be a CUDA
+// graph on several ranks too: `base` points at a counter that a one-thread kernel
+// at the head of every chunk advances by the chunk's length (k_xr_chunk_begin),
+// `seq` is the position inside the chunk -- baked into the captured launch -- and
+// the number that travels is *base + seq.  Every rank queues the same chunks, so
+// the counters agree without ever being exchanged.
+//
+// Kind 2 is the flag of the halo exchange over peer memory (dist.cu halo_peer_setup,
+// k_halo_push / k_halo_wait): the rows a neighbour reads are stored straight into
+// its vector's halo section, then the sequence number into its mailbox.
 #define B2_XR_MAX_RANKS 16
-#define B2_XR_KINDS 2  // 0: p.q    1: r.z, r.r
+#define B2_XR_KINDS 3  // 0: p.q    1: r.z, r.r    2: halo of p has landed
 struct XrArgs {
   double *const *peers;  // device array, peers[r] = rank r's mailbox; nullptr = off
   double *mine;          // this rank's mailbox
   int nranks, me, kind;
-  unsigned long long seq;
+  unsigned long long seq;              // position inside the chunk (or the number itself)
+  const unsigned long long *base;      // device counter added to seq; nullptr = 0
 };
+#if defined(__CUDACC__) || defined(B2_SIMT_EMUL)
+__device__ __forceinline__ unsigned long long xr_seq_of(const XrArgs &xr) {
+  return xr.seq + (xr.base ? *xr.base : 0ull);
+}
+#endif
 
 struct b200_ctx {
   int device = 0;
@@ -73,8 +90,9 @@ struct b200_ctx {
   double *xr_mail = nullptr;      // my mailbox
   double **xr_peers = nullptr;    // device array of the ranks' mailboxes
   void *xr_opened[B2_XR_MAX_RANKS] = {nullptr};  // IPC mappings to close
+  double *xr_peers_h[B2_XR_MAX_RANKS] = {nullptr};  // the same pointers on the host
   bool xr_on = false;
-  unsigned long long xr_seq = 0;  // last sequence number handed out
+  unsigned long long *d_seq = nullptr;  // device: {base of the running chunk, next base}
   int *h_flag = nullptr;  // pinned: PCG progress word read by the host
   uint64_t launches = 0;  // kernels of this library queued so far
 };
@@ -88,6 +106,18 @@ struct PlainCsr {
   double *vals = nullptr;
 };
 
+// the halo exchange over peer memory: where the entries I own go, and whose flags I wait for
+struct HaloPushArgs {
+  int n_dst;                                   // neighbours that read rows of mine
+  uint32_t seg_begin[B2_XR_MAX_RANKS + 1];     // their runs in the send list
+  double *dst[B2_XR_MAX_RANKS];                // first halo slot of mine in their vector
+  unsigned long long *flag[B2_XR_MAX_RANKS];   // my flag word in their mailbox
+};
+struct HaloWaitArgs {
+  int n_src;                                   // neighbours whose rows I read
+  int src[B2_XR_MAX_RANKS];
+};
+
 struct HaloPlan {
   // receive side: halo slots are sorted by global column, grouped by owner
   uint64_t n_halo = 0;
@@ -99,6 +129,12 @@ struct HaloPlan {
   uint32_t *d_send_idx = nullptr;        // local row ids to pack
   double *d_send_buf = nullptr;
   uint64_t n_send = 0;
+  // peer-memory path (dist.cu halo_peer_setup): set up once the solver workspace exists
+  bool peer_tried = false, peer_ready = false;
+  HaloPushArgs push;
+  HaloWaitArgs wait;
+  unsigned *d_push_ticket = nullptr;
+  void *peer_opened[B2_XR_MAX_RANKS] = {nullptr};  // IPC mappings of the neighbours' p vectors
 };
 
 struct SpmvPlan {
@@ -209,6 +245,10 @@ int partition_and_renumber(b200_ctx *ctx, PlainCsr *A, uint64_t n_global,
 int halo_setup(b200_mat *M);
 int halo_exchange_begin(b200_mat *M, double *d_x_ext);  // on comm stream
 int halo_exchange_wait(b200_mat *M);
+int halo_peer_setup(b200_mat *M);                 // collective; after w_p exists
+int halo_peer_push(b200_mat *M, const double *x_ext, unsigned seq_off);   // on the comm stream
+int halo_peer_wait(b200_mat *M, unsigned seq_off);                       // on the compute stream
+int xr_chunk_begin(b200_ctx *c, unsigned count);  // advance the device sequence counter
 void halo_free(b200_mat *M);
 int ensure_workspace(b200_mat *M);
 int launch_spmv(b200_mat *M, const double *x_ext, double *y, bool fuse_dot,
@@ -295,7 +335,7 @@ __device__ __forceinline__ void xr_push(const XrArgs &xr, const double *vals /*s
     for (int v = 0; v < NV; v++)
       st_relaxed_sys(slot + v, vals[v]);
     __threadfence_system();
-    st_relaxed_sys(reinterpret_cast<unsigned long long *>(slot) + 3, xr.seq);
+    st_relaxed_sys(reinterpret_cast<unsigned long long *>(slot) + 3, xr_seq_of(xr));
   }
 }
 
@@ -314,8 +354,9 @@ __device__ __forceinline__ bool xr_wait_sum(const XrArgs &xr, double (&tot)[NV],
     const double *slot = xr.mine + ((size_t)xr.kind * B2_XR_MAX_RANKS + r) * 4;
     const unsigned long long *flag = reinterpret_cast<const unsigned long long *>(slot) + 3;
     const long long t0 = clock64();
+    const unsigned long long want = xr_seq_of(xr);
     bool got = true;
-    while (ld_acquire_sys(flag) != xr.seq)
+    while (ld_acquire_sys(flag) != want)
       if (clock64() - t0 > 8000000000ll) {
         got = false;
         break;

@@ -173,6 +173,10 @@ static int xr_setup(b200_ctx *c) {
   CU_TRY(cudaStreamSynchronize(s));
   cudaFree(d_all);
   if (ok) {
+    for (int r = 0; r < B2_XR_MAX_RANKS; r++)
+      c->xr_peers_h[r] = peers[r];
+    CU_TRY(cudaMalloc(&c->d_seq, 2 * sizeof(unsigned long long)));
+    CU_TRY(cudaMemsetAsync(c->d_seq, 0, 2 * sizeof(unsigned long long), s));
     CU_TRY(cudaMalloc(&c->xr_peers, sizeof(double *) * B2_XR_MAX_RANKS));
     CU_TRY(cudaMemcpyAsync(c->xr_peers, peers.data(), sizeof(double *) * B2_XR_MAX_RANKS,
                            cudaMemcpyHostToDevice, s));
@@ -201,6 +205,8 @@ void dist_comm_destroy(b200_ctx *c) {
       cudaIpcCloseMemHandle(p), p = nullptr;
   if (c->xr_peers) cudaFree(c->xr_peers);
   if (c->xr_mail) cudaFree(c->xr_mail);
+  if (c->d_seq) cudaFree(c->d_seq);
+  c->d_seq = nullptr;
   c->xr_peers = nullptr, c->xr_mail = nullptr, c->xr_on = false;
   if (c->nccl_comm)
     g_nccl.CommDestroy((ncclComm_t)c->nccl_comm);
@@ -457,6 +463,10 @@ int halo_setup(b200_mat *M) {
 
 void halo_free(b200_mat *M) {
   HaloPlan &H = M->halo;
+  for (void *&p : H.peer_opened)
+    if (p)
+      cudaIpcCloseMemHandle(p), p = nullptr;
+  if (H.d_push_ticket) cudaFree(H.d_push_ticket);
   if (H.d_gcols) cudaFree(H.d_gcols);
   if (H.d_send_idx) cudaFree(H.d_send_idx);
   if (H.d_send_buf) cudaFree(H.d_send_buf);
@@ -507,6 +517,195 @@ int halo_exchange_wait(b200_mat *M) {
   if (c->nranks == 1)
     return B200_OK;
   CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+  return B200_OK;
+}
+
+// ---- halo exchange over peer memory -----------------------------------------------------
+// Inside the PCG iteration the halo of p does not go through NCCL: a small kernel
+// stores the rows the neighbours read STRAIGHT into the halo section of their p
+// vector over NVLink (the vector is mapped here: peer access between host threads,
+// CUDA IPC between processes), then -- last CTA, after a system-scope fence -- this
+// iteration's sequence number into their mailbox (kind 2).  The neighbour's boundary
+// rows start behind a one-warp kernel that waits for the sequence number of everyone
+// it reads from.  No collective call, nothing the host has to do per iteration: the
+// chunk of iterations is a CUDA graph on several ranks as well.
+//
+// Why no neighbour can overwrite a halo that is still being read: rank A pushes p of
+// iteration k+1 after its K3(k), which needs {r.z, r.r}(k) from every rank, which rank
+// B sends from its K2(k) -- behind B's boundary rows of iteration k in B's stream.
+// That chain only exists inside the iteration; the stand-alone SpMV, the start-up
+// and the exit products keep the NCCL exchange.
+struct PeerHaloInfo {
+  long long pid;
+  int dev, ok;
+  unsigned long long ptr;      // w_p
+  unsigned long long n_local;
+  unsigned long long first[B2_XR_MAX_RANKS];  // where owner o's entries begin in my halo section
+  cudaIpcMemHandle_t handle;
+};
+
+int halo_peer_setup(b200_mat *M) {
+  b200_ctx *c = M->ctx;
+  HaloPlan &H = M->halo;
+  if (H.peer_tried || c->nranks == 1)
+    return B200_OK;
+  H.peer_tried = true;
+  const char *e = getenv("B200_HALO");
+  const int want = c->xr_on && !(e && strcmp(e, "nccl") == 0);
+  ncclComm_t comm = (ncclComm_t)c->nccl_comm;
+  cudaStream_t s = c->stream;
+  const int P = c->nranks, me = c->rank;
+  PeerHaloInfo mine;
+  memset(&mine, 0, sizeof mine);
+  mine.pid = (long long)getpid(), mine.dev = c->device, mine.ok = want && M->w_p != nullptr;
+  mine.ptr = (unsigned long long)M->w_p, mine.n_local = M->n_local;
+  for (int k = 0; k < H.n_peers; k++)
+    mine.first[H.peer[k]] = H.recv_off[2 * k];
+  if (mine.ok && cudaIpcGetMemHandle(&mine.handle, M->w_p) != cudaSuccess)
+    cudaGetLastError(), mine.ok = 0;
+  PeerHaloInfo *d_all = nullptr;
+  std::vector<PeerHaloInfo> all(P);
+  CU_TRY(cudaMalloc(&d_all, sizeof(PeerHaloInfo) * P));
+  CU_TRY(cudaMemcpyAsync(d_all + me, &mine, sizeof mine, cudaMemcpyHostToDevice, s));
+  NC_TRY(g_nccl.AllGather(d_all + me, d_all, sizeof(PeerHaloInfo), ncclChar, comm, s));
+  CU_TRY(cudaMemcpyAsync(all.data(), d_all, sizeof(PeerHaloInfo) * P, cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  int ok = 1;
+  for (int r = 0; r < P; r++)
+    ok &= all[r].ok;
+  memset(&H.push, 0, sizeof H.push);
+  memset(&H.wait, 0, sizeof H.wait);
+  for (int k = 0; k < H.n_peers && ok; k++) {
+    const int o = H.peer[k];
+    if (H.recv_off[2 * k + 1])
+      H.wait.src[H.wait.n_src++] = o;
+    if (!H.send_off[2 * k + 1])
+      continue;
+    double *base = nullptr;
+    if (all[o].pid == mine.pid) {
+      base = (double *)all[o].ptr;  // peer access was enabled for the mailboxes (xr_setup)
+    } else {
+      void *p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, all[o].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError(), ok = 0;
+        break;
+      }
+      H.peer_opened[o] = p, base = (double *)p;
+    }
+    const int j = H.push.n_dst++;
+    H.push.seg_begin[j] = (uint32_t)H.send_off[2 * k];
+    H.push.seg_begin[j + 1] = (uint32_t)(H.send_off[2 * k] + H.send_off[2 * k + 1]);
+    H.push.dst[j] = base + all[o].n_local + all[o].first[me];
+    H.push.flag[j] = reinterpret_cast<unsigned long long *>(
+                         c->xr_peers_h[o] + ((size_t)2 * B2_XR_MAX_RANKS + me) * 4) + 3;
+  }
+  // (the send list is grouped by neighbour in the order of H.peer, so the runs are adjacent)
+  int *d_ok = (int *)d_all;
+  CU_TRY(cudaMemcpyAsync(d_ok, &ok, sizeof ok, cudaMemcpyHostToDevice, s));
+  NC_TRY(g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, comm, s));
+  CU_TRY(cudaMemcpyAsync(&ok, d_ok, sizeof ok, cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  cudaFree(d_all);
+  if (ok) {
+    CU_TRY(cudaMalloc(&H.d_push_ticket, sizeof(unsigned)));
+    CU_TRY(cudaMemsetAsync(H.d_push_ticket, 0, sizeof(unsigned), s));
+  }
+  H.peer_ready = ok != 0;
+  if (getenv("B200_VERBOSE") && me == 0)
+    fprintf(stderr, "b200: halo of p exchanged over %s\n",
+            H.peer_ready ? "peer memory (stores into the neighbours' vectors)" : "NCCL send/recv");
+  return B200_OK;
+}
+
+__global__ void k_xr_chunk_begin(unsigned long long *seq, unsigned count) {
+  seq[0] = seq[1];
+  seq[1] += count;
+}
+
+int xr_chunk_begin(b200_ctx *c, unsigned count) {
+  if (!c->d_seq)
+    return B200_OK;
+  k_xr_chunk_begin<<<1, 1, 0, c->stream>>>(c->d_seq, count);
+  c->launches += 1;
+  CU_TRY(cudaGetLastError());
+  return B200_OK;
+}
+
+#define HP_THREADS 256
+__global__ void __launch_bounds__(HP_THREADS)
+k_halo_push(const double *__restrict__ x, const uint32_t *__restrict__ idx, uint32_t n_send,
+            const HaloPushArgs a, const int *done, const unsigned long long *seq_base,
+            unsigned seq_off, unsigned *ticket) {
+  if (done && *done)
+    return;
+  __shared__ bool is_last;
+  for (uint32_t i = blockIdx.x * HP_THREADS + threadIdx.x; i < n_send; i += gridDim.x * HP_THREADS) {
+    int k = 0;
+    while (k + 1 < a.n_dst && i >= a.seg_begin[k + 1])
+      k++;
+    a.dst[k][i - a.seg_begin[k]] = x[idx[i]];
+  }
+  __threadfence_system();  // my stores, before the ticket says this CTA is through
+  __syncthreads();
+  if (threadIdx.x == 0)
+    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last)
+    return;
+  if ((int)threadIdx.x < a.n_dst) {
+    __threadfence_system();
+    st_relaxed_sys(a.flag[threadIdx.x], *seq_base + seq_off);
+  }
+  if (threadIdx.x == 0)
+    *ticket = 0;
+}
+
+__global__ void k_halo_wait(const double *mine, const HaloWaitArgs a, const unsigned long long *seq_base,
+                            unsigned seq_off, PcgState *st) {
+  if (st && st->done)
+    return;
+  const int k = threadIdx.x;
+  if (k >= a.n_src)
+    return;
+  const unsigned long long want = *seq_base + seq_off;
+  const unsigned long long *flag =
+      reinterpret_cast<const unsigned long long *>(mine + ((size_t)2 * B2_XR_MAX_RANKS + a.src[k]) * 4) + 3;
+  const long long t0 = clock64();
+  while (ld_acquire_sys(flag) != want)
+    if (clock64() - t0 > 8000000000ll) {  // ~4 s: a neighbour is gone; stop, do not hang the GPU
+      if (st)
+        st->done = 1, st->status = 3;
+      break;
+    }
+}
+
+int halo_peer_push(b200_mat *M, const double *x_ext, unsigned seq_off) {
+  b200_ctx *c = M->ctx;
+  HaloPlan &H = M->halo;
+  CU_TRY(cudaEventRecord(c->ev_ready, c->stream));
+  CU_TRY(cudaStreamWaitEvent(c->comm_stream, c->ev_ready, 0));
+  if (H.n_send && H.push.n_dst) {
+    unsigned g = nblk(H.n_send, HP_THREADS);
+    g = g > 64u ? 64u : g;
+    k_halo_push<<<g, HP_THREADS, 0, c->comm_stream>>>(x_ext, H.d_send_idx, (uint32_t)H.n_send, H.push,
+                                                     M->state ? &M->state->done : nullptr, c->d_seq,
+                                                     seq_off, H.d_push_ticket);
+    c->launches += 1;
+    CU_TRY(cudaGetLastError());
+  }
+  CU_TRY(cudaEventRecord(c->ev_halo, c->comm_stream));
+  return B200_OK;
+}
+
+int halo_peer_wait(b200_mat *M, unsigned seq_off) {
+  b200_ctx *c = M->ctx;
+  HaloPlan &H = M->halo;
+  CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));  // my own push read p: before p changes
+  if (H.wait.n_src) {
+    k_halo_wait<<<1, 32, 0, c->stream>>>(c->xr_mail, H.wait, c->d_seq, seq_off, M->state);
+    c->launches += 1;
+    CU_TRY(cudaGetLastError());
+  }
   return B200_OK;
 }
 

@@ -33,7 +33,7 @@
 #include "pcg_kernels.cuh"
 
 int spmv_full_internal(b200_mat *M, double *x_ext, double *y, bool dot,
-                       const XrArgs *xr = nullptr);
+                       const XrArgs *xr = nullptr, unsigned peer_seq = 0);
 
 // residual replacements per solve at most (each one is an exit check that found
 // ||b - A x|| above the bar although the recurrence was below it), and the
@@ -70,6 +70,9 @@ int ensure_workspace(b200_mat *M) {
   B_TRY(dev_alloc(M, (void **)&M->partials, (size_t)slots * 3 * 8));
   B_TRY(dev_alloc(M, (void **)&M->state, sizeof(PcgState)));
   CU_TRY(cudaMemsetAsync(M->state, 0, sizeof(PcgState), c->stream));
+  // several ranks: map the neighbours' p vectors (collective: every rank gets here in
+  // its first solve or product)
+  B_TRY(halo_peer_setup(M));
   return B200_OK;
 }
 
@@ -84,27 +87,30 @@ static int reduce_ranks(b200_mat *M, double *red, double *loc, int count) {
   return allreduce_sum(M->ctx, loc, red, count);
 }
 
-static XrArgs xr_args(b200_ctx *c, int kind) {
-  XrArgs a = {nullptr, nullptr, c->nranks, c->rank, kind, 0ull};
+// seq: position of the iteration inside its chunk, 1-based (xr_chunk_begin)
+static XrArgs xr_args(b200_ctx *c, int kind, unsigned seq) {
+  XrArgs a = {nullptr, nullptr, c->nranks, c->rank, kind, 0ull, nullptr};
   if (c->xr_on)
-    a.peers = c->xr_peers, a.mine = c->xr_mail, a.seq = ++c->xr_seq;
+    a.peers = c->xr_peers, a.mine = c->xr_mail, a.seq = seq, a.base = c->d_seq;
   return a;
 }
 
 // One iteration.  ev (4 events) brackets the three kernel classes when the
 // caller times them.  With the peer-memory all-reduce the two NCCL calls
 // disappear: K1's last CTA ships p.q to every rank and K2 collects it, K2's
-// last CTA ships {r.z, r.r} and K3 collects them.
-static int queue_iteration(b200_mat *M, int par, cudaEvent_t *ev = nullptr) {
+// last CTA ships {r.z, r.r} and K3 collects them; the halo of p travels the
+// same way (dist.cu), so nothing in here needs the host or NCCL.
+static int queue_iteration(b200_mat *M, int par, unsigned seq, cudaEvent_t *ev = nullptr) {
   b200_ctx *c = M->ctx;
   cudaStream_t s = c->stream;
   uint64_t n = M->n_local;
   PcgState *st = M->state;
   const int nx = (par ^ 1) * 2;
-  const XrArgs x_pq = xr_args(c, 0), x_rz = xr_args(c, 1);
-  const XrArgs none = {nullptr, nullptr, 1, 0, 0, 0ull};
+  const XrArgs x_pq = xr_args(c, 0, seq), x_rz = xr_args(c, 1, seq);
+  const XrArgs none = {nullptr, nullptr, 1, 0, 0, 0ull, nullptr};
   if (ev) CU_TRY(cudaEventRecord(ev[0], s));
-  B_TRY(spmv_full_internal(M, M->w_p, M->w_q, true, c->xr_on ? &x_pq : nullptr));  // K1
+  B_TRY(spmv_full_internal(M, M->w_p, M->w_q, true, c->xr_on ? &x_pq : nullptr,
+                           c->xr_on ? seq : 0u));  // K1
   if (!c->xr_on)
     B_TRY(reduce_ranks(M, &st->pq, &st->pq_loc, 1));
   if (ev) CU_TRY(cudaEventRecord(ev[1], s));
@@ -151,8 +157,10 @@ static int queue_chunk(b200_mat *M, int chunk, bool sr) {
     k_sr_chunk_begin<<<1, 1, 0, M->ctx->stream>>>(M->state, chunk);
     M->ctx->launches += 1;
   }
+  if (!sr)
+    B_TRY(xr_chunk_begin(M->ctx, (unsigned)chunk));
   for (int i = 0; i < chunk; i++)
-    B_TRY(sr ? queue_iteration_sr(M, i) : queue_iteration(M, i & 1));
+    B_TRY(sr ? queue_iteration_sr(M, i) : queue_iteration(M, i & 1, (unsigned)i + 1u));
   return B200_OK;
 }
 
@@ -209,8 +217,10 @@ static int pcg_stream(b200_mat *M, const double *d_b, double *d_x,
   }
   int chunk = o->check_every > 0 ? o->check_every : 32;
   chunk = (chunk + 1) & ~1;  // even: the parity pattern repeats per chunk
-  // (multi-rank: plain launches; the NCCL calls stay outside any capture)
-  const bool use_graph = !(o->flags & B200_PCG_NO_GRAPH) && c->nranks == 1;
+  // (several ranks: a graph only when nothing in the iteration is an NCCL call, i.e. the
+  // sums and the halo both go over peer memory)
+  const bool use_graph = !(o->flags & B200_PCG_NO_GRAPH) &&
+                         (c->nranks == 1 || (!sr && c->xr_on && M->halo.peer_ready));
   const uint64_t launches0 = c->launches;
 
   CU_TRY(cudaEventRecord(c->ev_a, s));
@@ -258,6 +268,8 @@ static int pcg_stream(b200_mat *M, const double *d_b, double *d_x,
         k_sr_chunk_begin<<<1, 1, 0, s>>>(M->state, chunk);
         c->launches += 1;
       }
+      if (!sr)
+        B_TRY(xr_chunk_begin(c, (unsigned)chunk));
       for (int i = 0; i < chunk; i++) {
         if (sr) {
           B_TRY(queue_iteration_sr(M, i, ev));
@@ -269,7 +281,7 @@ static int pcg_stream(b200_mat *M, const double *d_b, double *d_x,
           t_cls[0] += t;
           continue;
         }
-        B_TRY(queue_iteration(M, i & 1, ev));
+        B_TRY(queue_iteration(M, i & 1, (unsigned)i + 1u, ev));
         CU_TRY(cudaEventSynchronize(ev[3]));
         for (int k = 0; k < 3; k++) {
           float t;
@@ -323,7 +335,7 @@ static int pcg_stream(b200_mat *M, const double *d_b, double *d_x,
         sum_target(M, &M->state->red[nx], &M->state->loc[nx]));
     B_TRY(reduce_ranks(M, &M->state->red[nx], &M->state->loc[nx], 2));
     k_pcg_resume<<<1, 1, 0, s>>>(M->state, nx);
-    const XrArgs none = {nullptr, nullptr, 1, 0, 0, 0ull};
+    const XrArgs none = {nullptr, nullptr, 1, 0, 0, 0ull, nullptr};
     k_pcg_pupdate<<<M->grid_ew, EW_THREADS, 0, s>>>(n, M->w_r, M->dinv, M->w_p, M->state,
                                                     par_last, none, 1);
     c->launches += 3;
@@ -332,8 +344,9 @@ static int pcg_stream(b200_mat *M, const double *d_b, double *d_x,
     // never meets the bar: the tail is bounded, then status 4)
     const int tail = h.iter + (h.iter / 8 > 8 ? h.iter / 8 : 8);
     for (int q = h.iter;;) {
+      B_TRY(xr_chunk_begin(c, B2_TAIL_CHUNK));
       for (int i = 0; i < B2_TAIL_CHUNK; i++, q++)
-        B_TRY(queue_iteration(M, q & 1));
+        B_TRY(queue_iteration(M, q & 1, (unsigned)i + 1u));
       CU_TRY(cudaMemcpyAsync((void *)flag, &M->state->iter, 16, cudaMemcpyDeviceToHost, s));
       CU_TRY(cudaStreamSynchronize(s));
       if (flag[1])

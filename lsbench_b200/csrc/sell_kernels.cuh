@@ -16,21 +16,26 @@
 template <bool FULL, typename ColF>
 __device__ __forceinline__ double sell_chunk(const double *vp, const double *__restrict__ x,
                                              uint32_t k, uint32_t rem, double sum, ColF colf) {
+  // A partial chunk (rem < 8 entries) clamps the ENTRY INDEX of the surplus loads to the
+  // chunk's last entry and leaves them unused; it must not select on the loaded VALUE
+  // (j < rem ? load : 0): that select consumes every load where it stands, and the loads
+  // of a 3-entry tail go out one after the other, a round trip each (round 2, ncu source
+  // page of the bulk-copy-fed kernel, where the same pattern cost 8 us per slice).
   constexpr int N = FULL ? 8 : 7;
   uint32_t c[8];
   double a[8], xv[8];
 #pragma unroll
   for (int j = 0; j < N; j++)
-    c[j] = (FULL || j < rem) ? colf(j) : 0u;
+    c[j] = colf(FULL || (uint32_t)j < rem ? j : (int)rem - 1);
 #pragma unroll
   for (int j = 0; j < N; j++)
-    a[j] = (FULL || j < rem) ? ld_stream(vp + (size_t)(k + j) * B2_SLICE) : 0.0;
+    a[j] = ld_stream(vp + (size_t)(k + (FULL || (uint32_t)j < rem ? (uint32_t)j : rem - 1u)) * B2_SLICE);
 #pragma unroll
   for (int j = 0; j < N; j++)
-    xv[j] = (FULL || j < rem) ? __ldg(x + c[j]) : 0.0;
+    xv[j] = __ldg(x + c[j]);
 #pragma unroll
   for (int j = 0; j < N; j++)
-    if (FULL || j < rem)
+    if (FULL || (uint32_t)j < rem)
       sum = fma(a[j], xv[j], sum);
   return sum;
 }
@@ -45,19 +50,20 @@ __device__ __forceinline__ double sell_chunk(const float *vp, const double *__re
                                              uint32_t k, uint32_t rem, double sum, ColF colf) {
   constexpr int N = FULL ? 16 : 15;
   float a[16];
+  // (surplus loads of a partial chunk: entry index clamped, value never selected -- see above)
 #pragma unroll
   for (int j = 0; j < N; j++)
-    a[j] = (FULL || j < rem) ? ld_stream(vp + (size_t)(k + j) * B2_SLICE) : 0.0f;
+    a[j] = ld_stream(vp + (size_t)(k + (FULL || (uint32_t)j < rem ? (uint32_t)j : rem - 1u)) * B2_SLICE);
 #pragma unroll
   for (int h = 0; h < 2; h++) {
     uint32_t c[8];
     double xv[8];
 #pragma unroll
     for (int j = 0; j < 8; j++)
-      c[j] = (h * 8 + j < N && (FULL || h * 8 + j < rem)) ? colf(h * 8 + j) : 0u;
+      c[j] = colf(FULL || (uint32_t)(h * 8 + j) < rem ? h * 8 + j : (int)rem - 1);
 #pragma unroll
     for (int j = 0; j < 8; j++)
-      xv[j] = (h * 8 + j < N && (FULL || h * 8 + j < rem)) ? __ldg(x + c[j]) : 0.0;
+      xv[j] = __ldg(x + c[j]);
 #pragma unroll
     for (int j = 0; j < 8; j++)
       if (h * 8 + j < N && (FULL || h * 8 + j < rem))

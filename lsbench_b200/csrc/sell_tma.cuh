@@ -186,10 +186,15 @@ k_spmv_sellc_tma(const uint4 *__restrict__ meta, const uint32_t *__restrict__ co
     if (!(m.y >> 31))
       return;
     const uint32_t w = m.y & 0x7fffffffu;
+    // NEVER select on the loaded value (k < w ? load : 0): the select consumes the load
+    // where it stands and the 27 gathers go out one after the other, each a full round
+    // trip -- that was the ~8 us per slice per warp of the first two versions (ncu source
+    // page: every sample on the conditional moves behind the loads).  Select the ADDRESS:
+    // entries past the slice's width read x[row] again (same line) and are never used.
 #pragma unroll
     for (int k = 0; k < WCAP; k++) {
       const int32_t d = __shfl_sync(FULL, dl, k);
-      xv[k] = (uint32_t)k < w ? __ldg(x + (row + (uint32_t)d)) : 0.0;
+      xv[k] = __ldg(x + ((uint32_t)k < w ? row + (uint32_t)d : row));
     }
   };
   for (int i = 0; i < nstages; i++)
@@ -234,12 +239,13 @@ k_spmv_sellc_tma(const uint4 *__restrict__ meta, const uint32_t *__restrict__ co
         const uint32_t nk = w - k < 8u ? w - k : 8u;
         uint32_t c[8];
         double xe[8];
+        // (addresses clamped to the slice's last entry instead of values selected: see G)
 #pragma unroll
         for (int j = 0; j < 8; j++)
-          c[j] = (uint32_t)j < nk ? ld_stream(cp + (size_t)(k + j) * B2_SLICE) : 0u;
+          c[j] = ld_stream(cp + (size_t)(k + ((uint32_t)j < nk ? j : nk - 1u)) * B2_SLICE);
 #pragma unroll
         for (int j = 0; j < 8; j++)
-          xe[j] = (uint32_t)j < nk ? __ldg(x + c[j]) : 0.0;
+          xe[j] = __ldg(x + c[j]);
         if (!waited) {
           tma_wait(bar + stage, phase);
           waited = true;

@@ -300,8 +300,10 @@ static int spmv_col_blocked(b200_mat *M, const double *x, double *y) {
 }
 
 // Full SpMV with halo exchange overlapped with the interior rows (piece 5).
+// peer_seq != 0 (PCG iterations only, x_ext = the p vector): the halo goes over peer
+// memory with that sequence offset (dist.cu), not through NCCL.
 static int spmv_full(b200_mat *M, double *x_ext, double *y, bool dot,
-                     const XrArgs *xr = nullptr) {
+                     const XrArgs *xr = nullptr, unsigned peer_seq = 0) {
   if (!M->blocks.empty()) {
     if (dot)
       B_FAIL(B200_EINVAL, "a column-blocked matrix is SpMV-only");
@@ -309,14 +311,21 @@ static int spmv_full(b200_mat *M, double *x_ext, double *y, bool dot,
   }
   if (!M->halo.n_halo && M->ctx->nranks == 1)
     return launch_spmv(M, x_ext, y, dot, 0, nullptr);
+  if (peer_seq && M->halo.peer_ready && x_ext == M->w_p) {
+    B_TRY(halo_peer_push(M, x_ext, peer_seq));
+    B_TRY(launch_spmv(M, x_ext, y, dot, 1, xr));
+    B_TRY(halo_peer_wait(M, peer_seq));
+    return launch_spmv(M, x_ext, y, dot, 2, xr);
+  }
   B_TRY(halo_exchange_begin(M, x_ext));
   B_TRY(launch_spmv(M, x_ext, y, dot, 1, xr));
   B_TRY(halo_exchange_wait(M));
   return launch_spmv(M, x_ext, y, dot, 2, xr);
 }
 
-int spmv_full_internal(b200_mat *M, double *x_ext, double *y, bool dot, const XrArgs *xr) {
-  return spmv_full(M, x_ext, y, dot, xr);
+int spmv_full_internal(b200_mat *M, double *x_ext, double *y, bool dot, const XrArgs *xr,
+                       unsigned peer_seq) {
+  return spmv_full(M, x_ext, y, dot, xr, peer_seq);
 }
 
 extern "C" int b200_spmv(b200_mat *M, const double *d_x, double *d_y) {

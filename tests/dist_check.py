@@ -112,10 +112,58 @@ def main():
         assert orc.true_relres(Mo, b, xfull) <= 1e-10
         print("dist_check tj7a_A_18 ranks=%d iters=%d ok" % (world, r.iters))
     M.close()
+    ctx.close()
+
+    # ---- the ways the ranks can talk to each other must not change the answer -----------------
+    # default: CG sums and the halo of p over peer memory, the chunk of iterations a CUDA graph;
+    # B200_HALO=nccl: halo by ncclSend/Recv (no graph); B200_ALLREDUCE=nccl: sums by
+    # ncclAllReduce as well; plus the single-reduction iteration (NCCL sums).  A grid large
+    # enough for several chunks of 32 iterations and a halo of two planes per neighbour.
+    def fresh_ctx():
+        t = torch.zeros(abi.NCCL_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(abi.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        return abi.Context(local, rank, world, bytes(t.cpu().numpy().tobytes()))
+
+    N = 64
+    b = orc.rhs(N ** 3)
+    got = {}
+    for mode, env, pflags in (("peer", {}, 0), ("peer_nograph", {}, abi.PCG_NO_GRAPH),
+                              ("halo_nccl", {"B200_HALO": "nccl"}, 0),
+                              ("all_nccl", {"B200_ALLREDUCE": "nccl"}, 0),
+                              ("single_reduction", {}, abi.PCG_SINGLE_REDUCTION)):
+        for k in ("B200_HALO", "B200_ALLREDUCE"):
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        c2 = fresh_ctx()
+        M = abi.Matrix.generate(c2, abi.GEN_POISSON27, N)
+        i = M.info()
+        r0, r1 = i.row_begin, i.row_begin + i.n_local
+        x, r, rc = M.pcg_host(b[r0:r1], tol=1e-10, flags=abi.PCG_NO_SMALL | pflags)
+        x2, r2, _ = M.pcg_host(b[r0:r1], tol=1e-10, flags=abi.PCG_NO_SMALL | pflags)
+        assert rc == 0 and r.status == 0 and r.true_relres <= 1e-10, (mode, rc, r.status, r.true_relres)
+        assert r2.iters == r.iters and x2.tobytes() == x.tobytes(), mode     # reproducible
+        got[mode] = (r.iters, gather(x), r.solve_ms)
+        M.close()
+        c2.close()
+    for k in ("B200_HALO", "B200_ALLREDUCE"):
+        os.environ.pop(k, None)
+    it0, x0, _ = got["peer"]
+    # the same sums in the same order: bit for bit, with or without the graph, whichever way the halo goes
+    for mode in ("peer_nograph", "halo_nccl"):
+        assert got[mode][0] == it0 and got[mode][1].tobytes() == x0.tobytes(), mode
+    for mode in ("all_nccl", "single_reduction"):
+        assert abs(got[mode][0] - it0) <= 2, (mode, got[mode][0], it0)
+        assert np.linalg.norm(got[mode][1] - x0) / np.linalg.norm(x0) <= 1e-9, mode
+    if rank == 0:
+        Mfull = orc.gen_poisson27(N)
+        assert orc.true_relres(Mfull, b, x0) <= 1e-10
+        print("dist_check modes ranks=%d: " % world
+              + ", ".join("%s %d its %.2f ms" % (m, v[0], v[2]) for m, v in got.items()))
     dist.barrier()
     if rank == 0:
         print("DIST_CHECK OK")
-    ctx.close()
     dist.destroy_process_group()
 
 
