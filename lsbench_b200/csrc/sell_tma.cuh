@@ -42,11 +42,14 @@ __device__ __forceinline__ void tma_fence_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-// arm the stage's barrier with the byte count and start the copy (one lane)
+// arm the stage's barrier with the byte count and start the copy (one lane).  No proxy
+// fence here: the stage being overwritten was READ by the lanes (values already in
+// registers and multiplied) before the __syncwarp that precedes this call; a
+// fence.proxy.async compiles to MEMBAR.ALL.CTA and would wait for every load the warp
+// has in flight -- the gathers requested ahead for the next slice -- once per slice.
 __device__ __forceinline__ void tma_fetch(void *dst, const void *src, uint32_t bytes, uint64_t *bar,
                                           uint64_t policy) {
   const uint32_t b = tma_s32(bar);
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
   if (bytes)
     asm volatile(
@@ -95,15 +98,15 @@ static inline uint64_t tma_policy_stream() { return 0; }
 // slice needs is now requested AHEAD of the slice, each level one step before the next:
 //
 //   step it:   descriptors  a window of 32 per warp (one lane each), refreshed every 32
-//              D(it+2)      deltas of slice it+2 (lane l holds delta l) and its rows
-//              G(it+1)      the w gathers of slice it+1, all in flight at once
+//              G(it+1)      the w gathers of slice it+1, all in flight at once (+ x[row] for p.q)
+//              D(it+2)      columns of slice it+2 (deltas: lane l holds delta l) and its rows
 //              C(it)        wait for the values of slice it (bulk copy, requested S
 //                           slices ago), w fma in row order, y
 //              F(it+S)      request the values of slice it+S into the stage just freed
 //
 // so a warp's step costs one memory round trip, not six, and 8 warps keep up with the
-// value stream.  Slices with explicit columns (12 % on a stencil) load and gather on
-// demand inside C as before.
+// value stream.  Slices with explicit columns (12 - 25 % on a stencil) go the same way:
+// their w columns are requested in D (registers), their gathers in G.
 template <bool DOT, typename VT, int WARPS, int WCAP>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 k_spmv_sellc_tma(const uint4 *__restrict__ meta, const uint32_t *__restrict__ cols,
@@ -114,6 +117,10 @@ k_spmv_sellc_tma(const uint4 *__restrict__ meta, const uint32_t *__restrict__ co
                  PcgState *st, double *dot_out, const XrArgs xr, uint32_t stage_bytes,
                  int nstages) {
   static_assert(WCAP <= 32, "one delta per lane");
+  // explicit slices: columns requested a step ahead into registers (8 warps), or loaded on
+  // demand inside C (12 warps: 384 threads x two gather buffers leave no room for them)
+  constexpr bool CBUF = WARPS <= 8;
+  constexpr int NCB = CBUF ? WCAP : 1;
   if (DOT && st->done)
     return;
 #ifdef B2_SIMT_EMUL
@@ -167,49 +174,69 @@ k_spmv_sellc_tma(const uint4 *__restrict__ meta, const uint32_t *__restrict__ co
       tma_fetch(ring + (size_t)stage * stage_bytes, vals + (size_t)m.x * B2_SLICE,
                 (m.y & 0x7fffffffu) * B2_SLICE * (uint32_t)sizeof(VT), bar + stage, policy);
   };
-  // D: the deltas (lane l: delta l) and the row of this lane, of step `it`
-  auto D = [&](uint32_t it, int32_t &dl, uint32_t &row) {
+  // D: what the gathers of step `it` need -- its row, and the columns: a uniform slice's
+  // deltas (lane l holds delta l), an explicit slice's own w columns in cb[]
+  auto D = [&](uint32_t it, int32_t &dl, uint32_t &row, uint32_t (&cb)[NCB]) {
     dl = 0, row = 0xffffffffu;
     if (it >= cnt)
       return;
     const uint4 m = meta_at(it);
+    const uint32_t w = m.y & 0x7fffffffu;
     const uint32_t pos = slice_of(it) * B2_SLICE + lane;
     row = perm ? __ldg(perm + pos) : pos;
-    if ((m.y >> 31) && lane < (m.y & 0x7fffffffu))
-      dl = __ldg(dcols + m.z + lane);
+    if (m.y >> 31) {
+      if (lane < w)
+        dl = __ldg(dcols + m.z + lane);
+    } else if (CBUF && w) {
+      const uint32_t *cp = cols + (size_t)m.z * B2_SLICE + lane;
+#pragma unroll
+      for (int k = 0; k < NCB; k++)  // (entry index clamped: no select on a loaded value)
+        cb[k] = ld_stream(cp + (size_t)((uint32_t)k < w ? (uint32_t)k : w - 1u) * B2_SLICE);
+    }
   };
-  // G: all gathers of step `it` (uniform slices; the others gather inside C)
-  auto G = [&](uint32_t it, int32_t dl, uint32_t row, double (&xv)[WCAP]) {
+  // G: all gathers of step `it`, in flight at once, and x[row] for the fused dot
+  auto G = [&](uint32_t it, int32_t dl, uint32_t row, const uint32_t (&cb)[NCB], double (&xv)[WCAP],
+               double &xrow) {
     if (it >= cnt)
       return;
     const uint4 m = meta_at(it);
-    if (!(m.y >> 31))
-      return;
     const uint32_t w = m.y & 0x7fffffffu;
+    if (DOT)
+      xrow = __ldg(x + (row < n_rows ? row : 0u));
     // NEVER select on the loaded value (k < w ? load : 0): the select consumes the load
     // where it stands and the 27 gathers go out one after the other, each a full round
     // trip -- that was the ~8 us per slice per warp of the first two versions (ncu source
     // page: every sample on the conditional moves behind the loads).  Select the ADDRESS:
-    // entries past the slice's width read x[row] again (same line) and are never used.
+    // entries past the slice's width read an address already read and are never used.
+    if (m.y >> 31) {
 #pragma unroll
-    for (int k = 0; k < WCAP; k++) {
-      const int32_t d = __shfl_sync(FULL, dl, k);
-      xv[k] = __ldg(x + ((uint32_t)k < w ? row + (uint32_t)d : row));
+      for (int k = 0; k < WCAP; k++) {
+        const int32_t d = __shfl_sync(FULL, dl, k);
+        xv[k] = __ldg(x + ((uint32_t)k < w ? row + (uint32_t)d : row));
+      }
+    } else if (CBUF && w) {
+#pragma unroll
+      for (int k = 0; k < NCB; k++)
+        xv[k] = __ldg(x + cb[k]);
     }
   };
   for (int i = 0; i < nstages; i++)
     fetch((uint32_t)i, i);
   int32_t dl_a, dl_b;
   uint32_t row_c, row_a, row_b;
-  double xvA[WCAP], xvB[WCAP];
+  uint32_t cb[NCB];
+  double xvA[WCAP], xvB[WCAP], xrow_c = 0.0, xrow_n = 0.0;
 #pragma unroll
   for (int k = 0; k < WCAP; k++)
     xvA[k] = 0.0, xvB[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < NCB; k++)
+    cb[k] = 0u;
   {
     int32_t dl_c;
-    D(0u, dl_c, row_c);
-    D(1u, dl_a, row_a);
-    G(0u, dl_c, row_c, xvA);
+    D(0u, dl_c, row_c, cb);
+    G(0u, dl_c, row_c, cb, xvA, xrow_c);
+    D(1u, dl_a, row_a, cb);
   }
   double dot = 0.0;
   int stage = 0;
@@ -219,27 +246,28 @@ k_spmv_sellc_tma(const uint4 *__restrict__ meta, const uint32_t *__restrict__ co
       mA = mB, wbase += 32u;
       mB = load_meta(wbase + 32u + lane);
     }
-    D(it + 2u, dl_b, row_b);
-    G(it + 1u, dl_a, row_a, nxt);
+    // gathers of the next slice (its columns were requested a step ago), then the columns
+    // of the one after it (cb is free again once the gathers have their addresses)
+    G(it + 1u, dl_a, row_a, cb, nxt, xrow_n);
+    D(it + 2u, dl_b, row_b, cb);
     // ---- C(it) -----------------------------------------------------------------------------
     const uint4 m = meta_at(it);
     const uint32_t w = m.y & 0x7fffffffu;
     const VT *sv = reinterpret_cast<const VT *>(ring + (size_t)stage * stage_bytes) + lane;
     double sum = 0.0;
-    if (m.y >> 31) {
+    if (CBUF || (m.y >> 31)) {
       tma_wait(bar + stage, phase);
 #pragma unroll
       for (int k = 0; k < WCAP; k++)
         if ((uint32_t)k < w)
           sum = fma((double)sv[(size_t)k * B2_SLICE], cur[k], sum);
-    } else {
+    } else {  // explicit columns on demand, 8 at a time
       const uint32_t *cp = cols + (size_t)m.z * B2_SLICE + lane;
       bool waited = false;
       for (uint32_t k = 0; k < w; k += 8) {
         const uint32_t nk = w - k < 8u ? w - k : 8u;
         uint32_t c[8];
         double xe[8];
-        // (addresses clamped to the slice's last entry instead of values selected: see G)
 #pragma unroll
         for (int j = 0; j < 8; j++)
           c[j] = ld_stream(cp + (size_t)(k + ((uint32_t)j < nk ? j : nk - 1u)) * B2_SLICE);
@@ -264,11 +292,11 @@ k_spmv_sellc_tma(const uint4 *__restrict__ meta, const uint32_t *__restrict__ co
     if (row_c < n_rows) {
       y[row_c] = sum;
       if (DOT)
-        dot = fma(sum, __ldg(x + row_c), dot);
+        dot = fma(sum, xrow_c, dot);
     }
     if (++stage == nstages)
       stage = 0, phase ^= 1;
-    row_c = row_a, dl_a = dl_b, row_a = row_b;
+    row_c = row_a, dl_a = dl_b, row_a = row_b, xrow_c = xrow_n;
   };
   for (uint32_t it = 0; it < cnt; it += 2) {
     step(it, xvA, xvB);

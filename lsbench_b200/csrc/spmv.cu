@@ -63,7 +63,9 @@ static TmaCfg tma_cfg(const b200_mat *M) {
     return t;
   const uint32_t vsz = M->sell_vals32 ? 4u : 8u;
   const uint32_t stage = (M->sell_max_width * B2_SLICE * vsz + 127u) & ~127u;
-  const int warps = warps_env == 12 ? 12 : 8;
+  // (12 warps only for rows of at most 8 entries: with 32 gather registers twice over,
+  // 384 threads do not fit the register file without spilling)
+  const int warps = warps_env == 12 && (M->sell_max_width <= 8 || M->sell_max_width <= 28) ? 12 : 8;
   int nst = (int)((size_t)smem_kb * 1024 / ((size_t)warps * stage));
   if (nst > TMA_MAX_STAGES)
     nst = TMA_MAX_STAGES;
@@ -78,7 +80,7 @@ static const void *tma_kernel_of(int warps, bool dot, bool narrow) {
 #define B2_TMA_K(W, C) (dot ? (const void *)k_spmv_sellc_tma<true, VT, W, C> : (const void *)k_spmv_sellc_tma<false, VT, W, C>)
   if (narrow)
     return warps == 12 ? B2_TMA_K(12, 8) : B2_TMA_K(8, 8);
-  return warps == 12 ? B2_TMA_K(12, 32) : B2_TMA_K(8, 32);
+  return warps == 12 ? B2_TMA_K(12, 28) : B2_TMA_K(8, 32);
 #undef B2_TMA_K
 }
 static const void *tma_kernel(const b200_mat *M, int warps, bool dot) {

@@ -94,8 +94,9 @@ def run(emul, Lay, n, x, wmax, grid, ranges=None):
     ys = []
     for f64, vals in ((0, Lay["vals"]), (1, Lay["vals"].astype(np.float64))) if wmax else ():
         for stages in (2, 3):
-            if 8 * stages * ((Lay["wmax"] * 32 * (8 if f64 else 4) + 127) & ~127) > 168 * 1024:
-                continue   # the ring does not fit (spmv.cu tma_cfg): the product takes the plain kernel
+            if Lay["wmax"] > 32 or 8 * stages * ((Lay["wmax"] * 32 * (8 if f64 else 4) + 127) & ~127) > 168 * 1024:
+                continue   # slices wider than a warp, or a ring that does not fit (spmv.cu tma_cfg):
+                           # the product takes the plain kernel
             y = np.full(n, np.nan)
             assert emul.fiber.emul_sellc_tma(f64, stages, min(grid, 5), p(Lay["meta"]), p(Lay["ecols"]),
                                              p(Lay["dcols"]), p(vals), p(Lay["list"]), p(x), p(y),
