@@ -380,7 +380,7 @@ def main():
         sg = stored_bytes / (spmv_ms * 1e-3) / 1e9
         ag = spmv_bytes / (spmv_ms * 1e-3) / 1e9
         roof = {"bound": "hbm",
-                "kernel": "SELL SpMV fused with p.Ap (q = A p, p.q): k_spmv_sellc_tma / k_spmv_sellc / k_spmv_sell",
+                "kernel": "SELL SpMV fused with p.Ap (q = A p, p.q): k_spmv_sellc (index-compressed) / k_spmv_sell",
                 "achieved": sg, "peak": peak, "unit": "GB/s", "frac": sg / peak,
                 "bytes_per_launch": stored_bytes,
                 "achieved_algorithmic": ag, "frac_algorithmic": ag / peak,

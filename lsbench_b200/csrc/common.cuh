@@ -219,7 +219,6 @@ struct b200_mat {
   PcgState *state = nullptr;
   SpmvPlan plan[3];              // phase 0 all, 1 interior, 2 boundary
   bool plan_ready = false;
-  bool tma_attr_set[2] = {false, false};  // dynamic shared memory opted in (no dot / dot)
   // column-blocked operator (B200_MAT_COL_BLOCK): the column ranges as matrices of
   // their own (all n rows, global column ids); this one then holds no entries
   std::vector<b200_mat *> blocks;

@@ -209,9 +209,6 @@ k_spmv_sellc(const uint4 *__restrict__ meta, const uint32_t *__restrict__ cols,
   }
 }
 
-#ifndef B2_NO_TMA_KERNEL
-#include "sell_tma.cuh"
-#endif
 
 // ---- the row-major bins: one warp per row, one CTA per row ----------------------------
 template <bool DOT, bool ACC = false>

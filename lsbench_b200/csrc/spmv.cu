@@ -37,57 +37,6 @@ static int persistent_grid(b200_ctx *c, const void *kernel, uint64_t work_ctas,
   return g < 1 ? 1 : (int)g;
 }
 
-// The bulk-copy-fed kernel (sell_tma.cuh) runs where it applies: index-compressed
-// layout, ONE value stream resident, slices narrow enough for a ring of at least two
-// stages per warp.  B200_SPMV_TMA=0 keeps the plain kernel; B200_TMA_WARPS (8, 12 or
-// 16 warps per CTA, one CTA per SM) and B200_TMA_SMEM_KB (ring budget) are the
-// knobs the measurements of DESIGN.md section 3 were taken with.
-struct TmaCfg {
-  int warps = 0;          // 0: not used for this matrix
-  int nstages = 0;
-  uint32_t stage_bytes = 0;
-  size_t smem = 0;
-};
-static int env_int(const char *name, int dflt) {
-  const char *v = getenv(name);
-  return v && *v ? atoi(v) : dflt;
-}
-static TmaCfg tma_cfg(const b200_mat *M) {
-  TmaCfg t;
-  static const int on = env_int("B200_SPMV_TMA", 0);
-  static const int warps_env = env_int("B200_TMA_WARPS", 8);
-  static const int smem_kb = env_int("B200_TMA_SMEM_KB", 168);
-  if (!on || !M->sell_meta || M->sell_max_width == 0 || M->sell_max_width > 32)
-    return t;  // (one delta per lane: slices of at most 32 entries)
-  if (M->sell_vals32 && M->sell_vals)  // refinement mode alternates the streams
-    return t;
-  const uint32_t vsz = M->sell_vals32 ? 4u : 8u;
-  const uint32_t stage = (M->sell_max_width * B2_SLICE * vsz + 127u) & ~127u;
-  // (12 warps only for rows of at most 8 entries: with 32 gather registers twice over,
-  // 384 threads do not fit the register file without spilling)
-  const int warps = warps_env == 12 && (M->sell_max_width <= 8 || M->sell_max_width <= 28) ? 12 : 8;
-  int nst = (int)((size_t)smem_kb * 1024 / ((size_t)warps * stage));
-  if (nst > TMA_MAX_STAGES)
-    nst = TMA_MAX_STAGES;
-  if (nst < 2)
-    return t;
-  t.warps = warps, t.nstages = nst, t.stage_bytes = stage;
-  t.smem = (size_t)warps * nst * stage;
-  return t;
-}
-template <typename VT>
-static const void *tma_kernel_of(int warps, bool dot, bool narrow) {
-#define B2_TMA_K(W, C) (dot ? (const void *)k_spmv_sellc_tma<true, VT, W, C> : (const void *)k_spmv_sellc_tma<false, VT, W, C>)
-  if (narrow)
-    return warps == 12 ? B2_TMA_K(12, 8) : B2_TMA_K(8, 8);
-  return warps == 12 ? B2_TMA_K(12, 28) : B2_TMA_K(8, 32);
-#undef B2_TMA_K
-}
-static const void *tma_kernel(const b200_mat *M, int warps, bool dot) {
-  const bool narrow = M->sell_max_width <= 8;  // 7-point rows: 8 gather registers, not 32
-  return M->sell_vals32 ? tma_kernel_of<float>(warps, dot, narrow) : tma_kernel_of<double>(warps, dot, narrow);
-}
-
 static SpmvPlan compute_plan(b200_mat *M, int phase) {
   SpmvPlan P = {0, 0, 0, 0, 0, 0, 0};
   b200_ctx *c = M->ctx;
@@ -119,20 +68,13 @@ static SpmvPlan compute_plan(b200_mat *M, int phase) {
   if (nv) {
     // one grid per matrix (fixed count of dot partials = fixed summation
     // order): sized for the instantiation that will run
-    const TmaCfg tc = tma_cfg(M);
-    if (tc.warps) {
-      // one CTA per SM: the ring takes most of the shared memory
-      uint64_t need = (nv + tc.warps - 1) / tc.warps, g = c->sm_count;
-      P.g_sell = (int)(g < need ? g : need);
-    } else {
-      P.g_sell = persistent_grid(
-          c,
-          M->sell_vals32 ? (M->sell_meta ? (const void *)k_spmv_sellc<true, float>
-                                         : (const void *)k_spmv_sell<true, float>)
-                         : (M->sell_meta ? (const void *)k_spmv_sellc<true, double>
-                                         : (const void *)k_spmv_sell<true, double>),
-          (nv + SPMV_WARPS - 1) / SPMV_WARPS);
-    }
+    P.g_sell = persistent_grid(
+        c,
+        M->sell_vals32 ? (M->sell_meta ? (const void *)k_spmv_sellc<true, float>
+                                       : (const void *)k_spmv_sell<true, float>)
+                       : (M->sell_meta ? (const void *)k_spmv_sellc<true, double>
+                                       : (const void *)k_spmv_sell<true, double>),
+        (nv + SPMV_WARPS - 1) / SPMV_WARPS);
   }
   if (others && M->vec_rows)
     P.g_vec = persistent_grid(c, (const void *)k_spmv_vec<true>,
@@ -196,27 +138,7 @@ int launch_spmv(b200_mat *M, const double *x, double *y, bool dot, int phase,
       k_spmv_sell<false, VT><<<P.g_sell, SPMV_THREADS, 0, s>>>(                   \
           M->sell_off, M->sell_cols, VALS, B2_SELL_ARGS(false));                  \
   } while (0)
-    const TmaCfg tc = tma_cfg(M);
-    if (tc.warps) {
-      const void *kfn = tma_kernel(M, tc.warps, dot);
-      if (!M->tma_attr_set[dot ? 1 : 0]) {
-        CU_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc.smem));
-        M->tma_attr_set[dot ? 1 : 0] = true;
-      }
-      const void *vals_p = f32 ? (const void *)M->sell_vals32 : (const void *)M->sell_vals;
-      double *part = dot ? M->partials : nullptr;
-      unsigned sb = dot ? slot_base : 0u, tot = dot ? total : 0u;
-      PcgState *stp = dot ? M->state : nullptr;
-      double *dout = dot ? dot_out : nullptr;
-      uint32_t stage_bytes = tc.stage_bytes;
-      int nst = tc.nstages;
-      void *args[] = {(void *)&meta, (void *)&M->sell_cols, (void *)&M->sell_dcols, (void *)&vals_p,
-                      (void *)&M->sell_perm, (void *)&x, (void *)&y, (void *)&P.b0, (void *)&P.e0,
-                      (void *)&P.b1, (void *)&P.e1, (void *)&n, (void *)&part, (void *)&sb,
-                      (void *)&tot, (void *)&stp, (void *)&dout, (void *)&xr, (void *)&stage_bytes,
-                      (void *)&nst};
-      CU_TRY(cudaLaunchKernel(kfn, dim3(P.g_sell), dim3(tc.warps * 32), args, tc.smem, s));
-    } else if (f32)
+    if (f32)
       B2_SELL_LAUNCH(float, M->sell_vals32);
     else
       B2_SELL_LAUNCH(double, M->sell_vals);

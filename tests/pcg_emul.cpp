@@ -23,34 +23,12 @@ struct Layout {  // the index-compressed SELL layout, built by the caller (numpy
   const uint32_t *perm;
   const double *dinv;
   const float *vals32;  // the same values as fp32 (exact), for the fp32-value kernels
-  int kernel;           // 0 k_spmv_sellc fp64 | 1 k_spmv_sellc fp32 | 2 bulk-copy-fed fp64 | 3 fp32
-  int wmax;             // ring depth (stages per warp) of the bulk-copy-fed kernel
+  int kernel;           // 0 k_spmv_sellc fp64 | 1 k_spmv_sellc fp32
+  int wmax;             // (unused)
 };
 
 static const XrArgs NOXR = {nullptr, nullptr, 1, 0, 0, 0ull};
 
-// the bulk-copy-fed kernel (sell_tma.cuh): L.wmax carries the ring depth, 8 warps per CTA,
-// as many CTAs as the slices need up to `grid`
-template <bool DOT, typename VT>
-static void pipe_any(const Layout &L, const VT *vals, const double *x, double *y, double *partials,
-                     PcgState *st) {
-  constexpr int WARPS = 8;
-  const unsigned grid = std::min<unsigned>((L.ns + WARPS - 1) / WARPS, 5u);  // > 1 slice per warp
-  uint32_t wmaxw = 0;
-  for (uint32_t s_ = 0; s_ < L.ns; s_++)
-    wmaxw = std::max(wmaxw, L.meta[s_].y & 0x7fffffffu);
-  const uint32_t stage = (wmaxw * 32 * (uint32_t)sizeof(VT) + 127u) & ~127u;
-  simt::launch(grid, WARPS * 32, [&] {
-    if (wmaxw <= 8)
-      k_spmv_sellc_tma<DOT, VT, WARPS, 8>(L.meta, L.cols, L.dcols, vals, L.perm, x, y, 0, L.ns, 0, 0, L.n,
-                                          DOT ? partials : nullptr, 0, DOT ? grid : 0u, DOT ? st : nullptr,
-                                          DOT ? &st->pq : nullptr, NOXR, stage, L.wmax);
-    else
-      k_spmv_sellc_tma<DOT, VT, WARPS, 32>(L.meta, L.cols, L.dcols, vals, L.perm, x, y, 0, L.ns, 0, 0, L.n,
-                                           DOT ? partials : nullptr, 0, DOT ? grid : 0u, DOT ? st : nullptr,
-                                           DOT ? &st->pq : nullptr, NOXR, stage, L.wmax);
-  });
-}
 template <bool DOT, typename VT>
 static void plain_launch(const Layout &L, const VT *vals, unsigned grid, const double *x, double *y,
                          double *partials, PcgState *st) {
@@ -68,10 +46,6 @@ static void spmv(const Layout &L, unsigned grid, const double *x, double *y, boo
   case 1: plain_launch<true, double>(L, L.vals, grid, x, y, partials, st); break;
   case 2: plain_launch<false, float>(L, L.vals32, grid, x, y, partials, st); break;
   case 3: plain_launch<true, float>(L, L.vals32, grid, x, y, partials, st); break;
-  case 4: pipe_any<false, double>(L, L.vals, x, y, partials, st); break;
-  case 5: pipe_any<true, double>(L, L.vals, x, y, partials, st); break;
-  case 6: pipe_any<false, float>(L, L.vals32, x, y, partials, st); break;
-  default: pipe_any<true, float>(L, L.vals32, x, y, partials, st); break;
   }
 }
 
@@ -209,26 +183,6 @@ extern "C" int emul_rowmajor(int long_kernel, unsigned grid, uint32_t nrows, con
 // ---- the two-launch form of the overlapped multi-GPU SpMV: interior slices, then
 // boundary slices, ONE fused dot product (the partial slots and the ticket span
 // both launches; the last CTA of the second launch adds all of them) -----------------
-template <typename VT>
-static void two_phase_pipe(const Layout &L, const VT *vals, const double *x, double *y, uint32_t ib,
-                           uint32_t ie, double *partials, PcgState *st) {
-  constexpr int WARPS = 8;
-  const unsigned g1 = std::max(1u, std::min<unsigned>((ie - ib + WARPS - 1) / WARPS, 3u)),
-                 g2 = std::max(1u, std::min<unsigned>((ib + (L.ns - ie) + WARPS - 1) / WARPS, 3u));
-  uint32_t wmaxw = 0;
-  for (uint32_t s_ = 0; s_ < L.ns; s_++)
-    wmaxw = std::max(wmaxw, L.meta[s_].y & 0x7fffffffu);
-  const uint32_t stage = (wmaxw * 32 * (uint32_t)sizeof(VT) + 127u) & ~127u;
-  simt::launch(g1, WARPS * 32, [&] {
-    k_spmv_sellc_tma<true, VT, WARPS, 32>(L.meta, L.cols, L.dcols, vals, L.perm, x, y, ib, ie, 0, 0, L.n,
-                                          partials, 0, g1 + g2, st, &st->pq, NOXR, stage, L.wmax);
-  });
-  simt::launch(g2, WARPS * 32, [&] {
-    k_spmv_sellc_tma<true, VT, WARPS, 32>(L.meta, L.cols, L.dcols, vals, L.perm, x, y, 0, ib, ie, L.ns,
-                                          L.n, partials, g1, g1 + g2, st, &st->pq, NOXR, stage, L.wmax);
-  });
-}
-
 extern "C" int emul_spmv_two_phase(uint32_t n, uint32_t ns, const uint4 *meta, const uint32_t *cols,
                                    const int32_t *dcols, const double *vals, const float *vals32,
                                    int kernel, int wmax, uint32_t ib, uint32_t ie, const double *x,
@@ -238,11 +192,7 @@ extern "C" int emul_spmv_two_phase(uint32_t n, uint32_t ns, const uint4 *meta, c
   std::vector<double> partials((size_t)stride * 3, 0.0);
   PcgState st;
   std::memset(&st, 0, sizeof st);
-  if (kernel == 2)
-    two_phase_pipe<double>(L, vals, x, y, ib, ie, partials.data(), &st);
-  else if (kernel == 3)
-    two_phase_pipe<float>(L, vals32, x, y, ib, ie, partials.data(), &st);
-  else {
+  {
     const unsigned g1 = (ie - ib + SPMV_WARPS - 1) / SPMV_WARPS,
                    g2 = (ib + (ns - ie) + SPMV_WARPS - 1) / SPMV_WARPS;
     simt::launch(g1, SPMV_THREADS, [&] {
@@ -256,39 +206,6 @@ extern "C" int emul_spmv_two_phase(uint32_t n, uint32_t ns, const uint4 *meta, c
   }
   *dot_out = st.pq;
   return st.ticket[0] == 0 ? 0 : 1;  // the last CTA must have reset the ticket
-}
-
-// y = A x with the bulk-copy-fed kernel alone (no dot): every path of it against a CSR
-// product -- uniform and explicit slices, ragged tails, permuted lists, the two-range form
-extern "C" int emul_sellc_tma(int f64, int stages, unsigned grid, const uint4 *meta,
-                              const uint32_t *cols, const int32_t *dcols, const void *vals,
-                              const uint32_t *perm, const double *x, double *y, uint32_t b0,
-                              uint32_t e0, uint32_t b1, uint32_t e1, uint32_t n_rows, uint32_t wmax) {
-  constexpr int WARPS = 8;
-  const uint32_t stage = (wmax * 32 * (f64 ? 8u : 4u) + 127u) & ~127u;
-  if (f64)
-    simt::launch(grid, WARPS * 32, [&] {
-      if (wmax <= 8)
-        k_spmv_sellc_tma<false, double, WARPS, 8>(meta, cols, dcols, (const double *)vals, perm, x, y, b0,
-                                                  e0, b1, e1, n_rows, nullptr, 0, 0, nullptr, nullptr, NOXR,
-                                                  stage, stages);
-      else
-        k_spmv_sellc_tma<false, double, WARPS, 32>(meta, cols, dcols, (const double *)vals, perm, x, y, b0,
-                                                   e0, b1, e1, n_rows, nullptr, 0, 0, nullptr, nullptr, NOXR,
-                                                   stage, stages);
-    });
-  else
-    simt::launch(grid, WARPS * 32, [&] {
-      if (wmax <= 8)
-        k_spmv_sellc_tma<false, float, WARPS, 8>(meta, cols, dcols, (const float *)vals, perm, x, y, b0, e0,
-                                                 b1, e1, n_rows, nullptr, 0, 0, nullptr, nullptr, NOXR,
-                                                 stage, stages);
-      else
-        k_spmv_sellc_tma<false, float, WARPS, 32>(meta, cols, dcols, (const float *)vals, perm, x, y, b0, e0,
-                                                  b1, e1, n_rows, nullptr, 0, 0, nullptr, nullptr, NOXR,
-                                                  stage, stages);
-    });
-  return 0;
 }
 
 // ---- column blocking (csrc/colblock_kernels.cuh): cut a CSR into column ranges, then

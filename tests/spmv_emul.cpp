@@ -1,8 +1,7 @@
 // spmv_emul.cpp -- TEST INFRASTRUCTURE.  Compiles the bodies of the SELL SpMV
 // kernels (lsbench_b200/csrc/sell_kernels.cuh: k_spmv_sell, k_spmv_sellc) for the
 // host, with one-line stand-ins for the CUDA built-ins, and runs them thread by
-// thread over a launch grid.  (The bulk-copy-fed k_spmv_sellc_tma of sell_tma.cuh
-// has lanes that work together: it runs on the fiber emulator, pcg_emul.cpp.)  Without the fused dot product a thread talks to no other thread,
+// thread over a launch grid.  Without the fused dot product a thread talks to no other thread,
 // so running the threads one after another is exactly what the GPU computes.
 // The caller (tests/test_spmv_emul.py) builds the index-compressed SELL layout
 // of DESIGN.md section 2 with numpy and compares y with a CSR product bit for bit.
@@ -46,7 +45,6 @@ template <int NV, int NW>
 static void grid_sum_finish(const double (&)[NV], double *, unsigned, unsigned, unsigned,
                             unsigned *, double *, double *, const XrArgs &) {}
 
-#define B2_NO_TMA_KERNEL
 #include "sell_kernels.cuh"
 
 // ---- the default kernels: k_spmv_sellc (index-compressed) and k_spmv_sell ----------

@@ -95,21 +95,15 @@ def test_product_pcg_stopping_rules_on_the_emulator(emul, sr):
 
 @pytest.mark.parametrize("gen,N", [("poisson27", 8), ("poisson7", 10)])
 def test_every_spmv_kernel_inside_the_solve(emul, gen, N):
-    """the same solve with the SpMV + fused dot of each SELL kernel: the default
-    one on fp64 and on fp32-stored values, and the software-pipelined one (not yet
-    run on hardware) on both.  fp32 storage is exact for the stencils and a kernel
-    changes neither the row sums nor -- at equal grids -- the order of the dot
-    product: the iterates of the fp64 / fp32 default kernels are bit-identical, the
-    pipelined ones (other CTA sizes, other partial counts) agree to rounding"""
+    """the same solve with the SpMV + fused dot on fp64 and on fp32-stored values: fp32
+    storage is exact for the stencils and changes neither the row sums nor the order
+    of the dot product, so the iterates are bit-identical"""
     M = getattr(orc, "gen_" + gen)(N)
     b = orc.rhs(M.n)
-    runs = [solve(emul, M, b, kernel=k) for k in range(4)]
+    runs = [solve(emul, M, b, kernel=k) for k in range(2)]
     assert all(r[2] == 0 for r in runs)
     assert runs[0][0].tobytes() == runs[1][0].tobytes() and runs[0][1] == runs[1][1]
-    for x, it, st, rel in runs[2:]:
-        assert abs(it - runs[0][1]) <= 1
-        assert np.linalg.norm(x - runs[0][0]) / np.linalg.norm(runs[0][0]) <= 1e-10
-        assert orc.true_relres(M, b, x) <= 1e-10
+    assert orc.true_relres(M, b, runs[0][0]) <= 1e-10
 
 
 def nek_solve(emul, name, sr=False, tol=1e-10, maxit=5000):
@@ -244,8 +238,8 @@ def test_breakdown_is_reported_by_the_product_kernels(emul, sr):
 def test_two_launch_spmv_with_one_fused_dot(emul, gen, N):
     """what the overlapped multi-GPU SpMV launches: interior slices while the halo
     is in flight, boundary slices after it, ONE p.Ap -- the partial slots and the
-    ticket span both launches.  Default and pipelined kernels: y with the bits of
-    the CSR product, x.y to rounding, the ticket back at zero"""
+    ticket span both launches: y with the bits of the CSR product, x.y to rounding,
+    the ticket back at zero"""
     emul.emul_spmv_two_phase.argtypes = ([C.c_uint32, C.c_uint32] + [C.c_void_p] * 5 + [C.c_int, C.c_int,
                                          C.c_uint32, C.c_uint32] + [C.c_void_p] * 3)
     M = getattr(orc, "gen_" + gen)(N)
@@ -254,9 +248,9 @@ def test_two_launch_spmv_with_one_fused_dot(emul, gen, N):
     x = np.random.default_rng(9).standard_normal(M.n)
     want = orc.spmv_fma(M, x)
     ns = Lay["ns"]
-    wmax = 2      # ring depth of the bulk-copy-fed kernel
+    wmax = 0
     p = lambda a: a.ctypes.data
-    for kernel in (0, 2, 3):
+    for kernel in (0,):
         for ib, ie in ((ns // 4, 3 * ns // 4), (0, ns - 1), (1, ns)):
             y, d = np.full(M.n, np.nan), np.zeros(1)
             assert emul.emul_spmv_two_phase(M.n, ns, p(Lay["meta"]), p(Lay["ecols"]), p(Lay["dcols"]), p(vals),

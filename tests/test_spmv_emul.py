@@ -2,9 +2,7 @@
 tests/spmv_emul.cpp and run thread by thread over a launch grid: indexing and
 the order of the additions against the oracle's fma CSR product, bit for bit,
 without a GPU.  Covered: the default kernels k_spmv_sellc / k_spmv_sell
-(lsbench_b200/csrc/sell_kernels.cuh; fp64 and fp32 value streams) thread by thread,
-and the bulk-copy-fed k_spmv_sellc_tma (sell_tma.cuh: lanes work together through a
-shared-memory ring) on the fiber emulator of pcg_emul.cpp.  The index-compressed SELL layout (DESIGN.md
+(lsbench_b200/csrc/sell_kernels.cuh; fp64 and fp32 value streams).  The index-compressed SELL layout (DESIGN.md
 section 2, csrc/convert.cu k_sell_fill / k_slice_uniform / k_compact_cols) is
 restated here with numpy."""
 import ctypes as C
@@ -27,15 +25,6 @@ def emul(tmp_path_factory):
                     "-I", os.path.join(ROOT, "lsbench_b200", "csrc"),
                     os.path.join(ROOT, "tests", "spmv_emul.cpp"), "-o", so], check=True)
     L = C.CDLL(so)
-    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
-    so2 = str(tmp_path_factory.mktemp("emul") / "libpcg_emul.so")
-    subprocess.run(["/usr/bin/g++", "-std=c++20", "-O1", "-w", "-DB2_SIMT_EMUL", "-shared", "-fPIC",
-                    "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "lsbench_b200", "csrc"),
-                    "-I", os.path.join(cuda, "include"), "-I", os.path.join(ROOT, "tests"),
-                    os.path.join(ROOT, "tests", "pcg_emul.cpp"), "-o", so2], check=True)
-    L.fiber = C.CDLL(so2)
-    L.fiber.emul_sellc_tma.restype = C.c_int
-    L.fiber.emul_sellc_tma.argtypes = [C.c_int, C.c_int, C.c_uint] + [C.c_void_p] * 7 + [C.c_uint32] * 6
     L.emul_sellc.argtypes = [C.c_int, C.c_uint] + [C.c_void_p] * 7 + [C.c_uint32] * 5
     L.emul_sell.argtypes = [C.c_int, C.c_uint] + [C.c_void_p] * 6 + [C.c_uint32] * 5
     return L
@@ -86,22 +75,11 @@ def sellc_layout(M, perm=None):
 
 
 def run(emul, Lay, n, x, wmax, grid, ranges=None):
-    """every kernel on the same layout -- bulk-copy-fed (wmax: ring depths 2 and 3,
-    at most 5 CTAs so that a warp walks several slices), k_spmv_sellc and k_spmv_sell,
-    each with both value types; the answers must not differ"""
+    """every kernel on the same layout -- k_spmv_sellc and k_spmv_sell, each with both
+    value types; the answers must not differ"""
     b0, e0, b1, e1 = ranges or (0, Lay["ns"], 0, 0)
     p = lambda a: None if a is None else a.ctypes.data
     ys = []
-    for f64, vals in ((0, Lay["vals"]), (1, Lay["vals"].astype(np.float64))) if wmax else ():
-        for stages in (2, 3):
-            if Lay["wmax"] > 32 or 8 * stages * ((Lay["wmax"] * 32 * (8 if f64 else 4) + 127) & ~127) > 168 * 1024:
-                continue   # slices wider than a warp, or a ring that does not fit (spmv.cu tma_cfg):
-                           # the product takes the plain kernel
-            y = np.full(n, np.nan)
-            assert emul.fiber.emul_sellc_tma(f64, stages, min(grid, 5), p(Lay["meta"]), p(Lay["ecols"]),
-                                             p(Lay["dcols"]), p(vals), p(Lay["list"]), p(x), p(y),
-                                             b0, e0, b1, e1, n, Lay["wmax"]) == 0
-            ys.append(y)
     # the default kernels on the same layout: index-compressed and explicit columns
     for f64, vals in ((0, Lay["vals"]), (1, Lay["vals"].astype(np.float64))):
         y = np.full(n, np.nan)

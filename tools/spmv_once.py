@@ -1,5 +1,5 @@
 """A few SpMV launches on a generated stencil operator, for profiler captures:
-    [B200_SPMV_TMA=1] python tools/spmv_once.py [poisson27|poisson7] [N] [f32]"""
+    python tools/spmv_once.py [poisson27|poisson7] [N] [f32]"""
 import os
 import sys
 
