@@ -304,7 +304,7 @@ def main():
 
     def solve_host():
         x_host.zero_()
-        o, r = abi.PcgOpts(TOL, MAXIT, 0, abi.PCG_NO_SMALL), abi.PcgResult()
+        o, r = abi.PcgOpts(TOL, MAXIT, 0, flags), abi.PcgResult()
         rc = abi.load().b200_pcg_solve_host(M.h, b_host.data_ptr(), x_host.data_ptr(),
                                             abi.C.byref(o), abi.C.byref(r))
         if rc != 0:
@@ -418,6 +418,8 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": config_of(args.workload, iters),
             "run": {"parallelism": "row-block x%d" % world, "nnz_rank0": info.nnz,
+                    "halo": os.environ.get("B200_HALO", "peer memory where it can be mapped"),
+                    "allreduce": os.environ.get("B200_ALLREDUCE", "peer memory where it can be mapped"),
                     "device_GB_rank0": info.device_bytes / 1e9, "setup_s": t_setup,
                     "stream": "explicit torch.cuda.Stream shared with the library"},
             "parity": parity,

@@ -44,8 +44,9 @@ extern "C" {
 #endif
 
 /* 2: b200_mat_info grew (index compression), ingest and row-block entry points
- * 3: b200_mat_info.values_f32, b200_pcg_result.outer_iters, new flags */
-#define B200_ABI_VERSION 3
+ * 3: b200_mat_info.values_f32, b200_pcg_result.outer_iters, new flags
+ * 4: b200_pcg_result.replacements, status 4, Chebyshev flags; single-reduction flag gone */
+#define B200_ABI_VERSION 4
 
 enum {
   B200_OK = 0,
@@ -224,10 +225,16 @@ enum {
   B200_PCG_TIME_KERNELS = 1u << 0, /* per-class CUDA-event timing */
   B200_PCG_NO_GRAPH = 1u << 1,
   B200_PCG_NO_SMALL = 1u << 2,     /* never take the on-chip small-matrix path */
-  /* Chronopoulos-Gear CG -- both dot products of an iteration
-   * in one place (one reduction / one all-reduce point per iteration), two
-   * kernels per iteration instead of three, same HBM bytes.  Streaming path. */
-  B200_PCG_SINGLE_REDUCTION = 1u << 3
+  /* (1u << 3 was B200_PCG_SINGLE_REDUCTION, Chronopoulos-Gear CG: measured on 1, 2 and
+   * 8 B200 in round 2, slower everywhere -- 27-point 512^3 on 8 GPUs 1.199 s against
+   * 1.115 s -- and removed; profiles/r02_single_reduction_lost.txt) */
+  /* SURVEY 8f row 2, the preconditioner half: Chebyshev-Jacobi of degree 2 / 3 on the
+   * on-chip coarse-grid path (z = P(D^-1 A) D^-1 r, interval [lmax / 30, lmax]): one /
+   * two more products per iteration, about 1/2 / 1/3 of the iterations -- and of the
+   * cluster-wide reductions each of them waits for.  Ignored on the streaming path,
+   * where the product is the cost and CG is already optimal per product. */
+  B200_PCG_CHEBYSHEV2 = 1u << 4,
+  B200_PCG_CHEBYSHEV3 = 1u << 5
 };
 
 typedef struct {
@@ -243,7 +250,8 @@ typedef struct {
   float spmv_ms, update_ms, pupdate_ms; /* B200_PCG_TIME_KERNELS only */
   int32_t kernel_launches;
   int32_t path;        /* 0 = streaming kernels, 1 = on-chip small-matrix */
-  int32_t outer_iters; /* refinement passes (values_f32 == 2), else 0 */
+  int32_t outer_iters; /* refinement passes (values_f32 == 2); on the on-chip path the
+                          degree of the preconditioner that ran (1 = Jacobi); else 0 */
   int32_t replacements; /* residual replacements: exit checks that found ||b - A x|| above
                            the bar with the recurrence below it, after which the solve went on */
 } b200_pcg_result;

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libb200.so")
+LIB_PATH = os.environ.get("B200_LIB") or os.path.join(PKG, "libb200.so")   # (B200_LIB: A/B runs of two builds)
 
 HIST_BINS = 24
 NCCL_ID_BYTES = 128
@@ -28,7 +28,8 @@ GEN_POISSON7, GEN_POISSON27, GEN_POWERLAW = 1, 2, 3
 PCG_TIME_KERNELS = 1 << 0
 PCG_NO_GRAPH = 1 << 1
 PCG_NO_SMALL = 1 << 2
-PCG_SINGLE_REDUCTION = 1 << 3
+PCG_CHEBYSHEV2 = 1 << 4
+PCG_CHEBYSHEV3 = 1 << 5
 
 # every symbol include/b200.h declares (tests check the library exports them)
 SYMBOLS = [

@@ -158,10 +158,7 @@ struct PcgState {
   double true_rr;
   int iter, done, status, maxit;
   unsigned ticket[4];
-  // single-reduction CG (pcg.cu k_sr_update): alpha of the iteration by parity,
-  // iterations finished before the chunk being replayed / after it
-  double sr_alpha[2];
-  int sr_base, sr_next;
+  int replacements, pad0;  // residual replacements of the on-chip solve (small.cu)
 };
 
 struct b200_mat {
@@ -208,11 +205,9 @@ struct b200_mat {
   // --- solver workspace (lazily allocated) ----------------------------------
   double *w_r = nullptr, *w_p = nullptr, *w_q = nullptr;  // p has halo room
   double *w_x = nullptr;          // iterate (graph-stable pointer)
-  double *w_pp = nullptr, *w_s = nullptr;   // single-reduction CG: p and s = A p
   double *w_d = nullptr, *w_rhs = nullptr;  // refinement: correction and residual
   double *stage_b = nullptr, *stage_x = nullptr;  // b200_pcg_solve_host staging
   int grid_ew = 0;                // element-wise kernels
-  int grid_sr = 0;                // single-reduction update kernel
   unsigned partial_stride = 0;
   double *x_ext = nullptr;        // spmv staging: n_local + n_halo
   double *partials = nullptr;     // per-CTA partial sums, 4 lanes of them
@@ -229,7 +224,6 @@ struct b200_mat {
   int graph_chunk = 0;
   int graph_kernels = 0;         // kernel nodes in the captured chunk
   void *graph_stream = nullptr;
-  bool graph_sr = false;         // the chunk was captured in the single-reduction form
 };
 
 // ---- helpers implemented across the .cu files --------------------------------

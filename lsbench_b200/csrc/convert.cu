@@ -928,7 +928,7 @@ extern "C" int b200_mat_destroy(b200_mat *M) {
   halo_free(M);
   if (M->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)M->graph_exec);
   void *ptrs[] = {M->sell_off, M->sell_cols, M->sell_vals, M->sell_vals32, M->sell_perm,
-                  M->w_pp, M->w_s, M->w_d, M->w_rhs,
+                  M->w_d, M->w_rhs,
                   M->sell_meta, M->sell_dcols,
                   M->vec_row_ids, M->long_row_ids, M->vec_off, M->long_off,
                   M->vl_cols, M->vl_vals, M->dinv, M->row_len, M->w_r, M->w_p,

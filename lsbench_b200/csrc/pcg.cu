@@ -19,12 +19,6 @@
 // Every reduction has a fixed order (common.cuh grid_sum_finish), hence
 // bit-identical iterates and iteration counts run to run.
 //
-// the Chronopoulos-Gear form of
-// the same method -- two kernels per iteration, one place where sums are needed:
-//   K1' w = A u            + u.w                  (u = D^-1 r)
-//   K2' p = u + b p; s = w + b s; x += a p; r -= a s; u = D^-1 r  + r.u, r.r
-// with a = (r.u) / (u.w - b (r.u) / a_prev), the same 104 n vector bytes.
-//
 // SURVEY 8(f) row 4, matrices converted with B200_MAT_VALUES_F32 whose values do
 // not all survive the rounding: iterative refinement (pcg_refine below) -- inner
 // iterations stream the fp32 values, the residual b - A x the fp64 ones.
@@ -129,45 +123,16 @@ static int queue_iteration(b200_mat *M, int par, unsigned seq, cudaEvent_t *ev =
   return B200_OK;
 }
 
-// One single-reduction iteration: K2' then K1'.  On several ranks the sums go
-// through the NCCL all-reduce (the peer-memory mailboxes are sequenced for the
-// three-kernel iteration; a single exchange point per iteration is what this
-// form allows next).
-static int queue_iteration_sr(b200_mat *M, int idx, cudaEvent_t *ev = nullptr) {
-  b200_ctx *c = M->ctx;
-  cudaStream_t s = c->stream;
-  PcgState *st = M->state;
-  const int nx = ((idx & 1) ^ 1) * 2;
-  if (ev) CU_TRY(cudaEventRecord(ev[0], s));  // ev: before K2', between, after K1'
-  k_sr_update<<<M->grid_sr, EW_THREADS, 0, s>>>(
-      M->n_local, M->w_x, M->w_r, M->w_pp, M->w_s, M->w_q, M->w_p, M->dinv, M->partials,
-      M->partial_stride, st, idx, sum_target(M, &st->red[nx], &st->loc[nx]));
-  B_TRY(reduce_ranks(M, &st->red[nx], &st->loc[nx], 2));
-  if (ev) CU_TRY(cudaEventRecord(ev[1], s));
-  B_TRY(spmv_full_internal(M, M->w_p, M->w_q, true, nullptr));  // K1'
-  B_TRY(reduce_ranks(M, &st->pq, &st->pq_loc, 1));
-  if (ev) CU_TRY(cudaEventRecord(ev[2], s));
-  c->launches += 1;
-  CU_TRY(cudaGetLastError());
-  return B200_OK;
-}
-
-static int queue_chunk(b200_mat *M, int chunk, bool sr) {
-  if (sr) {
-    k_sr_chunk_begin<<<1, 1, 0, M->ctx->stream>>>(M->state, chunk);
-    M->ctx->launches += 1;
-  }
-  if (!sr)
-    B_TRY(xr_chunk_begin(M->ctx, (unsigned)chunk));
+static int queue_chunk(b200_mat *M, int chunk) {
+  B_TRY(xr_chunk_begin(M->ctx, (unsigned)chunk));
   for (int i = 0; i < chunk; i++)
-    B_TRY(sr ? queue_iteration_sr(M, i) : queue_iteration(M, i & 1, (unsigned)i + 1u));
+    B_TRY(queue_iteration(M, i & 1, (unsigned)i + 1u));
   return B200_OK;
 }
 
 // One graph = `chunk` (even) iterations; replayed until the device says done.
-static int ensure_graph(b200_mat *M, int chunk, bool sr) {
-  if (M->graph_exec && M->graph_chunk == chunk && M->graph_stream == (void *)M->ctx->stream &&
-      M->graph_sr == sr)
+static int ensure_graph(b200_mat *M, int chunk) {
+  if (M->graph_exec && M->graph_chunk == chunk && M->graph_stream == (void *)M->ctx->stream)
     return B200_OK;
   if (M->graph_exec) {
     cudaGraphExecDestroy((cudaGraphExec_t)M->graph_exec);
@@ -178,7 +143,7 @@ static int ensure_graph(b200_mat *M, int chunk, bool sr) {
   CU_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
   int rc = B200_OK;
   const uint64_t before = M->ctx->launches;
-  rc = queue_chunk(M, chunk, sr);
+  rc = queue_chunk(M, chunk);
   cudaError_t e = cudaStreamEndCapture(s, &g);
   M->graph_kernels = (int)(M->ctx->launches - before);
   M->ctx->launches = before;  // captured, not launched
@@ -189,7 +154,6 @@ static int ensure_graph(b200_mat *M, int chunk, bool sr) {
   CU_TRY(cudaGraphInstantiate(&ge, g, 0));
   cudaGraphDestroy(g);
   M->graph_exec = ge, M->graph_chunk = chunk, M->graph_stream = (void *)s;
-  M->graph_sr = sr;
   return B200_OK;
 }
 
@@ -201,26 +165,12 @@ static int pcg_stream(b200_mat *M, const double *d_b, double *d_x,
   cudaStream_t s = c->stream;
   const uint64_t n = M->n_local;
   const bool timing = o->flags & B200_PCG_TIME_KERNELS;
-  const bool sr = o->flags & B200_PCG_SINGLE_REDUCTION;
-  if (sr && !M->w_pp) {
-    B_TRY(dev_alloc(M, (void **)&M->w_pp, (n + 2) * 8));
-    B_TRY(dev_alloc(M, (void **)&M->w_s, (n + 2) * 8));
-    // K2' holds more registers than K2 / K3: its own one-wave grid
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sr_update, EW_THREADS, 0) !=
-            cudaSuccess || per_sm < 1)
-      per_sm = 4;
-    uint64_t g = (uint64_t)c->sm_count * per_sm, need = (n + EW_THREADS - 1) / EW_THREADS;
-    g = g > need ? need : g;
-    g = g > (uint64_t)M->grid_ew ? (uint64_t)M->grid_ew : g;  // never more partial slots than sized for
-    M->grid_sr = g < 1 ? 1 : (int)g;
-  }
   int chunk = o->check_every > 0 ? o->check_every : 32;
   chunk = (chunk + 1) & ~1;  // even: the parity pattern repeats per chunk
   // (several ranks: a graph only when nothing in the iteration is an NCCL call, i.e. the
   // sums and the halo both go over peer memory)
   const bool use_graph = !(o->flags & B200_PCG_NO_GRAPH) &&
-                         (c->nranks == 1 || (!sr && c->xr_on && M->halo.peer_ready));
+                         (c->nranks == 1 || (c->xr_on && M->halo.peer_ready));
   const uint64_t launches0 = c->launches;
 
   CU_TRY(cudaEventRecord(c->ev_a, s));
@@ -235,15 +185,6 @@ static int pcg_stream(b200_mat *M, const double *d_b, double *d_x,
   B_TRY(reduce_ranks(M, &M->state->red[4], &M->state->loc[4], 3));
   k_pcg_start<<<1, 1, 0, s>>>(M->state, o->tol, o->maxit);
   c->launches += 2;
-  if (sr) {
-    // w_p holds u = D^-1 r; p = s = 0; w = A u with u.w
-    k_sr_start<<<1, 1, 0, s>>>(M->state);
-    CU_TRY(cudaMemsetAsync(M->w_pp, 0, n * 8, s));
-    CU_TRY(cudaMemsetAsync(M->w_s, 0, n * 8, s));
-    B_TRY(spmv_full_internal(M, M->w_p, M->w_q, true, nullptr));
-    B_TRY(reduce_ranks(M, &M->state->pq, &M->state->pq_loc, 1));
-    c->launches += 1;
-  }
   CU_TRY(cudaGetLastError());
 
   // ---- iterations ---------------------------------------------------------------
@@ -255,32 +196,15 @@ static int pcg_stream(b200_mat *M, const double *d_b, double *d_x,
     CU_TRY(cudaMemcpyAsync((void *)flag, &M->state->iter, 16, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaEventRecord(c->ev_poll, s));
     CU_TRY(cudaEventSynchronize(c->ev_poll));
-    // (single-reduction: the stopping test of iteration k sits at the head of
-    // iteration k + 1, so one more than maxit may have to be queued)
-    if (flag[1] || queued >= o->maxit + (sr ? 1 : 0))
+    if (flag[1] || queued >= o->maxit)
       break;
     if (timing && timed_iters == 0) {
       // per-class device time over one chunk, events on the launch stream
       cudaEvent_t ev[4];
       for (auto &e : ev)
         CU_TRY(cudaEventCreate(&e));
-      if (sr) {
-        k_sr_chunk_begin<<<1, 1, 0, s>>>(M->state, chunk);
-        c->launches += 1;
-      }
-      if (!sr)
-        B_TRY(xr_chunk_begin(c, (unsigned)chunk));
+      B_TRY(xr_chunk_begin(c, (unsigned)chunk));
       for (int i = 0; i < chunk; i++) {
-        if (sr) {
-          B_TRY(queue_iteration_sr(M, i, ev));
-          CU_TRY(cudaEventSynchronize(ev[2]));
-          float t;
-          CU_TRY(cudaEventElapsedTime(&t, ev[0], ev[1]));
-          t_cls[1] += t;
-          CU_TRY(cudaEventElapsedTime(&t, ev[1], ev[2]));
-          t_cls[0] += t;
-          continue;
-        }
         B_TRY(queue_iteration(M, i & 1, (unsigned)i + 1u, ev));
         CU_TRY(cudaEventSynchronize(ev[3]));
         for (int k = 0; k < 3; k++) {
@@ -293,11 +217,11 @@ static int pcg_stream(b200_mat *M, const double *d_b, double *d_x,
       for (auto &e : ev)
         cudaEventDestroy(e);
     } else if (use_graph) {
-      B_TRY(ensure_graph(M, chunk, sr));
+      B_TRY(ensure_graph(M, chunk));
       CU_TRY(cudaGraphLaunch((cudaGraphExec_t)M->graph_exec, s));
       c->launches += M->graph_kernels;
     } else {
-      B_TRY(queue_chunk(M, chunk, sr));
+      B_TRY(queue_chunk(M, chunk));
     }
     queued += chunk;
   }
@@ -325,7 +249,7 @@ static int pcg_stream(b200_mat *M, const double *d_b, double *d_x,
       h.status = 4;
       break;
     }
-    if (sr || h.status != 0 || h.iter == 0 || !(h.true_rr > h.thr2) || h.iter >= o->maxit ||
+    if (h.status != 0 || h.iter == 0 || !(h.true_rr > h.thr2) || h.iter >= o->maxit ||
         replacements >= B2_MAX_REPLACEMENTS)
       break;
     replacements++;
@@ -365,8 +289,6 @@ static int pcg_stream(b200_mat *M, const double *d_b, double *d_x,
 
   const int parity = h.iter & 1;  // {rz, rr} of the last finished iteration
   double rr = h.iter == 0 ? h.red[1] : h.red[parity * 2 + 1];
-  if (sr && h.status == 1 && rr <= h.thr2)
-    h.status = 0;  // the last queued iteration converged; no later kernel said so
   res->iters = h.iter, res->status = h.status;
   res->bnorm = sqrt(h.bb);
   res->relres = h.bb > 0 ? sqrt(rr / h.bb) : sqrt(rr);
@@ -483,7 +405,7 @@ extern "C" int b200_pcg_solve(b200_mat *M, const double *d_b, double *d_x,
   memset(res, 0, sizeof *res);
   if (!M->blocks.empty())
     B_FAIL(B200_EINVAL, "b200_pcg_solve: a column-blocked matrix (B200_MAT_COL_BLOCK) is SpMV-only");
-  if (!(o->flags & (B200_PCG_NO_SMALL | B200_PCG_SINGLE_REDUCTION)) && c->nranks == 1) {
+  if (!(o->flags & B200_PCG_NO_SMALL) && c->nranks == 1) {
     B_TRY(small_try_build(M));
     if (M->small)
       return small_solve(M, d_b, d_x, o, res);

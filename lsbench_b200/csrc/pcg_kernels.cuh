@@ -192,97 +192,6 @@ __global__ void k_pcg_resume(PcgState *st, int nx) {
   st->done = 0, st->status = 1;
 }
 
-// ---- single-reduction CG ----------------------------------------------------------
-__global__ void k_sr_start(PcgState *st) {
-  // first pass: beta = gamma / inf = 0, alpha = gamma / (delta - 0 * gamma / 1)
-  st->red[2] = __longlong_as_double(0x7ff0000000000000ll);
-  st->sr_alpha[0] = 1.0, st->sr_alpha[1] = 1.0;
-  st->sr_base = 0, st->sr_next = 0;
-}
-
-// head of every chunk of queued iterations (one per graph replay): the kernels
-// of the chunk know their index inside it, this is where the chunk starts
-__global__ void k_sr_chunk_begin(PcgState *st, int chunk) {
-  st->sr_base = st->sr_next;
-  st->sr_next += chunk;
-}
-
-// K2'.  idx: position of the iteration inside its chunk (chunks are even, so
-// idx & 1 is the parity of the iteration).  Everything a CTA reads to decide
-// and to form alpha / beta was written by earlier kernels; thread 0 of CTA 0
-// writes only what this kernel does not read.
-__global__ void __launch_bounds__(EW_THREADS)
-k_sr_update(uint64_t n, double *__restrict__ x, double *__restrict__ r,
-            double *__restrict__ p, double *__restrict__ sv,
-            const double *__restrict__ w, double *__restrict__ u,
-            const double *__restrict__ dinv, double *partials, unsigned stride,
-            PcgState *st, int idx, double *out) {
-  if (st->done)
-    return;
-  __shared__ double red[EW_WARPS];
-  const int par = idx & 1;
-  const int it = st->sr_base + idx;  // iterations finished before this one
-  const double gamma = st->red[par * 2], rr = st->red[par * 2 + 1];
-  const double gamma_prev = st->red[(par ^ 1) * 2];
-  const double delta = st->pq, alpha_prev = st->sr_alpha[par ^ 1];
-  const bool first = blockIdx.x == 0 && threadIdx.x == 0;
-  if (rr <= st->thr2) {
-    if (first)
-      st->done = 1, st->status = 0;
-    return;
-  }
-  if (!(rr == rr)) {
-    if (first)
-      st->done = 1, st->status = 2;
-    return;
-  }
-  if (it >= st->maxit) {
-    if (first)
-      st->done = 1;  // status stays 1
-    return;
-  }
-  const double beta = gamma / gamma_prev;
-  const double den = delta - beta * gamma / alpha_prev;  // = p.Ap
-  if (!(den > 0.0)) {  // not SPD, or NaN crept in
-    if (first)
-      st->done = 1, st->status = 2;
-    return;
-  }
-  const double alpha = gamma / den;
-  if (first)
-    st->sr_alpha[par] = alpha, st->iter = it + 1;
-  double s[2] = {0.0, 0.0};
-  const uint64_t stride_e = (uint64_t)gridDim.x * EW_THREADS;
-  uint64_t i = blockIdx.x * (uint64_t)EW_THREADS + threadIdx.x;
-  for (; i + stride_e < n; i += 2 * stride_e) {
-    const uint64_t j = i + stride_e;
-    double ri = r[i], di = __ldcs(dinv + i), pi = p[i], si = sv[i], wi = __ldcs(w + i), xi = x[i];
-    double rj = r[j], dj = __ldcs(dinv + j), pj = p[j], sj = sv[j], wj = __ldcs(w + j), xj = x[j];
-    pi = fma(beta, pi, di * ri), si = fma(beta, si, wi);
-    pj = fma(beta, pj, dj * rj), sj = fma(beta, sj, wj);
-    xi = fma(alpha, pi, xi), ri = fma(-alpha, si, ri);
-    xj = fma(alpha, pj, xj), rj = fma(-alpha, sj, rj);
-    const double ui = di * ri, uj = dj * rj;
-    p[i] = pi, sv[i] = si, x[i] = xi, r[i] = ri, u[i] = ui;
-    p[j] = pj, sv[j] = sj, x[j] = xj, r[j] = rj, u[j] = uj;
-    s[0] = fma(ri, ui, s[0]), s[1] = fma(ri, ri, s[1]);
-    s[0] = fma(rj, uj, s[0]), s[1] = fma(rj, rj, s[1]);
-  }
-  if (i < n) {
-    double ri = r[i], di = dinv[i], pi = p[i], si = sv[i], wi = w[i], xi = x[i];
-    pi = fma(beta, pi, di * ri), si = fma(beta, si, wi);
-    xi = fma(alpha, pi, xi), ri = fma(-alpha, si, ri);
-    const double ui = di * ri;
-    p[i] = pi, sv[i] = si, x[i] = xi, r[i] = ri, u[i] = ui;
-    s[0] = fma(ri, ui, s[0]), s[1] = fma(ri, ri, s[1]);
-  }
-  double bs[2];
-  bs[0] = block_sum<EW_WARPS>(s[0], red);
-  bs[1] = block_sum<EW_WARPS>(s[1], red);
-  grid_sum_finish<2, EW_WARPS>(bs, partials, stride, blockIdx.x, gridDim.x,
-                               &st->ticket[2], out, red);
-}
-
 // ---- refinement (B200_MAT_VALUES_F32, rounded values) ---------------------------------
 // rhs = b - q (q = A x with the fp64 values); sums ||rhs||^2 and ||b||^2
 __global__ void __launch_bounds__(EW_THREADS)

@@ -69,28 +69,42 @@ struct SmallPlan {
   uint16_t *d_cols = nullptr;
   long long *d_prof = nullptr;
   PcgState *d_state = nullptr;
+  // Chebyshev-Jacobi: bound of the spectrum of D^-1 A, largest degree whose shared
+  // memory fits, shared-memory bytes per degree
+  double lmax = 0.0;
+  int max_kdeg = 1;
+  size_t smem_k[4] = {0, 0, 0, 0};
   // largest per-CTA extents (shared memory carve-up is uniform)
   uint32_t max_ent = 0, max_groups = 0, max_stage = 0;
 };
 
 struct SmemMap {
-  size_t stage, zwin, vals, xs, rs, ds, qs, slots, wred, bars, win, goff, rowid, orig, dmask, cols, total;
+  size_t stage, zwin, dwin0, dwin1, vals, xs, rs, ds, qs, rhs, dds, zzs, slots, wred, bars, win, goff, rowid,
+      orig, dmask, cols, total;
 };
 
+// kdeg > 1 (Chebyshev-Jacobi): two more windows (the direction d of the polynomial
+// recurrence lands in them alternately) and three more vectors on the owned rows
 __host__ __device__ inline SmemMap smem_map(uint32_t max_ent, uint32_t max_groups,
-                                            uint32_t max_stage) {
+                                            uint32_t max_stage, int kdeg) {
   SmemMap m;
   size_t rows = (size_t)max_groups * 8, o = 0;
-  m.stage = o, o += ((size_t)max_stage + 1) / 2 * 2 * 8;
-  m.zwin = o, o += ((size_t)max_stage + 1) / 2 * 2 * 8;
+  const size_t win_bytes = ((size_t)max_stage + 1) / 2 * 2 * 8;
+  m.stage = o, o += win_bytes;
+  m.zwin = o, o += win_bytes;
+  m.dwin0 = o, o += kdeg > 1 ? win_bytes : 0;
+  m.dwin1 = o, o += kdeg > 2 ? win_bytes : 0;
   m.vals = o, o += (size_t)max_ent * 8;
   m.xs = o, o += rows * 8;
   m.rs = o, o += rows * 8;
   m.ds = o, o += rows * 8;
   m.qs = o, o += rows * 8;
+  m.rhs = o, o += kdeg > 1 ? rows * 8 : 0;
+  m.dds = o, o += kdeg > 1 ? rows * 8 : 0;
+  m.zzs = o, o += kdeg > 1 ? rows * 8 : 0;
   m.slots = o, o += 4 * SM_MAX_CLUSTER * 8;  // pq | rz | rr | bb
   m.wred = o, o += 3 * SM_WARPS * 8;
-  m.bars = o, o += 2 * 8;
+  m.bars = o, o += 4 * 8;
   m.win = o, o += 2 * SM_MAX_CLUSTER * 4;
   m.goff = o, o += ((size_t)max_groups + 2) * 4;
   m.rowid = o, o += rows * 4;
@@ -179,6 +193,14 @@ __device__ __forceinline__ double small_spmv(const SmallCta &me, const RegMat &R
   // conflicts of eight unrelated rows -- so batching the loads or keeping the
   // values in shared memory changes nothing; registers only free the
   // shared-memory port for the gathers.)
+  // (Round 2, ncu source page of this kernel: ~670 issued instructions per warp and
+  // iteration for ~40 fma -- the walk counted steps against group widths re-read from
+  // shared memory and branched twice per step.  Now a slot that is not in use multiplies
+  // by a stored 0.0, and one precomputed mask bit per slot says where a group ends.)
+  // (Round 2 tried a leaner walk -- unused slots multiply a stored 0.0, one mask bit per
+  // slot says where a group ends, no width re-read: 670 -> ~450 issued instructions per
+  // warp and iteration -- and measured it 1.5 - 7 % SLOWER on all seven Nek matrices
+  // (A/B of two builds, gpurun_out/r02m_small_*): removed.)
   {
     uint32_t g = warp, w = g < me.n_groups ? goff[g + 1] - goff[g] : 1u, t = 0;
     double s = 0.0;
@@ -298,7 +320,17 @@ __device__ __forceinline__ void read_totals(unsigned C, const double *slots, int
 
 // PROF: thread 0 of CTA 0 accumulates clock64() per phase into prof[0..5]
 // (spmv, wait 1, update + push, wait 2, p window, -) -- B200_SMALL_PROFILE=1.
-template <bool PROF>
+//
+// KDEG: degree of the Chebyshev-Jacobi preconditioner (Saad, Iterative
+// Methods, Alg. 12.1).  KDEG = 1 is plain Jacobi, z = D^-1 r.  KDEG = 2, 3:
+//   rh = D^-1 r;  d = rh / theta;  z = d
+//   KDEG - 1 times:  rh -= D^-1 (A d);  rho' = 1 / (2 sigma - rho);
+//                    d = rho' rho d + (2 rho' / delta) rh;  z += d;  rho = rho'
+// for the interval [lmax / 30, lmax] of D^-1 A: KDEG - 1 more products per iteration,
+// each behind one more exchange of d between the CTAs that share columns (its own
+// mbarrier, no all-reduce), and about 1 / KDEG of the iterations -- i.e. of the two
+// all-reduces that every iteration of this kernel waits for.
+template <bool PROF, int KDEG>
 __global__ void __launch_bounds__(SM_THREADS, 1)
 k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_goff,
             const uint32_t *__restrict__ g_rowid, const uint32_t *__restrict__ g_dmask,
@@ -307,18 +339,20 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
             const uint16_t *__restrict__ g_cols, const double *__restrict__ g_dinv,
             const double *__restrict__ b, double *__restrict__ x, PcgState *st,
             uint32_t max_ent, uint32_t max_groups, uint32_t max_stage, double tol,
-            int maxit, long long *prof) {
+            int maxit, long long *prof, double cheb_theta, double cheb_delta) {
   extern __shared__ __align__(16) unsigned char smem[];
   cg::cluster_group cl = cg::this_cluster();
   const unsigned C = cl.num_blocks(), rank = cl.block_rank();
   const SmallCta me = ctas[rank];
-  const SmemMap mp = smem_map(max_ent, max_groups, max_stage);
+  const SmemMap mp = smem_map(max_ent, max_groups, max_stage, KDEG);
   double *p_w = (double *)(smem + mp.stage), *z_w = (double *)(smem + mp.zwin);
+  double *d_w[2] = {(double *)(smem + mp.dwin0), (double *)(smem + (KDEG > 2 ? mp.dwin1 : mp.dwin0))};
+  double *rh_s = (double *)(smem + mp.rhs), *dd_s = (double *)(smem + mp.dds), *zz_s = (double *)(smem + mp.zzs);
   double *vals = (double *)(smem + mp.vals);
   double *x_s = (double *)(smem + mp.xs), *r_s = (double *)(smem + mp.rs);
   double *d_s = (double *)(smem + mp.ds), *q_s = (double *)(smem + mp.qs);
   double *slots = (double *)(smem + mp.slots), *wred = (double *)(smem + mp.wred);
-  uint64_t *bar_a = (uint64_t *)(smem + mp.bars), *bar_b = bar_a + 1;
+  uint64_t *bar_a = (uint64_t *)(smem + mp.bars), *bar_b = bar_a + 1, *bar_x = bar_a + 2;
   uint32_t *win_lo = (uint32_t *)(smem + mp.win), *win_n = win_lo + SM_MAX_CLUSTER;
   uint32_t *goff = (uint32_t *)(smem + mp.goff), *rowid = (uint32_t *)(smem + mp.rowid);
   uint32_t *dmask = (uint32_t *)(smem + mp.dmask), *orig = (uint32_t *)(smem + mp.orig);
@@ -349,7 +383,7 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
   for (uint32_t i = tid; i < me.col_n; i += SM_THREADS)
     p_w[i] = x[g_perm[me.col_lo + i]], z_w[i] = 0.0;  // the window of x0, for r = b - A x0
   if (tid == 0) {
-    bar_init(bar_a, 1), bar_init(bar_b, 1);
+    bar_init(bar_a, 1), bar_init(bar_b, 1), bar_init(bar_x, 1), bar_init(bar_x + 1, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -362,17 +396,57 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
   // the other one, which needed a contribution every CTA sends only after it
   // has itself passed phase k of the first: so no store can land in a phase,
   // a slot or a window that its receiver has not finished with.
-  uint32_t par_a = 0, par_b = 0;
+  uint32_t par_a = 0, par_b = 0, par_x[2] = {0, 0};
   const uint32_t my_bar_b = s_u32(bar_b), my_zw = s_u32(z_w);
-  // the value of owned row `row`, into the window of every CTA that reads it
-  // (mask: bit k set when some row of CTA k has an entry in column `row`, or
-  // owns it)
-  auto push = [&](uint32_t row, uint32_t mask, double v) {
+  // the value of owned row `row`, into the window `win` of every CTA that reads it,
+  // counted on that CTA's barrier `bar` (mask: bit k set when some row of CTA k has
+  // an entry in column `row`, or owns it)
+  auto push_to = [&](uint32_t win, uint32_t bar, uint32_t row, uint32_t mask, double v) {
     while (mask) {
       const unsigned k = __ffs(mask) - 1;
       mask &= mask - 1;
-      st_async_f64(s_remote(my_zw + (row - win_lo[k]) * 8u, k), v, s_remote(my_bar_b, k));
+      st_async_f64(s_remote(win + (row - win_lo[k]) * 8u, k), v, s_remote(bar, k));
     }
+  };
+  auto push = [&](uint32_t row, uint32_t mask, double v) { push_to(my_zw, my_bar_b, row, mask, v); };
+  // Chebyshev-Jacobi: zz_s = P(D^-1 A) D^-1 r_s on the owned rows (KDEG > 1 only).  Every
+  // exchange of d has its own barrier, used once per application; two applications are
+  // always separated by an all-to-all phase (barrier A or B), so no store of the next
+  // one can land in a phase or a window its receiver has not finished with.
+  const double cheb_sigma = cheb_theta / cheb_delta;
+  auto chebyshev = [&]() {
+    double rho = 1.0 / cheb_sigma;
+    if (tid == 0)
+      bar_arm(bar_x, me.n_recv * 8);
+    for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
+      const uint32_t row = rowid[i];
+      if (row == 0xffffffffu)
+        continue;
+      const double c = d_s[i] * r_s[i], dd = c / cheb_theta;
+      rh_s[i] = c, dd_s[i] = dd, zz_s[i] = dd;
+      push_to(s_u32(d_w[0]), s_u32(bar_x), row, dmask[i], dd);
+    }
+#pragma unroll
+    for (int j = 1; j < KDEG; j++) {
+      bar_wait(bar_x + (j - 1), par_x[j - 1]), par_x[j - 1] ^= 1;
+      small_spmv<false>(me, R, goff, vals, cols, rowid, d_w[(j - 1) & 1], q_s);  // t = A d
+      __syncthreads();
+      const double rhon = 1.0 / (2.0 * cheb_sigma - rho);
+      if (j + 1 < KDEG && tid == 0)
+        bar_arm(bar_x + j, me.n_recv * 8);
+      for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
+        const uint32_t row = rowid[i];
+        if (row == 0xffffffffu)
+          continue;
+        const double rh = fma(-d_s[i], q_s[i], rh_s[i]);
+        const double dd = fma(rhon * rho, dd_s[i], (2.0 * rhon / cheb_delta) * rh);
+        rh_s[i] = rh, dd_s[i] = dd, zz_s[i] += dd;
+        if (j + 1 < KDEG)
+          push_to(s_u32(d_w[j & 1]), s_u32(bar_x + j), row, dmask[i], dd);
+      }
+      rho = rhon;
+    }
+    __syncthreads();
   };
 
   // ---- r = b - A x0, z = D^-1 r, p = z ----------------------------------------------
@@ -381,11 +455,20 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
   if (tid == 0)
     bar_arm(bar_b, (3 * C + me.n_recv) * 8);
   double acc3[3] = {0.0, 0.0, 0.0}, tot3[3];
+  if (KDEG > 1) {
+    for (uint32_t i = tid; i < nslot; i += SM_THREADS)
+      if (rowid[i] != 0xffffffffu)
+        r_s[i] = b[orig[i]] - q_s[i];
+    __syncthreads();
+    chebyshev();
+  }
   for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
     uint32_t row = rowid[i];
     if (row == 0xffffffffu)
       continue;
-    double bi = b[orig[i]], ri = bi - q_s[i], zi = d_s[i] * ri;
+    double bi = b[orig[i]], ri = bi - q_s[i], zi = KDEG > 1 ? zz_s[i] : d_s[i] * ri;
+    if (KDEG > 1)
+      ri = r_s[i];
     r_s[i] = ri;
     push(row, dmask[i], zi);
     acc3[0] = fma(ri, zi, acc3[0]), acc3[1] = fma(ri, ri, acc3[1]), acc3[2] = fma(bi, bi, acc3[2]);
@@ -428,17 +511,37 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
     if (tid == 0)
       bar_arm(bar_b, (2 * C + me.n_recv) * 8);
     double a2[2] = {0.0, 0.0}, t2[2];
-    for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
-      uint32_t row = rowid[i];
-      if (row == 0xffffffffu)
-        continue;
-      double pi = p_w[row - me.col_lo];
-      x_s[i] = fma(alpha, pi, x_s[i]);
-      double ri = fma(-alpha, q_s[i], r_s[i]);
-      r_s[i] = ri;
-      const double zi = d_s[i] * ri;
-      push(row, dmask[i], zi);
-      a2[0] = fma(ri, zi, a2[0]), a2[1] = fma(ri, ri, a2[1]);
+    if (KDEG == 1) {
+      for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
+        uint32_t row = rowid[i];
+        if (row == 0xffffffffu)
+          continue;
+        double pi = p_w[row - me.col_lo];
+        x_s[i] = fma(alpha, pi, x_s[i]);
+        double ri = fma(-alpha, q_s[i], r_s[i]);
+        r_s[i] = ri;
+        const double zi = d_s[i] * ri;
+        push(row, dmask[i], zi);
+        a2[0] = fma(ri, zi, a2[0]), a2[1] = fma(ri, ri, a2[1]);
+      }
+    } else {
+      for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
+        uint32_t row = rowid[i];
+        if (row == 0xffffffffu)
+          continue;
+        x_s[i] = fma(alpha, p_w[row - me.col_lo], x_s[i]);
+        r_s[i] = fma(-alpha, q_s[i], r_s[i]);
+      }
+      __syncthreads();
+      chebyshev();
+      for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
+        uint32_t row = rowid[i];
+        if (row == 0xffffffffu)
+          continue;
+        const double ri = r_s[i], zi = zz_s[i];
+        push(row, dmask[i], zi);
+        a2[0] = fma(ri, zi, a2[0]), a2[1] = fma(ri, ri, a2[1]);
+      }
     }
     B2_TICK(2)
     send_partials<2>(C, rank, a2, wred, slots, 1, bar_b);
@@ -505,11 +608,18 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
   if (tid == 0)
     bar_arm(bar_b, (2 * C + me.n_recv) * 8);
   double a5[2] = {0.0, 0.0}, t5[2];
+  if (KDEG > 1) {
+    for (uint32_t i = tid; i < nslot; i += SM_THREADS)
+      if (rowid[i] != 0xffffffffu)
+        r_s[i] = b[orig[i]] - q_s[i];
+    __syncthreads();
+    chebyshev();
+  }
   for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
     uint32_t row = rowid[i];
     if (row == 0xffffffffu)
       continue;
-    const double ri = b[orig[i]] - q_s[i], zi = d_s[i] * ri;
+    const double ri = KDEG > 1 ? r_s[i] : b[orig[i]] - q_s[i], zi = KDEG > 1 ? zz_s[i] : d_s[i] * ri;
     r_s[i] = ri;
     push(row, dmask[i], zi);
     a5[0] = fma(ri, zi, a5[0]), a5[1] = fma(ri, ri, a5[1]);
@@ -539,9 +649,53 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
   if (rank == 0 && tid == 0) {
     st->iter = it, st->status = status, st->done = 1;
     st->bb = bb, st->red[1] = rr, st->pq = pq, st->true_rr = t4[0];
-    st->sr_next = replacements;
+    st->replacements = replacements;
   }
   cl.sync();  // nobody leaves while a neighbour may still be storing into it
+}
+
+// the instantiations: profiling on / off x preconditioner degree 1..3
+typedef void (*small_kernel_t)(const SmallCta *, const uint32_t *, const uint32_t *, const uint32_t *,
+                               const uint32_t *, const uint32_t *, const double *, const uint16_t *,
+                               const double *, const double *, double *, PcgState *, uint32_t, uint32_t,
+                               uint32_t, double, int, long long *, double, double);
+static small_kernel_t small_kernel(bool prof, int kdeg) {
+  if (prof)
+    return kdeg == 3 ? k_pcg_small<true, 3> : kdeg == 2 ? k_pcg_small<true, 2> : k_pcg_small<true, 1>;
+  return kdeg == 3 ? k_pcg_small<false, 3> : kdeg == 2 ? k_pcg_small<false, 2> : k_pcg_small<false, 1>;
+}
+
+// Upper bound of the spectrum of D^-1 A for the Chebyshev interval: min(Gershgorin
+// bound, 1.15 x the power-iteration estimate after 40 steps from the vector of ones)
+// (the checker restates the same rule).
+static double cheb_lmax(uint64_t n, const std::vector<uint64_t> &offs, const std::vector<uint32_t> &cols,
+                        const std::vector<double> &vals, const std::vector<double> &dinv) {
+  double gersh = 0.0;
+  for (uint64_t i = 0; i < n; i++) {
+    double t = 0.0;
+    for (uint64_t e = offs[i]; e < offs[i + 1]; e++)
+      t += fabs(vals[e]);
+    t *= fabs(dinv[i]);
+    gersh = t > gersh ? t : gersh;
+  }
+  std::vector<double> v(n, 1.0), w(n);
+  double lam = 0.0;
+  for (int it = 0; it < 40; it++) {
+    double nw = 0.0, nv = 0.0;
+    for (uint64_t i = 0; i < n; i++) {
+      double t = 0.0;
+      for (uint64_t e = offs[i]; e < offs[i + 1]; e++)
+        t += vals[e] * v[cols[e]];
+      w[i] = t * dinv[i];
+      nw += w[i] * w[i], nv += v[i] * v[i];
+    }
+    lam = sqrt(nw / nv);
+    const double sc = 1.0 / sqrt(nw);
+    for (uint64_t i = 0; i < n; i++)
+      v[i] = w[i] * sc;
+  }
+  const double est = 1.15 * lam;
+  return est < gersh ? est : gersh;
 }
 
 // ---------------------------------------------------------------------------
@@ -683,8 +837,11 @@ int small_try_build(b200_mat *M) {
 
   int dev_smem = 0;
   CU_TRY(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
-  CU_TRY(cudaFuncSetAttribute(k_pcg_small<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  CU_TRY(cudaFuncSetAttribute(k_pcg_small<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  for (int kd = 1; kd <= 3; kd++)
+    for (int pf = 0; pf < 2; pf++)
+      CU_TRY(cudaFuncSetAttribute((const void *)small_kernel(pf != 0, kd),
+                                  cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  const double lmax = cheb_lmax(n, offs, cols, vals, dinv);
 
   // B200_SMALL_CLUSTER=8|16 pins the cluster size (experiment switch)
   int only = 0;
@@ -786,17 +943,28 @@ int small_try_build(b200_mat *M) {
         ctas[k].n_recv += (readers[r] >> k) & 1u;
     for (size_t i = 0; i < rowid.size(); i++)
       dmask[i] = rowid[i] == 0xffffffffu ? 0u : readers[rowid[i]];
-    SmemMap mp = smem_map(max_ent, max_groups, max_stage);
+    SmemMap mp = smem_map(max_ent, max_groups, max_stage, 1);
     if (mp.total > (size_t)dev_smem)
       continue;
     SmallPlan *P = new SmallPlan();
     P->C = C, P->n = (uint32_t)n, P->smem = mp.total;
     P->max_ent = max_ent, P->max_groups = max_groups, P->max_stage = max_stage;
-    if (cudaFuncSetAttribute(k_pcg_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)mp.total) != cudaSuccess ||
-        cudaFuncSetAttribute(k_pcg_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)mp.total) != cudaSuccess) {
-      cudaGetLastError();
+    P->lmax = lmax;
+    bool fits = true;
+    for (int kd = 1; kd <= 3 && fits; kd++) {
+      const size_t bytes = smem_map(max_ent, max_groups, max_stage, kd).total;
+      if (bytes > (size_t)dev_smem)
+        break;
+      for (int pf = 0; pf < 2; pf++)
+        if (cudaFuncSetAttribute((const void *)small_kernel(pf != 0, kd),
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+          cudaGetLastError();
+          fits = false;
+        }
+      if (fits)
+        P->max_kdeg = kd, P->smem_k[kd] = bytes;
+    }
+    if (!P->smem_k[1]) {
       delete P;
       continue;
     }
@@ -804,7 +972,7 @@ int small_try_build(b200_mat *M) {
     cudaLaunchAttribute attr[1];
     small_launch_config(P, &cfg, attr, c->stream);
     int nclusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&nclusters, k_pcg_small<false>, &cfg) != cudaSuccess ||
+    if (cudaOccupancyMaxActiveClusters(&nclusters, (const void *)small_kernel(false, 1), &cfg) != cudaSuccess ||
         nclusters < 1) {
       cudaGetLastError();
       delete P;
@@ -843,16 +1011,25 @@ int small_solve(b200_mat *M, const double *d_b, double *d_x,
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
   small_launch_config(P, &cfg, attr, s);
+  // preconditioner degree: B200_PCG_CHEBYSHEV2 / 3 (or B200_SMALL_CHEB=2|3), at most what fits
+  static const int env_deg = [] {
+    const char *v = getenv("B200_SMALL_CHEB");
+    return v ? atoi(v) : 0;
+  }();
+  int kdeg = (o->flags & B200_PCG_CHEBYSHEV3) ? 3 : (o->flags & B200_PCG_CHEBYSHEV2) ? 2 : env_deg;
+  kdeg = kdeg < 1 ? 1 : kdeg > P->max_kdeg ? P->max_kdeg : kdeg;
+  cfg.dynamicSmemBytes = P->smem_k[kdeg];
+  const double la = P->lmax / 30.0, theta = 0.5 * (P->lmax + la), delta = 0.5 * (P->lmax - la);
   CU_TRY(cudaEventRecord(c->ev_a, s));
   static const bool prof = getenv("B200_SMALL_PROFILE") != nullptr;
-  CU_TRY(cudaLaunchKernelEx(&cfg, prof ? k_pcg_small<true> : k_pcg_small<false>,
+  CU_TRY(cudaLaunchKernelEx(&cfg, small_kernel(prof, kdeg),
                             (const SmallCta *)P->d_cta,
                             (const uint32_t *)P->d_goff, (const uint32_t *)P->d_rowid,
                             (const uint32_t *)P->d_dmask, (const uint32_t *)P->d_orig,
                             (const uint32_t *)P->d_perm, (const double *)P->d_vals, (const uint16_t *)P->d_cols,
                             (const double *)P->d_dinv, d_b, d_x,
                             P->d_state, P->max_ent, P->max_groups, P->max_stage,
-                            o->tol, (int)o->maxit, P->d_prof));
+                            o->tol, (int)o->maxit, P->d_prof, theta, delta));
   c->launches += 1;
   CU_TRY(cudaEventRecord(c->ev_b, s));
   PcgState h;
@@ -865,7 +1042,8 @@ int small_solve(b200_mat *M, const double *d_b, double *d_x,
   res->true_relres = h.bb > 0 ? sqrt(h.true_rr / h.bb) : sqrt(h.true_rr);
   res->kernel_launches = 1;
   res->path = 1;
-  res->replacements = h.sr_next;
+  res->replacements = h.replacements;
+  res->outer_iters = kdeg;  // (on this path: the degree of the preconditioner that ran)
   if (prof && h.iter > 0) {
     long long hp[6];
     CU_TRY(cudaMemcpy(hp, P->d_prof, sizeof hp, cudaMemcpyDeviceToHost));

@@ -77,12 +77,16 @@ static struct settings read_settings(void) {
    * (src/cusparse.c:55-63); the default mirrors the upper triangle. */
   if ((v = getenv("LSBENCH_B200_OPERATOR")) && strcmp(v, "full") == 0)
     s.flags = 0;
-  /* "sr": single-reduction (Chronopoulos-Gear) CG on the streaming kernels */
-  if ((v = getenv("LSBENCH_B200_PCG")) && strcmp(v, "sr") == 0)
-    s.pcg_flags |= B200_PCG_SINGLE_REDUCTION;
-  /* "stream": never the on-chip coarse-grid kernel, always the streaming kernels */
-  if (v && strcmp(v, "stream") == 0)
-    s.pcg_flags |= B200_PCG_NO_SMALL;
+  /* "stream": never the on-chip coarse-grid kernel, always the streaming kernels;
+   * "cheb2" / "cheb3": Chebyshev-Jacobi of that degree on the on-chip path */
+  if ((v = getenv("LSBENCH_B200_PCG"))) {
+    if (strcmp(v, "stream") == 0)
+      s.pcg_flags |= B200_PCG_NO_SMALL;
+    else if (strcmp(v, "cheb2") == 0)
+      s.pcg_flags |= B200_PCG_CHEBYSHEV2;
+    else if (strcmp(v, "cheb3") == 0)
+      s.pcg_flags |= B200_PCG_CHEBYSHEV3;
+  }
   if ((v = getenv("LSBENCH_B200_ORDERING"))) {
     if (strcmp(v, "cli") == 0)
       s.ordering = 1;

@@ -281,73 +281,6 @@ int orc_pcg_omp(const orc_op *M, const double *b, double *x, double tol,
   PCG_BODY(OMP_FOR, OMP_RED1, OMP_RED2, orc_spmv_omp)
 }
 
-/* ---- single-reduction CG (Chronopoulos & Gear 1989) ------
- * The same Krylov method with the two dot products of an iteration moved next
- * to each other, so a multi-GPU or on-chip solve pays one reduction per
- * iteration instead of two.  u = D^-1 r, w = A u; p and s = A p follow by
- * recurrence:
- *   r = b - A x0; u = D^-1 r; w = A u; gamma = r.u; delta = w.u; p = s = 0
- *   loop: stop if ||r|| <= tol ||b||
- *         beta = gamma / gamma_prev            (0 in the first pass)
- *         alpha = gamma / (delta - beta gamma / alpha_prev)     (= gamma / p.Ap)
- *         p = u + beta p; s = w + beta s; x += alpha p; r -= alpha s
- *         u = D^-1 r; gamma' = r.u; rr = r.r;  w = A u; delta = w.u
- * What csrc/pcg.cu runs with B200_PCG_SINGLE_REDUCTION. */
-int orc_pcg_sr(const orc_op *M, const double *b, double *x, double tol,
-               int maxit, int *iters, double *relres) {
-  int64_t n = (int64_t)M->n;
-  double *dinv = inv_diag(M);
-  double *r = (double *)calloc(5 * (size_t)n + 1, sizeof(double));
-  double *u = r + n, *w = u + n, *p = w + n, *s = p + n;
-  double bb = 0, gamma = 0, rr = 0, delta = 0;
-  orc_spmv(M, x, w, NULL);
-  for (int64_t i = 0; i < n; i++) {
-    r[i] = b[i] - w[i];
-    u[i] = dinv[i] * r[i];
-    bb += b[i] * b[i], gamma += r[i] * u[i], rr += r[i] * r[i];
-  }
-  orc_spmv(M, u, w, NULL);
-  for (int64_t i = 0; i < n; i++)
-    delta += w[i] * u[i];
-  double bnorm = sqrt(bb), thr = tol * bnorm;
-  double gamma_prev = INFINITY, alpha_prev = 1.0;
-  int it = 0, rc = 1;
-  while (it < maxit || sqrt(rr) <= thr) {
-    if (sqrt(rr) <= thr) {
-      rc = 0;
-      break;
-    }
-    double beta = gamma / gamma_prev;
-    double den = delta - beta * gamma / alpha_prev;
-    if (!(den > 0.0)) {
-      rc = 2;
-      break;
-    }
-    double alpha = gamma / den, gn = 0;
-    rr = 0;
-    for (int64_t i = 0; i < n; i++) {
-      p[i] = u[i] + beta * p[i];
-      s[i] = w[i] + beta * s[i];
-      x[i] += alpha * p[i];
-      double ri = r[i] - alpha * s[i];
-      r[i] = ri, u[i] = dinv[i] * ri;
-      gn += ri * u[i], rr += ri * ri;
-    }
-    it++;
-    gamma_prev = gamma, gamma = gn, alpha_prev = alpha;
-    orc_spmv(M, u, w, NULL);
-    delta = 0;
-    for (int64_t i = 0; i < n; i++)
-      delta += w[i] * u[i];
-  }
-  if (iters)
-    *iters = it;
-  if (relres)
-    *relres = bnorm > 0 ? sqrt(rr) / bnorm : sqrt(rr);
-  free(r), free(dinv);
-  return rc;
-}
-
 /* ---- fp32-stored operator + fp64 refinement --------------
  * What b200_pcg_solve does on a B200_MAT_VALUES_F32 matrix whose values do not
  * all survive the rounding to fp32: A32 = fl32(A); repeat { r = b - A x in
@@ -410,5 +343,128 @@ int orc_pcg_refine32(const orc_op *M, const double *b, double *x, double tol,
   if (relres)
     *relres = bb > 0 ? sqrt(rr / bb) : sqrt(rr);
   free(M32.vals), free(r);
+  return rc;
+}
+
+/* ---- Chebyshev-Jacobi preconditioned CG ---------------------------
+ * The reference reaches for algebraic multigrid on these systems (src/hypre.c:126-188
+ * BoomerAMG, src/amgx.c:78-85); a polynomial in D^-1 A is the preconditioner of that
+ * family that needs nothing but the product the solver already has.  Chebyshev
+ * iteration (Saad, Iterative Methods, Alg. 12.1) for B z = c with B = D^-1 A, c = D^-1 r,
+ * z0 = 0, eigenvalues of B assumed in [a, b]:
+ *   theta = (b + a) / 2, delta = (b - a) / 2, sigma = theta / delta, rho = 1 / sigma
+ *   rh = c; d = rh / theta; z = d
+ *   repeat degree - 1 times:  rh -= B d;  rho' = 1 / (2 sigma - rho);
+ *                             d = rho' rho d + (2 rho' / delta) rh;  z += d;  rho = rho'
+ * z = P(B) c with P a fixed polynomial, so the preconditioner is a fixed SPD operator
+ * as long as b bounds the spectrum, and CG theory applies unchanged. */
+double orc_cheb_lmax(const orc_op *M) {
+  const int64_t n = (int64_t)M->n;
+  double *dinv = inv_diag(M);
+  double gersh = 0.0;
+  for (int64_t i = 0; i < n; i++) {
+    double s = 0.0;
+    for (uint64_t k = M->offs[i]; k < M->offs[i + 1]; k++)
+      s += fabs(M->vals[k]);
+    s *= fabs(dinv[i]);
+    gersh = s > gersh ? s : gersh;
+  }
+  double *v = (double *)malloc(2 * (size_t)n * sizeof(double)), *w = v + n;
+  for (int64_t i = 0; i < n; i++)
+    v[i] = 1.0;
+  double lam = 0.0;
+  for (int it = 0; it < 40; it++) {
+    orc_spmv(M, v, w, NULL);
+    double nw = 0.0, nv = 0.0;
+    for (int64_t i = 0; i < n; i++) {
+      w[i] *= dinv[i];
+      nw += w[i] * w[i], nv += v[i] * v[i];
+    }
+    lam = sqrt(nw / nv);
+    const double s = 1.0 / sqrt(nw);
+    for (int64_t i = 0; i < n; i++)
+      v[i] = w[i] * s;
+  }
+  free(v), free(dinv);
+  const double est = 1.15 * lam;
+  return est < gersh ? est : gersh;
+}
+
+int orc_pcg_cheb(const orc_op *M, const double *b, double *x, double tol, int maxit,
+                 int degree, double lmax, double ratio, int *iters, double *relres) {
+  const int64_t n = (int64_t)M->n;
+  double *dinv = inv_diag(M);
+  double *r = (double *)malloc(7 * (size_t)n * sizeof(double));
+  double *p = r + n, *q = p + n, *z = q + n, *rh = z + n, *d = rh + n, *t = d + n;
+  const double lb = lmax, la = lmax / ratio;
+  const double theta = 0.5 * (lb + la), delta = 0.5 * (lb - la), sigma = theta / delta;
+#define ORC_CHEB_APPLY()                                                       \
+  do {                                                                         \
+    double rho = 1.0 / sigma;                                                  \
+    for (int64_t i = 0; i < n; i++) {                                          \
+      rh[i] = dinv[i] * r[i];                                                  \
+      d[i] = rh[i] / theta;                                                    \
+      z[i] = d[i];                                                             \
+    }                                                                          \
+    for (int j = 1; j < degree; j++) {                                         \
+      orc_spmv(M, d, t, NULL);                                                 \
+      const double rhon = 1.0 / (2.0 * sigma - rho);                           \
+      for (int64_t i = 0; i < n; i++) {                                        \
+        rh[i] -= dinv[i] * t[i];                                               \
+        d[i] = rhon * rho * d[i] + (2.0 * rhon / delta) * rh[i];               \
+        z[i] += d[i];                                                          \
+      }                                                                        \
+      rho = rhon;                                                              \
+    }                                                                          \
+  } while (0)
+  double bb = 0, rz = 0, rr = 0;
+  orc_spmv(M, x, q, NULL);
+  for (int64_t i = 0; i < n; i++) {
+    r[i] = b[i] - q[i];
+    bb += b[i] * b[i], rr += r[i] * r[i];
+  }
+  ORC_CHEB_APPLY();
+  for (int64_t i = 0; i < n; i++)
+    p[i] = z[i], rz += r[i] * z[i];
+  const double bnorm = sqrt(bb), thr = tol * bnorm;
+  int it = 0, rc = 1;
+  if (sqrt(rr) <= thr)
+    rc = 0;
+  while (rc == 1 && it < maxit) {
+    double pq = 0;
+    orc_spmv(M, p, q, NULL);
+    for (int64_t i = 0; i < n; i++)
+      pq += p[i] * q[i];
+    if (!(pq > 0.0)) {
+      rc = 2;
+      break;
+    }
+    const double alpha = rz / pq;
+    rr = 0;
+    for (int64_t i = 0; i < n; i++) {
+      x[i] += alpha * p[i];
+      r[i] -= alpha * q[i];
+      rr += r[i] * r[i];
+    }
+    it++;
+    if (sqrt(rr) <= thr) {
+      rc = 0;
+      break;
+    }
+    ORC_CHEB_APPLY();
+    double rzn = 0;
+    for (int64_t i = 0; i < n; i++)
+      rzn += r[i] * z[i];
+    const double beta = rzn / rz;
+    rz = rzn;
+    for (int64_t i = 0; i < n; i++)
+      p[i] = z[i] + beta * p[i];
+  }
+#undef ORC_CHEB_APPLY
+  if (iters)
+    *iters = it;
+  if (relres)
+    *relres = bnorm > 0 ? sqrt(rr) / bnorm : sqrt(rr);
+  free(r), free(dinv);
   return rc;
 }

@@ -80,9 +80,16 @@ int orc_pcg(const orc_op *M, const double *b, double *x, double tol,
             int maxit, int *iters, double *relres);
 int orc_pcg_omp(const orc_op *M, const double *b, double *x, double tol,
                 int maxit, int *iters, double *relres);
-/* Single-reduction CG (Chronopoulos-Gear), same contract. */
-int orc_pcg_sr(const orc_op *M, const double *b, double *x, double tol,
-               int maxit, int *iters, double *relres);
+/* SURVEY 8(f) row 2, the preconditioner half: Chebyshev-Jacobi.  z = P(D^-1 A) D^-1 r
+ * with P the degree-(k-1) Chebyshev polynomial for the interval [lmax / ratio, lmax]
+ * of D^-1 A (k = 1 is plain Jacobi): k - 1 more products per iteration, no more
+ * reductions, fewer iterations.  Same contract as orc_pcg.  What the on-chip
+ * coarse-grid kernel (csrc/small.cu) runs with B200_PCG_CHEBYSHEV. */
+int orc_pcg_cheb(const orc_op *M, const double *b, double *x, double tol, int maxit,
+                 int degree, double lmax, double ratio, int *iters, double *relres);
+/* Upper bound of the spectrum of D^-1 A the product uses: min(Gershgorin bound,
+ * 1.15 x power-iteration estimate after 40 steps from the vector of ones). */
+double orc_cheb_lmax(const orc_op *M);
 /* fp32-stored operator + fp64 iterative refinement; iters =
  * inner iterations in total, outer = refinement passes, relres = true one. */
 int orc_pcg_refine32(const orc_op *M, const double *b, double *x, double tol,

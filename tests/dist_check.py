@@ -117,7 +117,7 @@ def main():
     # ---- the ways the ranks can talk to each other must not change the answer -----------------
     # default: CG sums and the halo of p over peer memory, the chunk of iterations a CUDA graph;
     # B200_HALO=nccl: halo by ncclSend/Recv (no graph); B200_ALLREDUCE=nccl: sums by
-    # ncclAllReduce as well; plus the single-reduction iteration (NCCL sums).  A grid large
+    # ncclAllReduce as well.  A grid large
     # enough for several chunks of 32 iterations and a halo of two planes per neighbour.
     def fresh_ctx():
         t = torch.zeros(abi.NCCL_ID_BYTES, dtype=torch.uint8, device=dev)
@@ -131,8 +131,7 @@ def main():
     got = {}
     for mode, env, pflags in (("peer", {}, 0), ("peer_nograph", {}, abi.PCG_NO_GRAPH),
                               ("halo_nccl", {"B200_HALO": "nccl"}, 0),
-                              ("all_nccl", {"B200_ALLREDUCE": "nccl"}, 0),
-                              ("single_reduction", {}, abi.PCG_SINGLE_REDUCTION)):
+                              ("all_nccl", {"B200_ALLREDUCE": "nccl"}, 0)):
         for k in ("B200_HALO", "B200_ALLREDUCE"):
             os.environ.pop(k, None)
         os.environ.update(env)
@@ -153,7 +152,7 @@ def main():
     # the same sums in the same order: bit for bit, with or without the graph, whichever way the halo goes
     for mode in ("peer_nograph", "halo_nccl"):
         assert got[mode][0] == it0 and got[mode][1].tobytes() == x0.tobytes(), mode
-    for mode in ("all_nccl", "single_reduction"):
+    for mode in ("all_nccl",):
         assert abs(got[mode][0] - it0) <= 2, (mode, got[mode][0], it0)
         assert np.linalg.norm(got[mode][1] - x0) / np.linalg.norm(x0) <= 1e-9, mode
     if rank == 0:

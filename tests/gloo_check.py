@@ -122,30 +122,6 @@ def main():
             its += 1
             p = dinv * r + (rzn / rz) * p
             rz = rzn
-        # ---- the single-reduction form (pcg.cu k_sr_update): ONE all-reduce per iteration,
-        # carrying {r.u, r.r, u.w} -- where the multi-rank use of SURVEY 8(f) row 2 lies
-        xr_, r_ = np.zeros(nloc), b.copy()
-        u_ = dinv * r_
-        w_ = orc.spmv_fma(Ml, exchange(u_))
-        gam, rr_, dlt, _bb = allreduce([r_ @ u_, r_ @ r_, u_ @ w_, b @ b])
-        p_, s_ = np.zeros(nloc), np.zeros(nloc)
-        gam_prev, alpha_prev, its_sr, n_allreduce = np.inf, 1.0, 0, 0
-        while rr_ > 1e-20 * bb and its_sr < 2000:
-            beta = gam / gam_prev
-            alpha = gam / (dlt - beta * gam / alpha_prev)
-            p_ = u_ + beta * p_
-            s_ = w_ + beta * s_
-            xr_ += alpha * p_
-            r_ -= alpha * s_
-            u_ = dinv * r_
-            w_ = orc.spmv_fma(Ml, exchange(u_))
-            gam_prev, alpha_prev = gam, alpha
-            gam, rr_, dlt = allreduce([r_ @ u_, r_ @ r_, u_ @ w_])
-            its_sr += 1
-            n_allreduce += 1
-        assert n_allreduce == its_sr and abs(its_sr - its) <= 2, (its_sr, its)
-        assert np.linalg.norm(xr_ - x) <= 1e-9 * np.linalg.norm(x) + 1e-300
-
         xs = [torch.zeros(c[1] - c[0], dtype=torch.float64) for c in cuts]
         sizes = [c[1] - c[0] for c in cuts]
         mx = max(sizes)

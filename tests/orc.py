@@ -73,8 +73,6 @@ def lib():
             getattr(L, f).argtypes = [C.POINTER(_Op), C.c_void_p, C.c_void_p,
                                       C.c_double, C.c_int,
                                       C.POINTER(C.c_int), C.POINTER(C.c_double)]
-        L.orc_pcg_sr.restype = C.c_int
-        L.orc_pcg_sr.argtypes = L.orc_pcg.argtypes
         L.orc_pcg_refine32.restype = C.c_int
         L.orc_pcg_refine32.argtypes = [C.POINTER(_Op), C.c_void_p, C.c_void_p, C.c_double, C.c_int,
                                        C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_int),
@@ -270,14 +268,24 @@ def pcg(M, b, x0=None, tol=1e-10, maxit=10000, omp=False):
     return x, it.value, rel.value, rc
 
 
-def pcg_sr(M, b, x0=None, tol=1e-10, maxit=10000):
-    """single-reduction (Chronopoulos-Gear) Jacobi-PCG, oracle/krylov.c"""
+def cheb_lmax(M):
+    s = M.as_struct()
+    f = lib().orc_cheb_lmax
+    f.restype = C.c_double
+    return f(C.byref(s))
+
+
+def pcg_cheb(M, b, degree=2, lmax=None, ratio=30.0, x0=None, tol=1e-10, maxit=10000):
+    """Chebyshev-Jacobi preconditioned CG, oracle/krylov.c"""
     b = np.ascontiguousarray(b, dtype=np.float64)
     x = np.zeros(M.n) if x0 is None else np.array(x0, dtype=np.float64)
     it, rel = C.c_int(0), C.c_double(0)
     s = M.as_struct()
-    rc = lib().orc_pcg_sr(C.byref(s), b.ctypes.data, x.ctypes.data, tol, maxit,
-                          C.byref(it), C.byref(rel))
+    f = lib().orc_pcg_cheb
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double,
+                  C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    rc = f(C.byref(s), b.ctypes.data, x.ctypes.data, tol, maxit, degree,
+           cheb_lmax(M) if lmax is None else lmax, ratio, C.byref(it), C.byref(rel))
     return x, it.value, rel.value, rc
 
 

@@ -2,7 +2,7 @@
 // (lsbench_b200/csrc/pcg_kernels.cuh) and its SELL SpMV with the fused dot
 // product (sell_kernels.cuh), compiled for the host and run on the SIMT
 // emulator of simt_emul.hpp.  The loop around them restates what pcg.cu queues
-// (start-up, K1 K2 K3 per iteration, or K2' K1' in the single-reduction form);
+// (start-up, K1 K2 K3 per iteration, exit check and residual replacement);
 // the arithmetic -- every fma, every reduction tree -- is the product's.
 //   g++ -std=c++20 -O1 -DB2_SIMT_EMUL -I include -I lsbench_b200/csrc -I $CUDA/include
 #include <cuda_runtime.h>  // first: its own declarations of threadIdx etc. stay untouched
@@ -53,11 +53,11 @@ static void spmv(const Layout &L, unsigned grid, const double *x, double *y, boo
 extern "C" int emul_pcg(uint32_t n, uint32_t ns, const uint4 *meta, const uint32_t *cols,
                         const int32_t *dcols, const double *vals, const uint32_t *perm,
                         const double *dinv, const double *b, double *x, double tol, int maxit,
-                        int single_reduction, unsigned grid_spmv, unsigned grid_ew, int *iters,
+                        int /*unused*/, unsigned grid_spmv, unsigned grid_ew, int *iters,
                         int *status, double *relres, const float *vals32, int kernel, int wmax,
                         int *replacements, double *true_relres) {
   Layout L{n, ns, meta, cols, dcols, vals, perm, dinv, vals32, kernel, wmax};
-  std::vector<double> r(n + 2), p(n + 2), q(n + 2), pp(n + 2, 0.0), sv(n + 2, 0.0);
+  std::vector<double> r(n + 2), p(n + 2), q(n + 2);
   const unsigned stride = 148 * 32 * 3 + 64;
   std::vector<double> partials((size_t)stride * 3, 0.0);
   PcgState st;
@@ -69,25 +69,13 @@ extern "C" int emul_pcg(uint32_t n, uint32_t ns, const uint4 *meta, const uint32
     k_pcg_init(n, b, q.data(), dinv, r.data(), p.data(), partials.data(), stride, &st, &st.red[4]);
   });
   simt::launch(1, 1, [&] { k_pcg_start(&st, tol, maxit); });
-  if (single_reduction) {
-    simt::launch(1, 1, [&] { k_sr_start(&st); });
-    spmv(L, grid_spmv, p.data(), q.data(), true, partials.data(), &st);
-  }
   // ---- iterations, in chunks as the product queues them -----------------------------------
   const int chunk = 8;
   int queued = 0;
-  while (!st.done && queued < maxit + (single_reduction ? 1 : 0)) {
-    if (single_reduction)
-      simt::launch(1, 1, [&] { k_sr_chunk_begin(&st, chunk); });
+  while (!st.done && queued < maxit) {
     for (int i = 0; i < chunk; i++) {
       const int par = i & 1, nx = (par ^ 1) * 2;
-      if (single_reduction) {
-        simt::launch(grid_ew, EW_THREADS, [&] {
-          k_sr_update(n, x, r.data(), pp.data(), sv.data(), q.data(), p.data(), dinv,
-                      partials.data(), stride, &st, i, &st.red[nx]);
-        });
-        spmv(L, grid_spmv, p.data(), q.data(), true, partials.data(), &st);
-      } else {
+      {
         spmv(L, grid_spmv, p.data(), q.data(), true, partials.data(), &st);
         simt::launch(grid_ew, EW_THREADS, [&] {
           k_pcg_update(n, x, r.data(), p.data(), q.data(), dinv, partials.data(), stride, &st, par,
@@ -114,7 +102,7 @@ extern "C" int emul_pcg(uint32_t n, uint32_t ns, const uint4 *meta, const uint32
       st.status = 4;
       break;
     }
-    if (single_reduction || st.status != 0 || st.iter == 0 || !(st.true_rr > st.thr2) ||
+    if (st.status != 0 || st.iter == 0 || !(st.true_rr > st.thr2) ||
         st.iter >= maxit || replaced >= 4)
       break;
     replaced++;
@@ -149,8 +137,6 @@ extern "C" int emul_pcg(uint32_t n, uint32_t ns, const uint4 *meta, const uint32
     *true_relres = st.bb > 0 ? std::sqrt(st.true_rr / st.bb) : std::sqrt(st.true_rr);
   const int parity = st.iter & 1;
   double rr = st.iter == 0 ? st.red[1] : st.red[parity * 2 + 1];
-  if (single_reduction && st.status == 1 && rr <= st.thr2)
-    st.status = 0;
   *iters = st.iter, *status = st.status;
   *relres = st.bb > 0 ? std::sqrt(rr / st.bb) : std::sqrt(rr);
   return 0;

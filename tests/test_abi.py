@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(abi):
     L = ctypes.CDLL(abi.LIB_PATH)
     for s in declared_symbols():
         assert hasattr(L, s), s
-    assert abi.load().b200_abi_version() == 3
+    assert abi.load().b200_abi_version() == 4
 
 
 def test_struct_sizes_match_header(abi, tmp_path):

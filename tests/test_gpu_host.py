@@ -128,10 +128,10 @@ def test_driver_applies_the_ordering(bh, name, env, tmp_path):
         assert np.linalg.norm(x - g) / np.linalg.norm(g) <= 1e-8
 
 
-def test_driver_precision_fp32_and_single_reduction(bh, tmp_path):
+def test_driver_precision_fp32_and_chebyshev(bh, tmp_path):
     """--precision FP32 (fp32-stored operator: rounded on a Nek file -> refinement
-    passes, lossless on a stencil) and LSBENCH_B200_PCG=sr through the harness:
-    the same bars as the default run"""
+    passes, lossless on a stencil) and LSBENCH_B200_PCG=cheb2 (Chebyshev-Jacobi on the
+    on-chip kernel) through the harness: the same bars as the default run"""
     name = "xn3b_A_18"
     A = orc.matrix_read(orc.matrix_path(name))
     out = str(tmp_path / "x.bin")
@@ -147,12 +147,23 @@ def test_driver_precision_fp32_and_single_reduction(bh, tmp_path):
     r = subprocess.run([bh.DRIVER, "--solver", "b200", "--matrix", "poisson27:40", "--trials=2",
                         "--precision=FP32", "--verbose=1", "--dump-x", out],
                        capture_output=True, text=True, timeout=600,
-                       env=dict(os.environ, LSBENCH_B200_PCG="sr"))
+                       )
     assert r.returncode == 0, r.stderr
     row, ext = parse(r.stdout)
     assert int(ext[2]) == 0 and "precision=fp32 values lossless" in r.stdout
     M = orc.gen_poisson27(40)
     assert orc.true_relres(M, orc.rhs(M.n), np.fromfile(out)) <= 1e-10
+    r0 = subprocess.run([bh.DRIVER, "--solver", "b200", "--matrix", orc.matrix_path(name), "--trials=2"],
+                        capture_output=True, text=True, timeout=600)
+    r = subprocess.run([bh.DRIVER, "--solver", "b200", "--matrix", orc.matrix_path(name), "--trials=2",
+                        "--dump-x", out], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, LSBENCH_B200_PCG="cheb2"))
+    assert r.returncode == 0 and r0.returncode == 0, r.stderr
+    (_, e0), (_, e2) = parse(r0.stdout), parse(r.stdout)
+    assert int(e2[2]) == 0 and float(e2[4]) <= 1e-10 and int(e2[7]) == 1
+    assert int(e2[1]) < 0.62 * int(e0[1])                      # about half of Jacobi's iterations
+    x = np.fromfile(out)
+    assert np.linalg.norm(x - g) / np.linalg.norm(g) <= 1e-8
 
 
 def test_stock_lsbench_tree_with_b200_dropped_in(bh):

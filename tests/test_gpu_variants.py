@@ -3,9 +3,9 @@
   B200_MAT_VALUES_F32        SELL values stored as fp32 -- lossless on the
                              stencils (same bits as the fp64-stored matrix),
                              fp64 refinement otherwise (same fp64 bars)
-  B200_PCG_SINGLE_REDUCTION  Chronopoulos-Gear CG on the streaming kernels
+  B200_PCG_CHEBYSHEV2 / 3    Chebyshev-Jacobi on the on-chip coarse-grid kernel
 
-Oracles: oracle/krylov.c orc_pcg_sr / orc_pcg_refine32, the SuperLU direct
+Oracles: oracle/krylov.c orc_pcg_cheb / orc_pcg_refine32, the SuperLU direct
 solves (tests/golden/direct.npz), and the default fp64 path of the same library.
 """
 import os
@@ -122,68 +122,31 @@ def test_f32_values_rounded_then_refined(abi, ctx, name):
     Md.close()
 
 
-# ------------------------------------------------------------------ single-reduction CG
-@pytest.mark.parametrize("name", orc.NEK)
-def test_single_reduction_pcg_nek(abi, ctx, name):
+# ------------------------------------------------------------------ Chebyshev-Jacobi on the on-chip path
+@pytest.mark.parametrize("name", ["tj7a_A_12", "tj7a_A_18", "xn3b_A_10", "xn3b_A_18"])
+def test_chebyshev_jacobi_on_the_onchip_kernel(abi, ctx, name):
+    """SURVEY 8(f) row 2, the preconditioner half (B200_PCG_CHEBYSHEV2 / 3): the on-chip
+    coarse-grid kernel with a polynomial in D^-1 A as preconditioner against the
+    oracle's statement of the method (orc_pcg_cheb: same interval rule, iteration counts
+    within 2) and the direct solve (1e-8), at the 1e-10 bar on the true residual;
+    reproducible bit for bit; degree 1 is the kernel as it was."""
     A = orc.matrix_read(orc.matrix_path(name))
-    M = orc.op_upper_mirror(A)
-    Md = make(abi, ctx, A, abi.MAT_SYM_UPPER)
-    b = orc.rhs(M.n)
-    x, r, rc = Md.pcg_host(b, flags=abi.PCG_SINGLE_REDUCTION)
-    assert rc == 0 and r.status == 0 and r.path == 0 and r.relres <= 1e-10
-    assert orc.true_relres(M, b, x) <= 1e-10
-    xg = DIRECT[name]
-    assert np.linalg.norm(x - xg) / np.linalg.norm(xg) <= 1e-8
-    _, it_cpu, _, _ = orc.pcg_sr(M, b)
-    assert abs(r.iters - it_cpu) <= 3, (r.iters, it_cpu)
-    # bit-for-bit reproducible; graph replay, plain launches and the timed path agree
-    x2, r2, _ = Md.pcg_host(b, flags=abi.PCG_SINGLE_REDUCTION | abi.PCG_NO_GRAPH, check_every=6)
-    x3, r3, _ = Md.pcg_host(b, flags=abi.PCG_SINGLE_REDUCTION | abi.PCG_TIME_KERNELS)
-    assert r2.iters == r.iters == r3.iters and x2.tobytes() == x.tobytes() == x3.tobytes()
-    assert r3.spmv_ms > 0 and r3.update_ms > 0 and r3.pupdate_ms == 0
-    # two kernels per iteration instead of three
-    _, r4, _ = Md.pcg_host(b, flags=abi.PCG_NO_SMALL)
-    assert r.kernel_launches < 0.75 * r4.kernel_launches
-    Md.close()
-
-
-def test_single_reduction_pcg_edges(abi, ctx):
-    M = orc.gen_poisson7(16)
-    Md = make(abi, ctx, op_to_csr(M))
-    b = orc.rhs(M.n)
-    SR = abi.PCG_SINGLE_REDUCTION
-    xs, rs, _ = Md.pcg_host(b, flags=SR)
-    assert rs.status == 0 and orc.true_relres(M, b, xs) <= 1e-10
-    x, r, rc = Md.pcg_host(b, x0=xs, tol=1e-9, flags=SR)          # starting at the solution
-    assert (r.iters, r.status) == (0, 0)
-    x, r, rc = Md.pcg_host(b, maxit=5, flags=SR)                  # stops at maxit, says so
-    xc, itc, _, rcc = orc.pcg_sr(M, b, maxit=5)
-    assert (r.iters, r.status) == (5, 1) == (itc, rcc)
-    assert np.linalg.norm(x - xc) / np.linalg.norm(xc) < 1e-12
-    x, r, rc = Md.pcg_host(b, maxit=32, check_every=32, flags=SR)  # maxit on a chunk boundary
-    assert (r.iters, r.status) == (32, 1)
-    x, r, rc = Md.pcg_host(b, maxit=rs.iters, flags=SR)           # converges exactly at maxit
-    assert (r.iters, r.status) == (rs.iters, 0) and x.tobytes() == xs.tobytes()
-    Md.close()
-    A = orc.matrix_read(orc.matrix_path("A0_02x02"))              # indefinite: breakdown is reported
-    Md = make(abi, ctx, A)
-    x, r, rc = Md.pcg_host(np.array([1.0, -1.0]), flags=SR)
-    assert (rc, r.status) in ((5, 2), (0, 0))
-    Md.close()
-
-
-def test_single_reduction_with_f32_values_large_enough_to_leave_l2(abi, ctx):
-    """27-point 160^3 (4.1 M rows, 0.9 GB of matrix): both variants together
-    against the default path -- same solution, iteration counts within 1"""
-    M0 = abi.Matrix.generate(ctx, abi.GEN_POISSON27, 160, 1, 0)
-    M1 = abi.Matrix.generate(ctx, abi.GEN_POISSON27, 160, 1, abi.MAT_VALUES_F32)
-    assert M1.info().values_f32 == 1
-    n = M0.info().n_local
-    b = orc.rhs(n)
-    x0, r0, _ = M0.pcg_host(b)
-    x1, r1, _ = M1.pcg_host(b, flags=abi.PCG_SINGLE_REDUCTION)
-    assert r0.status == r1.status == 0 and abs(r0.iters - r1.iters) <= 1
-    assert np.linalg.norm(x1 - x0) / np.linalg.norm(x0) <= 1e-9
-    print("27-pt 160^3: default %.3f ms/it, f32 values + single reduction %.3f ms/it (%d / %d its)"
-          % (r0.solve_ms / r0.iters, r1.solve_ms / r1.iters, r0.iters, r1.iters))
-    M0.close(), M1.close()
+    Mo = orc.op_upper_mirror(A)
+    b = orc.rhs(Mo.n)
+    M = make(abi, ctx, A, abi.MAT_SYM_UPPER)
+    x1, r1, rc1 = M.pcg_host(b, tol=1e-10, maxit=5000)
+    assert rc1 == 0 and r1.path == 1 and r1.outer_iters == 1
+    for deg, fl in ((2, abi.PCG_CHEBYSHEV2), (3, abi.PCG_CHEBYSHEV3)):
+        x, r, rc = M.pcg_host(b, tol=1e-10, maxit=5000, flags=fl)
+        assert rc == 0 and r.status == 0 and r.path == 1 and r.outer_iters == deg
+        assert r.true_relres <= 1e-10 and orc.true_relres(Mo, b, x) <= 1e-10
+        assert np.linalg.norm(x - DIRECT[name]) / np.linalg.norm(DIRECT[name]) <= 1e-8
+        _, ito, _, rco = orc.pcg_cheb(Mo, b, degree=deg)
+        assert rco == 0 and abs(r.iters - ito) <= 2, (deg, r.iters, ito)
+        assert r.iters < 0.62 * r1.iters
+        x2, r2, _ = M.pcg_host(b, tol=1e-10, maxit=5000, flags=fl)
+        assert r2.iters == r.iters and x2.tobytes() == x.tobytes()
+    # the streaming path ignores the flag
+    xs, rs, _ = M.pcg_host(b, tol=1e-10, maxit=5000, flags=abi.PCG_NO_SMALL | abi.PCG_CHEBYSHEV2)
+    assert rs.path == 0 and rs.status == 0 and abs(rs.iters - r1.iters) <= 2
+    M.close()

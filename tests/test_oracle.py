@@ -261,39 +261,6 @@ def test_pcg_iteration_counts_poisson():
 
 
 # ---- the restatements the new GPU variants are held against
-@pytest.mark.parametrize("name", orc.NEK)
-def test_single_reduction_cg_is_the_same_method(name):
-    """Chronopoulos-Gear CG (oracle/krylov.c orc_pcg_sr): same iteration count
-    as the two-reduction form (+-2), same solution to the parity bar, residual
-    bar met; direct solve as the judge"""
-    A = orc.matrix_read(orc.matrix_path(name))
-    M = orc.op_upper_mirror(A)
-    b = orc.rhs(M.n)
-    x0, it0, _, _ = orc.pcg(M, b)
-    x1, it1, rel1, rc1 = orc.pcg_sr(M, b)
-    assert rc1 == 0 and rel1 <= 1e-10 and abs(it1 - it0) <= 2
-    assert orc.true_relres(M, b, x1) <= 1e-10
-    xg = DIRECT[name]
-    assert np.linalg.norm(x1 - xg) / np.linalg.norm(xg) < 1e-8
-
-
-def test_single_reduction_cg_edges():
-    M = orc.gen_poisson7(16)
-    b = orc.rhs(M.n)
-    x, it, rel, rc = orc.pcg_sr(M, b, maxit=5)            # stops at maxit, says so
-    xs, its, _, rcs = orc.pcg(M, b, maxit=5)
-    assert (it, rc) == (5, 1) == (its, rcs) and np.linalg.norm(x - xs) / np.linalg.norm(xs) < 1e-12
-    xf, itf, _, rcf = orc.pcg_sr(M, b)
-    x, it, rel, rc = orc.pcg_sr(M, b, x0=xf, tol=1e-9)    # starting at the solution
-    assert (it, rc) == (0, 0)
-    A = orc.matrix_read(orc.matrix_path("I1_05x05"))      # diagonal: one iteration, exact
-    x, it, rel, rc = orc.pcg_sr(orc.op_upper_mirror(A), orc.rhs(5))
-    assert (it, rc) == (1, 0)
-    np.testing.assert_allclose(x, [0, 1 / 2, 2 / 3, 3 / 4, 4 / 5], rtol=1e-15)
-    A = orc.matrix_read(orc.matrix_path("A0_02x02"))      # indefinite: breakdown, not garbage
-    assert orc.pcg_sr(orc.op_full(A), np.array([1.0, -1.0]))[3] in (0, 2)
-
-
 @pytest.mark.parametrize("name", ["tj7a_A_18", "xn3b_A_18"])
 def test_fp32_operator_with_fp64_refinement_meets_the_fp64_bar(name):
     """values rounded to fp32 (they do not survive: the Nek values carry 17
@@ -321,3 +288,34 @@ def test_fp32_storage_is_lossless_on_the_stencils():
         x0, it0, _, _ = orc.pcg(M, b)
         x, it, outer, rel, rc = orc.pcg_refine32(M, b)
         assert (it, outer, rc) == (it0, 0, 0) and x.tobytes() == x0.tobytes()
+
+
+# --------------------------------------------------------------------------- Chebyshev-Jacobi
+@pytest.mark.parametrize("name", ["tj7a_A_18", "xn3b_A_18"])
+def test_chebyshev_jacobi_pcg_restated(name):
+    """The polynomial preconditioner of the on-chip coarse-grid kernel, restated
+    (oracle/krylov.c orc_pcg_cheb): same solution as the direct solve to the 1e-8 bar at
+    the 1e-10 residual bar, the spectral bound really is one (checked against ARPACK),
+    and the point of it -- about 1/2 and 1/3 of Jacobi's iterations at degree 2 and 3,
+    i.e. of the reductions a latency-bound solve waits for."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as sla
+    A = orc.matrix_read(orc.matrix_path(name))
+    M = orc.op_upper_mirror(A)
+    b = orc.rhs(M.n)
+    S = M.scipy()
+    d = S.diagonal()
+    Bs = sp.diags(1 / np.sqrt(d)) @ S @ sp.diags(1 / np.sqrt(d))
+    lam = sla.eigsh(Bs, k=1, which="LA", return_eigenvectors=False)[0]
+    lmax = orc.cheb_lmax(M)
+    assert lam <= lmax <= 1.3 * lam
+    _, it1, _, rc1 = orc.pcg(M, b)
+    its = {}
+    for deg in (1, 2, 3):
+        x, it, rel, rc = orc.pcg_cheb(M, b, degree=deg)
+        assert rc == 0 and rel <= 1e-10 and orc.true_relres(M, b, x) <= 1e-10
+        assert np.linalg.norm(x - DIRECT[name]) / np.linalg.norm(DIRECT[name]) <= 1e-8
+        its[deg] = it
+    # degree 1 is Jacobi scaled by 1 / theta: the same Krylov iteration
+    assert abs(its[1] - it1) <= 2
+    assert 0.45 * it1 <= its[2] <= 0.60 * it1 and 0.30 * it1 <= its[3] <= 0.42 * it1
