@@ -907,7 +907,36 @@ extern "C" int b200_mat_from_csr(b200_ctx *c, uint32_t nrows, uint32_t base,
   CU_TRY(cudaSetDevice(c->device));
   *out = nullptr;
   PlainCsr A;
-  int rc = upload_csr(c, nrows, base, offs, cols, vals, &A);
+  int rc;
+  if (c->nranks > 1) {
+    // Several ranks, one host CSR: a rank uploads what ITS row block [r0, r1) is made of,
+    // not the whole matrix -- its own rows, and (upper triangle mirrored) the entries of
+    // the rows above that fall into its columns, which become its mirrored entries.  The
+    // rows it does not hold stay empty; the block is cut out after the mirror
+    // (dist.cu partition_and_renumber).  Filtered on the host in one pass.
+    uint64_t r0, r1;
+    b200_row_block(nrows, c->rank, c->nranks, &r0, &r1);
+    const bool sym = flags & B200_MAT_SYM_UPPER;
+    std::vector<uint32_t> fo((size_t)nrows + 1, 0u), fc;
+    std::vector<double> fv;
+    for (uint64_t i = sym ? 0 : r0; i < r1; i++) {
+      const bool own = i >= r0;
+      for (uint32_t e = offs[i]; e < offs[i + 1]; e++) {
+        const uint64_t cc = (uint64_t)cols[e] - base;
+        if (own || (cc >= r0 && cc < r1))
+          fc.push_back(cols[e]), fv.push_back(vals[e]);
+      }
+      fo[i + 1] = (uint32_t)fc.size();
+    }
+    for (uint64_t i = 0; i < nrows; i++)
+      if (fo[i + 1] < fo[i])
+        fo[i + 1] = fo[i];  // rows not held: empty
+    if (fc.empty())
+      fc.push_back(base), fv.push_back(0.0);
+    rc = upload_csr(c, nrows, base, fo.data(), fc.data(), fv.data(), &A);
+  } else {
+    rc = upload_csr(c, nrows, base, offs, cols, vals, &A);
+  }
   if (rc != B200_OK) {
     plain_free(&A);
     return rc;

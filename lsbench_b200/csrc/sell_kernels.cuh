@@ -13,7 +13,7 @@
 
 // One k-chunk of up to 8 entries of a slice: columns -> values -> gathers ->
 // fma in row order.  `colf(j)` yields the column of entry k + j.
-template <bool FULL, typename ColF>
+template <bool FULL, int NCH = 8, typename ColF>
 __device__ __forceinline__ double sell_chunk(const double *vp, const double *__restrict__ x,
                                              uint32_t k, uint32_t rem, double sum, ColF colf) {
   // A partial chunk (rem < 8 entries) clamps the ENTRY INDEX of the surplus loads to the
@@ -21,9 +21,9 @@ __device__ __forceinline__ double sell_chunk(const double *vp, const double *__r
   // (j < rem ? load : 0): that select consumes every load where it stands, and the loads
   // of a 3-entry tail go out one after the other, a round trip each (round 2, ncu source
   // page of the bulk-copy-fed kernel, where the same pattern cost 8 us per slice).
-  constexpr int N = FULL ? 8 : 7;
-  uint32_t c[8];
-  double a[8], xv[8];
+  constexpr int N = FULL ? NCH : NCH - 1;
+  uint32_t c[NCH];
+  double a[NCH], xv[NCH];
 #pragma unroll
   for (int j = 0; j < N; j++)
     c[j] = colf(FULL || (uint32_t)j < rem ? j : (int)rem - 1);
@@ -45,9 +45,10 @@ __device__ __forceinline__ double sell_chunk(const double *vp, const double *__r
 // the gathers and the fma chain run in two halves of 8, in row order, on the
 // values widened to fp64 -- when the stored fp32 equals the original fp64 the
 // result has the same bits as the fp64 kernel's.
-template <bool FULL, typename ColF>
+template <bool FULL, int NCH = 16, typename ColF>
 __device__ __forceinline__ double sell_chunk(const float *vp, const double *__restrict__ x,
                                              uint32_t k, uint32_t rem, double sum, ColF colf) {
+  static_assert(NCH == 16, "the fp32-value chunk is 16 entries");
   constexpr int N = FULL ? 16 : 15;
   float a[16];
   // (surplus loads of a partial chunk: entry index clamped, value never selected -- see above)
@@ -147,8 +148,11 @@ k_spmv_sell(const uint32_t *__restrict__ sell_off,
 // 5.73 ms in PCG; 6 CTAs/SM spills and loses again).  The fp32-value
 // instantiation holds 16 values per chunk and is compiled for 4 CTAs per SM
 // (64 registers; at 48 it spills 112 bytes in the loop).
+//
+// CHD: entries per chunk with fp64 values, 8 or 9.  A 27-wide row is 8 + 8 + 8 + 3 with
+// 8 (four dependent rounds of loads per slice) and 9 + 9 + 9 with 9 (three).
 #define SELLC_MINB 5
-template <bool DOT, typename VT, bool ACC = false>
+template <bool DOT, typename VT, bool ACC = false, int CHD = 8>
 __global__ void __launch_bounds__(SPMV_THREADS, sizeof(VT) == 8 ? SELLC_MINB : 4)
 k_spmv_sellc(const uint4 *__restrict__ meta, const uint32_t *__restrict__ cols,
              const int32_t *__restrict__ dcols, const VT *__restrict__ vals,
@@ -159,7 +163,7 @@ k_spmv_sellc(const uint4 *__restrict__ meta, const uint32_t *__restrict__ cols,
   if (DOT && st->done)
     return;
   __shared__ double red[SPMV_WARPS];
-  constexpr uint32_t CH = ChunkOf<VT>::n;
+  constexpr uint32_t CH = sizeof(VT) == 8 ? (uint32_t)CHD : ChunkOf<VT>::n;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t n0 = e0 - b0, nv = n0 + (e1 - b1);
   const uint32_t stride = gridDim.x * SPMV_WARPS;
@@ -178,21 +182,21 @@ k_spmv_sellc(const uint4 *__restrict__ meta, const uint32_t *__restrict__ cols,
     if (m.y >> 31) {
       const int32_t *dp = dcols + m.z;
       for (; k + CH <= w; k += CH)
-        sum = sell_chunk<true>(vp, x, k, CH, sum, [&](int j) {
+        sum = sell_chunk<true, (int)CH>(vp, x, k, CH, sum, [&](int j) {
           return row + (uint32_t)__ldg(dp + k + j);
         });
       if (k < w)
-        sum = sell_chunk<false>(vp, x, k, w - k, sum, [&](int j) {
+        sum = sell_chunk<false, (int)CH>(vp, x, k, w - k, sum, [&](int j) {
           return row + (uint32_t)__ldg(dp + k + j);
         });
     } else {
       const uint32_t *cp = cols + (size_t)m.z * B2_SLICE + lane;
       for (; k + CH <= w; k += CH)
-        sum = sell_chunk<true>(vp, x, k, CH, sum, [&](int j) {
+        sum = sell_chunk<true, (int)CH>(vp, x, k, CH, sum, [&](int j) {
           return ld_stream(cp + (size_t)(k + j) * B2_SLICE);
         });
       if (k < w)
-        sum = sell_chunk<false>(vp, x, k, w - k, sum, [&](int j) {
+        sum = sell_chunk<false, (int)CH>(vp, x, k, w - k, sum, [&](int j) {
           return ld_stream(cp + (size_t)(k + j) * B2_SLICE);
         });
     }

@@ -123,9 +123,23 @@ int launch_spmv(b200_mat *M, const double *x, double *y, bool dot, int phase,
       DOTV ? dot_out : nullptr, xr
     const uint4 *meta = (const uint4 *)M->sell_meta;
     const bool f32 = M->sell_vals32 && (M->spmv_use32 || !M->sell_vals);
+    // chunks of 9 where the rows are a multiple of 9 and not of 8 wide (27-point: 9 + 9 + 9
+    // instead of 8 + 8 + 8 + 3: three dependent rounds of loads per slice instead of four,
+    // same 48 registers; measured 2.420 against 2.472 ms at 400^3); B200_SPMV_CH=8 keeps 8
+    static const int ch_env = [] {
+      const char *v = getenv("B200_SPMV_CH");
+      return v ? atoi(v) : 0;
+    }();
+    const bool ch9 = !f32 && ch_env != 8 && M->sell_max_width % 9 == 0 && M->sell_max_width % 8 != 0;
 #define B2_SELL_LAUNCH(VT, VALS)                                                  \
   do {                                                                            \
-    if (dot && meta)                                                              \
+    if (dot && meta && ch9)                                                       \
+      k_spmv_sellc<true, VT, false, 9><<<P.g_sell, SPMV_THREADS, 0, s>>>(         \
+          meta, M->sell_cols, M->sell_dcols, VALS, B2_SELL_ARGS(true));           \
+    else if (meta && ch9)                                                         \
+      k_spmv_sellc<false, VT, false, 9><<<P.g_sell, SPMV_THREADS, 0, s>>>(        \
+          meta, M->sell_cols, M->sell_dcols, VALS, B2_SELL_ARGS(false));          \
+    else if (dot && meta)                                                         \
       k_spmv_sellc<true, VT><<<P.g_sell, SPMV_THREADS, 0, s>>>(                   \
           meta, M->sell_cols, M->sell_dcols, VALS, B2_SELL_ARGS(true));           \
     else if (meta)                                                                \

@@ -61,6 +61,20 @@ static void run_sellc(unsigned grid, const uint4 *meta, const uint32_t *cols, co
     }
 }
 
+// the same kernel with chunks of 9 entries (fp64 values; what 27-wide rows run)
+extern "C" int emul_sellc9(unsigned grid, const uint4 *meta, const uint32_t *cols, const int32_t *dcols,
+                           const double *vals, const uint32_t *perm, const double *x, double *y,
+                           uint32_t b0, uint32_t e0, uint32_t b1, uint32_t e1, uint32_t n_rows) {
+  gridDim.x = grid;
+  for (unsigned b = 0; b < grid; b++)
+    for (unsigned t = 0; t < SPMV_THREADS; t++) {
+      blockIdx.x = b, threadIdx.x = t;
+      k_spmv_sellc<false, double, false, 9>(meta, cols, dcols, vals, perm, x, y, b0, e0, b1, e1, n_rows,
+                                            nullptr, 0, 0, nullptr, nullptr, XrArgs{});
+    }
+  return 0;
+}
+
 extern "C" int emul_sellc(int f64, unsigned grid, const uint4 *meta, const uint32_t *cols,
                           const int32_t *dcols, const void *vals, const uint32_t *perm,
                           const double *x, double *y, uint32_t b0, uint32_t e0, uint32_t b1,

@@ -26,6 +26,7 @@ def emul(tmp_path_factory):
                     os.path.join(ROOT, "tests", "spmv_emul.cpp"), "-o", so], check=True)
     L = C.CDLL(so)
     L.emul_sellc.argtypes = [C.c_int, C.c_uint] + [C.c_void_p] * 7 + [C.c_uint32] * 5
+    L.emul_sellc9.argtypes = [C.c_uint] + [C.c_void_p] * 7 + [C.c_uint32] * 5
     L.emul_sell.argtypes = [C.c_int, C.c_uint] + [C.c_void_p] * 6 + [C.c_uint32] * 5
     return L
 
@@ -80,6 +81,10 @@ def run(emul, Lay, n, x, wmax, grid, ranges=None):
     b0, e0, b1, e1 = ranges or (0, Lay["ns"], 0, 0)
     p = lambda a: None if a is None else a.ctypes.data
     ys = []
+    y = np.full(n, np.nan)    # chunks of 9 (what the product runs on 27-wide rows), any width
+    assert emul.emul_sellc9(grid, p(Lay["meta"]), p(Lay["ecols"]), p(Lay["dcols"]),
+                            p(Lay["vals"].astype(np.float64)), p(Lay["list"]), p(x), p(y), b0, e0, b1, e1, n) == 0
+    ys.append(y)
     # the default kernels on the same layout: index-compressed and explicit columns
     for f64, vals in ((0, Lay["vals"]), (1, Lay["vals"].astype(np.float64))):
         y = np.full(n, np.nan)
