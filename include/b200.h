@@ -112,7 +112,7 @@ enum {
   B200_MAT_VALUES_F32 = 1u << 5,
   /* Column blocking for operators whose SpMV is bound by random gathers (the
    * power-law matrix: 101 B of DRAM traffic per 8-byte gather): the columns are
-   * cut into ranges of B200_COL_BLOCK_MB (environment, default 48) megabytes of
+   * cut into ranges of B200_COL_BLOCK_MB (environment, default 64) megabytes of
    * x, every range becomes a matrix of its own over all rows, and y = A x runs
    * as y = A_0 x; y += A_1 x; ... so that the gathers of one pass stay inside
    * one L2-sized piece of x.  Single rank, SpMV only (b200_pcg_solve refuses);

@@ -756,7 +756,7 @@ int build_layout(b200_ctx *c, PlainCsr *A, uint64_t n_global,
 // build_layout when blocking does not apply.
 int build_layout_or_blocks(b200_ctx *c, PlainCsr *A, uint64_t n_global, uint64_t row_begin,
                            uint32_t flags, b200_mat **out) {
-  uint64_t mb = 48;
+  uint64_t mb = 64;
   if (const char *v = getenv("B200_COL_BLOCK_MB"))
     if (atoll(v) > 0)
       mb = (uint64_t)atoll(v);

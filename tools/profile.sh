@@ -8,10 +8,10 @@ OUT=gpurun_out
 mkdir -p $OUT
 # (1) the bench line itself, then the launch list of the same command: per-launch
 #     device time, cold-cache and serialised -- compare SHARES of the step
-python bench.py --steps 2 --warmup 3 > $OUT/${TAG}_bench_n1.json 2> $OUT/${TAG}_bench_n1.err
-python bench.py --steps 1 --warmup 3 --no-cpu --no-spmv > $OUT/${TAG}_bench_plain.json 2> $OUT/${TAG}_bench_plain.err &&
+python bench.py --steps 3 --warmup 3 > $OUT/${TAG}_bench_n1.json 2> $OUT/${TAG}_bench_n1.err
+python bench.py --steps 1 --warmup 3 --no-cpu --no-extras > $OUT/${TAG}_bench_plain.json 2> $OUT/${TAG}_bench_plain.err &&
 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 600 --csv \
-    --log-file $OUT/${TAG}_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu --no-spmv \
+    --log-file $OUT/${TAG}_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu --no-extras \
     > $OUT/${TAG}_bench_ncu.log 2>&1
 # (2) DRAM traffic per launch of the three PCG kernels at the bench workload
 #     (single-pass metrics: no replay, no 45 GB save/restore)
