@@ -13,9 +13,9 @@
 
 // One k-chunk of up to 8 entries of a slice: columns -> values -> gathers ->
 // fma in row order.  `colf(j)` yields the column of entry k + j.
-template <bool FULL, int NCH = 8, typename ColF>
-__device__ __forceinline__ double sell_chunk(const double *vp, const double *__restrict__ x,
-                                             uint32_t k, uint32_t rem, double sum, ColF colf) {
+template <bool FULL, int NCH = 8, typename VT, typename ColF>
+__device__ __forceinline__ double sell_chunk_n(const VT *vp, const double *__restrict__ x,
+                                               uint32_t k, uint32_t rem, double sum, ColF colf) {
   // A partial chunk (rem < 8 entries) clamps the ENTRY INDEX of the surplus loads to the
   // chunk's last entry and leaves them unused; it must not select on the loaded VALUE
   // (j < rem ? load : 0): that select consumes every load where it stands, and the loads
@@ -23,7 +23,8 @@ __device__ __forceinline__ double sell_chunk(const double *vp, const double *__r
   // page of the bulk-copy-fed kernel, where the same pattern cost 8 us per slice).
   constexpr int N = FULL ? NCH : NCH - 1;
   uint32_t c[NCH];
-  double a[NCH], xv[NCH];
+  VT a[NCH];
+  double xv[NCH];
 #pragma unroll
   for (int j = 0; j < N; j++)
     c[j] = colf(FULL || (uint32_t)j < rem ? j : (int)rem - 1);
@@ -36,8 +37,13 @@ __device__ __forceinline__ double sell_chunk(const double *vp, const double *__r
 #pragma unroll
   for (int j = 0; j < N; j++)
     if (FULL || (uint32_t)j < rem)
-      sum = fma(a[j], xv[j], sum);
+      sum = fma((double)a[j], xv[j], sum);
   return sum;
+}
+template <bool FULL, int NCH = 8, typename ColF>
+__device__ __forceinline__ double sell_chunk(const double *vp, const double *__restrict__ x,
+                                             uint32_t k, uint32_t rem, double sum, ColF colf) {
+  return sell_chunk_n<FULL, NCH>(vp, x, k, rem, sum, colf);
 }
 
 // The same for fp32-stored values (B200_MAT_VALUES_F32): a chunk is 16 entries
@@ -48,7 +54,8 @@ __device__ __forceinline__ double sell_chunk(const double *vp, const double *__r
 template <bool FULL, int NCH = 16, typename ColF>
 __device__ __forceinline__ double sell_chunk(const float *vp, const double *__restrict__ x,
                                              uint32_t k, uint32_t rem, double sum, ColF colf) {
-  static_assert(NCH == 16, "the fp32-value chunk is 16 entries");
+  if constexpr (NCH != 16)  // chunks of 9 (27-wide rows): the plain chunk, values widened at the fma
+    return sell_chunk_n<FULL, NCH>(vp, x, k, rem, sum, colf);
   constexpr int N = FULL ? 16 : 15;
   float a[16];
   // (surplus loads of a partial chunk: entry index clamped, value never selected -- see above)
@@ -153,7 +160,7 @@ k_spmv_sell(const uint32_t *__restrict__ sell_off,
 // 8 (four dependent rounds of loads per slice) and 9 + 9 + 9 with 9 (three).
 #define SELLC_MINB 5
 template <bool DOT, typename VT, bool ACC = false, int CHD = 8>
-__global__ void __launch_bounds__(SPMV_THREADS, sizeof(VT) == 8 ? SELLC_MINB : 4)
+__global__ void __launch_bounds__(SPMV_THREADS, (sizeof(VT) == 8 || CHD == 9) ? SELLC_MINB : 4)
 k_spmv_sellc(const uint4 *__restrict__ meta, const uint32_t *__restrict__ cols,
              const int32_t *__restrict__ dcols, const VT *__restrict__ vals,
              const uint32_t *__restrict__ perm, const double *__restrict__ x,
@@ -163,7 +170,7 @@ k_spmv_sellc(const uint4 *__restrict__ meta, const uint32_t *__restrict__ cols,
   if (DOT && st->done)
     return;
   __shared__ double red[SPMV_WARPS];
-  constexpr uint32_t CH = sizeof(VT) == 8 ? (uint32_t)CHD : ChunkOf<VT>::n;
+  constexpr uint32_t CH = CHD == 9 ? 9u : ChunkOf<VT>::n;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t n0 = e0 - b0, nv = n0 + (e1 - b1);
   const uint32_t stride = gridDim.x * SPMV_WARPS;

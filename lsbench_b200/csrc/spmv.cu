@@ -37,6 +37,18 @@ static int persistent_grid(b200_ctx *c, const void *kernel, uint64_t work_ctas,
   return g < 1 ? 1 : (int)g;
 }
 
+// chunks of 9 where the rows are a multiple of 9 and not of 8 wide (27-point: 9 + 9 + 9
+// instead of 8 + 8 + 8 + 3: three dependent rounds of loads per slice instead of four, same
+// 48 registers; inside the headline solve 5.794 -> 5.468 ms per SpMV); index-compressed
+// layout only.  B200_SPMV_CH=8 keeps 8.
+static bool use_chunks_of_9(const b200_mat *M) {
+  static const int ch_env = [] {
+    const char *v = getenv("B200_SPMV_CH");
+    return v ? atoi(v) : 0;
+  }();
+  return M->sell_meta && ch_env != 8 && M->sell_max_width % 9 == 0 && M->sell_max_width % 8 != 0;
+}
+
 static SpmvPlan compute_plan(b200_mat *M, int phase) {
   SpmvPlan P = {0, 0, 0, 0, 0, 0, 0};
   b200_ctx *c = M->ctx;
@@ -68,13 +80,14 @@ static SpmvPlan compute_plan(b200_mat *M, int phase) {
   if (nv) {
     // one grid per matrix (fixed count of dot partials = fixed summation
     // order): sized for the instantiation that will run
-    P.g_sell = persistent_grid(
-        c,
-        M->sell_vals32 ? (M->sell_meta ? (const void *)k_spmv_sellc<true, float>
-                                       : (const void *)k_spmv_sell<true, float>)
-                       : (M->sell_meta ? (const void *)k_spmv_sellc<true, double>
-                                       : (const void *)k_spmv_sell<true, double>),
-        (nv + SPMV_WARPS - 1) / SPMV_WARPS);
+    const bool ch9 = use_chunks_of_9(M);
+    const void *fn =
+        M->sell_vals32
+            ? (M->sell_meta ? (ch9 ? (const void *)k_spmv_sellc<true, float, false, 9> : (const void *)k_spmv_sellc<true, float>)
+                            : (const void *)k_spmv_sell<true, float>)
+            : (M->sell_meta ? (ch9 ? (const void *)k_spmv_sellc<true, double, false, 9> : (const void *)k_spmv_sellc<true, double>)
+                            : (const void *)k_spmv_sell<true, double>);
+    P.g_sell = persistent_grid(c, fn, (nv + SPMV_WARPS - 1) / SPMV_WARPS);
   }
   if (others && M->vec_rows)
     P.g_vec = persistent_grid(c, (const void *)k_spmv_vec<true>,
@@ -123,14 +136,7 @@ int launch_spmv(b200_mat *M, const double *x, double *y, bool dot, int phase,
       DOTV ? dot_out : nullptr, xr
     const uint4 *meta = (const uint4 *)M->sell_meta;
     const bool f32 = M->sell_vals32 && (M->spmv_use32 || !M->sell_vals);
-    // chunks of 9 where the rows are a multiple of 9 and not of 8 wide (27-point: 9 + 9 + 9
-    // instead of 8 + 8 + 8 + 3: three dependent rounds of loads per slice instead of four,
-    // same 48 registers; measured 2.420 against 2.472 ms at 400^3); B200_SPMV_CH=8 keeps 8
-    static const int ch_env = [] {
-      const char *v = getenv("B200_SPMV_CH");
-      return v ? atoi(v) : 0;
-    }();
-    const bool ch9 = !f32 && ch_env != 8 && M->sell_max_width % 9 == 0 && M->sell_max_width % 8 != 0;
+    const bool ch9 = use_chunks_of_9(M);
 #define B2_SELL_LAUNCH(VT, VALS)                                                  \
   do {                                                                            \
     if (dot && meta && ch9)                                                       \
