@@ -115,7 +115,10 @@ enum {
    * cut into ranges of B200_COL_BLOCK_MB (environment, default 64) megabytes of
    * x, every range becomes a matrix of its own over all rows, and y = A x runs
    * as y = A_0 x; y += A_1 x; ... so that the gathers of one pass stay inside
-   * one L2-sized piece of x.  Single rank, SpMV only (b200_pcg_solve refuses);
+   * one L2-sized piece of x.  A range sorts its rows by length inside windows of
+   * B200_COL_BLOCK_SIGMA rows (default 32768; 0 = the whole list) and multiplies
+   * four slices per warp trip (k_spmv_sell_grp; B200_COL_BLOCK_KERNEL=plain keeps
+   * one slice per trip).  Single rank, SpMV only (b200_pcg_solve refuses);
    * row sums are formed block by block, i.e. equal to the CSR product to
    * rounding, not bit for bit.  Ignored when one block would hold everything. */
   B200_MAT_COL_BLOCK = 1u << 6

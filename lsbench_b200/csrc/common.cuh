@@ -217,6 +217,11 @@ struct b200_mat {
   // column-blocked operator (B200_MAT_COL_BLOCK): the column ranges as matrices of
   // their own (all n rows, global column ids); this one then holds no entries
   std::vector<b200_mat *> blocks;
+  bool grouped_slices = false;   // a column range: k_spmv_sell_grp takes its slices four at a time
+  int plan_grp = 1;
+  unsigned *grp_work = nullptr;  // k_spmv_sell_grp: {next unit of work, CTAs done}
+  uint64_t sell_sigma_cap = 0;   // a column range: widest sort window (0 = the whole list)
+  uint32_t pad_col = 0xffffffffu; // a column range: padding gathers this column (inside the range), not x[own row]
   uint64_t col_block_width = 0;
   void *small = nullptr;          // on-chip small-matrix plan (small.cu)
   bool small_tried = false;

@@ -134,6 +134,206 @@ k_spmv_sell(const uint32_t *__restrict__ sell_off,
   }
 }
 
+// ---- SELL slices taken several at a time (the column ranges of a column-blocked operator) ----
+// A column range of a power-law operator holds one or two entries in most of its rows.  A warp
+// that takes one slice per trip pays the same dependent round trips for those 32-64 entries --
+// offsets, then columns / values / row ids, then the gathers and y -- as for a chunk of 256, and
+// the pass is bound by that latency (round 2: DRAM at 50 % with 49 % of the warp slots busy,
+// profiles/r02_powerlaw_colblock_ncu.txt).  Here a warp takes FOUR consecutive slices per trip and,
+// when they are narrow, issues the loads of all of them together: 4 slices x <= 2 entries or
+// 2 slices x <= 4 entries = 8 loads of each stream in flight per lane, the same as a full chunk.
+// Wider slices run the chunked loop of k_spmv_sell.  Surplus loads have their ADDRESS clamped
+// (never a select on the loaded value, see sell_chunk_n); each row still adds its entries left to
+// right with fma, so a row's result has the bits k_spmv_sell gives it.
+//
+// The loads are volatile asm: they leave in the order written (columns, values, row ids, y,
+// gathers).  Left to itself the compiler interleaves the fma chain of the first slices with
+// the loads of the last ones -- half the loads then wait for a round trip of the other half.
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ uint32_t ldo_stream(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.global.cs.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ldo_stream(const double *p) {
+  double v;
+  asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t ldo_nc(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ldo_nc(const double *p) {
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ldo(const double *p) {
+  double v;
+  asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+#else
+template <typename T> __device__ __forceinline__ T ldo_stream(const T *p) { return *p; }
+template <typename T> __device__ __forceinline__ T ldo_nc(const T *p) { return *p; }
+template <typename T> __device__ __forceinline__ T ldo(const T *p) { return *p; }
+#endif
+
+template <int U, int W, bool ACC>
+__device__ __forceinline__ void sell_narrow(const uint32_t *o, const uint32_t *w, uint32_t s0, uint32_t ns,
+                                            uint32_t safe_o, uint32_t safe_s, uint32_t lane,
+                                            const uint32_t *__restrict__ cols, const double *__restrict__ vals,
+                                            const uint32_t *__restrict__ perm, const double *__restrict__ x,
+                                            double *__restrict__ y, uint32_t n_rows) {
+  // safe_o / safe_s: offset and index of a live slice of the group -- where the loads of an
+  // empty slice (or of one past the end of the list) point; nothing of them is used
+  uint32_t row[U], c[U][W];
+  double a[U][W], xv[U][W], yv[U];
+  size_t e[U][W];
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const uint32_t pos = (s0 + u < ns ? s0 + u : safe_s) * B2_SLICE + lane;
+    row[u] = perm ? ldo_nc(perm + pos) : pos;
+#pragma unroll
+    for (int k = 0; k < W; k++)
+      e[u][k] = (size_t)(w[u] ? o[u] + ((uint32_t)k < w[u] ? (uint32_t)k : w[u] - 1u) : safe_o) * B2_SLICE + lane;
+  }
+#pragma unroll
+  for (int u = 0; u < U; u++)
+#pragma unroll
+    for (int k = 0; k < W; k++)
+      c[u][k] = ldo_stream(cols + e[u][k]);
+#pragma unroll
+  for (int u = 0; u < U; u++)
+#pragma unroll
+    for (int k = 0; k < W; k++)
+      a[u][k] = ldo_stream(vals + e[u][k]);
+  bool live[U];
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    live[u] = s0 + u < ns && row[u] < n_rows && (!ACC || w[u] != 0);
+    if (ACC)
+      yv[u] = ldo(y + (live[u] ? row[u] : 0u));
+  }
+#pragma unroll
+  for (int u = 0; u < U; u++)
+#pragma unroll
+    for (int k = 0; k < W; k++)
+      xv[u][k] = ldo_nc(x + c[u][k]);
+#if defined(__CUDA_ARCH__)
+  // nothing of the arithmetic may move above this point
+#pragma unroll
+  for (int u = 0; u < U; u++)
+#pragma unroll
+    for (int k = 0; k < W; k++)
+      asm volatile("" : "+d"(xv[u][k]));
+  __syncwarp();
+#endif
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    double sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < W; k++)
+      if ((uint32_t)k < w[u])
+        sum = fma(a[u][k], xv[u][k], sum);
+    if (live[u])
+      y[row[u]] = ACC ? yv[u] + sum : sum;  // (y = A x: the rows of an empty slice are zero)
+  }
+}
+
+#define SELL_GRP 4
+#ifndef SELL_GRP_MINB
+#define SELL_GRP_MINB 3  // 80 registers: the loads of four slices in flight need them (4 CTAs/SM spills)
+#endif
+#define SELL_UNIT 64  // groups per unit of work: 256 slices, a quarter of a sort window
+template <bool ACC>
+__global__ void __launch_bounds__(SPMV_THREADS, SELL_GRP_MINB)
+k_spmv_sell_grp(const uint32_t *__restrict__ sell_off, const uint32_t *__restrict__ cols,
+                const double *__restrict__ vals, const uint32_t *__restrict__ perm,
+                const double *__restrict__ x, double *__restrict__ y, uint32_t ns, uint32_t n_rows,
+                unsigned *work /* {next unit, CTAs done}, both 0 between launches */) {
+  // Work is handed out in units of SELL_UNIT consecutive groups, first come first served.  A
+  // static grid-stride walk resonates with the length-sort windows (a window is 1024 slices
+  // that run from its widest rows down to its empty ones; the stride is a fixed number of
+  // slices, so a warp lands on the same few window phases every time and some warps only ever
+  // see wide slices): measured 2 x slower than the same layout sorted as a whole.  No sum is
+  // formed across rows here, so who multiplies which slice does not change any bit of y.
+  __shared__ uint32_t unit_s;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t ngroups = (ns + SELL_GRP - 1) / SELL_GRP;
+  const uint32_t nunits = (ngroups + SELL_UNIT - 1) / SELL_UNIT;
+  for (;;) {
+    if (threadIdx.x == 0)
+      unit_s = atomicAdd(&work[0], 1u);
+    __syncthreads();
+    const uint32_t unit = unit_s;
+    __syncthreads();
+    if (unit >= nunits)
+      break;
+    const uint32_t g_end = (unit + 1) * SELL_UNIT < ngroups ? (unit + 1) * SELL_UNIT : ngroups;
+  for (uint32_t g = unit * SELL_UNIT + warp; g < g_end; g += SPMV_WARPS) {
+    const uint32_t s0 = g * SELL_GRP;
+    // offsets of the group's slices: one load, broadcast (slices past the end are empty)
+    const uint32_t mine = __ldg(sell_off + (s0 + lane < ns ? s0 + lane : ns));
+    uint32_t o[SELL_GRP + 1], w[SELL_GRP];
+#pragma unroll
+    for (int u = 0; u <= SELL_GRP; u++)
+      o[u] = __shfl_sync(0xffffffffu, mine, u);
+    uint32_t wmax = 0, safe_o = 0, safe_s = s0;
+#pragma unroll
+    for (int u = SELL_GRP - 1; u >= 0; u--) {
+      w[u] = o[u + 1] - o[u];
+      wmax = w[u] > wmax ? w[u] : wmax;
+      if (w[u])
+        safe_o = o[u], safe_s = s0 + u;
+    }
+    if (ACC && wmax == 0)  // nothing to add: leave y alone (no read-modify-write traffic)
+      continue;
+    if (wmax != 0 && wmax <= 2) {
+      sell_narrow<SELL_GRP, 2, ACC>(o, w, s0, ns, safe_o, safe_s, lane, cols, vals, perm, x, y, n_rows);
+      continue;
+    }
+    if (wmax != 0 && wmax <= 4) {
+      sell_narrow<2, 4, ACC>(o, w, s0, ns, safe_o, safe_s, lane, cols, vals, perm, x, y, n_rows);
+      sell_narrow<2, 4, ACC>(o + 2, w + 2, s0 + 2, ns, safe_o, safe_s, lane, cols, vals, perm, x, y, n_rows);
+      continue;
+    }
+#pragma unroll 1
+    for (int u = 0; u < SELL_GRP; u++) {
+      if (s0 + u >= ns)
+        break;
+      const uint32_t ou = __shfl_sync(0xffffffffu, mine, u), wu = __shfl_sync(0xffffffffu, mine, u + 1) - ou;
+      if (ACC && wu == 0)
+        continue;
+      const size_t base = (size_t)ou * B2_SLICE + lane;
+      const uint32_t *cp = cols + base;
+      const double *vp = vals + base;
+      const uint32_t pos = (s0 + u) * B2_SLICE + lane;
+      const uint32_t row = perm ? __ldg(perm + pos) : pos;
+      double sum = 0.0;
+      uint32_t k = 0;
+      for (; k + 8 <= wu; k += 8)
+        sum = sell_chunk<true>(vp, x, k, 8, sum, [&](int j) {
+          return ld_stream(cp + (size_t)(k + j) * B2_SLICE);
+        });
+      if (k < wu)
+        sum = sell_chunk<false>(vp, x, k, wu - k, sum, [&](int j) {
+          return ld_stream(cp + (size_t)(k + j) * B2_SLICE);
+        });
+      if (row < n_rows)
+        y[row] = ACC ? y[row] + sum : sum;
+    }
+  }
+  }
+  // the last CTA out rearms the counters (every CTA has drawn its final, empty unit by then)
+  if (threadIdx.x == 0 && atomicAdd(&work[1], 1u) == gridDim.x - 1) {
+    work[0] = 0u;
+    work[1] = 0u;
+  }
+}
+
 // Index-compressed SELL (convert.cu, step 6).  A slice whose 32 rows all have
 // the slice's width and whose k-th column is `row + d_k` with the same d_k in
 // every lane (the interior of any stencil or banded operator, in any numbering

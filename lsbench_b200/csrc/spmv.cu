@@ -101,6 +101,9 @@ static const SpmvPlan &plan_phase(b200_mat *M, int phase) {
   if (!M->plan_ready) {
     for (int p = 0; p < 3; p++)
       M->plan[p] = compute_plan(M, p);
+    if (M->grouped_slices && M->sell_slices)
+      M->plan_grp = persistent_grid(M->ctx, (const void *)k_spmv_sell_grp<true>,
+                                    ((M->sell_slices + SELL_GRP - 1) / SELL_GRP + SPMV_WARPS - 1) / SPMV_WARPS);
     M->plan_ready = true;
   }
   return M->plan[phase];
@@ -129,7 +132,11 @@ int launch_spmv(b200_mat *M, const double *x, double *y, bool dot, int phase,
   }
   uint32_t n = (uint32_t)M->n_local;
   double *dot_out = dot ? (c->nranks > 1 ? &M->state->pq_loc : &M->state->pq) : nullptr;
-  if (P.g_sell) {
+  if (P.g_sell && M->grouped_slices && !dot && !M->sell_meta && M->sell_vals && phase == 0) {
+    // a column range of a column-blocked operator: four slices per warp trip (sell_kernels.cuh)
+    k_spmv_sell_grp<false><<<M->plan_grp, SPMV_THREADS, 0, s>>>(M->sell_off, M->sell_cols, M->sell_vals,
+                                                                  M->sell_perm, x, y, M->sell_slices, n, M->grp_work);
+  } else if (P.g_sell) {
 #define B2_SELL_ARGS(DOTV)                                                        \
   M->sell_perm, x, y, P.b0, P.e0, P.b1, P.e1, n, DOTV ? M->partials : nullptr,    \
       DOTV ? slot_base : 0u, DOTV ? total : 0u, DOTV ? M->state : nullptr,        \
@@ -200,7 +207,10 @@ static int launch_spmv_acc(b200_mat *M, const double *x, double *y) {
   const SpmvPlan P = plan_phase(M, 0);
   const XrArgs xr = XrArgs{nullptr, nullptr, 1, 0, 0, 0ull};
   const uint32_t n = (uint32_t)M->n_local;
-  if (P.g_sell) {
+  if (P.g_sell && M->grouped_slices && !M->sell_meta && M->sell_vals) {
+    k_spmv_sell_grp<true><<<M->plan_grp, SPMV_THREADS, 0, s>>>(M->sell_off, M->sell_cols, M->sell_vals,
+                                                                 M->sell_perm, x, y, M->sell_slices, n, M->grp_work);
+  } else if (P.g_sell) {
     const uint4 *meta = (const uint4 *)M->sell_meta;
     const bool f32 = M->sell_vals32 && (M->spmv_use32 || !M->sell_vals);
 #define B2_ACC_ARGS M->sell_perm, x, y, P.b0, P.e0, P.b1, P.e1, n, nullptr, 0u, 0u, nullptr, nullptr, xr

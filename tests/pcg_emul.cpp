@@ -216,7 +216,20 @@ extern "C" int emul_colblock_split(uint64_t n, const uint64_t *offs, const uint3
 extern "C" int emul_sell_acc(int acc, unsigned grid, uint32_t ns, const uint32_t *sell_off,
                              const uint32_t *cols, const double *vals, const double *x, double *y,
                              uint32_t n_rows) {
-  if (acc)
+  // bit 1: the grouped kernel (four slices per warp trip), what a column range runs by default
+  static unsigned work[2] = {0, 0};
+  if (acc & 2) {
+    if (acc == 3)
+      simt::launch(grid, SPMV_THREADS, [&] {
+        k_spmv_sell_grp<true>(sell_off, cols, vals, nullptr, x, y, ns, n_rows, work);
+      });
+    else
+      simt::launch(grid, SPMV_THREADS, [&] {
+        k_spmv_sell_grp<false>(sell_off, cols, vals, nullptr, x, y, ns, n_rows, work);
+      });
+    return work[0] == 0 && work[1] == 0 ? 0 : 1;  // the last CTA out rearms the counters
+  }
+  else if (acc)
     simt::launch(grid, SPMV_THREADS, [&] {
       k_spmv_sell<false, double, true>(sell_off, cols, vals, nullptr, x, y, 0, ns, 0, 0, n_rows, nullptr,
                                        0, 0, nullptr, nullptr, NOXR);

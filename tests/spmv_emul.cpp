@@ -35,6 +35,12 @@ template <typename T> static inline T ld_stream(const T *p) { return *p; }
 // (the row-major kernels of the same header reduce over a warp: they compile here
 // and run on the SIMT emulator of pcg_emul.cpp, not thread by thread)
 static inline double warp_sum(double v) { return v; }
+// (k_spmv_sell_grp hands out its work through a shared counter: compiled here, run on the
+// SIMT emulator of pcg_emul.cpp)
+static inline void __syncthreads() {}
+static inline void __syncwarp() {}
+static inline unsigned atomicAdd(unsigned *p, unsigned v) { unsigned o = *p; *p += v; return o; }
+static inline unsigned __shfl_sync(unsigned, unsigned v, int) { return v; }
 struct PcgState {
   int done;
   unsigned ticket[4];

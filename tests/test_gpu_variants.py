@@ -150,3 +150,48 @@ def test_chebyshev_jacobi_on_the_onchip_kernel(abi, ctx, name):
     xs, rs, _ = M.pcg_host(b, tol=1e-10, maxit=5000, flags=abi.PCG_NO_SMALL | abi.PCG_CHEBYSHEV2)
     assert rs.path == 0 and rs.status == 0 and abs(rs.iters - r1.iters) <= 2
     M.close()
+
+
+# ------------------------------------------------------------------ column blocking (config 5)
+@pytest.mark.parametrize("kernel,sigma", [("grouped", "32768"), ("grouped", "1024"), ("plain", "0")])
+def test_column_blocked_spmv(abi, ctx, kernel, sigma, monkeypatch):
+    """B200_MAT_COL_BLOCK on the power-law operator (BASELINE.json config 5, 1.7 M rows, 13
+    ranges of 1 MB of x): the layout exports the generator's CSR bit for bit, the SpMV meets
+    the 1e-13 bar against the oracle's rows (row sums are formed range by range), agrees with
+    the unblocked layout, and is bit-reproducible -- with the default kernel (four slices per
+    warp trip, work handed out first come first served) and with the plain one."""
+    monkeypatch.setenv("B200_COL_BLOCK_MB", "1")
+    monkeypatch.setenv("B200_COL_BLOCK_KERNEL", kernel)
+    monkeypatch.setenv("B200_COL_BLOCK_SIGMA", sigma)
+    n = 1_700_000
+    Mo = orc.gen_powerlaw(n, 1, 0, 4096)          # the oracle's first 4096 rows, global columns
+    M = abi.Matrix.generate(ctx, abi.GEN_POWERLAW, n, seed=1, flags=abi.MAT_COL_BLOCK)
+    assert M.info().col_blocks == 13
+    x = np.random.default_rng(0).standard_normal(n)
+    y = M.spmv_host(x)
+    ref, scale = orc.spmv(Mo, x, want_abs=True)
+    assert np.all(np.abs(y[:4096] - ref) <= 1e-13 * np.maximum(scale, 1e-300))
+    assert M.spmv_host(x).tobytes() == y.tobytes()
+    M0 = abi.Matrix.generate(ctx, abi.GEN_POWERLAW, n, seed=1, flags=0)
+    y0 = M0.spmv_host(x)
+    assert np.max(np.abs(y - y0)) <= 1e-11 * np.max(np.abs(y0))
+    o0, c0, v0 = M0.export()
+    o1, c1, v1 = M.export()
+    assert np.array_equal(o0, o1) and np.array_equal(c0, c1) and v0.tobytes() == v1.tobytes()
+    M.close(), M0.close()
+
+
+def test_column_blocked_spmv_small_shapes(abi, ctx, monkeypatch):
+    """ranges narrower than a sort window, a last range that is nearly empty, rows with no
+    entry in a range (their y must survive the accumulate passes untouched), fewer slices
+    than one unit of work"""
+    monkeypatch.setenv("B200_COL_BLOCK_MB", "1")
+    for n in (131_072 + 77, 300_001):
+        Mo = orc.gen_powerlaw(n, 3)
+        M = abi.Matrix.generate(ctx, abi.GEN_POWERLAW, n, seed=3, flags=abi.MAT_COL_BLOCK)
+        assert M.info().col_blocks == -(-n // 131072)
+        x = np.random.default_rng(n).standard_normal(n)
+        y = M.spmv_host(x)
+        ref, scale = orc.spmv(Mo, x, want_abs=True)
+        assert np.all(np.abs(y - ref) <= 1e-13 * np.maximum(scale, 1e-300))
+        M.close()

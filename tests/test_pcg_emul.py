@@ -299,6 +299,7 @@ def test_column_blocked_spmv_on_the_emulator(emul):
     S = M.scipy()
     x = np.random.default_rng(6).standard_normal(n)
     y = np.full(n, np.nan)
+    yg = np.full(n, np.nan)                        # the same through the grouped kernel
     total = 0
     for b in range(nb):
         nnz_b = int(boffs[b, n])
@@ -318,6 +319,9 @@ def test_column_blocked_spmv_on_the_emulator(emul):
                     vals[32 * o + l:32 * (o + e - a) + l:32] = Mb.vals[a:e]
             o += w
         emul.emul_sell_acc(int(b > 0), 3, Lay["ns"], p(Lay["sell_off"]), p(Lay["allcols"]), p(vals), p(x), p(y), n)
+        emul.emul_sell_acc(2 + int(b > 0), 2, Lay["ns"], p(Lay["sell_off"]), p(Lay["allcols"]), p(vals), p(x), p(yg), n)
+        # four slices per warp trip: every row still adds its entries left to right
+        assert yg.tobytes() == y.tobytes(), b
     assert total == M.nnz
     ref, scale = orc.spmv(M, x, want_abs=True)
     assert np.all(np.abs(y - ref) <= 1e-13 * np.maximum(scale, 1e-300))

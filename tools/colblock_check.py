@@ -31,6 +31,8 @@ if len(sys.argv) > 2 and sys.argv[1] == "--time":
     ms = min(M.spmv_time(dx, dy, reps=10) for _ in range(3))
     sp, _ = M.algorithmic_bytes()
     print(json.dumps({"rows": rows, "col_block_mb": os.environ.get("B200_COL_BLOCK_MB") if blocked else None,
+                      "kernel": os.environ.get("B200_COL_BLOCK_KERNEL", "grouped") if blocked else None,
+                      "sigma": os.environ.get("B200_COL_BLOCK_SIGMA", "32768") if blocked else None,
                       "col_blocks": i.col_blocks, "ms_per_spmv": ms, "algorithmic_gbs": sp / ms / 1e6,
                       "matrix_stream_bytes": i.matrix_stream_bytes, "device_GB": i.device_bytes / 1e9}))
     sys.exit(0)
@@ -63,10 +65,20 @@ print("parity: ok (13 column ranges, export bit for bit, SpMV to 1e-13)")
 ctx.close()
 # ---- time ----------------------------------------------------------------------------------------
 out = []
-for blocked, mb in [(0, None), (1, "24"), (1, "48"), (1, "64"), (1, "100")]:
+SWEEP = [(0, None, None, None), (1, "64", "plain", "0"), (1, "64", "plain", "32768"), (1, "64", "grouped", "32768"),
+         (1, "64", "grouped", "1024"), (1, "48", "grouped", "32768"), (1, "32", "grouped", "32768"),
+         (1, "100", "grouped", "32768")]
+if os.environ.get("COLBLOCK_SWEEP"):
+    SWEEP = [tuple(None if f == "-" else f for f in t.split(":")) for t in os.environ["COLBLOCK_SWEEP"].split(",")]
+    SWEEP = [(int(t[0]),) + t[1:] for t in SWEEP]
+for blocked, mb, kern, sigma in SWEEP:
     env = dict(os.environ)
     if mb:
         env["B200_COL_BLOCK_MB"] = mb
+    if kern:
+        env["B200_COL_BLOCK_KERNEL"] = kern
+    if sigma:
+        env["B200_COL_BLOCK_SIGMA"] = sigma
     r = subprocess.run([sys.executable, __file__, "--time", str(rows), str(blocked)], env=env,
                        capture_output=True, text=True, timeout=600)
     line = r.stdout.strip().splitlines()[-1] if r.returncode == 0 and r.stdout.strip() else \
