@@ -452,9 +452,7 @@ def extras_all_ranks(args, abi, torch, dist, ctx, dev, world, rank, stream, peak
     import numpy as np
     out = {}
     rows = 50_000_000
-    legs = [("auto", 0)]
-    if world == 1:
-        legs.append(("column_blocked", abi.MAT_COL_BLOCK))
+    legs = [("auto", 0), ("column_blocked", abi.MAT_COL_BLOCK)]
     res = {}
     for label, fl in legs:
         try:
@@ -478,8 +476,8 @@ def extras_all_ranks(args, abi, torch, dist, ctx, dev, world, rank, stream, peak
         except Exception as e:
             res[label] = {"error": str(e)[:200]}
     res["workload"] = "powerlaw:%d seed 1 (mean row 18, max 65 536, half the columns uniform)" % rows
-    res["traffic_note"] = ("DRAM traffic per SpMV from committed ncu captures, not this run: auto 49 GB "
-                           "(profiles/r01_*), column-blocked see profiles/r02_powerlaw_colblock_ncu.txt")
+    res["traffic_note"] = ("DRAM traffic per SpMV on one GPU from committed ncu captures, not this run: auto 49 GB "
+                           "(profiles/r01_*), column-blocked 28 GB (profiles/r02_powerlaw_colblock_ncu.txt)")
     out["powerlaw_50m"] = res
     return out
 

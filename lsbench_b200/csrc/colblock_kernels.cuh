@@ -4,11 +4,22 @@
 #pragma once
 
 // ---- column blocking (B200_MAT_COL_BLOCK) ------------------------------------------------
-// Rows hold their columns in ascending order (every input path sorts them), so
-// the entries of row i that fall into column range b are one contiguous piece.
+// Rows hold their columns in ascending GLOBAL order (every input path sorts them), so
+// the entries of row i that fall into column range b are one contiguous piece.  On one
+// rank a column id is its own position in that order.  On several ranks the columns have
+// been renumbered (dist.cu): owned columns -> [0, n_own), remote ones -> n_own + slot with
+// the slots in ascending global order, of which the first n_low lie below the rank's own
+// rows.  col_ord gives the position in global order back: [slots below | owned | slots
+// above]; the ranges are cut in that order (cuts[b] <= ord < cuts[b + 1]), never across
+// one of the two seams, so every range is one contiguous piece of the extended x vector.
 // cnt is block-major: cnt[b * (n + 1) + i]; entry n of every block is 0 (scan tail).
+__host__ __device__ __forceinline__ uint64_t col_ord(uint32_t c, uint64_t n_own, uint64_t n_low) {
+  return c < n_own ? n_low + c : (c - n_own < n_low ? c - n_own : (uint64_t)c);
+}
+
 __global__ void k_colblock_count(uint64_t n, const uint64_t *__restrict__ offs,
-                                 const uint32_t *__restrict__ cols, uint64_t width, uint32_t nb,
+                                 const uint32_t *__restrict__ cols, const uint64_t *__restrict__ cuts,
+                                 uint32_t nb, uint64_t n_own, uint64_t n_low,
                                  uint64_t *__restrict__ cnt) {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i > n)
@@ -21,12 +32,12 @@ __global__ void k_colblock_count(uint64_t n, const uint64_t *__restrict__ offs,
   uint64_t e = offs[i];
   const uint64_t end = offs[i + 1];
   for (uint32_t b = 0; b < nb; b++) {
-    // first entry at or after e whose column is >= (b + 1) * width
-    const uint64_t lim = (uint64_t)(b + 1) * width;
+    // first entry at or after e whose column lies at or beyond the end of range b
+    const uint64_t lim = cuts[b + 1];
     uint64_t lo = e, hi = end;
     while (lo < hi) {
       const uint64_t mid = lo + (hi - lo) / 2;
-      if ((uint64_t)cols[mid] < lim)
+      if (col_ord(cols[mid], n_own, n_low) < lim)
         lo = mid + 1;
       else
         hi = mid;
@@ -58,15 +69,16 @@ __global__ void k_colblock_fill(uint64_t n, const uint64_t *__restrict__ offs,
   }
 }
 
-// *unsorted is set when some row does not hold its columns in ascending order
+// *unsorted is set when some row does not hold its columns in ascending (global) order
 __global__ void k_rows_sorted(uint64_t n, const uint64_t *__restrict__ offs,
-                              const uint32_t *__restrict__ cols, unsigned *unsorted) {
+                              const uint32_t *__restrict__ cols, uint64_t n_own, uint64_t n_low,
+                              unsigned *unsorted) {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= n)
     return;
   bool bad = false;
   for (uint64_t e = offs[i] + 1; e < offs[i + 1]; e++)
-    bad |= cols[e] < cols[e - 1];
+    bad |= col_ord(cols[e], n_own, n_low) < col_ord(cols[e - 1], n_own, n_low);
   if (bad)
     *unsorted = 1u;
 }

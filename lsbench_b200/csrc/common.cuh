@@ -121,6 +121,7 @@ struct HaloWaitArgs {
 struct HaloPlan {
   // receive side: halo slots are sorted by global column, grouped by owner
   uint64_t n_halo = 0;
+  uint64_t n_low = 0;                    // halo slots whose global column lies below the own rows
   uint64_t *d_gcols = nullptr;           // n_halo global ids
   int n_peers = 0;                       // ranks we exchange with
   int *peer = nullptr;                   // host arrays, n_peers long
@@ -216,7 +217,9 @@ struct b200_mat {
   bool plan_ready = false;
   // column-blocked operator (B200_MAT_COL_BLOCK): the column ranges as matrices of
   // their own (all n rows, global column ids); this one then holds no entries
-  std::vector<b200_mat *> blocks;
+  std::vector<b200_mat *> blocks;            // pass order: ranges of owned columns first
+  std::vector<uint32_t> block_in_col_order;  // blocks[] indices in global column order
+  uint32_t n_local_blocks = 0;               // how many of blocks[] hold owned columns only
   bool grouped_slices = false;   // a column range: k_spmv_sell_grp takes its slices four at a time
   int plan_grp = 1;
   unsigned *grp_work = nullptr;  // k_spmv_sell_grp: {next unit of work, CTAs done}

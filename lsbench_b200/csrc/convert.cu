@@ -777,8 +777,31 @@ int build_layout_or_blocks(b200_ctx *c, PlainCsr *A, uint64_t n_global, uint64_t
     if (atoll(v) > 0)
       mb = (uint64_t)atoll(v);
   const uint64_t width = (mb << 20) / 8 / 32 * 32;
-  const uint64_t nb64 = width ? (n_global + width - 1) / width : 1;
-  if (!(flags & B200_MAT_COL_BLOCK) || c->nranks > 1 || nb64 < 2 || A->n != n_global || A->nnz == 0)
+  // The columns in global order: [remote below the own rows | owned | remote above] (one rank:
+  // owned only).  Each of the three segments is cut into equal pieces of at most `width`
+  // columns, so that a range never crosses a seam and is one contiguous piece of the
+  // extended x vector.
+  const uint64_t n_own = A->n;
+  const uint64_t n_halo = *out ? (*out)->halo.n_halo : 0, n_low = *out ? (*out)->halo.n_low : 0;
+  std::vector<uint64_t> cuts(1, 0);
+  std::vector<int> local_piece;  // per range: 1 when it holds owned columns only
+  {
+    const uint64_t seg[3] = {n_low, n_own, n_halo - n_low};
+    uint64_t at = 0;
+    for (int g = 0; g < 3 && width; g++) {
+      const uint64_t pieces = (seg[g] + width - 1) / width;
+      for (uint64_t k = 0; k < pieces; k++) {
+        uint64_t hi = k + 1 == pieces ? seg[g] : ((seg[g] * (k + 1) / pieces) + 31) / 32 * 32;
+        hi = hi < seg[g] ? hi : seg[g];
+        if (at + hi > cuts.back())
+          cuts.push_back(at + hi), local_piece.push_back(g == 1);
+      }
+      at += seg[g];
+    }
+  }
+  const uint64_t nb64 = cuts.size() - 1;
+  if (!(flags & B200_MAT_COL_BLOCK) || nb64 < 2 || A->nnz == 0 ||
+      (c->nranks == 1 && A->n != n_global))
     return build_layout(c, A, n_global, row_begin, flags & ~(uint32_t)B200_MAT_COL_BLOCK, out);
   if (nb64 > 64)
     B_FAIL(B200_EINVAL, "B200_MAT_COL_BLOCK: %llu column blocks of %llu MB (at most 64)",
@@ -790,7 +813,8 @@ int build_layout_or_blocks(b200_ctx *c, PlainCsr *A, uint64_t n_global, uint64_t
   *out = M;
   M->ctx = c, M->n_global = n_global, M->row_begin = row_begin;
   M->n_local = n, M->nnz = A->nnz, M->flags = flags, M->col_block_width = width;
-  M->interior_begin = 0, M->interior_end = n;
+  if (!n_halo)
+    M->interior_begin = 0, M->interior_end = n;
   // ---- what describes the whole operator: row lengths, histogram, D^-1 ---------------------
   B_TRY(dev_alloc(M, (void **)&M->row_len, (n + 1) * 4));
   B_TRY(dev_alloc(M, (void **)&M->dinv, (n + 1) * 8));
@@ -813,18 +837,22 @@ int build_layout_or_blocks(b200_ctx *c, PlainCsr *A, uint64_t n_global, uint64_t
     unsigned *d_bad, h_bad = 0;
     CU_TRY(cudaMalloc(&d_bad, 4));
     CU_TRY(cudaMemsetAsync(d_bad, 0, 4, s));
-    k_rows_sorted<<<nblk(n), T256, 0, s>>>(n, A->offs, A->cols, d_bad);
+    k_rows_sorted<<<nblk(n), T256, 0, s>>>(n, A->offs, A->cols, n_own, n_low, d_bad);
     CU_TRY(cudaMemcpyAsync(&h_bad, d_bad, 4, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaStreamSynchronize(s));
     cudaFree(d_bad);
     if (h_bad)
       B_FAIL(B200_EINVAL, "B200_MAT_COL_BLOCK needs rows with ascending columns");
   }
-  uint64_t *cnt = nullptr, *boffs = nullptr;
+  uint64_t *cnt = nullptr, *boffs = nullptr, *d_cuts = nullptr;
   CU_TRY(cudaMalloc(&cnt, (size_t)nb * (n + 1) * 8));
   CU_TRY(cudaMalloc(&boffs, (size_t)nb * (n + 1) * 8));
-  k_colblock_count<<<nblk(n + 1), T256, 0, s>>>(n, A->offs, A->cols, width, nb, cnt);
+  CU_TRY(cudaMalloc(&d_cuts, (nb + 1ull) * 8));
+  CU_TRY(cudaMemcpyAsync(d_cuts, cuts.data(), (nb + 1ull) * 8, cudaMemcpyHostToDevice, s));
+  k_colblock_count<<<nblk(n + 1), T256, 0, s>>>(n, A->offs, A->cols, d_cuts, nb, n_own, n_low, cnt);
   CU_TRY(cudaGetLastError());
+  CU_TRY(cudaStreamSynchronize(s));  // (cuts: pageable source, landed before the vector goes)
+  cudaFree(d_cuts);
   std::vector<PlainCsr> sub(nb);
   std::vector<uint32_t *> h_cols(nb, nullptr);
   std::vector<double *> h_vals(nb, nullptr);
@@ -873,20 +901,34 @@ int build_layout_or_blocks(b200_ctx *c, PlainCsr *A, uint64_t n_global, uint64_t
     sigma_cap = (uint64_t)atoll(v);
   const char *kv = getenv("B200_COL_BLOCK_KERNEL");
   const bool grouped = !(kv && !strcmp(kv, "plain"));
+  std::vector<b200_mat *> kids(nb, nullptr);
   for (uint32_t b = 0; b < nb; b++) {
     if (rc == B200_OK) {
       b200_mat *child = new b200_mat();
       child->sell_sigma_cap = sigma_cap;
       child->grouped_slices = grouped && !(flags & B200_MAT_VALUES_F32);
-      child->pad_col = grouped ? (uint32_t)(b * width) : 0xffffffffu;
+      // (a column id inside the range, for the padding: first column of the range)
+      const uint64_t o = cuts[b];
+      const uint64_t first_col = o < n_low ? n_own + o : (o < n_low + n_own ? o - n_low : o);
+      child->pad_col = grouped ? (uint32_t)first_col : 0xffffffffu;
       rc = build_layout(c, &sub[b], n_global, row_begin, child_flags, &child);
-      if (child) {
-        M->blocks.push_back(child);
+      kids[b] = child;
+      if (child)
         M->device_bytes += child->device_bytes;
-      }
     }
     plain_free(&sub[b]);
   }
+  // pass order: the ranges of owned columns first -- on several ranks they are multiplied while
+  // the halo is on its way -- then the remote ones; block_in_col_order keeps the global order
+  // (a row of the operator = its pieces in that order, b200_mat_export)
+  M->block_in_col_order.assign(nb, 0);
+  for (int want = 1; want >= 0; want--)
+    for (uint32_t b = 0; b < nb; b++)
+      if (local_piece[b] == want && kids[b]) {
+        M->block_in_col_order[b] = (uint32_t)M->blocks.size();
+        M->blocks.push_back(kids[b]);
+        M->n_local_blocks += want;
+      }
   return rc;
 }
 
@@ -1117,7 +1159,8 @@ extern "C" int b200_mat_export(const b200_mat *M, uint64_t *offs,
     std::vector<uint64_t> ho(n + 1), at(n + 1);
     CU_TRY(cudaMemcpy(ho.data(), ooffs, (n + 1) * 8, cudaMemcpyDeviceToHost));
     at = ho;
-    for (const b200_mat *child : M->blocks) {
+    for (uint32_t b : M->block_in_col_order) {
+      const b200_mat *child = M->blocks[b];
       std::vector<uint64_t> co(n + 1);
       std::vector<uint32_t> cc(child->nnz ? child->nnz : 1);
       std::vector<double> cv(child->nnz ? child->nnz : 1);

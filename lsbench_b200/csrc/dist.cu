@@ -349,6 +349,11 @@ int partition_and_renumber(b200_ctx *c, PlainCsr *A, uint64_t n_global,
   if (nloc + (uint64_t)n_halo >= 0xffffffffull)
     B_FAIL(B200_ERANGE, "partition: local + halo columns exceed 32 bits");
   M->halo.n_halo = n_halo;
+  {  // (row-block cuts are multiples of 32: the word of r0 starts at r0)
+    uint32_t below = 0;
+    CU_TRY(cudaMemcpy(&below, rank_of_word + r0 / 32, 4, cudaMemcpyDeviceToHost));
+    M->halo.n_low = below;
+  }
   CU_TRY(cudaMalloc(&M->halo.d_gcols, (n_halo + 1ull) * 8));
   k_emit_halo<<<nblk(nwords), T256, 0, s>>>(bits, nwords, rank_of_word, M->halo.d_gcols);
   if (A->nnz)

@@ -242,14 +242,21 @@ static int launch_spmv_acc(b200_mat *M, const double *x, double *y) {
 }
 
 // A column-blocked operator: y = A_0 x, then y += A_b x block after block, so that
-// the random gathers of one pass stay inside one L2-sized range of x.
-static int spmv_col_blocked(b200_mat *M, const double *x, double *y) {
+// the random gathers of one pass stay inside one L2-sized range of x.  On several ranks the
+// ranges of owned columns come first and are multiplied while the halo is on its way.
+static int spmv_col_blocked(b200_mat *M, double *x, double *y, bool exchange) {
+  if (exchange)
+    B_TRY(halo_exchange_begin(M, x));
   for (size_t b = 0; b < M->blocks.size(); b++) {
+    if (exchange && b == M->n_local_blocks)
+      B_TRY(halo_exchange_wait(M));
     if (b == 0)
       B_TRY(launch_spmv(M->blocks[b], x, y, false, 0, nullptr));
     else
       B_TRY(launch_spmv_acc(M->blocks[b], x, y));
   }
+  if (exchange && M->n_local_blocks >= M->blocks.size())
+    B_TRY(halo_exchange_wait(M));
   return B200_OK;
 }
 
@@ -261,7 +268,7 @@ static int spmv_full(b200_mat *M, double *x_ext, double *y, bool dot,
   if (!M->blocks.empty()) {
     if (dot)
       B_FAIL(B200_EINVAL, "a column-blocked matrix is SpMV-only");
-    return spmv_col_blocked(M, x_ext, y);
+    return spmv_col_blocked(M, x_ext, y, M->ctx->nranks > 1);
   }
   if (!M->halo.n_halo && M->ctx->nranks == 1)
     return launch_spmv(M, x_ext, y, dot, 0, nullptr);
@@ -287,8 +294,8 @@ extern "C" int b200_spmv(b200_mat *M, const double *d_x, double *d_y) {
     B_FAIL(B200_EINVAL, "b200_spmv: null argument");
   b200_ctx *c = M->ctx;
   CU_TRY(cudaSetDevice(c->device));
-  if (!M->blocks.empty())
-    return spmv_col_blocked(M, d_x, d_y);
+  if (!M->blocks.empty() && c->nranks == 1)
+    return spmv_col_blocked(M, const_cast<double *>(d_x), d_y, false);
   if (c->nranks == 1)
     return launch_spmv(M, d_x, d_y, false, 0, nullptr);
   B_TRY(ensure_workspace(M));

@@ -98,6 +98,34 @@ def main():
                   % (name, size, world, i.n_halo, i.interior_begin, i.interior_end, i.n_local))
         M.close()
 
+    # ---- column blocking on several ranks (BASELINE.json config 5): the ranges follow the global
+    # column order [remote below | owned | remote above], the owned ranges are multiplied while
+    # the halo travels; export and SpMV as for the plain layout --------------------------------
+    os.environ["B200_COL_BLOCK_MB"] = "1"
+    size = 1_000_000
+    M = abi.Matrix.generate(ctx, abi.GEN_POWERLAW, size, seed=9, flags=abi.MAT_COL_BLOCK)
+    M0 = abi.Matrix.generate(ctx, abi.GEN_POWERLAW, size, seed=9)
+    i = M.info()
+    assert i.col_blocks >= 3, i.col_blocks
+    r0, r1 = i.row_begin, i.row_begin + i.n_local
+    o0, c0, v0 = M0.export()
+    o1, c1, v1 = M.export()
+    assert np.array_equal(o0, o1) and np.array_equal(c0, c1) and v0.tobytes() == v1.tobytes()
+    assert np.array_equal(M.halo_cols(), M0.halo_cols())
+    xg = np.random.default_rng(5).standard_normal(size)
+    y, y0 = M.spmv_host(xg[r0:r1]), M0.spmv_host(xg[r0:r1])
+    rows = min(i.n_local, 3000)
+    Mo = orc.gen_powerlaw(size, 9, r0, r0 + rows)
+    yr, ya = orc.spmv(Mo, xg, want_abs=True)
+    assert np.all(np.abs(y[:rows] - yr) <= 1e-13 * ya + 1e-300)
+    assert np.max(np.abs(y - y0)) <= 1e-11 * np.max(np.abs(y0))
+    assert M.spmv_host(xg[r0:r1]).tobytes() == y.tobytes()
+    if rank == 0:
+        print("dist_check powerlaw:%d column-blocked ranks=%d ranges=%d halo=%d ok"
+              % (size, world, i.col_blocks, i.n_halo))
+    M.close(), M0.close()
+    del os.environ["B200_COL_BLOCK_MB"]
+
     # a file matrix: every rank reads it, keeps its row block of the CHOLMOD operator
     A = orc.matrix_read(orc.matrix_path("tj7a_A_18"))
     M = abi.Matrix.from_csr(ctx, A.nrows, A.base, A.offs, A.cols, A.vals, abi.MAT_SYM_UPPER)

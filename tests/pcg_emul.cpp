@@ -199,13 +199,15 @@ extern "C" int emul_spmv_two_phase(uint32_t n, uint32_t ns, const uint4 *meta, c
 #include "colblock_kernels.cuh"
 
 extern "C" int emul_colblock_split(uint64_t n, const uint64_t *offs, const uint32_t *cols,
-                                   const double *vals, uint64_t width, uint32_t nb,
+                                   const double *vals, const uint64_t *cuts /* nb + 1, global order */,
+                                   uint32_t nb, uint64_t n_own, uint64_t n_low,
                                    uint64_t *cnt /* nb x (n+1) */, uint64_t *boffs /* nb x (n+1) */,
                                    uint32_t **ocols, double **ovals, int stage, unsigned *unsorted) {
   if (stage == 0) {
     simt::launch((unsigned)((n + 1 + 255) / 256), 256,
-                 [&] { k_colblock_count(n, offs, cols, width, nb, cnt); });
-    simt::launch((unsigned)((n + 255) / 256), 256, [&] { k_rows_sorted(n, offs, cols, unsorted); });
+                 [&] { k_colblock_count(n, offs, cols, cuts, nb, n_own, n_low, cnt); });
+    simt::launch((unsigned)((n + 255) / 256), 256,
+                 [&] { k_rows_sorted(n, offs, cols, n_own, n_low, unsorted); });
   } else {
     simt::launch(3, 256, [&] { k_colblock_fill(n, offs, cols, vals, nb, boffs, ocols, ovals); });
   }

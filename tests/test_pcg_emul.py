@@ -266,7 +266,7 @@ def test_column_blocked_spmv_on_the_emulator(emul):
     rows, and y = A_0 x; y += A_1 x; ... runs through the accumulate instantiation
     of the SELL kernel.  The pieces add up to the operator bit for bit; the product
     is the CSR product to the 1e-13 bar (row sums are formed block by block)."""
-    emul.emul_colblock_split.argtypes = ([C.c_uint64] + [C.c_void_p] * 3 + [C.c_uint64, C.c_uint32]
+    emul.emul_colblock_split.argtypes = ([C.c_uint64] + [C.c_void_p] * 4 + [C.c_uint32, C.c_uint64, C.c_uint64]
                                          + [C.c_void_p] * 4 + [C.c_int, C.c_void_p])
     emul.emul_sell_acc.argtypes = [C.c_int, C.c_uint, C.c_uint32] + [C.c_void_p] * 5 + [C.c_uint32]
     n = 3000
@@ -279,9 +279,11 @@ def test_column_blocked_spmv_on_the_emulator(emul):
     width, nb = 704, 5                             # 5 ranges of 704 columns (a multiple of 32)
     assert (nb - 1) * width < n <= nb * width
     p = lambda a: a.ctypes.data
+    cuts = np.minimum(np.arange(nb + 1, dtype=np.uint64) * np.uint64(width), np.uint64(n))
     cnt = np.zeros(nb * (n + 1), dtype=np.uint64)
     bad = np.zeros(1, dtype=np.uint32)
-    emul.emul_colblock_split(n, p(M.offs), p(M.cols), p(M.vals), width, nb, p(cnt), None, None, None, 0, p(bad))
+    emul.emul_colblock_split(n, p(M.offs), p(M.cols), p(M.vals), p(cuts), nb, n, 0, p(cnt), None, None, None, 0,
+                             p(bad))
     assert bad[0] == 0
     cnt = cnt.reshape(nb, n + 1)
     want_cnt = np.array([[np.sum((M.cols[offs2[0]:offs2[1]] // width) == b) for offs2 in
@@ -294,7 +296,7 @@ def test_column_blocked_spmv_on_the_emulator(emul):
     ovals = [np.zeros(max(int(boffs[b, n]), 1)) for b in range(nb)]
     pc = (C.c_void_p * nb)(*[p(a) for a in ocols])
     pv = (C.c_void_p * nb)(*[p(a) for a in ovals])
-    emul.emul_colblock_split(n, p(M.offs), p(M.cols), p(M.vals), width, nb, None, p(boffs), pc, pv, 1, None)
+    emul.emul_colblock_split(n, p(M.offs), p(M.cols), p(M.vals), p(cuts), nb, n, 0, None, p(boffs), pc, pv, 1, None)
     # the pieces, row by row and in range order, are the operator
     S = M.scipy()
     x = np.random.default_rng(6).standard_normal(n)
@@ -332,5 +334,35 @@ def test_column_blocked_spmv_on_the_emulator(emul):
     cols2[a], cols2[a + 1] = cols2[a + 1], cols2[a]
     bad[:] = 0
     scratch = np.zeros(nb * (n + 1), dtype=np.uint64)
-    emul.emul_colblock_split(n, p(M.offs), p(cols2), p(M.vals), width, nb, p(scratch), None, None, None, 0, p(bad))
+    emul.emul_colblock_split(n, p(M.offs), p(cols2), p(M.vals), p(cuts), nb, n, 0, p(scratch), None, None, None, 0,
+                             p(bad))
     assert bad[0] == 1
+    # ---- the same cut on a rank's renumbered columns (dist.cu: owned -> [0, n_own), remote ->
+    # n_own + slot, slots in ascending global order, the first n_low of them below the own rows):
+    # ranges follow the GLOBAL order [slots below | owned | slots above] and never cross a seam
+    r0, r1 = 1024, 2048                            # this rank's rows
+    n_own = r1 - r0
+    rows = slice(int(M.offs[r0]), int(M.offs[r1]))
+    gcols = M.cols[rows].astype(np.int64)
+    remote = np.unique(gcols[(gcols < r0) | (gcols >= r1)])
+    n_low = int(np.sum(remote < r0))
+    slot = {int(g): i for i, g in enumerate(remote)}
+    lcols = np.array([g - r0 if r0 <= g < r1 else n_own + slot[int(g)] for g in gcols], dtype=np.uint32)
+    loffs = (M.offs[r0:r1 + 1] - M.offs[r0]).astype(np.uint64)
+    ncols = n_own + len(remote)
+    seams = [0, n_low // 2, n_low, n_low + n_own // 2, n_low + n_own, ncols]
+    cuts2 = np.array(sorted(set(seams)), dtype=np.uint64)
+    nb2 = len(cuts2) - 1
+    cnt2 = np.zeros(nb2 * (n_own + 1), dtype=np.uint64)
+    bad[:] = 0
+    emul.emul_colblock_split(n_own, p(loffs), p(lcols), p(M.vals[rows]), p(cuts2), nb2, n_own, n_low, p(cnt2),
+                             None, None, None, 0, p(bad))
+    assert bad[0] == 0                             # renumbered rows are still in global order
+    ordv = np.where(lcols < n_own, n_low + lcols.astype(np.int64),
+                    np.where(lcols.astype(np.int64) - n_own < n_low, lcols.astype(np.int64) - n_own, lcols))
+    cnt2 = cnt2.reshape(nb2, n_own + 1)
+    for i in range(n_own):
+        o = ordv[int(loffs[i]):int(loffs[i + 1])]
+        assert np.all(np.diff(o) > 0)
+        want = [int(np.sum((o >= cuts2[b]) & (o < cuts2[b + 1]))) for b in range(nb2)]
+        assert list(cnt2[:, i]) == want

@@ -41,9 +41,10 @@ ctx = abi.Context(local, rank, world, nccl_id)
 
 SEL = [("auto", 0), ("sell_only", abi.MAT_FORCE_SELL), ("vector_only", abi.MAT_FORCE_VECTOR),
        ("auto_nosort", abi.MAT_NO_SORT)]
-if world == 1:
-    # column blocking (B200_MAT_COL_BLOCK; width from B200_COL_BLOCK_MB, default 48 MB of x)
-    SEL.insert(1, ("auto_colblock", abi.MAT_COL_BLOCK))
+# column blocking (B200_MAT_COL_BLOCK; width from B200_COL_BLOCK_MB, default 64 MB of x)
+SEL.insert(1, ("auto_colblock", abi.MAT_COL_BLOCK))
+if os.environ.get("POWERLAW_SWEEP_ONLY"):
+    SEL = [s_ for s_ in SEL if s_[0] in os.environ["POWERLAW_SWEEP_ONLY"].split(",")]
 for seed in seeds:
     for name, fl in (SEL if seed == seeds[0] else SEL[:1]):
         t0 = time.time()
