@@ -45,8 +45,9 @@ extern "C" {
 
 /* 2: b200_mat_info grew (index compression), ingest and row-block entry points
  * 3: b200_mat_info.values_f32, b200_pcg_result.outer_iters, new flags
- * 4: b200_pcg_result.replacements, status 4, Chebyshev flags; single-reduction flag gone */
-#define B200_ABI_VERSION 4
+ * 4: b200_pcg_result.replacements, status 4, Chebyshev flags; single-reduction flag gone
+ * 5: B200_PCG_BLOCK_JACOBI, b200_pcg_result.block_jacobi, b200_mat_block_jacobi_partition */
+#define B200_ABI_VERSION 5
 
 enum {
   B200_OK = 0,
@@ -205,6 +206,10 @@ int b200_mat_export(const b200_mat *M, uint64_t *offs, uint32_t *cols,
 /* Global column id of halo slot j (j < n_halo). */
 int b200_mat_halo_cols(const b200_mat *M, uint64_t *gcols);
 int b200_mat_inv_diag(const b200_mat *M, double *h_dinv);
+/* The partition B200_PCG_BLOCK_JACOBI works on: block_of_row[i] = id of the diagonal
+ * block row i (caller's numbering) belongs to, *block_size = rows per block (0 and
+ * B200_OK when the matrix does not take the on-chip path or no block size fits). */
+int b200_mat_block_jacobi_partition(b200_mat *M, uint32_t *block_of_row, uint32_t *block_size);
 
 /* ---- SpMV ------------------------------------------------------------------ */
 /* y = A x on the local rows.  d_x holds the n_local owned entries; the halo is
@@ -237,7 +242,16 @@ enum {
    * cluster-wide reductions each of them waits for.  Ignored on the streaming path,
    * where the product is the cost and CG is already optimal per product. */
   B200_PCG_CHEBYSHEV2 = 1u << 4,
-  B200_PCG_CHEBYSHEV3 = 1u << 5
+  B200_PCG_CHEBYSHEV3 = 1u << 5,
+  /* SURVEY 8f row 2, block-Jacobi on the on-chip coarse-grid path: z = B^-1 r, B the
+   * diagonal blocks of 32 (16 when shared memory is short) consecutive rows of a CTA's
+   * row chunk, inverted once on the host and kept as fp32 in shared memory.  No exchange
+   * and no reduction more than Jacobi, 0.4 - 0.8 x the iterations on the Nek matrices.
+   * What the reference reaches for on these systems is algebraic multigrid
+   * (src/hypre.c:126-188, src/amgx.c:78-85); this is the step in that direction that
+   * costs a CTA nothing it has to wait for.  Ignored on the streaming path and when a
+   * diagonal block is not positive definite. */
+  B200_PCG_BLOCK_JACOBI = 1u << 6
 };
 
 typedef struct {
@@ -257,6 +271,7 @@ typedef struct {
                           degree of the preconditioner that ran (1 = Jacobi); else 0 */
   int32_t replacements; /* residual replacements: exit checks that found ||b - A x|| above
                            the bar with the recurrence below it, after which the solve went on */
+  uint32_t block_jacobi; /* block size of the block-Jacobi preconditioner that ran, else 0 */
 } b200_pcg_result;
 
 /* x: in x0, out solution (n_local).  b: n_local.  Device pointers. */

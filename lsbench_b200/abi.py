@@ -30,6 +30,7 @@ PCG_NO_GRAPH = 1 << 1
 PCG_NO_SMALL = 1 << 2
 PCG_CHEBYSHEV2 = 1 << 4
 PCG_CHEBYSHEV3 = 1 << 5
+PCG_BLOCK_JACOBI = 1 << 6
 
 # every symbol include/b200.h declares (tests check the library exports them)
 SYMBOLS = [
@@ -42,7 +43,7 @@ SYMBOLS = [
     "b200_mat_from_csr", "b200_mat_generate", "b200_mat_destroy",
     "b200_coo_to_csr", "b200_mat_from_coo", "b200_text_to_csr",
     "b200_mat_get_info", "b200_mat_export", "b200_mat_halo_cols",
-    "b200_mat_inv_diag", "b200_spmv", "b200_spmv_host", "b200_spmv_time",
+    "b200_mat_inv_diag", "b200_mat_block_jacobi_partition", "b200_spmv", "b200_spmv_host", "b200_spmv_time",
     "b200_pcg_solve", "b200_pcg_solve_host", "b200_mat_algorithmic_bytes",
 ]
 
@@ -76,7 +77,8 @@ class PcgResult(C.Structure):
                 ("bnorm", C.c_double), ("solve_ms", C.c_float),
                 ("spmv_ms", C.c_float), ("update_ms", C.c_float),
                 ("pupdate_ms", C.c_float), ("kernel_launches", C.c_int32),
-                ("path", C.c_int32), ("outer_iters", C.c_int32), ("replacements", C.c_int32)]
+                ("path", C.c_int32), ("outer_iters", C.c_int32), ("replacements", C.c_int32),
+                ("block_jacobi", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -124,6 +126,7 @@ def load():
         "b200_mat_export": [vp, vp, vp, vp],
         "b200_mat_halo_cols": [vp, vp],
         "b200_mat_inv_diag": [vp, vp],
+        "b200_mat_block_jacobi_partition": [vp, vp, vp],
         "b200_spmv": [vp, vp, vp],
         "b200_spmv_host": [vp, vp, vp],
         "b200_spmv_time": [vp, vp, vp, i32, C.POINTER(C.c_float)],
@@ -313,6 +316,13 @@ class Matrix:
         g = np.empty(max(i.n_halo, 1), dtype=np.uint64)
         _chk(load().b200_mat_halo_cols(self.h, g.ctypes.data))
         return g[:i.n_halo]
+
+    def block_jacobi_partition(self):
+        """(block id of every row, block size) of B200_PCG_BLOCK_JACOBI; size 0 = not in use"""
+        blk = np.zeros(max(self.info().n_local, 1), dtype=np.uint32)
+        bs = C.c_uint32(0)
+        _chk(load().b200_mat_block_jacobi_partition(self.h, blk.ctypes.data, C.byref(bs)))
+        return blk[:self.info().n_local], bs.value
 
     def inv_diag(self):
         d = np.empty(self.info().n_local, dtype=np.float64)

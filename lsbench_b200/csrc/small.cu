@@ -54,6 +54,7 @@ struct SmallCta {         // one per CTA, in global memory
   uint32_t goff_at;       // into goff[]   (n_groups + 1 values, units of 32 entries)
   uint32_t row_at;        // into rowid[] / dinv[] / dmask[] (8 n_groups values, 0xffffffff = none)
   uint32_t n_recv;        // window entries some row of this CTA reads (incl. its own rows)
+  uint32_t row_lo;        // first row of the chunk (block-Jacobi: blocks are counted from here)
   uint64_t ent_at;        // into vals[] / cols[]
 };
 
@@ -74,19 +75,29 @@ struct SmallPlan {
   double lmax = 0.0;
   int max_kdeg = 1;
   size_t smem_k[4] = {0, 0, 0, 0};
+  // block-Jacobi: block size in use (0 = none fits), the inverted diagonal
+  // blocks as fp32 rows of bj + 1 values per chunk row, chunk row -> slot, shared memory, and
+  // the block every row of the caller's numbering belongs to (b200_mat_block_jacobi_partition)
+  int bj = 0;
+  float *d_binv = nullptr;
+  uint16_t *d_slotof = nullptr;
+  size_t smem_bj = 0;
+  std::vector<uint32_t> block_of_row;
   // largest per-CTA extents (shared memory carve-up is uniform)
   uint32_t max_ent = 0, max_groups = 0, max_stage = 0;
 };
 
 struct SmemMap {
-  size_t stage, zwin, dwin0, dwin1, vals, xs, rs, ds, qs, rhs, dds, zzs, slots, wred, bars, win, goff, rowid,
-      orig, dmask, cols, total;
+  size_t stage, zwin, dwin0, dwin1, vals, xs, rs, ds, qs, rhs, dds, zzs, rrow, slots, wred, bars, win, goff, rowid,
+      orig, dmask, binv, slotof, cols, total;
 };
 
 // kdeg > 1 (Chebyshev-Jacobi): two more windows (the direction d of the polynomial
 // recurrence lands in them alternately) and three more vectors on the owned rows
+// bj > 0 (block-Jacobi): r once more in chunk-row order (blocks padded to bj + 1 entries
+// apart: no two blocks start in the same bank), the inverted blocks, chunk row -> slot
 __host__ __device__ inline SmemMap smem_map(uint32_t max_ent, uint32_t max_groups,
-                                            uint32_t max_stage, int kdeg) {
+                                            uint32_t max_stage, int kdeg, int bj = 0) {
   SmemMap m;
   size_t rows = (size_t)max_groups * 8, o = 0;
   const size_t win_bytes = ((size_t)max_stage + 1) / 2 * 2 * 8;
@@ -102,6 +113,7 @@ __host__ __device__ inline SmemMap smem_map(uint32_t max_ent, uint32_t max_group
   m.rhs = o, o += kdeg > 1 ? rows * 8 : 0;
   m.dds = o, o += kdeg > 1 ? rows * 8 : 0;
   m.zzs = o, o += kdeg > 1 ? rows * 8 : 0;
+  m.rrow = o, o += bj ? (rows / bj + 2) * (size_t)(bj + 1) * 8 : 0;
   m.slots = o, o += 4 * SM_MAX_CLUSTER * 8;  // pq | rz | rr | bb
   m.wred = o, o += 3 * SM_WARPS * 8;
   m.bars = o, o += 4 * 8;
@@ -110,6 +122,8 @@ __host__ __device__ inline SmemMap smem_map(uint32_t max_ent, uint32_t max_group
   m.rowid = o, o += rows * 4;
   m.orig = o, o += rows * 4;
   m.dmask = o, o += rows * 4;
+  m.binv = o, o += bj ? rows * (size_t)(bj + 1) * 4 : 0;
+  m.slotof = o, o += bj ? (rows * 2 + 7) / 8 * 8 : 0;
   m.cols = o, o += (size_t)max_ent * 2;
   m.total = (o + 15) / 16 * 16;
   return m;
@@ -330,13 +344,22 @@ __device__ __forceinline__ void read_totals(unsigned C, const double *slots, int
 // each behind one more exchange of d between the CTAs that share columns (its own
 // mbarrier, no all-reduce), and about 1 / KDEG of the iterations -- i.e. of the two
 // all-reduces that every iteration of this kernel waits for.
-template <bool PROF, int KDEG>
+//
+// BJ: block-Jacobi.  z = B^-1 r with B the diagonal blocks of BJ consecutive
+// rows of a CTA's chunk, inverted on the host, stored as fp32 (a preconditioner may be
+// rounded: symmetric, still positive definite; the recurrences stay fp64).  No exchange
+// and no reduction is added: the rows of a block live in one CTA.  The update runs in two
+// passes: x, r in slot order (r also into chunk-row order); then, one thread per chunk row --
+// the lanes of a warp are then rows of the same one or two blocks and read the block's r as
+// broadcasts -- z = B^-1 r, the push of z and the partial sums.
+template <bool PROF, int KDEG, int BJ>
 __global__ void __launch_bounds__(SM_THREADS, 1)
 k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_goff,
             const uint32_t *__restrict__ g_rowid, const uint32_t *__restrict__ g_dmask,
             const uint32_t *__restrict__ g_orig, const uint32_t *__restrict__ g_perm,
             const double *__restrict__ g_vals,
             const uint16_t *__restrict__ g_cols, const double *__restrict__ g_dinv,
+            const float *__restrict__ g_binv, const uint16_t *__restrict__ g_slotof,
             const double *__restrict__ b, double *__restrict__ x, PcgState *st,
             uint32_t max_ent, uint32_t max_groups, uint32_t max_stage, double tol,
             int maxit, long long *prof, double cheb_theta, double cheb_delta) {
@@ -344,7 +367,8 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
   cg::cluster_group cl = cg::this_cluster();
   const unsigned C = cl.num_blocks(), rank = cl.block_rank();
   const SmallCta me = ctas[rank];
-  const SmemMap mp = smem_map(max_ent, max_groups, max_stage, KDEG);
+  static_assert(BJ == 0 || KDEG == 1, "block-Jacobi and Chebyshev-Jacobi do not combine");
+  const SmemMap mp = smem_map(max_ent, max_groups, max_stage, KDEG, BJ);
   double *p_w = (double *)(smem + mp.stage), *z_w = (double *)(smem + mp.zwin);
   double *d_w[2] = {(double *)(smem + mp.dwin0), (double *)(smem + (KDEG > 2 ? mp.dwin1 : mp.dwin0))};
   double *rh_s = (double *)(smem + mp.rhs), *dd_s = (double *)(smem + mp.dds), *zz_s = (double *)(smem + mp.zzs);
@@ -357,6 +381,9 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
   uint32_t *goff = (uint32_t *)(smem + mp.goff), *rowid = (uint32_t *)(smem + mp.rowid);
   uint32_t *dmask = (uint32_t *)(smem + mp.dmask), *orig = (uint32_t *)(smem + mp.orig);
   uint16_t *cols = (uint16_t *)(smem + mp.cols);
+  double *rrow_s = (double *)(smem + mp.rrow);
+  float *binv_s = (float *)(smem + mp.binv);
+  uint16_t *slotof = (uint16_t *)(smem + mp.slotof);
   const uint32_t tid = threadIdx.x, nslot = me.n_groups * 8;
   long long pt[6] = {0, 0, 0, 0, 0, 0}, t0 = 0;
 #define B2_TICK(i)                                                                \
@@ -377,6 +404,14 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
     dmask[i] = g_dmask[me.row_at + i];
     d_s[i] = g_dinv[me.row_at + i];
     x_s[i] = row != 0xffffffffu ? x[og] : 0.0;
+  }
+  if (BJ) {
+    for (uint32_t i = tid; i < me.n_rows * (BJ + 1); i += SM_THREADS)
+      binv_s[i] = g_binv[(size_t)me.row_at * (BJ + 1) + i];
+    for (uint32_t i = tid; i < me.n_rows; i += SM_THREADS)
+      slotof[i] = g_slotof[me.row_at + i];
+    for (uint32_t i = tid; i < (nslot / (BJ ? BJ : 1) + 2) * (BJ + 1); i += SM_THREADS)
+      rrow_s[i] = 0.0;  // (rows past the end of the last block stay zero)
   }
   if (tid < SM_MAX_CLUSTER)  // window base of every CTA, as a byte offset into its z window
     win_lo[tid] = tid < C ? ctas[tid].col_lo : 0u, win_n[tid] = tid < C ? ctas[tid].col_n : 0u;
@@ -449,6 +484,24 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
     __syncthreads();
   };
 
+  // block-Jacobi, second pass (after a __syncthreads behind the pass that wrote r_s and
+  // rrow_s): thread t takes chunk row t; adds its r.z and r.r to acc[0], acc[1]
+  auto rrow_at = [&](uint32_t lr) { return lr + lr / (BJ ? BJ : 1); };  // blocks BJ + 1 apart
+  auto block_jacobi = [&](double *acc) {
+    for (uint32_t lr = tid; lr < me.n_rows; lr += SM_THREADS) {
+      const uint32_t i = slotof[lr];
+      const float *bi = binv_s + (size_t)lr * (BJ + 1);
+      const double *rb = rrow_s + (size_t)(lr / (BJ ? BJ : 1)) * (BJ + 1);
+      double zi = 0.0;
+#pragma unroll
+      for (int j = 0; j < BJ; j++)
+        zi = fma((double)bi[j], rb[j], zi);
+      const double ri = r_s[i];
+      push(me.row_lo + lr, dmask[i], zi);
+      acc[0] = fma(ri, zi, acc[0]), acc[1] = fma(ri, ri, acc[1]);
+    }
+  };
+
   // ---- r = b - A x0, z = D^-1 r, p = z ----------------------------------------------
   small_spmv<false>(me, R, goff, vals, cols, rowid, p_w, q_s);
   __syncthreads();
@@ -462,6 +515,18 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
     __syncthreads();
     chebyshev();
   }
+  if (BJ) {
+    for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
+      uint32_t row = rowid[i];
+      if (row == 0xffffffffu)
+        continue;
+      const double bi = b[orig[i]], ri = bi - q_s[i];
+      r_s[i] = ri, rrow_s[rrow_at(row - me.row_lo)] = ri;
+      acc3[2] = fma(bi, bi, acc3[2]);
+    }
+    __syncthreads();
+    block_jacobi(acc3);
+  } else
   for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
     uint32_t row = rowid[i];
     if (row == 0xffffffffu)
@@ -511,7 +576,18 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
     if (tid == 0)
       bar_arm(bar_b, (2 * C + me.n_recv) * 8);
     double a2[2] = {0.0, 0.0}, t2[2];
-    if (KDEG == 1) {
+    if (BJ) {
+      for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
+        uint32_t row = rowid[i];
+        if (row == 0xffffffffu)
+          continue;
+        x_s[i] = fma(alpha, p_w[row - me.col_lo], x_s[i]);
+        const double ri = fma(-alpha, q_s[i], r_s[i]);
+        r_s[i] = ri, rrow_s[rrow_at(row - me.row_lo)] = ri;
+      }
+      __syncthreads();
+      block_jacobi(a2);
+    } else if (KDEG == 1) {
       for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
         uint32_t row = rowid[i];
         if (row == 0xffffffffu)
@@ -615,6 +691,17 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
     __syncthreads();
     chebyshev();
   }
+  if (BJ) {
+    for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
+      uint32_t row = rowid[i];
+      if (row == 0xffffffffu)
+        continue;
+      const double ri = b[orig[i]] - q_s[i];
+      r_s[i] = ri, rrow_s[rrow_at(row - me.row_lo)] = ri;
+    }
+    __syncthreads();
+    block_jacobi(a5);
+  } else
   for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
     uint32_t row = rowid[i];
     if (row == 0xffffffffu)
@@ -657,12 +744,17 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
 // the instantiations: profiling on / off x preconditioner degree 1..3
 typedef void (*small_kernel_t)(const SmallCta *, const uint32_t *, const uint32_t *, const uint32_t *,
                                const uint32_t *, const uint32_t *, const double *, const uint16_t *,
-                               const double *, const double *, double *, PcgState *, uint32_t, uint32_t,
-                               uint32_t, double, int, long long *, double, double);
-static small_kernel_t small_kernel(bool prof, int kdeg) {
+                               const double *, const float *, const uint16_t *, const double *, double *,
+                               PcgState *, uint32_t, uint32_t, uint32_t, double, int, long long *, double,
+                               double);
+static small_kernel_t small_kernel(bool prof, int kdeg, int bj = 0) {
+  if (bj == 32)
+    return prof ? k_pcg_small<true, 1, 32> : k_pcg_small<false, 1, 32>;
+  if (bj == 16)
+    return prof ? k_pcg_small<true, 1, 16> : k_pcg_small<false, 1, 16>;
   if (prof)
-    return kdeg == 3 ? k_pcg_small<true, 3> : kdeg == 2 ? k_pcg_small<true, 2> : k_pcg_small<true, 1>;
-  return kdeg == 3 ? k_pcg_small<false, 3> : kdeg == 2 ? k_pcg_small<false, 2> : k_pcg_small<false, 1>;
+    return kdeg == 3 ? k_pcg_small<true, 3, 0> : kdeg == 2 ? k_pcg_small<true, 2, 0> : k_pcg_small<true, 1, 0>;
+  return kdeg == 3 ? k_pcg_small<false, 3, 0> : kdeg == 2 ? k_pcg_small<false, 2, 0> : k_pcg_small<false, 1, 0>;
 }
 
 // Upper bound of the spectrum of D^-1 A for the Chebyshev interval: min(Gershgorin
@@ -703,8 +795,8 @@ void small_free(b200_mat *M) {
   SmallPlan *P = (SmallPlan *)M->small;
   if (!P)
     return;
-  void *ptrs[] = {P->d_cta, P->d_goff, P->d_rowid, P->d_vals, P->d_dinv,
-                  P->d_cols, P->d_state, P->d_prof, P->d_dmask, P->d_orig, P->d_perm};
+  void *ptrs[] = {P->d_cta, P->d_goff, P->d_rowid, P->d_vals, P->d_dinv, P->d_cols,
+                  P->d_state, P->d_prof, P->d_dmask, P->d_orig, P->d_perm, P->d_binv, P->d_slotof};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   delete P;
@@ -878,7 +970,7 @@ int small_try_build(b200_mat *M) {
       T.n_groups = (T.n_rows + 7) / 8;
       T.col_lo = lo, T.col_n = rows.empty() ? 0 : hi - lo + 1;
       T.goff_at = (uint32_t)goff.size(), T.row_at = (uint32_t)rowid.size();
-      T.ent_at = pv.size(), T.n_recv = 0;
+      T.ent_at = pv.size(), T.n_recv = 0, T.row_lo = (uint32_t)r0;
       if (T.col_n > 65536)
         ok = false;
       uint32_t units = 0;
@@ -946,6 +1038,96 @@ int small_try_build(b200_mat *M) {
     SmemMap mp = smem_map(max_ent, max_groups, max_stage, 1);
     if (mp.total > (size_t)dev_smem)
       continue;
+    // ---- block-Jacobi: the largest block size whose shared memory fits (B200_SMALL_BJ pins
+    // it, 0 = none); the diagonal blocks of bj consecutive chunk rows, inverted (Cholesky),
+    // rounded to fp32 symmetrically.  A block that is not positive definite: no block-Jacobi.
+    int bj = 0;
+    std::vector<float> binv;
+    std::vector<uint16_t> slotof(rowid.size(), 0);
+    std::vector<uint32_t> block_of_row(n, 0);
+    {
+      int want = -1;
+      if (const char *e = getenv("B200_SMALL_BJ"))
+        want = atoi(e);
+      for (int cand : {32, 16}) {
+        if (want >= 0 && cand != want)
+          continue;
+        if (smem_map(max_ent, max_groups, max_stage, 1, cand).total <= (size_t)dev_smem) {
+          bj = cand;
+          break;
+        }
+      }
+      for (int k = 0; k < C; k++)
+        for (uint32_t sl = 0; sl < ctas[k].n_rows; sl++)
+          slotof[ctas[k].row_at + (rowid[ctas[k].row_at + sl] - ctas[k].row_lo)] = (uint16_t)sl;
+      if (bj) {
+        binv.assign(rowid.size() * (size_t)(bj + 1), 0.0f);
+        std::vector<double> B((size_t)bj * bj), L((size_t)bj * bj), Li((size_t)bj * bj), Bi((size_t)bj * bj);
+        uint32_t block_id = 0;
+        for (int k = 0; k < C && bj; k++) {
+          const uint64_t r0 = ctas[k].row_lo, r1 = r0 + ctas[k].n_rows;
+          for (uint64_t s0 = r0; s0 < r1 && bj; s0 += bj, block_id++) {
+            const int m = (int)std::min<uint64_t>(bj, r1 - s0);
+            std::fill(B.begin(), B.end(), 0.0);
+            for (int a = 0; a < m; a++)
+              for (uint64_t e = offs[s0 + a]; e < offs[s0 + a + 1]; e++)
+                if (cols[e] >= s0 && cols[e] < s0 + m)
+                  B[(size_t)a * bj + (cols[e] - s0)] += vals[e];
+            for (int a = 0; a < m; a++)  // the operator may be unsymmetric at 1e-8 (as stored)
+              for (int q = 0; q < a; q++) {
+                const double v = 0.5 * (B[(size_t)a * bj + q] + B[(size_t)q * bj + a]);
+                B[(size_t)a * bj + q] = B[(size_t)q * bj + a] = v;
+              }
+            // B = L L^T
+            bool spd = true;
+            std::fill(L.begin(), L.end(), 0.0);
+            for (int a = 0; a < m && spd; a++)
+              for (int q = 0; q <= a; q++) {
+                double v = B[(size_t)a * bj + q];
+                for (int t = 0; t < q; t++)
+                  v -= L[(size_t)a * bj + t] * L[(size_t)q * bj + t];
+                if (a == q) {
+                  if (!(v > 0.0)) {
+                    spd = false;
+                    break;
+                  }
+                  L[(size_t)a * bj + a] = sqrt(v);
+                } else {
+                  L[(size_t)a * bj + q] = v / L[(size_t)q * bj + q];
+                }
+              }
+            if (!spd) {
+              bj = 0;
+              break;
+            }
+            // Li = L^-1 (lower), B^-1 = Li^T Li
+            std::fill(Li.begin(), Li.end(), 0.0);
+            for (int q = 0; q < m; q++) {
+              Li[(size_t)q * bj + q] = 1.0 / L[(size_t)q * bj + q];
+              for (int a = q + 1; a < m; a++) {
+                double v = 0.0;
+                for (int t = q; t < a; t++)
+                  v -= L[(size_t)a * bj + t] * Li[(size_t)t * bj + q];
+                Li[(size_t)a * bj + q] = v / L[(size_t)a * bj + a];
+              }
+            }
+            for (int a = 0; a < m; a++)
+              for (int q = 0; q <= a; q++) {
+                double v = 0.0;
+                for (int t = a; t < m; t++)
+                  v += Li[(size_t)t * bj + a] * Li[(size_t)t * bj + q];
+                Bi[(size_t)a * bj + q] = Bi[(size_t)q * bj + a] = v;
+              }
+            for (int a = 0; a < m; a++) {
+              float *dst = binv.data() + ((size_t)ctas[k].row_at + (s0 - r0) + a) * (bj + 1);
+              for (int q = 0; q < m; q++)
+                dst[q] = (float)Bi[(size_t)a * bj + q];
+              block_of_row[perm[s0 + a]] = block_id;
+            }
+          }
+        }
+      }
+    }
     SmallPlan *P = new SmallPlan();
     P->C = C, P->n = (uint32_t)n, P->smem = mp.total;
     P->max_ent = max_ent, P->max_groups = max_groups, P->max_stage = max_stage;
@@ -967,6 +1149,19 @@ int small_try_build(b200_mat *M) {
     if (!P->smem_k[1]) {
       delete P;
       continue;
+    }
+    if (bj) {
+      const size_t bytes = smem_map(max_ent, max_groups, max_stage, 1, bj).total;
+      for (int pf = 0; pf < 2; pf++)
+        if (cudaFuncSetAttribute((const void *)small_kernel(pf != 0, 1, bj),
+                                 cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+            cudaFuncSetAttribute((const void *)small_kernel(pf != 0, 1, bj),
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+          cudaGetLastError();
+          bj = 0;
+        }
+      if (bj)
+        P->bj = bj, P->smem_bj = bytes, P->block_of_row = block_of_row;
     }
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[1];
@@ -995,11 +1190,26 @@ int small_try_build(b200_mat *M) {
     B_TRY(up((void **)&P->d_vals, pv.data(), pv.size() * 8));
     B_TRY(up((void **)&P->d_cols, pc.data(), pc.size() * 2));
     B_TRY(up((void **)&P->d_dinv, pd.data(), pd.size() * 8));
+    if (P->bj)
+      B_TRY(up((void **)&P->d_binv, binv.data(), binv.size() * 4));
+    B_TRY(up((void **)&P->d_slotof, slotof.data(), slotof.size() * 2));
     CU_TRY(cudaMalloc(&P->d_state, sizeof(PcgState)));
     CU_TRY(cudaMalloc(&P->d_prof, 16 * sizeof(long long)));
     M->small = P;
     return B200_OK;
   }
+  return B200_OK;
+}
+
+extern "C" int b200_mat_block_jacobi_partition(b200_mat *M, uint32_t *block_of_row, uint32_t *block_size) {
+  if (!M || !block_of_row || !block_size)
+    B_FAIL(B200_EINVAL, "b200_mat_block_jacobi_partition: null argument");
+  CU_TRY(cudaSetDevice(M->ctx->device));
+  B_TRY(small_try_build(M));
+  const SmallPlan *P = (const SmallPlan *)M->small;
+  *block_size = P ? (uint32_t)P->bj : 0u;
+  if (P && P->bj)
+    memcpy(block_of_row, P->block_of_row.data(), P->block_of_row.size() * sizeof(uint32_t));
   return B200_OK;
 }
 
@@ -1018,16 +1228,19 @@ int small_solve(b200_mat *M, const double *d_b, double *d_x,
   }();
   int kdeg = (o->flags & B200_PCG_CHEBYSHEV3) ? 3 : (o->flags & B200_PCG_CHEBYSHEV2) ? 2 : env_deg;
   kdeg = kdeg < 1 ? 1 : kdeg > P->max_kdeg ? P->max_kdeg : kdeg;
-  cfg.dynamicSmemBytes = P->smem_k[kdeg];
+  // block-Jacobi: B200_PCG_BLOCK_JACOBI, when a block size fits (Chebyshev-Jacobi wins a tie)
+  const int bj = ((o->flags & B200_PCG_BLOCK_JACOBI) && kdeg == 1) ? P->bj : 0;
+  cfg.dynamicSmemBytes = bj ? P->smem_bj : P->smem_k[kdeg];
   const double la = P->lmax / 30.0, theta = 0.5 * (P->lmax + la), delta = 0.5 * (P->lmax - la);
   CU_TRY(cudaEventRecord(c->ev_a, s));
   static const bool prof = getenv("B200_SMALL_PROFILE") != nullptr;
-  CU_TRY(cudaLaunchKernelEx(&cfg, small_kernel(prof, kdeg),
+  CU_TRY(cudaLaunchKernelEx(&cfg, small_kernel(prof, kdeg, bj),
                             (const SmallCta *)P->d_cta,
                             (const uint32_t *)P->d_goff, (const uint32_t *)P->d_rowid,
                             (const uint32_t *)P->d_dmask, (const uint32_t *)P->d_orig,
                             (const uint32_t *)P->d_perm, (const double *)P->d_vals, (const uint16_t *)P->d_cols,
-                            (const double *)P->d_dinv, d_b, d_x,
+                            (const double *)P->d_dinv, (const float *)P->d_binv,
+                            (const uint16_t *)P->d_slotof, d_b, d_x,
                             P->d_state, P->max_ent, P->max_groups, P->max_stage,
                             o->tol, (int)o->maxit, P->d_prof, theta, delta));
   c->launches += 1;
@@ -1044,6 +1257,7 @@ int small_solve(b200_mat *M, const double *d_b, double *d_x,
   res->path = 1;
   res->replacements = h.replacements;
   res->outer_iters = kdeg;  // (on this path: the degree of the preconditioner that ran)
+  res->block_jacobi = (uint32_t)bj;
   if (prof && h.iter > 0) {
     long long hp[6];
     CU_TRY(cudaMemcpy(hp, P->d_prof, sizeof hp, cudaMemcpyDeviceToHost));

@@ -78,10 +78,13 @@ static struct settings read_settings(void) {
   if ((v = getenv("LSBENCH_B200_OPERATOR")) && strcmp(v, "full") == 0)
     s.flags = 0;
   /* "stream": never the on-chip coarse-grid kernel, always the streaming kernels;
-   * "cheb2" / "cheb3": Chebyshev-Jacobi of that degree on the on-chip path */
+   * "cheb2" / "cheb3": Chebyshev-Jacobi of that degree on the on-chip path;
+   * "bj": block-Jacobi on the on-chip path; "jacobi": plain Jacobi everywhere */
   if ((v = getenv("LSBENCH_B200_PCG"))) {
     if (strcmp(v, "stream") == 0)
       s.pcg_flags |= B200_PCG_NO_SMALL;
+    else if (strcmp(v, "bj") == 0)
+      s.pcg_flags |= B200_PCG_BLOCK_JACOBI;
     else if (strcmp(v, "cheb2") == 0)
       s.pcg_flags |= B200_PCG_CHEBYSHEV2;
     else if (strcmp(v, "cheb3") == 0)

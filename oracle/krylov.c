@@ -468,3 +468,170 @@ int orc_pcg_cheb(const orc_op *M, const double *b, double *x, double tol, int ma
   free(r), free(dinv);
   return rc;
 }
+
+/* ---- block-Jacobi PCG -----------------------------------------------
+ * z = B^-1 r with B the diagonal blocks of A over a given partition of the rows
+ * (block_of_row[i] = block id of row i; ids are arbitrary, a block may be any subset).
+ * A block is symmetrised, inverted through its Cholesky factor and -- as the product
+ * keeps it in shared memory -- rounded to fp32; everything else is fp64.  The method
+ * csrc/small.cu runs with B200_PCG_BLOCK_JACOBI, on the partition
+ * b200_mat_block_jacobi_partition reports.  What the reference reaches for on these
+ * systems is algebraic multigrid (src/hypre.c:126-188, src/amgx.c:78-85).  Same
+ * contract as orc_pcg; rc 3 when a block is not positive definite. */
+typedef struct {
+  uint32_t m;     /* rows */
+  uint32_t *rows; /* ascending */
+  float *inv;     /* m x m, symmetric */
+} bj_block;
+
+static int cmp_u64(const void *a, const void *b) {
+  const uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
+  return x < y ? -1 : x > y;
+}
+
+int orc_pcg_bj(const orc_op *M, const double *b, double *x, double tol, int maxit,
+               const uint32_t *block_of_row, int *iters, double *relres) {
+  const int64_t n = (int64_t)M->n;
+  /* rows grouped by block id: sort (id, row) pairs */
+  uint64_t *key = (uint64_t *)malloc((size_t)(n ? n : 1) * sizeof(uint64_t));
+  for (int64_t i = 0; i < n; i++)
+    key[i] = ((uint64_t)block_of_row[i] << 32) | (uint64_t)i;
+  qsort(key, (size_t)n, sizeof(uint64_t), cmp_u64);
+  int64_t nblocks = 0;
+  for (int64_t i = 0; i < n; i++)
+    nblocks += i == 0 || (key[i] >> 32) != (key[i - 1] >> 32);
+  bj_block *blk = (bj_block *)calloc((size_t)(nblocks ? nblocks : 1), sizeof(bj_block));
+  uint32_t *pos = (uint32_t *)malloc((size_t)(n ? n : 1) * sizeof(uint32_t)); /* row -> index in its block */
+  int rc = 1;
+  int64_t k = -1;
+  for (int64_t i = 0; i < n;) {
+    int64_t j = i;
+    while (j < n && (key[j] >> 32) == (key[i] >> 32))
+      j++;
+    bj_block *B = &blk[++k];
+    B->m = (uint32_t)(j - i);
+    B->rows = (uint32_t *)malloc(B->m * sizeof(uint32_t));
+    for (int64_t t = i; t < j; t++)
+      B->rows[t - i] = (uint32_t)(key[t] & 0xffffffffu), pos[B->rows[t - i]] = (uint32_t)(t - i);
+    i = j;
+  }
+  for (k = 0; k < nblocks && rc == 1; k++) {
+    bj_block *B = &blk[k];
+    const uint32_t m = B->m;
+    double *D = (double *)calloc((size_t)m * m * 3, sizeof(double)), *L = D + (size_t)m * m, *Li = L + (size_t)m * m;
+    for (uint32_t a = 0; a < m; a++) {
+      const uint32_t r = B->rows[a];
+      for (uint64_t e = M->offs[r]; e < M->offs[r + 1]; e++) {
+        const uint32_t c = M->cols[e];
+        if (c < (uint64_t)n && block_of_row[c] == block_of_row[r])
+          D[(size_t)a * m + pos[c]] += M->vals[e];
+      }
+    }
+    for (uint32_t a = 0; a < m; a++)
+      for (uint32_t q = 0; q < a; q++) {
+        const double v = 0.5 * (D[(size_t)a * m + q] + D[(size_t)q * m + a]);
+        D[(size_t)a * m + q] = D[(size_t)q * m + a] = v;
+      }
+    for (uint32_t a = 0; a < m && rc == 1; a++) /* D = L L^T */
+      for (uint32_t q = 0; q <= a; q++) {
+        double v = D[(size_t)a * m + q];
+        for (uint32_t t = 0; t < q; t++)
+          v -= L[(size_t)a * m + t] * L[(size_t)q * m + t];
+        if (a == q) {
+          if (!(v > 0.0)) {
+            rc = 3;
+            break;
+          }
+          L[(size_t)a * m + a] = sqrt(v);
+        } else {
+          L[(size_t)a * m + q] = v / L[(size_t)q * m + q];
+        }
+      }
+    B->inv = (float *)calloc((size_t)m * m, sizeof(float));
+    if (rc == 1) {
+      for (uint32_t q = 0; q < m; q++) { /* Li = L^-1 */
+        Li[(size_t)q * m + q] = 1.0 / L[(size_t)q * m + q];
+        for (uint32_t a = q + 1; a < m; a++) {
+          double v = 0.0;
+          for (uint32_t t = q; t < a; t++)
+            v -= L[(size_t)a * m + t] * Li[(size_t)t * m + q];
+          Li[(size_t)a * m + q] = v / L[(size_t)a * m + a];
+        }
+      }
+      for (uint32_t a = 0; a < m; a++) /* D^-1 = Li^T Li, rounded to fp32 */
+        for (uint32_t q = 0; q <= a; q++) {
+          double v = 0.0;
+          for (uint32_t t = a; t < m; t++)
+            v += Li[(size_t)t * m + a] * Li[(size_t)t * m + q];
+          B->inv[(size_t)a * m + q] = B->inv[(size_t)q * m + a] = (float)v;
+        }
+    }
+    free(D);
+  }
+  double *r = (double *)malloc(4 * (size_t)(n ? n : 1) * sizeof(double));
+  double *p = r + n, *q = p + n, *z = q + n;
+#define ORC_BJ_APPLY()                                                         \
+  for (int64_t kb = 0; kb < nblocks; kb++) {                                   \
+    const bj_block *B = &blk[kb];                                              \
+    for (uint32_t a = 0; a < B->m; a++) {                                      \
+      double s = 0.0;                                                          \
+      for (uint32_t c = 0; c < B->m; c++)                                      \
+        s += (double)B->inv[(size_t)a * B->m + c] * r[B->rows[c]];             \
+      z[B->rows[a]] = s;                                                       \
+    }                                                                          \
+  }
+  double bb = 0, rz = 0, rr = 0;
+  int it = 0;
+  if (rc == 1) {
+    orc_spmv(M, x, q, NULL);
+    for (int64_t i = 0; i < n; i++) {
+      r[i] = b[i] - q[i];
+      bb += b[i] * b[i], rr += r[i] * r[i];
+    }
+    ORC_BJ_APPLY();
+    for (int64_t i = 0; i < n; i++)
+      p[i] = z[i], rz += r[i] * z[i];
+  }
+  const double bnorm = sqrt(bb), thr = tol * bnorm;
+  if (rc == 1 && sqrt(rr) <= thr)
+    rc = 0;
+  while (rc == 1 && it < maxit) {
+    double pq = 0;
+    orc_spmv(M, p, q, NULL);
+    for (int64_t i = 0; i < n; i++)
+      pq += p[i] * q[i];
+    if (!(pq > 0.0)) {
+      rc = 2;
+      break;
+    }
+    const double alpha = rz / pq;
+    rr = 0;
+    for (int64_t i = 0; i < n; i++) {
+      x[i] += alpha * p[i];
+      r[i] -= alpha * q[i];
+      rr += r[i] * r[i];
+    }
+    it++;
+    if (sqrt(rr) <= thr) {
+      rc = 0;
+      break;
+    }
+    ORC_BJ_APPLY();
+    double rzn = 0;
+    for (int64_t i = 0; i < n; i++)
+      rzn += r[i] * z[i];
+    const double beta = rzn / rz;
+    rz = rzn;
+    for (int64_t i = 0; i < n; i++)
+      p[i] = z[i] + beta * p[i];
+  }
+#undef ORC_BJ_APPLY
+  if (iters)
+    *iters = it;
+  if (relres)
+    *relres = bnorm > 0 ? sqrt(rr) / bnorm : sqrt(rr);
+  for (k = 0; k < nblocks; k++)
+    free(blk[k].rows), free(blk[k].inv);
+  free(blk), free(pos), free(key), free(r);
+  return rc;
+}

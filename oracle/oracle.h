@@ -87,6 +87,12 @@ int orc_pcg_omp(const orc_op *M, const double *b, double *x, double tol,
  * coarse-grid kernel (csrc/small.cu) runs with B200_PCG_CHEBYSHEV. */
 int orc_pcg_cheb(const orc_op *M, const double *b, double *x, double tol, int maxit,
                  int degree, double lmax, double ratio, int *iters, double *relres);
+/* block-Jacobi.  z = B^-1 r, B = the diagonal blocks of A over the
+ * partition block_of_row[] (a block symmetrised, inverted by Cholesky, rounded to fp32 as
+ * the product stores it).  Same contract as orc_pcg; 3 = a block is not positive definite.
+ * What csrc/small.cu runs with B200_PCG_BLOCK_JACOBI. */
+int orc_pcg_bj(const orc_op *M, const double *b, double *x, double tol, int maxit,
+               const uint32_t *block_of_row, int *iters, double *relres);
 /* Upper bound of the spectrum of D^-1 A the product uses: min(Gershgorin bound,
  * 1.15 x power-iteration estimate after 40 steps from the vector of ones). */
 double orc_cheb_lmax(const orc_op *M);

@@ -289,6 +289,21 @@ def pcg_cheb(M, b, degree=2, lmax=None, ratio=30.0, x0=None, tol=1e-10, maxit=10
     return x, it.value, rel.value, rc
 
 
+def pcg_bj(M, b, block_of_row, x0=None, tol=1e-10, maxit=10000):
+    """block-Jacobi preconditioned CG on a given partition of the rows, oracle/krylov.c"""
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    blk = np.ascontiguousarray(block_of_row, dtype=np.uint32)
+    assert blk.size == M.n
+    x = np.zeros(M.n) if x0 is None else np.array(x0, dtype=np.float64)
+    it, rel = C.c_int(0), C.c_double(0)
+    s = M.as_struct()
+    f = lib().orc_pcg_bj
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p,
+                  C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    rc = f(C.byref(s), b.ctypes.data, x.ctypes.data, tol, maxit, blk.ctypes.data, C.byref(it), C.byref(rel))
+    return x, it.value, rel.value, rc
+
+
 def pcg_refine32(M, b, x0=None, tol=1e-10, maxit=10000, eta=1e-4):
     """fp32-stored operator + fp64 refinement, oracle/krylov.c"""
     b = np.ascontiguousarray(b, dtype=np.float64)

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(abi):
     L = ctypes.CDLL(abi.LIB_PATH)
     for s in declared_symbols():
         assert hasattr(L, s), s
-    assert abi.load().b200_abi_version() == 4
+    assert abi.load().b200_abi_version() == 5
 
 
 def test_struct_sizes_match_header(abi, tmp_path):
@@ -49,7 +49,7 @@ def test_struct_sizes_match_header(abi, tmp_path):
     assert got == [ctypes.sizeof(abi.MatInfo), ctypes.sizeof(abi.PcgOpts), ctypes.sizeof(abi.PcgResult),
                    abi.MatInfo.values_f32.offset, abi.PcgResult.outer_iters.offset]
     # b200_mat_info: 16 u64 + 24 u64 hist + u64 + 2 u32 + 3 u64 + 2 u32
-    assert got[:3] == [8 * (16 + 24 + 1) + 8 + 8 * 3 + 8, 24, 64]
+    assert got[:3] == [8 * (16 + 24 + 1) + 8 + 8 * 3 + 8, 24, 72]
 
 
 def test_product_does_not_reach_into_the_oracle():

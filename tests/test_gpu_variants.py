@@ -195,3 +195,42 @@ def test_column_blocked_spmv_small_shapes(abi, ctx, monkeypatch):
         ref, scale = orc.spmv(Mo, x, want_abs=True)
         assert np.all(np.abs(y - ref) <= 1e-13 * np.maximum(scale, 1e-300))
         M.close()
+
+
+# ------------------------------------------------------------------ block-Jacobi on the on-chip path
+@pytest.mark.parametrize("name", orc.NEK)
+def test_block_jacobi_on_the_onchip_kernel(abi, ctx, name):
+    """SURVEY 8(f) row 2 (B200_PCG_BLOCK_JACOBI): the on-chip coarse-grid kernel with the
+    inverted diagonal blocks of its row chunks as preconditioner, against the oracle's
+    statement of the method on the partition the library reports (orc_pcg_bj: iteration
+    counts within 3) and the direct solve (1e-8), at the 1e-10 bar on the true residual;
+    fewer iterations than Jacobi; reproducible bit for bit; the streaming path ignores it."""
+    A = orc.matrix_read(orc.matrix_path(name))
+    Mo = orc.op_upper_mirror(A)
+    b = orc.rhs(Mo.n)
+    M = make(abi, ctx, A, abi.MAT_SYM_UPPER)
+    part, bs = M.block_jacobi_partition()
+    assert bs in (16, 32)
+    sizes = np.bincount(part)
+    assert sizes.max() == bs and np.sum(sizes < bs) <= 16      # one short block per row chunk at most
+    x1, r1, _ = M.pcg_host(b, tol=1e-10, maxit=5000)
+    assert r1.path == 1 and r1.block_jacobi == 0
+    x, r, rc = M.pcg_host(b, tol=1e-10, maxit=5000, flags=abi.PCG_BLOCK_JACOBI)
+    assert rc == 0 and r.status == 0 and r.path == 1 and r.block_jacobi == bs
+    assert r.true_relres <= 1e-10 and orc.true_relres(Mo, b, x) <= 1e-10
+    assert np.linalg.norm(x - DIRECT[name]) / np.linalg.norm(DIRECT[name]) <= 1e-8
+    _, ito, _, rco = orc.pcg_bj(Mo, b, part)
+    assert rco == 0 and abs(r.iters - ito) <= 3 + 8 * r.replacements, (r.iters, ito, r.replacements)
+    assert r.iters < 0.9 * r1.iters
+    x2, r2, _ = M.pcg_host(b, tol=1e-10, maxit=5000, flags=abi.PCG_BLOCK_JACOBI)
+    assert r2.iters == r.iters and x2.tobytes() == x.tobytes()
+    xs, rs, _ = M.pcg_host(b, tol=1e-10, maxit=5000, flags=abi.PCG_NO_SMALL | abi.PCG_BLOCK_JACOBI)
+    assert rs.path == 0 and rs.status == 0 and rs.block_jacobi == 0 and abs(rs.iters - r1.iters) <= 2
+    # x0 given, and the operator as stored (unsymmetric at 1e-8: the blocks are symmetrised)
+    x3, r3, _ = M.pcg_host(b, x0=0.5 * x, tol=1e-10, maxit=5000, flags=abi.PCG_BLOCK_JACOBI)
+    assert r3.status == 0 and r3.true_relres <= 1e-10
+    M.close()
+    Mf = make(abi, ctx, A, 0)
+    xf, rf, rcf = Mf.pcg_host(b, tol=1e-10, maxit=5000, flags=abi.PCG_BLOCK_JACOBI)
+    assert rcf == 0 and rf.status == 0 and rf.true_relres <= 1e-10 and rf.block_jacobi in (16, 32)
+    Mf.close()

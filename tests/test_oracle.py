@@ -319,3 +319,63 @@ def test_chebyshev_jacobi_pcg_restated(name):
     # degree 1 is Jacobi scaled by 1 / theta: the same Krylov iteration
     assert abs(its[1] - it1) <= 2
     assert 0.45 * it1 <= its[2] <= 0.60 * it1 and 0.30 * it1 <= its[3] <= 0.42 * it1
+
+
+@pytest.mark.parametrize("name", ["tj7a_A_18", "xn3b_A_18"])
+def test_block_jacobi_pcg_restated(name):
+    """SURVEY 8(f) row 2, block-Jacobi (oracle/krylov.c orc_pcg_bj): blocks of one row are
+    plain Jacobi; blocks of 16 and 32 consecutive rows against an independent numpy
+    statement of the method (dense inverses in fp64 -- the oracle rounds them to fp32, which
+    moves the iteration count by at most 2), fewer iterations, the same solution (1e-8 of
+    the direct solve) at the 1e-10 bar; an irregular partition; a block that is not
+    positive definite is refused."""
+    A = orc.matrix_read(orc.matrix_path(name))
+    M = orc.op_upper_mirror(A)
+    S = M.scipy().tocsr()
+    b = orc.rhs(M.n)
+    _, it_j, _, rc_j = orc.pcg(M, b)
+    x1, it1, _, rc1 = orc.pcg_bj(M, b, np.arange(M.n))
+    assert rc_j == 0 and rc1 == 0 and abs(it1 - it_j) <= 1
+
+    def numpy_bj(blocks):
+        inv = [np.linalg.inv(S[r][:, r].toarray()) for r in blocks]
+        x, r = np.zeros(M.n), b.copy()
+
+        def apply(v):
+            z = np.empty_like(v)
+            for rows, Bi in zip(blocks, inv):
+                z[rows] = Bi @ v[rows]
+            return z
+        z = apply(r)
+        p, rz, thr = z.copy(), r @ z, 1e-10 * np.linalg.norm(b)
+        for it in range(1, 5000):
+            q = S @ p
+            a = rz / (p @ q)
+            x += a * p
+            r -= a * q
+            if np.linalg.norm(r) <= thr:
+                return x, it
+            z = apply(r)
+            rzn = r @ z
+            p, rz = z + (rzn / rz) * p, rzn
+        return x, 5000
+
+    last = it_j
+    for bs in (16, 32):
+        part = np.arange(M.n) // bs
+        x, it, rel, rc = orc.pcg_bj(M, b, part)
+        assert rc == 0 and rel <= 1e-10 and orc.true_relres(M, b, x) <= 1.01e-10
+        xn, itn = numpy_bj([np.arange(s, min(s + bs, M.n)) for s in range(0, M.n, bs)])
+        assert abs(it - itn) <= 2, (bs, it, itn)
+        assert it < last
+        last = it
+        assert np.linalg.norm(x - DIRECT[name]) / np.linalg.norm(DIRECT[name]) <= 1e-8
+    # any partition will do: block ids in any order, blocks of any shape
+    rng = np.random.default_rng(3)
+    part = rng.permutation(M.n // 7 + 1)[np.arange(M.n) // 7]
+    x, it, rel, rc = orc.pcg_bj(M, b, part)
+    assert rc == 0 and np.linalg.norm(x - DIRECT[name]) / np.linalg.norm(DIRECT[name]) <= 1e-8
+    # a block that is not positive definite
+    bad = orc.Op(M.n, M.offs, M.cols, np.where(M.cols == np.repeat(np.arange(M.n), np.diff(M.offs.astype(np.int64))),
+                                                -M.vals, M.vals))
+    assert orc.pcg_bj(bad, b, np.arange(M.n) // 4)[3] == 3

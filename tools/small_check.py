@@ -26,7 +26,10 @@ for name in orc.NEK:
     M = abi.Matrix.from_csr(ctx, A.nrows, A.base, A.offs, A.cols, A.vals, abi.MAT_SYM_UPPER)
     db, dx = ctx.array(Mo.n).upload(b), ctx.array(Mo.n)
     out = {"matrix": name, "n": int(Mo.n)}
-    for label, fl in (("jacobi", 0), ("cheb2", abi.PCG_CHEBYSHEV2), ("cheb3", abi.PCG_CHEBYSHEV3)):
+    modes = (("jacobi", 0), ("bj", abi.PCG_BLOCK_JACOBI), ("cheb2", abi.PCG_CHEBYSHEV2), ("cheb3", abi.PCG_CHEBYSHEV3))
+    if os.environ.get("SMALL_CHECK_MODES"):
+        modes = tuple(m for m in modes if m[0] in os.environ["SMALL_CHECK_MODES"].split(","))
+    for label, fl in modes:
         try:
             for _ in range(3):
                 dx.zero()
@@ -41,6 +44,7 @@ for name in orc.NEK:
             x = dx.download()
             out[label] = {"ms_wall": round(dt * 1e3, 4), "ms_kernel": round(r.solve_ms, 4), "iters": r.iters,
                           "status": r.status, "degree": r.outer_iters, "path": r.path,
+                          "block_jacobi": r.block_jacobi,
                           "true_relres": r.true_relres, "replacements": r.replacements,
                           "rel_diff_direct": float(np.linalg.norm(x - gold[name]) / np.linalg.norm(gold[name]))}
         except abi.B200Error as e:
@@ -50,8 +54,9 @@ for name in orc.NEK:
     M.close()
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "small_check.json"), "w"), indent=1)
-print("%-10s | %-22s | %-22s | %-22s" % ("matrix", "jacobi its / ms", "cheb2 its / ms", "cheb3 its / ms"))
+keys = [m[0] for m in modes]
+print("%-10s | " % "matrix" + " | ".join("%-22s" % (k + " its / ms") for k in keys))
 for o in rows:
     print("%-10s | " % o["matrix"] + " | ".join(
-        "%5d / %7.3f ms      " % (o[k]["iters"], o[k]["ms_wall"]) if "iters" in o[k] else "error                 "
-        for k in ("jacobi", "cheb2", "cheb3")))
+        "%5d / %7.3f ms      " % (o[k]["iters"], o[k]["ms_wall"]) if "iters" in o.get(k, {}) else "error                 "
+        for k in keys))
