@@ -608,7 +608,8 @@ def nek_legs(abi, ctx, trials=100, cu_trials=3):
     """BASELINE.json config 2 the way the reference runs it -- `driver --solver X --matrix
     F --trials=T` (bin/driver.c), warm-up + timed loop inside X_bench (src/cholmod-impl.h:
     45-63), `elapsed` from the CSV row: this repository's driver with --solver b200 (on-chip
-    kernel, and LSBENCH_B200_PCG=stream for the streaming kernels), the reference's own
+    kernel with its default block-Jacobi preconditioner, LSBENCH_B200_PCG=jacobi for plain
+    Jacobi on the same kernel, and LSBENCH_B200_PCG=stream for the streaming kernels), the reference's own
     cuSOLVER backend UNMODIFIED (oracle/_ref/driver_cusolver, src/cusparse.c:181-209; it
     refactors in every call), and the CPU direct-solve stand-in for the CHOLMOD backend
     (oracle LDL^T with RCM, factor untimed, one core).  x is checked against the direct
@@ -634,7 +635,8 @@ def nek_legs(abi, ctx, trials=100, cu_trials=3):
     for name in NEK:
         path = nek_file(name)
         o = {}
-        for label, env in (("onchip", {}), ("streaming", {"LSBENCH_B200_PCG": "stream"})):
+        for label, env in (("onchip", {}), ("onchip_jacobi", {"LSBENCH_B200_PCG": "jacobi"}),
+                           ("streaming", {"LSBENCH_B200_PCG": "stream"})):
             xf = os.path.join(os.path.dirname(path), name + ".%s.x" % label)
             e = dict(os.environ)
             e.update(env)
@@ -648,7 +650,7 @@ def nek_legs(abi, ctx, trials=100, cu_trials=3):
             o["n"], o["nnz"] = int(row[1]), int(row[2])
             o[label] = {"ms_per_solve": float(row[6]) / trials * 1e3, "trials": trials,
                         "iterations": int(ext[1]), "status": int(ext[2]), "true_relres": float(ext[4]),
-                        "path": int(ext[7]),
+                        "path": int(ext[7]), "block_jacobi": int(ext[8]) if len(ext) > 8 else 0,
                         "rel_diff_direct": float(np.linalg.norm(x - gold[name]) / np.linalg.norm(gold[name]))}
         o["ref_cusolver"] = None
         if os.path.exists(cu_drv):

@@ -154,16 +154,30 @@ def test_driver_precision_fp32_and_chebyshev(bh, tmp_path):
     M = orc.gen_poisson27(40)
     assert orc.true_relres(M, orc.rhs(M.n), np.fromfile(out)) <= 1e-10
     r0 = subprocess.run([bh.DRIVER, "--solver", "b200", "--matrix", orc.matrix_path(name), "--trials=2"],
-                        capture_output=True, text=True, timeout=600)
+                        capture_output=True, text=True, timeout=600,
+                        env=dict(os.environ, LSBENCH_B200_PCG="jacobi"))
     r = subprocess.run([bh.DRIVER, "--solver", "b200", "--matrix", orc.matrix_path(name), "--trials=2",
                         "--dump-x", out], capture_output=True, text=True, timeout=600,
                        env=dict(os.environ, LSBENCH_B200_PCG="cheb2"))
     assert r.returncode == 0 and r0.returncode == 0, r.stderr
     (_, e0), (_, e2) = parse(r0.stdout), parse(r.stdout)
     assert int(e2[2]) == 0 and float(e2[4]) <= 1e-10 and int(e2[7]) == 1
+    assert int(e0[8]) == 0 and int(e0[7]) == 1
     assert int(e2[1]) < 0.62 * int(e0[1])                      # about half of Jacobi's iterations
     x = np.fromfile(out)
     assert np.linalg.norm(x - g) / np.linalg.norm(g) <= 1e-8
+    # the default on the on-chip path: block-Jacobi (fewer iterations than Jacobi, same bars)
+    rb = subprocess.run([bh.DRIVER, "--solver", "b200", "--matrix", orc.matrix_path(name), "--trials=2",
+                         "--dump-x", out], capture_output=True, text=True, timeout=600)
+    assert rb.returncode == 0, rb.stderr
+    _, eb = parse(rb.stdout)
+    assert int(eb[2]) == 0 and float(eb[4]) <= 1e-10 and int(eb[7]) == 1 and int(eb[8]) in (16, 32)
+    assert int(eb[1]) < 0.9 * int(e0[1])
+    x = np.fromfile(out)
+    assert np.linalg.norm(x - g) / np.linalg.norm(g) <= 1e-8
+    bad = subprocess.run([bh.DRIVER, "--solver", "b200", "--matrix", orc.matrix_path(name), "--trials=1"],
+                         capture_output=True, text=True, timeout=600, env=dict(os.environ, LSBENCH_B200_PCG="ilu"))
+    assert bad.returncode != 0 and "LSBENCH_B200_PCG" in bad.stderr
 
 
 def test_stock_lsbench_tree_with_b200_dropped_in(bh):
