@@ -245,7 +245,8 @@ enum {
   B200_PCG_CHEBYSHEV3 = 1u << 5,
   /* SURVEY 8f row 2, block-Jacobi on the on-chip coarse-grid path: z = B^-1 r, B the
    * diagonal blocks of 32 (16 when shared memory is short) consecutive rows of a CTA's
-   * row chunk, inverted once on the host and kept as fp32 in shared memory.  No exchange
+   * row chunk, inverted once on the host and kept in shared memory as the high 32 bits of
+   * every fp64 entry (a preconditioner may be rounded; widening costs nothing).  No exchange
    * and no reduction more than Jacobi, 0.4 - 0.8 x the iterations on the Nek matrices.
    * What the reference reaches for on these systems is algebraic multigrid
    * (src/hypre.c:126-188, src/amgx.c:78-85); this is the step in that direction that

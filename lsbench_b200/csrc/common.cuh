@@ -228,6 +228,8 @@ struct b200_mat {
   uint64_t col_block_width = 0;
   void *small = nullptr;          // on-chip small-matrix plan (small.cu)
   bool small_tried = false;
+  void *small_bj = nullptr;       // the plan block-Jacobi runs on (rows regrouped into blocks)
+  bool small_bj_tried = false;
   void *graph_exec = nullptr;     // cudaGraphExec_t of one iteration chunk
   int graph_chunk = 0;
   int graph_kernels = 0;         // kernel nodes in the captured chunk
@@ -255,7 +257,7 @@ int ensure_workspace(b200_mat *M);
 int launch_spmv(b200_mat *M, const double *x_ext, double *y, bool fuse_dot,
                 int phase /*0 all, 1 interior, 2 boundary*/, const XrArgs *xr);
 int allreduce_sum(b200_ctx *ctx, const double *d_src, double *d_dst, int count);
-int small_try_build(b200_mat *M);
+int small_try_build(b200_mat *M, bool blocks = false);
 void small_free(b200_mat *M);
 int small_solve(b200_mat *M, const double *d_b, double *d_x,
                 const b200_pcg_opts *o, b200_pcg_result *res);

@@ -79,7 +79,7 @@ struct SmallPlan {
   // blocks as fp32 rows of bj + 1 values per chunk row, chunk row -> slot, shared memory, and
   // the block every row of the caller's numbering belongs to (b200_mat_block_jacobi_partition)
   int bj = 0;
-  float *d_binv = nullptr;
+  uint32_t *d_binv = nullptr;  // high words of the fp64 entries
   uint16_t *d_slotof = nullptr;
   size_t smem_bj = 0;
   std::vector<uint32_t> block_of_row;
@@ -94,8 +94,9 @@ struct SmemMap {
 
 // kdeg > 1 (Chebyshev-Jacobi): two more windows (the direction d of the polynomial
 // recurrence lands in them alternately) and three more vectors on the owned rows
-// bj > 0 (block-Jacobi): r once more in chunk-row order (blocks padded to bj + 1 entries
-// apart: no two blocks start in the same bank), the inverted blocks, chunk row -> slot
+// bj > 0 (block-Jacobi): r once more in chunk-row order (blocks bj + 2 entries apart: 16-byte
+// aligned, and the two blocks a warp may read start in different banks), the inverted blocks
+// (rows bj + 1 words apart: a warp's 32 rows in 32 banks), chunk row -> slot
 __host__ __device__ inline SmemMap smem_map(uint32_t max_ent, uint32_t max_groups,
                                             uint32_t max_stage, int kdeg, int bj = 0) {
   SmemMap m;
@@ -113,7 +114,8 @@ __host__ __device__ inline SmemMap smem_map(uint32_t max_ent, uint32_t max_group
   m.rhs = o, o += kdeg > 1 ? rows * 8 : 0;
   m.dds = o, o += kdeg > 1 ? rows * 8 : 0;
   m.zzs = o, o += kdeg > 1 ? rows * 8 : 0;
-  m.rrow = o, o += bj ? (rows / bj + 2) * (size_t)(bj + 1) * 8 : 0;
+  o = (o + 15) / 16 * 16;
+  m.rrow = o, o += bj ? (rows / bj + 2) * (size_t)(bj + 2) * 8 : 0;
   m.slots = o, o += 4 * SM_MAX_CLUSTER * 8;  // pq | rz | rr | bb
   m.wred = o, o += 3 * SM_WARPS * 8;
   m.bars = o, o += 4 * 8;
@@ -347,7 +349,10 @@ __device__ __forceinline__ void read_totals(unsigned C, const double *slots, int
 //
 // BJ: block-Jacobi.  z = B^-1 r with B the diagonal blocks of BJ consecutive
 // rows of a CTA's chunk, inverted on the host, stored as fp32 (a preconditioner may be
-// rounded: symmetric, still positive definite; the recurrences stay fp64).  No exchange
+// rounded: symmetric, still positive definite; the recurrences stay fp64) -- more exactly as
+// the HIGH WORD of the fp64 value, rounded to nearest: 20 bits of mantissa, and widening it
+// back is a register move, where an fp32 -> fp64 conversion issues at a quarter of the fma
+// rate and was half of what this phase cost.  No exchange
 // and no reduction is added: the rows of a block live in one CTA.  The update runs in two
 // passes: x, r in slot order (r also into chunk-row order); then, one thread per chunk row --
 // the lanes of a warp are then rows of the same one or two blocks and read the block's r as
@@ -359,7 +364,7 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
             const uint32_t *__restrict__ g_orig, const uint32_t *__restrict__ g_perm,
             const double *__restrict__ g_vals,
             const uint16_t *__restrict__ g_cols, const double *__restrict__ g_dinv,
-            const float *__restrict__ g_binv, const uint16_t *__restrict__ g_slotof,
+            const uint32_t *__restrict__ g_binv, const uint16_t *__restrict__ g_slotof,
             const double *__restrict__ b, double *__restrict__ x, PcgState *st,
             uint32_t max_ent, uint32_t max_groups, uint32_t max_stage, double tol,
             int maxit, long long *prof, double cheb_theta, double cheb_delta) {
@@ -382,7 +387,7 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
   uint32_t *dmask = (uint32_t *)(smem + mp.dmask), *orig = (uint32_t *)(smem + mp.orig);
   uint16_t *cols = (uint16_t *)(smem + mp.cols);
   double *rrow_s = (double *)(smem + mp.rrow);
-  float *binv_s = (float *)(smem + mp.binv);
+  uint32_t *binv_s = (uint32_t *)(smem + mp.binv);
   uint16_t *slotof = (uint16_t *)(smem + mp.slotof);
   const uint32_t tid = threadIdx.x, nslot = me.n_groups * 8;
   long long pt[6] = {0, 0, 0, 0, 0, 0}, t0 = 0;
@@ -410,7 +415,7 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
       binv_s[i] = g_binv[(size_t)me.row_at * (BJ + 1) + i];
     for (uint32_t i = tid; i < me.n_rows; i += SM_THREADS)
       slotof[i] = g_slotof[me.row_at + i];
-    for (uint32_t i = tid; i < (nslot / (BJ ? BJ : 1) + 2) * (BJ + 1); i += SM_THREADS)
+    for (uint32_t i = tid; i < (nslot / (BJ ? BJ : 1) + 2) * (BJ + 2); i += SM_THREADS)
       rrow_s[i] = 0.0;  // (rows past the end of the last block stay zero)
   }
   if (tid < SM_MAX_CLUSTER)  // window base of every CTA, as a byte offset into its z window
@@ -486,16 +491,19 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
 
   // block-Jacobi, second pass (after a __syncthreads behind the pass that wrote r_s and
   // rrow_s): thread t takes chunk row t; adds its r.z and r.r to acc[0], acc[1]
-  auto rrow_at = [&](uint32_t lr) { return lr + lr / (BJ ? BJ : 1); };  // blocks BJ + 1 apart
+  auto rrow_at = [&](uint32_t lr) { return lr + 2 * (lr / (BJ ? BJ : 1)); };  // blocks BJ + 2 apart
   auto block_jacobi = [&](double *acc) {
     for (uint32_t lr = tid; lr < me.n_rows; lr += SM_THREADS) {
       const uint32_t i = slotof[lr];
-      const float *bi = binv_s + (size_t)lr * (BJ + 1);
-      const double *rb = rrow_s + (size_t)(lr / (BJ ? BJ : 1)) * (BJ + 1);
+      const uint32_t *bi = binv_s + (size_t)lr * (BJ + 1);
+      const double2 *rb = reinterpret_cast<const double2 *>(rrow_s + (size_t)(lr / (BJ ? BJ : 1)) * (BJ + 2));
       double zi = 0.0;
 #pragma unroll
-      for (int j = 0; j < BJ; j++)
-        zi = fma((double)bi[j], rb[j], zi);
+      for (int j = 0; j < BJ; j += 2) {
+        const double2 rj = rb[j / 2];  // one 16-byte broadcast per pair
+        zi = fma(__hiloint2double((int)bi[j], 0), rj.x, zi);
+        zi = fma(__hiloint2double((int)bi[j + 1], 0), rj.y, zi);
+      }
       const double ri = r_s[i];
       push(me.row_lo + lr, dmask[i], zi);
       acc[0] = fma(ri, zi, acc[0]), acc[1] = fma(ri, ri, acc[1]);
@@ -744,7 +752,7 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
 // the instantiations: profiling on / off x preconditioner degree 1..3
 typedef void (*small_kernel_t)(const SmallCta *, const uint32_t *, const uint32_t *, const uint32_t *,
                                const uint32_t *, const uint32_t *, const double *, const uint16_t *,
-                               const double *, const float *, const uint16_t *, const double *, double *,
+                               const double *, const uint32_t *, const uint16_t *, const double *, double *,
                                PcgState *, uint32_t, uint32_t, uint32_t, double, int, long long *, double,
                                double);
 static small_kernel_t small_kernel(bool prof, int kdeg, int bj = 0) {
@@ -791,8 +799,13 @@ static double cheb_lmax(uint64_t n, const std::vector<uint64_t> &offs, const std
 }
 
 // ---------------------------------------------------------------------------
+static void small_free_plan(b200_mat *M, void *&slot);
 void small_free(b200_mat *M) {
-  SmallPlan *P = (SmallPlan *)M->small;
+  small_free_plan(M, M->small);
+  small_free_plan(M, M->small_bj);
+}
+static void small_free_plan(b200_mat *M, void *&slot) {
+  SmallPlan *P = (SmallPlan *)slot;
   if (!P)
     return;
   void *ptrs[] = {P->d_cta, P->d_goff, P->d_rowid, P->d_vals, P->d_dinv, P->d_cols,
@@ -800,7 +813,7 @@ void small_free(b200_mat *M) {
   for (void *p : ptrs)
     if (p) cudaFree(p);
   delete P;
-  M->small = nullptr;
+  slot = nullptr;
 }
 
 static int small_launch_config(SmallPlan *P, cudaLaunchConfig_t *cfg,
@@ -876,10 +889,73 @@ static uint64_t window_cost(uint64_t n, int C, const std::vector<uint64_t> &offs
 
 // Builds the on-chip plan when the matrix qualifies; leaves M->small null
 // (streaming path) when it does not.  Never an error just for not fitting.
-int small_try_build(b200_mat *M) {
-  if (M->small || M->small_tried)
+// Rows of every CTA chunk (n k / C .. n (k + 1) / C, C = 16) regrouped so that each run of
+// `bs` consecutive rows is a set of strongly coupled ones: a block starts at the first row
+// not yet taken and grows by the row of the chunk with the largest sum of
+// |a_ij| / sqrt(a_ii a_jj) over the block's members (ties: the lower index).  The chunk keeps
+// its set of rows, hence its column window.  Returns order[new] = old.
+static std::vector<uint32_t> block_growth_order(uint64_t n, int C, uint32_t bs,
+                                                const std::vector<uint64_t> &offs,
+                                                const std::vector<uint32_t> &cols,
+                                                const std::vector<double> &vals) {
+  std::vector<double> diag(n, 1.0), score(n, 0.0);
+  for (uint64_t r = 0; r < n; r++)
+    for (uint64_t e = offs[r]; e < offs[r + 1]; e++)
+      if (cols[e] == r && vals[e] > 0.0)
+        diag[r] = vals[e];
+  std::vector<char> taken(n, 0);
+  std::vector<uint32_t> order, cand;
+  order.reserve(n);
+  for (int k = 0; k < C; k++) {
+    const uint64_t r0 = n * k / C, r1 = n * (k + 1) / C;
+    uint64_t next = r0, left = r1 - r0;
+    while (left) {
+      while (taken[next])
+        next++;
+      uint32_t size = 0;
+      uint64_t row = next;
+      cand.clear();
+      for (;;) {
+        taken[row] = 1, order.push_back((uint32_t)row), size++, left--;
+        if (size == bs || !left)
+          break;
+        for (uint64_t e = offs[row]; e < offs[row + 1]; e++) {
+          const uint32_t c = cols[e];
+          if (c < r0 || c >= r1 || taken[c])
+            continue;
+          if (score[c] == 0.0)
+            cand.push_back(c);
+          score[c] += fabs(vals[e]) / sqrt(diag[row] * diag[c]) + 1e-300;
+        }
+        double best = 0.0;
+        uint64_t pick = n;
+        for (uint32_t c : cand)
+          if (!taken[c] && (score[c] > best || (score[c] == best && c < pick)))
+            best = score[c], pick = c;
+        if (pick == n) {  // nothing coupled to the block is left in the chunk
+          while (taken[next])
+            next++;
+          pick = next;
+        }
+        row = pick;
+      }
+      for (uint32_t c : cand)
+        score[c] = 0.0;
+    }
+  }
+  return order;
+}
+
+// `blocks`: the plan block-Jacobi runs on (M->small_bj) -- no RCM (compact chunks are worth
+// more to the blocks than narrow windows: xn3b_A_10 takes 132 iterations on blocks grown
+// inside the file's chunks, 180 inside RCM's), rows regrouped by block_growth_order, the
+// inverted diagonal blocks; otherwise the plan Jacobi and Chebyshev-Jacobi run on (M->small).
+int small_try_build(b200_mat *M, bool blocks) {
+  void *&slot = blocks ? M->small_bj : M->small;
+  bool &tried = blocks ? M->small_bj_tried : M->small_tried;
+  if (slot || tried)
     return B200_OK;
-  M->small_tried = true;
+  tried = true;
   b200_ctx *c = M->ctx;
   const uint64_t n = M->n_local;
   if (c->nranks != 1 || n > SM_MAX_ROWS || M->nnz > SM_MAX_NNZ || M->vec_rows ||
@@ -899,12 +975,14 @@ int small_try_build(b200_mat *M) {
   for (uint64_t i = 0; i < n; i++)
     perm[i] = (uint32_t)i;
   bool reordered = false;
-  if (!getenv("B200_SMALL_NO_RCM")) {
-    std::vector<uint32_t> cand = rcm_order(n, offs, cols), inv(n);
+  // the operator renumbered by cand[new] = old (columns of a row ascending again); taken
+  // when `accept` says so
+  auto renumber = [&](const std::vector<uint32_t> &cand, bool always) {
+    std::vector<uint32_t> inv(n);
     for (uint64_t i = 0; i < n; i++)
       inv[cand[i]] = (uint32_t)i;
     std::vector<uint64_t> o2(n + 1, 0);
-    std::vector<uint32_t> c2(cols.size());
+    std::vector<uint32_t> c2(cols.size()), p2(n);
     std::vector<double> v2(vals.size()), d2(n);
     for (uint64_t i = 0; i < n; i++)
       o2[i + 1] = o2[i] + (offs[cand[i] + 1] - offs[cand[i]]);
@@ -919,13 +997,17 @@ int small_try_build(b200_mat *M) {
                 });
       for (uint64_t e = 0; e < len; e++)
         c2[o2[i] + e] = row[e].first, v2[o2[i] + e] = row[e].second;
-      d2[i] = dinv[r];
+      d2[i] = dinv[r], p2[i] = perm[r];
     }
-    if (5 * window_cost(n, 16, o2, c2) <= 4 * window_cost(n, 16, offs, cols)) {
-      offs.swap(o2), cols.swap(c2), vals.swap(v2), dinv.swap(d2), perm.swap(cand);
+    if (always || 5 * window_cost(n, 16, o2, c2) <= 4 * window_cost(n, 16, offs, cols)) {
+      offs.swap(o2), cols.swap(c2), vals.swap(v2), dinv.swap(d2), perm.swap(p2);
       reordered = true;
     }
-  }
+  };
+  if (blocks)
+    renumber(block_growth_order(n, 16, 32, offs, cols, vals), true);
+  else if (!getenv("B200_SMALL_NO_RCM"))
+    renumber(rcm_order(n, offs, cols), false);
 
   int dev_smem = 0;
   CU_TRY(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
@@ -1042,13 +1124,13 @@ int small_try_build(b200_mat *M) {
     // it, 0 = none); the diagonal blocks of bj consecutive chunk rows, inverted (Cholesky),
     // rounded to fp32 symmetrically.  A block that is not positive definite: no block-Jacobi.
     int bj = 0;
-    std::vector<float> binv;
+    std::vector<uint32_t> binv;
     std::vector<uint16_t> slotof(rowid.size(), 0);
     std::vector<uint32_t> block_of_row(n, 0);
     {
-      int want = -1;
+      int want = blocks ? -1 : 0;
       if (const char *e = getenv("B200_SMALL_BJ"))
-        want = atoi(e);
+        want = blocks ? atoi(e) : 0;
       for (int cand : {32, 16}) {
         if (want >= 0 && cand != want)
           continue;
@@ -1061,7 +1143,7 @@ int small_try_build(b200_mat *M) {
         for (uint32_t sl = 0; sl < ctas[k].n_rows; sl++)
           slotof[ctas[k].row_at + (rowid[ctas[k].row_at + sl] - ctas[k].row_lo)] = (uint16_t)sl;
       if (bj) {
-        binv.assign(rowid.size() * (size_t)(bj + 1), 0.0f);
+        binv.assign(rowid.size() * (size_t)(bj + 1), 0u);
         std::vector<double> B((size_t)bj * bj), L((size_t)bj * bj), Li((size_t)bj * bj), Bi((size_t)bj * bj);
         uint32_t block_id = 0;
         for (int k = 0; k < C && bj; k++) {
@@ -1119,9 +1201,13 @@ int small_try_build(b200_mat *M) {
                 Bi[(size_t)a * bj + q] = Bi[(size_t)q * bj + a] = v;
               }
             for (int a = 0; a < m; a++) {
-              float *dst = binv.data() + ((size_t)ctas[k].row_at + (s0 - r0) + a) * (bj + 1);
-              for (int q = 0; q < m; q++)
-                dst[q] = (float)Bi[(size_t)a * bj + q];
+              uint32_t *dst = binv.data() + ((size_t)ctas[k].row_at + (s0 - r0) + a) * (bj + 1);
+              for (int q = 0; q < m; q++) {  // high word of the fp64 value, rounded to nearest
+                uint64_t bits;
+                const double v = Bi[(size_t)a * bj + q];
+                memcpy(&bits, &v, 8);
+                dst[q] = (uint32_t)((bits + 0x80000000ull) >> 32);
+              }
               block_of_row[perm[s0 + a]] = block_id;
             }
           }
@@ -1195,7 +1281,7 @@ int small_try_build(b200_mat *M) {
     B_TRY(up((void **)&P->d_slotof, slotof.data(), slotof.size() * 2));
     CU_TRY(cudaMalloc(&P->d_state, sizeof(PcgState)));
     CU_TRY(cudaMalloc(&P->d_prof, 16 * sizeof(long long)));
-    M->small = P;
+    slot = P;
     return B200_OK;
   }
   return B200_OK;
@@ -1205,8 +1291,8 @@ extern "C" int b200_mat_block_jacobi_partition(b200_mat *M, uint32_t *block_of_r
   if (!M || !block_of_row || !block_size)
     B_FAIL(B200_EINVAL, "b200_mat_block_jacobi_partition: null argument");
   CU_TRY(cudaSetDevice(M->ctx->device));
-  B_TRY(small_try_build(M));
-  const SmallPlan *P = (const SmallPlan *)M->small;
+  B_TRY(small_try_build(M, true));
+  const SmallPlan *P = (const SmallPlan *)M->small_bj;
   *block_size = P ? (uint32_t)P->bj : 0u;
   if (P && P->bj)
     memcpy(block_of_row, P->block_of_row.data(), P->block_of_row.size() * sizeof(uint32_t));
@@ -1215,7 +1301,14 @@ extern "C" int b200_mat_block_jacobi_partition(b200_mat *M, uint32_t *block_of_r
 
 int small_solve(b200_mat *M, const double *d_b, double *d_x,
                 const b200_pcg_opts *o, b200_pcg_result *res) {
+  // block-Jacobi runs on a plan of its own (rows regrouped into strongly coupled blocks)
   SmallPlan *P = (SmallPlan *)M->small;
+  const bool cheb = (o->flags & (B200_PCG_CHEBYSHEV2 | B200_PCG_CHEBYSHEV3)) != 0;
+  if ((o->flags & B200_PCG_BLOCK_JACOBI) && !cheb) {
+    B_TRY(small_try_build(M, true));
+    if (M->small_bj && ((SmallPlan *)M->small_bj)->bj)
+      P = (SmallPlan *)M->small_bj;
+  }
   b200_ctx *c = M->ctx;
   cudaStream_t s = c->stream;
   cudaLaunchConfig_t cfg;
@@ -1239,7 +1332,7 @@ int small_solve(b200_mat *M, const double *d_b, double *d_x,
                             (const uint32_t *)P->d_goff, (const uint32_t *)P->d_rowid,
                             (const uint32_t *)P->d_dmask, (const uint32_t *)P->d_orig,
                             (const uint32_t *)P->d_perm, (const double *)P->d_vals, (const uint16_t *)P->d_cols,
-                            (const double *)P->d_dinv, (const float *)P->d_binv,
+                            (const double *)P->d_dinv, (const uint32_t *)P->d_binv,
                             (const uint16_t *)P->d_slotof, d_b, d_x,
                             P->d_state, P->max_ent, P->max_groups, P->max_stage,
                             o->tol, (int)o->maxit, P->d_prof, theta, delta));

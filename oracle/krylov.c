@@ -473,7 +473,8 @@ int orc_pcg_cheb(const orc_op *M, const double *b, double *x, double tol, int ma
  * z = B^-1 r with B the diagonal blocks of A over a given partition of the rows
  * (block_of_row[i] = block id of row i; ids are arbitrary, a block may be any subset).
  * A block is symmetrised, inverted through its Cholesky factor and -- as the product
- * keeps it in shared memory -- rounded to fp32; everything else is fp64.  The method
+ * keeps it in shared memory -- cut to the high 32 bits of every fp64 entry (rounded to
+ * nearest); everything else is fp64.  The method
  * csrc/small.cu runs with B200_PCG_BLOCK_JACOBI, on the partition
  * b200_mat_block_jacobi_partition reports.  What the reference reaches for on these
  * systems is algebraic multigrid (src/hypre.c:126-188, src/amgx.c:78-85).  Same
@@ -481,8 +482,18 @@ int orc_pcg_cheb(const orc_op *M, const double *b, double *x, double tol, int ma
 typedef struct {
   uint32_t m;     /* rows */
   uint32_t *rows; /* ascending */
-  float *inv;     /* m x m, symmetric */
+  double *inv;    /* m x m, symmetric: fp64 values cut to their high 32 bits */
 } bj_block;
+
+/* what the product keeps of an entry of an inverted block: the high word of the fp64
+ * value, rounded to nearest (20 bits of mantissa; widening it back costs nothing) */
+static double high_word(double v) {
+  uint64_t bits;
+  memcpy(&bits, &v, 8);
+  bits = (bits + 0x80000000ull) & 0xffffffff00000000ull;
+  memcpy(&v, &bits, 8);
+  return v;
+}
 
 static int cmp_u64(const void *a, const void *b) {
   const uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
@@ -547,7 +558,7 @@ int orc_pcg_bj(const orc_op *M, const double *b, double *x, double tol, int maxi
           L[(size_t)a * m + q] = v / L[(size_t)q * m + q];
         }
       }
-    B->inv = (float *)calloc((size_t)m * m, sizeof(float));
+    B->inv = (double *)calloc((size_t)m * m, sizeof(double));
     if (rc == 1) {
       for (uint32_t q = 0; q < m; q++) { /* Li = L^-1 */
         Li[(size_t)q * m + q] = 1.0 / L[(size_t)q * m + q];
@@ -563,7 +574,7 @@ int orc_pcg_bj(const orc_op *M, const double *b, double *x, double tol, int maxi
           double v = 0.0;
           for (uint32_t t = a; t < m; t++)
             v += Li[(size_t)t * m + a] * Li[(size_t)t * m + q];
-          B->inv[(size_t)a * m + q] = B->inv[(size_t)q * m + a] = (float)v;
+          B->inv[(size_t)a * m + q] = B->inv[(size_t)q * m + a] = high_word(v);
         }
     }
     free(D);
@@ -576,7 +587,7 @@ int orc_pcg_bj(const orc_op *M, const double *b, double *x, double tol, int maxi
     for (uint32_t a = 0; a < B->m; a++) {                                      \
       double s = 0.0;                                                          \
       for (uint32_t c = 0; c < B->m; c++)                                      \
-        s += (double)B->inv[(size_t)a * B->m + c] * r[B->rows[c]];             \
+        s += B->inv[(size_t)a * B->m + c] * r[B->rows[c]];                     \
       z[B->rows[a]] = s;                                                       \
     }                                                                          \
   }

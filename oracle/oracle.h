@@ -88,8 +88,8 @@ int orc_pcg_omp(const orc_op *M, const double *b, double *x, double tol,
 int orc_pcg_cheb(const orc_op *M, const double *b, double *x, double tol, int maxit,
                  int degree, double lmax, double ratio, int *iters, double *relres);
 /* block-Jacobi.  z = B^-1 r, B = the diagonal blocks of A over the
- * partition block_of_row[] (a block symmetrised, inverted by Cholesky, rounded to fp32 as
- * the product stores it).  Same contract as orc_pcg; 3 = a block is not positive definite.
+ * partition block_of_row[] (a block symmetrised, inverted by Cholesky, its entries cut to
+ * the high word of the fp64 value as the product stores them).  Same contract as orc_pcg; 3 = a block is not positive definite.
  * What csrc/small.cu runs with B200_PCG_BLOCK_JACOBI. */
 int orc_pcg_bj(const orc_op *M, const double *b, double *x, double tol, int maxit,
                const uint32_t *block_of_row, int *iters, double *relres);

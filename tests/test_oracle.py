@@ -325,7 +325,7 @@ def test_chebyshev_jacobi_pcg_restated(name):
 def test_block_jacobi_pcg_restated(name):
     """SURVEY 8(f) row 2, block-Jacobi (oracle/krylov.c orc_pcg_bj): blocks of one row are
     plain Jacobi; blocks of 16 and 32 consecutive rows against an independent numpy
-    statement of the method (dense inverses in fp64 -- the oracle rounds them to fp32, which
+    statement of the method (dense inverses in fp64 -- the oracle keeps 32 bits of each, which
     moves the iteration count by at most 2), fewer iterations, the same solution (1e-8 of
     the direct solve) at the 1e-10 bar; an irregular partition; a block that is not
     positive definite is refused."""
