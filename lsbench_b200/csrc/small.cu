@@ -55,6 +55,8 @@ struct SmallCta {         // one per CTA, in global memory
   uint32_t row_at;        // into rowid[] / dinv[] / dmask[] (8 n_groups values, 0xffffffff = none)
   uint32_t n_recv;        // window entries some row of this CTA reads (incl. its own rows)
   uint32_t row_lo;        // first row of the chunk (block-Jacobi: blocks are counted from here)
+  uint32_t rest_lo;       // first entry kept in shared memory: what comes before it lives in
+                          // registers only (regmat_load), in every warp
   uint64_t ent_at;        // into vals[] / cols[]
 };
 
@@ -145,8 +147,12 @@ struct RegMat {
   uint32_t j_rest;               // first group of this warp left in shared memory
 };
 
+// (vals / cols: the CTA's entries in GLOBAL memory -- the entries a lane keeps in registers
+// are not staged in shared memory at all: up to 24 x 512 x 10 bytes = 120 KB per CTA that
+// the inverted blocks of block-Jacobi can use)
 __device__ __forceinline__ void regmat_load(RegMat &R, const SmallCta &me, const uint32_t *goff,
-                                            const double *vals, const uint16_t *cols) {
+                                            const double *__restrict__ vals,
+                                            const uint16_t *__restrict__ cols) {
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t total = 0, j = warp;
   for (; j < me.n_groups; j += SM_WARPS) {
@@ -237,7 +243,7 @@ __device__ __forceinline__ double small_spmv(const SmallCta &me, const RegMat &R
   // ---- the rest, from shared memory ----------------------------------------------------
   for (uint32_t j = R.j_rest; j < me.n_groups; j += SM_WARPS) {
     const uint32_t o = goff[j], w = goff[j + 1] - o;
-    const uint32_t base = o * 32 + lane;
+    const uint32_t base = o * 32 + lane - me.rest_lo;  // (shared memory starts at entry rest_lo)
     double s = 0.0;
     uint32_t t = 0;
     for (; t + 2 <= w; t += 2) {
@@ -398,8 +404,8 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
   }
 
   // ---- make the matrix resident ----------------------------------------------------
-  for (uint32_t i = tid; i < me.ent; i += SM_THREADS)
-    vals[i] = g_vals[me.ent_at + i], cols[i] = g_cols[me.ent_at + i];
+  for (uint32_t i = me.rest_lo + tid; i < me.ent; i += SM_THREADS)
+    vals[i - me.rest_lo] = g_vals[me.ent_at + i], cols[i - me.rest_lo] = g_cols[me.ent_at + i];
   for (uint32_t i = tid; i <= me.n_groups; i += SM_THREADS)
     goff[i] = g_goff[me.goff_at + i];
   for (uint32_t i = tid; i < nslot; i += SM_THREADS) {
@@ -428,7 +434,7 @@ k_pcg_small(const SmallCta *__restrict__ ctas, const uint32_t *__restrict__ g_go
   }
   __syncthreads();
   RegMat R;
-  regmat_load(R, me, goff, vals, cols);
+  regmat_load(R, me, goff, g_vals + me.ent_at, g_cols + me.ent_at);
   cl.sync();  // every CTA's barriers exist before anyone stores into a neighbour
 
   // Two mbarriers, used in strict alternation B A B A ... B | B A.  A CTA sends
@@ -1087,11 +1093,26 @@ int small_try_build(b200_mat *M, bool blocks) {
       }
       goff.push_back(units);
       T.ent = units * 32;
+      {  // the first group some warp does not keep in registers (the rule of regmat_load)
+        uint32_t first_rest = T.n_groups;
+        for (uint32_t warp = 0; warp < SM_WARPS && warp < T.n_groups; warp++) {
+          uint32_t total = 0, j = warp;
+          for (; j < T.n_groups; j += SM_WARPS) {
+            const uint32_t w = goff[T.goff_at + j + 1] - goff[T.goff_at + j];
+            if (total + w > SM_REG_STEPS)
+              break;
+            total += w;
+          }
+          first_rest = std::min(first_rest, j);
+        }
+        T.rest_lo = goff[T.goff_at + first_rest] * 32;
+      }
       for (uint32_t s = 0; s < T.n_groups * 8; s++) {
         rowid.push_back(s < T.n_rows ? rows[s] : 0xffffffffu);
         pd.push_back(s < T.n_rows ? dinv[rows[s]] : 1.0);
       }
-      max_ent = std::max(max_ent, T.ent), max_groups = std::max(max_groups, T.n_groups);
+      // (max_ent: the entries a CTA keeps in SHARED memory)
+      max_ent = std::max(max_ent, T.ent - T.rest_lo), max_groups = std::max(max_groups, T.n_groups);
       max_stage = std::max(max_stage, T.col_n);
     }
     if (!ok)
@@ -1354,8 +1375,9 @@ int small_solve(b200_mat *M, const double *d_b, double *d_x,
   if (prof && h.iter > 0) {
     long long hp[6];
     CU_TRY(cudaMemcpy(hp, P->d_prof, sizeof hp, cudaMemcpyDeviceToHost));
-    fprintf(stderr, "b200 small: C=%d rcm=%d iters=%d cycles/iter spmv=%lld reduce1=%lld update+push=%lld "
-                    "reduce2+halo=%lld pwindow=%lld\n", P->C, (int)P->reordered, h.iter, hp[0] / h.iter,
+    fprintf(stderr, "b200 small: n=%u C=%d reordered=%d bj=%d smem=%zu (entries in smem <= %u) iters=%d cycles/iter "
+                    "spmv=%lld reduce1=%lld update+push=%lld reduce2+halo=%lld pwindow=%lld\n", P->n, P->C,
+            (int)P->reordered, bj, (size_t)cfg.dynamicSmemBytes, P->max_ent, h.iter, hp[0] / h.iter,
             hp[1] / h.iter, hp[2] / h.iter, hp[3] / h.iter, hp[4] / h.iter);
   }
   if (h.status == 2)
