@@ -117,7 +117,7 @@ enum {
    * x, every range becomes a matrix of its own over all rows, and y = A x runs
    * as y = A_0 x; y += A_1 x; ... so that the gathers of one pass stay inside
    * one L2-sized piece of x.  A range sorts its rows by length inside windows of
-   * B200_COL_BLOCK_SIGMA rows (default 32768; 0 = the whole list) and multiplies
+   * B200_COL_BLOCK_SIGMA rows (default 131072; 0 = the whole list) and multiplies
    * four slices per warp trip (k_spmv_sell_grp; B200_COL_BLOCK_KERNEL=plain keeps
    * one slice per trip).  Single rank, SpMV only (b200_pcg_solve refuses);
    * row sums are formed block by block, i.e. equal to the CSR product to

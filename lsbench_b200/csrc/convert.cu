@@ -594,8 +594,9 @@ int build_layout(b200_ctx *c, PlainCsr *A, uint64_t n_global,
       // widen the window until the padding is small: 1024 rows, 32768, all
       // (a column range of a column-blocked operator keeps its windows small -- sell_sigma_cap:
       // rows that are multiplied together stay neighbours, so the y they update and the
-      // near-diagonal x they gather stay in cache; measured, power-law 50 M rows, 64 MB ranges:
-      // 32 768 rows 6.6 ms, 131 072 rows 7.5 ms, 524 288 rows 9.0 ms, the whole list 13.5 ms)
+      // near-diagonal x they gather stay in cache; measured, power-law 50 M rows, 64 MB ranges,
+      // work units of 8 groups: 65 536 rows 5.93 ms, 131 072 5.87, 262 144 5.89, 1 048 576 6.4,
+      // the whole list 7.2; with units of 64 groups 32 768 was the optimum, at 6.60)
       const uint64_t cap = M->sell_sigma_cap;
       const uint64_t sig[3] = {B2_SELL_SIGMA, cap ? cap : 32 * B2_SELL_SIGMA, sell_padded_rows};
       for (int t = 0; t < (cap ? 2 : 3); t++) {
@@ -896,7 +897,7 @@ int build_layout_or_blocks(b200_ctx *c, PlainCsr *A, uint64_t n_global, uint64_t
   const uint32_t child_flags = flags & ~(uint32_t)(B200_MAT_COL_BLOCK | B200_MAT_SYM_UPPER);
   // B200_COL_BLOCK_SIGMA: widest length-sort window of a range (rows; 0 = the whole list, as a
   // matrix of its own would choose); B200_COL_BLOCK_KERNEL=plain: one slice per warp trip
-  uint64_t sigma_cap = 32 * B2_SELL_SIGMA;
+  uint64_t sigma_cap = 128 * B2_SELL_SIGMA;
   if (const char *v = getenv("B200_COL_BLOCK_SIGMA"))
     sigma_cap = (uint64_t)atoll(v);
   const char *kv = getenv("B200_COL_BLOCK_KERNEL");

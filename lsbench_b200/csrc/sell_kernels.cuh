@@ -145,42 +145,6 @@ k_spmv_sell(const uint32_t *__restrict__ sell_off,
 // Wider slices run the chunked loop of k_spmv_sell.  Surplus loads have their ADDRESS clamped
 // (never a select on the loaded value, see sell_chunk_n); each row still adds its entries left to
 // right with fma, so a row's result has the bits k_spmv_sell gives it.
-//
-// The loads are volatile asm: they leave in the order written (columns, values, row ids, y,
-// gathers).  Left to itself the compiler interleaves the fma chain of the first slices with
-// the loads of the last ones -- half the loads then wait for a round trip of the other half.
-#if defined(__CUDA_ARCH__)
-__device__ __forceinline__ uint32_t ldo_stream(const uint32_t *p) {
-  uint32_t v;
-  asm volatile("ld.global.cs.u32 %0, [%1];" : "=r"(v) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ double ldo_stream(const double *p) {
-  double v;
-  asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(v) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ uint32_t ldo_nc(const uint32_t *p) {
-  uint32_t v;
-  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ double ldo_nc(const double *p) {
-  double v;
-  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ double ldo(const double *p) {
-  double v;
-  asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
-  return v;
-}
-#else
-template <typename T> __device__ __forceinline__ T ldo_stream(const T *p) { return *p; }
-template <typename T> __device__ __forceinline__ T ldo_nc(const T *p) { return *p; }
-template <typename T> __device__ __forceinline__ T ldo(const T *p) { return *p; }
-#endif
-
 template <int U, int W, bool ACC>
 __device__ __forceinline__ void sell_narrow(const uint32_t *o, const uint32_t *w, uint32_t s0, uint32_t ns,
                                             uint32_t safe_o, uint32_t safe_s, uint32_t lane,
@@ -195,7 +159,7 @@ __device__ __forceinline__ void sell_narrow(const uint32_t *o, const uint32_t *w
 #pragma unroll
   for (int u = 0; u < U; u++) {
     const uint32_t pos = (s0 + u < ns ? s0 + u : safe_s) * B2_SLICE + lane;
-    row[u] = perm ? ldo_nc(perm + pos) : pos;
+    row[u] = perm ? __ldg(perm + pos) : pos;
 #pragma unroll
     for (int k = 0; k < W; k++)
       e[u][k] = (size_t)(w[u] ? o[u] + ((uint32_t)k < w[u] ? (uint32_t)k : w[u] - 1u) : safe_o) * B2_SLICE + lane;
@@ -204,33 +168,27 @@ __device__ __forceinline__ void sell_narrow(const uint32_t *o, const uint32_t *w
   for (int u = 0; u < U; u++)
 #pragma unroll
     for (int k = 0; k < W; k++)
-      c[u][k] = ldo_stream(cols + e[u][k]);
+      c[u][k] = ld_stream(cols + e[u][k]);
 #pragma unroll
   for (int u = 0; u < U; u++)
 #pragma unroll
     for (int k = 0; k < W; k++)
-      a[u][k] = ldo_stream(vals + e[u][k]);
+      a[u][k] = ld_stream(vals + e[u][k]);
   bool live[U];
 #pragma unroll
   for (int u = 0; u < U; u++) {
     live[u] = s0 + u < ns && row[u] < n_rows && (!ACC || w[u] != 0);
     if (ACC)
-      yv[u] = ldo(y + (live[u] ? row[u] : 0u));
+      yv[u] = y[live[u] ? row[u] : 0u];
   }
 #pragma unroll
   for (int u = 0; u < U; u++)
 #pragma unroll
     for (int k = 0; k < W; k++)
-      xv[u][k] = ldo_nc(x + c[u][k]);
-#if defined(__CUDA_ARCH__)
-  // nothing of the arithmetic may move above this point
-#pragma unroll
-  for (int u = 0; u < U; u++)
-#pragma unroll
-    for (int k = 0; k < W; k++)
-      asm volatile("" : "+d"(xv[u][k]));
+      xv[u][k] = __ldg(x + c[u][k]);
+  // a scheduling fence: left to itself ptxas interleaves the fma chain of the first slices with
+  // the loads of the last ones, and half the loads wait for a round trip of the other half
   __syncwarp();
-#endif
 #pragma unroll
   for (int u = 0; u < U; u++) {
     double sum = 0.0;
@@ -247,7 +205,14 @@ __device__ __forceinline__ void sell_narrow(const uint32_t *o, const uint32_t *w
 #ifndef SELL_GRP_MINB
 #define SELL_GRP_MINB 3  // 80 registers: the loads of four slices in flight need them (4 CTAs/SM spills)
 #endif
-#define SELL_UNIT 64  // groups per unit of work: 256 slices, a quarter of a sort window
+// groups per unit of work: 8 = one group per warp per unit, 32 slices, 1 024 rows.  Measured on
+// the 50 M-row power-law operator (64 MB ranges, windows of 32 768 rows): 128 groups 7.11 ms,
+// 64 6.60, 32 6.41, 16 6.17, 8 6.19, 4 7.53 -- the finer the units, the narrower the front of
+// rows all CTAs work on, and the y they update and the x they gather near the diagonal stay in
+// cache; below 8 the warps of a CTA run out of work between two draws.
+#ifndef SELL_UNIT
+#define SELL_UNIT 8
+#endif
 template <bool ACC>
 __global__ void __launch_bounds__(SPMV_THREADS, SELL_GRP_MINB)
 k_spmv_sell_grp(const uint32_t *__restrict__ sell_off, const uint32_t *__restrict__ cols,
@@ -255,10 +220,10 @@ k_spmv_sell_grp(const uint32_t *__restrict__ sell_off, const uint32_t *__restric
                 const double *__restrict__ x, double *__restrict__ y, uint32_t ns, uint32_t n_rows,
                 unsigned *work /* {next unit, CTAs done}, both 0 between launches */) {
   // Work is handed out in units of SELL_UNIT consecutive groups, first come first served.  A
-  // static grid-stride walk resonates with the length-sort windows (a window is 1024 slices
-  // that run from its widest rows down to its empty ones; the stride is a fixed number of
-  // slices, so a warp lands on the same few window phases every time and some warps only ever
-  // see wide slices): measured 2 x slower than the same layout sorted as a whole.  No sum is
+  // static grid-stride walk resonates with the length-sort windows (a window runs from its
+  // widest rows down to its empty ones; the stride is a fixed number of slices, so a warp lands
+  // on the same few window phases every time and some warps only ever see wide slices):
+  // measured 2 x slower than the same layout sorted as a whole.  No sum is
   // formed across rows here, so who multiplies which slice does not change any bit of y.
   __shared__ uint32_t unit_s;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

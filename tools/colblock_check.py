@@ -32,7 +32,7 @@ if len(sys.argv) > 2 and sys.argv[1] == "--time":
     sp, _ = M.algorithmic_bytes()
     print(json.dumps({"rows": rows, "col_block_mb": os.environ.get("B200_COL_BLOCK_MB") if blocked else None,
                       "kernel": os.environ.get("B200_COL_BLOCK_KERNEL", "grouped") if blocked else None,
-                      "sigma": os.environ.get("B200_COL_BLOCK_SIGMA", "32768") if blocked else None,
+                      "sigma": os.environ.get("B200_COL_BLOCK_SIGMA", "131072") if blocked else None,
                       "col_blocks": i.col_blocks, "ms_per_spmv": ms, "algorithmic_gbs": sp / ms / 1e6,
                       "matrix_stream_bytes": i.matrix_stream_bytes, "device_GB": i.device_bytes / 1e9}))
     sys.exit(0)
