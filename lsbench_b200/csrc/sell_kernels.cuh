@@ -202,8 +202,13 @@ __device__ __forceinline__ void sell_narrow(const uint32_t *o, const uint32_t *w
 }
 
 #define SELL_GRP 4
+// CTAs per SM: 4 (64 registers, 8 bytes spilled in the accumulate instantiation) against 3 (80
+// registers, none): 5.62 against 5.87 ms per SpMV of the 50 M-row power-law operator -- once
+// the traffic was down (22 GB per SpMV) the pass was bound by its round trips at 24 warps per
+// SM (ncu: 36 % of the warp slots, 30 long-scoreboard stalls per issue), and 32 warps pay more
+// than the spill costs.  (With work units of 256 slices, at 28 GB, the two were equal.)
 #ifndef SELL_GRP_MINB
-#define SELL_GRP_MINB 3  // 80 registers: the loads of four slices in flight need them (4 CTAs/SM spills)
+#define SELL_GRP_MINB 4
 #endif
 // groups per unit of work: 8 = one group per warp per unit, 32 slices, 1 024 rows.  Measured on
 // the 50 M-row power-law operator (64 MB ranges, windows of 32 768 rows): 128 groups 7.11 ms,
