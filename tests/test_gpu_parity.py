@@ -551,6 +551,46 @@ def test_full_size_config4_poisson27_512(abi, ctx):
     Md.close()
 
 
+def test_full_size_config5_powerlaw_50m(abi, ctx):
+    """BASELINE.json config 5 at its full size on one GPU (50 M rows, 774 M entries, rows of 3
+    to 65 536 entries: every bin and every kernel, in the plain layout and in the column-blocked
+    one, whose ranges hold rows of more than 8 192 entries too).  Windows of rows -- the first
+    ones, a stretch in the middle, the last ones, and the longest row of the first 200 000 with
+    its neighbours -- equal the oracle's generator to the 1e-13 bar in both layouts; the two
+    layouts agree on all 50 M rows; SpMV is linear and reproducible bit for bit."""
+    n = 50_000_000
+    try:
+        M0 = abi.Matrix.generate(ctx, abi.GEN_POWERLAW, n, seed=1)
+        Mb = abi.Matrix.generate(ctx, abi.GEN_POWERLAW, n, seed=1, flags=abi.MAT_COL_BLOCK)
+    except abi.B200Error as e:            # a smaller device: not this test's subject
+        pytest.skip("powerlaw:50000000 does not fit twice: %s" % e)
+    i0, ib = M0.info(), Mb.info()
+    assert i0.n_local == ib.n_local == n and i0.nnz == ib.nnz
+    assert ib.col_blocks >= 4 and i0.col_blocks == 0
+    assert i0.long_rows > 0 and i0.vec_rows > 0 and i0.max_row_len == 65536
+    rng = np.random.default_rng(50)
+    x = rng.standard_normal(n)
+    y0, yb = M0.spmv_host(x), Mb.spmv_host(x)
+    assert np.max(np.abs(y0 - yb)) <= 1e-11 * np.max(np.abs(y0))
+    assert Mb.spmv_host(x).tobytes() == yb.tobytes() and M0.spmv_host(x).tobytes() == y0.tobytes()
+    rowlen = orc.lib().orc_powerlaw_rowlen
+    lens = np.array([rowlen(n, 1, r) for r in range(200_000)])
+    longest = int(np.argmax(lens))
+    assert lens[longest] > 2 * 8192          # its near-diagonal half alone: a CTA-per-row piece in one range
+    nnz_windows = 0
+    for r0, r1 in ((0, 512), (24_999_936, 25_000_448), (n - 512, n), (max(longest - 3, 0), longest + 4)):
+        Mo = orc.gen_powerlaw(n, 1, r0, r1)
+        nnz_windows += Mo.nnz
+        ref, ya = orc.spmv(Mo, x, want_abs=True)
+        for y in (y0, yb):
+            assert np.all(np.abs(y[r0:r1] - ref) <= 1e-13 * np.maximum(ya, 1e-300)), (r0, r1)
+    assert nnz_windows > lens[longest]
+    u = rng.standard_normal(n)
+    lin = Mb.spmv_host(2.0 * x - 3.0 * u)
+    assert np.max(np.abs(lin - (2.0 * yb - 3.0 * Mb.spmv_host(u)))) <= 1e-11 * np.max(np.abs(lin))
+    M0.close(), Mb.close()
+
+
 def test_pcg_against_the_oracles_solve_at_27pt_128(abi, ctx):
     """The streaming PCG against the CPU oracle's OpenMP PCG on the same system at a size
     the oracle still solves in seconds (27-point 128^3: 2.1 M rows, 55 M nnz, ~290
