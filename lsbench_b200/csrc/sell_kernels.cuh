@@ -223,25 +223,80 @@ __global__ void __launch_bounds__(SPMV_THREADS, SELL_GRP_MINB)
 k_spmv_sell_grp(const uint32_t *__restrict__ sell_off, const uint32_t *__restrict__ cols,
                 const double *__restrict__ vals, const uint32_t *__restrict__ perm,
                 const double *__restrict__ x, double *__restrict__ y, uint32_t ns, uint32_t n_rows,
-                unsigned *work /* {next unit, CTAs done}, both 0 between launches */) {
+                unsigned *work /* {next unit, CTAs done}, both 0 between launches */,
+                uint32_t long_rows, const uint32_t *__restrict__ long_ids, const uint64_t *__restrict__ long_off,
+                uint32_t vec_rows, const uint32_t *__restrict__ vec_ids, const uint64_t *__restrict__ vec_off,
+                const uint32_t *__restrict__ vl_cols, const double *__restrict__ vl_vals) {
   // Work is handed out in units of SELL_UNIT consecutive groups, first come first served.  A
   // static grid-stride walk resonates with the length-sort windows (a window runs from its
   // widest rows down to its empty ones; the stride is a fixed number of slices, so a warp lands
   // on the same few window phases every time and some warps only ever see wide slices):
   // measured 2 x slower than the same layout sorted as a whole.  No sum is
   // formed across rows here, so who multiplies which slice does not change any bit of y.
+  //
+  // The rows of the row-major bins (longer than 256 entries in this range) are units of the same
+  // list, longest first: a CTA-per-row unit per "long" row, then units of one warp-per-row row
+  // per warp, then the slices -- one launch per range instead of three, and the long rows do
+  // not wait for a tail of their own (same loops as k_spmv_long / k_spmv_vec, same bits).
   __shared__ uint32_t unit_s;
+  __shared__ double red[SPMV_WARPS];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t ngroups = (ns + SELL_GRP - 1) / SELL_GRP;
-  const uint32_t nunits = (ngroups + SELL_UNIT - 1) / SELL_UNIT;
+  const uint32_t vec_units = (vec_rows + SPMV_WARPS - 1) / SPMV_WARPS;
+  const uint32_t nunits = (ngroups + SELL_UNIT - 1) / SELL_UNIT + long_rows + vec_units;
   for (;;) {
     if (threadIdx.x == 0)
       unit_s = atomicAdd(&work[0], 1u);
     __syncthreads();
-    const uint32_t unit = unit_s;
+    uint32_t unit = unit_s;
     __syncthreads();
     if (unit >= nunits)
       break;
+    if (unit < long_rows) {  // one CTA, one row
+      const uint64_t s = __ldg(long_off + unit), e = __ldg(long_off + unit + 1);
+      double sum = 0.0;
+      for (uint64_t k = s + threadIdx.x * 4; k < e; k += SPMV_THREADS * 4) {
+        const uint4 c = __ldcs(reinterpret_cast<const uint4 *>(vl_cols + k));
+        const double2 v01 = __ldcs(reinterpret_cast<const double2 *>(vl_vals + k));
+        const double2 v23 = __ldcs(reinterpret_cast<const double2 *>(vl_vals + k + 2));
+        const double x0 = __ldg(x + c.x), x1 = __ldg(x + c.y), x2 = __ldg(x + c.z), x3 = __ldg(x + c.w);
+        sum = fma(v01.x, x0, sum);
+        sum = fma(v01.y, x1, sum);
+        sum = fma(v23.x, x2, sum);
+        sum = fma(v23.y, x3, sum);
+      }
+      sum = block_sum<SPMV_WARPS>(sum, red);
+      if (threadIdx.x == 0) {
+        const uint32_t row = __ldg(long_ids + unit);
+        y[row] = ACC ? y[row] + sum : sum;
+      }
+      continue;
+    }
+    unit -= long_rows;
+    if (unit < vec_units) {  // one warp, one row
+      const uint32_t r = unit * SPMV_WARPS + warp;
+      if (r < vec_rows) {
+        const uint64_t s = __ldg(vec_off + r), e = __ldg(vec_off + r + 1);
+        double sum = 0.0;
+        for (uint64_t k = s + lane * 4; k < e; k += 128) {
+          const uint4 c = __ldcs(reinterpret_cast<const uint4 *>(vl_cols + k));
+          const double2 v01 = __ldcs(reinterpret_cast<const double2 *>(vl_vals + k));
+          const double2 v23 = __ldcs(reinterpret_cast<const double2 *>(vl_vals + k + 2));
+          const double x0 = __ldg(x + c.x), x1 = __ldg(x + c.y), x2 = __ldg(x + c.z), x3 = __ldg(x + c.w);
+          sum = fma(v01.x, x0, sum);
+          sum = fma(v01.y, x1, sum);
+          sum = fma(v23.x, x2, sum);
+          sum = fma(v23.y, x3, sum);
+        }
+        sum = warp_sum(sum);
+        if (lane == 0) {
+          const uint32_t row = __ldg(vec_ids + r);
+          y[row] = ACC ? y[row] + sum : sum;
+        }
+      }
+      continue;
+    }
+    unit -= vec_units;
     const uint32_t g_end = (unit + 1) * SELL_UNIT < ngroups ? (unit + 1) * SELL_UNIT : ngroups;
   for (uint32_t g = unit * SELL_UNIT + warp; g < g_end; g += SPMV_WARPS) {
     const uint32_t s0 = g * SELL_GRP;

@@ -103,7 +103,8 @@ static const SpmvPlan &plan_phase(b200_mat *M, int phase) {
       M->plan[p] = compute_plan(M, p);
     if (M->grouped_slices && M->sell_slices)
       M->plan_grp = persistent_grid(M->ctx, (const void *)k_spmv_sell_grp<true>,
-                                    ((M->sell_slices + SELL_GRP - 1) / SELL_GRP + SPMV_WARPS - 1) / SPMV_WARPS);
+                                    ((M->sell_slices + SELL_GRP - 1) / SELL_GRP + SPMV_WARPS - 1) / SPMV_WARPS +
+                                        M->long_rows + M->vec_rows);
     M->plan_ready = true;
   }
   return M->plan[phase];
@@ -134,8 +135,12 @@ int launch_spmv(b200_mat *M, const double *x, double *y, bool dot, int phase,
   double *dot_out = dot ? (c->nranks > 1 ? &M->state->pq_loc : &M->state->pq) : nullptr;
   if (P.g_sell && M->grouped_slices && !dot && !M->sell_meta && M->sell_vals && phase == 0) {
     // a column range of a column-blocked operator: four slices per warp trip (sell_kernels.cuh)
-    k_spmv_sell_grp<false><<<M->plan_grp, SPMV_THREADS, 0, s>>>(M->sell_off, M->sell_cols, M->sell_vals,
-                                                                  M->sell_perm, x, y, M->sell_slices, n, M->grp_work);
+    k_spmv_sell_grp<false><<<M->plan_grp, SPMV_THREADS, 0, s>>>(
+        M->sell_off, M->sell_cols, M->sell_vals, M->sell_perm, x, y, M->sell_slices, n, M->grp_work,
+        M->long_rows, M->long_row_ids, M->long_off, M->vec_rows, M->vec_row_ids, M->vec_off, M->vl_cols, M->vl_vals);
+    c->launches += 1;
+    CU_TRY(cudaGetLastError());
+    return B200_OK;  // (the row-major bins are units of the same launch)
   } else if (P.g_sell) {
 #define B2_SELL_ARGS(DOTV)                                                        \
   M->sell_perm, x, y, P.b0, P.e0, P.b1, P.e1, n, DOTV ? M->partials : nullptr,    \
@@ -208,8 +213,12 @@ static int launch_spmv_acc(b200_mat *M, const double *x, double *y) {
   const XrArgs xr = XrArgs{nullptr, nullptr, 1, 0, 0, 0ull};
   const uint32_t n = (uint32_t)M->n_local;
   if (P.g_sell && M->grouped_slices && !M->sell_meta && M->sell_vals) {
-    k_spmv_sell_grp<true><<<M->plan_grp, SPMV_THREADS, 0, s>>>(M->sell_off, M->sell_cols, M->sell_vals,
-                                                                 M->sell_perm, x, y, M->sell_slices, n, M->grp_work);
+    k_spmv_sell_grp<true><<<M->plan_grp, SPMV_THREADS, 0, s>>>(
+        M->sell_off, M->sell_cols, M->sell_vals, M->sell_perm, x, y, M->sell_slices, n, M->grp_work,
+        M->long_rows, M->long_row_ids, M->long_off, M->vec_rows, M->vec_row_ids, M->vec_off, M->vl_cols, M->vl_vals);
+    c->launches += 1;
+    CU_TRY(cudaGetLastError());
+    return B200_OK;  // (the row-major bins are units of the same launch)
   } else if (P.g_sell) {
     const uint4 *meta = (const uint4 *)M->sell_meta;
     const bool f32 = M->sell_vals32 && (M->spmv_use32 || !M->sell_vals);

@@ -223,11 +223,11 @@ extern "C" int emul_sell_acc(int acc, unsigned grid, uint32_t ns, const uint32_t
   if (acc & 2) {
     if (acc == 3)
       simt::launch(grid, SPMV_THREADS, [&] {
-        k_spmv_sell_grp<true>(sell_off, cols, vals, nullptr, x, y, ns, n_rows, work);
+        k_spmv_sell_grp<true>(sell_off, cols, vals, nullptr, x, y, ns, n_rows, work, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
       });
     else
       simt::launch(grid, SPMV_THREADS, [&] {
-        k_spmv_sell_grp<false>(sell_off, cols, vals, nullptr, x, y, ns, n_rows, work);
+        k_spmv_sell_grp<false>(sell_off, cols, vals, nullptr, x, y, ns, n_rows, work, 0, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
       });
     return work[0] == 0 && work[1] == 0 ? 0 : 1;  // the last CTA out rearms the counters
   }
