@@ -214,6 +214,28 @@ extern "C" int emul_colblock_split(uint64_t n, const uint64_t *offs, const uint3
   return 0;
 }
 
+// k_spmv_sell_grp as a column range runs it: a permuted slice list, and the rows of the
+// row-major bins as units of the same work list (CTA-per-row and warp-per-row)
+extern "C" int emul_sell_grp_bins(int acc, unsigned grid, uint32_t ns, const uint32_t *sell_off,
+                                  const uint32_t *cols, const double *vals, const uint32_t *perm,
+                                  const double *x, double *y, uint32_t n_rows, uint32_t long_rows,
+                                  const uint32_t *long_ids, const uint64_t *long_off, uint32_t vec_rows,
+                                  const uint32_t *vec_ids, const uint64_t *vec_off,
+                                  const uint32_t *vl_cols, const double *vl_vals) {
+  unsigned work[2] = {0, 0};
+  if (acc)
+    simt::launch(grid, SPMV_THREADS, [&] {
+      k_spmv_sell_grp<true>(sell_off, cols, vals, perm, x, y, ns, n_rows, work, long_rows, long_ids, long_off,
+                            vec_rows, vec_ids, vec_off, vl_cols, vl_vals);
+    });
+  else
+    simt::launch(grid, SPMV_THREADS, [&] {
+      k_spmv_sell_grp<false>(sell_off, cols, vals, perm, x, y, ns, n_rows, work, long_rows, long_ids, long_off,
+                             vec_rows, vec_ids, vec_off, vl_cols, vl_vals);
+    });
+  return work[0] == 0 && work[1] == 0 ? 0 : 1;
+}
+
 // y (+)= A x with k_spmv_sell<false, double, ACC> on an explicit-column SELL layout
 extern "C" int emul_sell_acc(int acc, unsigned grid, uint32_t ns, const uint32_t *sell_off,
                              const uint32_t *cols, const double *vals, const double *x, double *y,

@@ -366,3 +366,74 @@ def test_column_blocked_spmv_on_the_emulator(emul):
         assert np.all(np.diff(o) > 0)
         want = [int(np.sum((o >= cuts2[b]) & (o < cuts2[b + 1]))) for b in range(nb2)]
         assert list(cnt2[:, i]) == want
+
+
+def test_grouped_kernel_with_row_major_bins_on_the_emulator(emul):
+    """What one launch per column range does (k_spmv_sell_grp): the short rows as SELL slices
+    in a length-sorted order (row ids through the permutation, rows past the end of the list,
+    empty slices), four slices per warp trip, and the rows of the two row-major bins as units of
+    the same work list -- a CTA per "long" row, a warp per "vector" row.  y = A x and y += A x
+    against the CSR product to the 1e-13 bar; the SELL rows bit for bit (they add left to right)."""
+    emul.emul_sell_grp_bins.argtypes = ([C.c_int, C.c_uint, C.c_uint32] + [C.c_void_p] * 6 + [C.c_uint32]
+                                        + [C.c_uint32, C.c_void_p, C.c_void_p] * 2 + [C.c_void_p] * 2)
+    n = 2500
+    M = orc.gen_powerlaw(n, 4)
+    lens = M.rowlens()
+    offs = M.offs.astype(np.int64)
+    sell_rows = np.flatnonzero(lens <= 12)
+    vec_rows = np.flatnonzero((lens > 12) & (lens <= 300))
+    long_rows = np.flatnonzero(lens > 300)
+    assert len(vec_rows) > 20 and len(long_rows) > 2
+    # SELL list: sorted by decreasing length inside windows of 256 rows, padded to 32, last slices empty
+    order = np.concatenate([w[np.argsort(-lens[w], kind="stable")] for w in np.array_split(sell_rows, 8)])
+    ns = (len(order) + 31) // 32 + 3                 # three empty slices at the end of the list
+    perm = np.full(ns * 32 + 1, 0xFFFFFFFF, dtype=np.uint32)
+    perm[:len(order)] = order
+    sell_off, cols, vals = [0], [], []
+    for s_ in range(ns):
+        rows = perm[32 * s_:32 * s_ + 32]
+        real = rows[rows != 0xFFFFFFFF]
+        w = int(lens[real].max()) if len(real) else 0
+        Cc, V = np.zeros((w, 32), dtype=np.uint32), np.zeros((w, 32))
+        for l, r in enumerate(rows):
+            if r == 0xFFFFFFFF:
+                continue
+            a, b = offs[r], offs[r + 1]
+            Cc[:b - a, l], V[:b - a, l] = M.cols[a:b], M.vals[a:b]
+            Cc[b - a:, l] = M.cols[b - 1]            # padding: the row's last column, value 0
+        cols += Cc.reshape(-1).tolist()
+        vals += V.reshape(-1).tolist()
+        sell_off.append(sell_off[-1] + w)
+    sell_off = np.array(sell_off, dtype=np.uint32)
+    cols, vals = np.array(cols + [0] * 32, dtype=np.uint32), np.array(vals + [0.0] * 32)
+
+    def row_major(rows, start):
+        o, cc, vv = [start], [], []
+        for r in rows:
+            a, b = offs[r], offs[r + 1]
+            pad = (-(b - a)) % 4
+            cc += M.cols[a:b].tolist() + [int(r)] * pad
+            vv += M.vals[a:b].tolist() + [0.0] * pad
+            o.append(o[-1] + (b - a) + pad)
+        return np.array(o, dtype=np.uint64), cc, vv
+    voff, vc, vv = row_major(vec_rows, 0)
+    loff, lc, lv = row_major(long_rows, int(voff[-1]))     # the long rows live after the vector rows
+    vl_cols = np.array(vc + lc + [0] * 8, dtype=np.uint32)
+    vl_vals = np.array(vv + lv + [0.0] * 8)
+    vids, lids = vec_rows.astype(np.uint32), long_rows.astype(np.uint32)
+    p = lambda a: a.ctypes.data
+    x = np.random.default_rng(8).standard_normal(n)
+    ref, scale = orc.spmv(M, x, want_abs=True)
+    fma = orc.spmv_fma(M, x)
+    for grid in (1, 3):
+        y = np.full(n, np.nan)
+        assert emul.emul_sell_grp_bins(0, grid, ns, p(sell_off), p(cols), p(vals), p(perm), p(x), p(y), n,
+                                       len(lids), p(lids), p(loff), len(vids), p(vids), p(voff), p(vl_cols),
+                                       p(vl_vals)) == 0
+        assert np.all(np.abs(y - ref) <= 1e-13 * np.maximum(scale, 1e-300))
+        assert y[sell_rows].tobytes() == fma[sell_rows].tobytes()
+        y2 = y.copy()
+        assert emul.emul_sell_grp_bins(1, grid, ns, p(sell_off), p(cols), p(vals), p(perm), p(x), p(y2), n,
+                                       len(lids), p(lids), p(loff), len(vids), p(vids), p(voff), p(vl_cols),
+                                       p(vl_vals)) == 0
+        assert np.all(np.abs(y2 - 2.0 * ref) <= 2e-13 * np.maximum(scale, 1e-300))
