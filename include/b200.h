@@ -119,9 +119,12 @@ enum {
    * one L2-sized piece of x.  A range sorts its rows by length inside windows of
    * B200_COL_BLOCK_SIGMA rows (default 131072; 0 = the whole list) and multiplies
    * four slices per warp trip (k_spmv_sell_grp; B200_COL_BLOCK_KERNEL=plain keeps
-   * one slice per trip).  Single rank, SpMV only (b200_pcg_solve refuses);
-   * row sums are formed block by block, i.e. equal to the CSR product to
-   * rounding, not bit for bit.  Ignored when one block would hold everything. */
+   * one slice per trip).  On several ranks the ranges follow the global column
+   * order -- remote columns below the own rows, owned columns, remote columns
+   * above -- and the owned ranges are multiplied while the halo travels.  SpMV
+   * only (b200_pcg_solve refuses); row sums are formed block by block, i.e.
+   * equal to the CSR product to rounding, not bit for bit.  Ignored when one
+   * block would hold everything. */
   B200_MAT_COL_BLOCK = 1u << 6
 };
 
