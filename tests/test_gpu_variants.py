@@ -234,3 +234,29 @@ def test_block_jacobi_on_the_onchip_kernel(abi, ctx, name):
     xf, rf, rcf = Mf.pcg_host(b, tol=1e-10, maxit=5000, flags=abi.PCG_BLOCK_JACOBI)
     assert rcf == 0 and rf.status == 0 and rf.true_relres <= 1e-10 and rf.block_jacobi in (16, 32)
     Mf.close()
+
+
+@pytest.mark.parametrize("flags_name", ["jacobi", "block_jacobi"])
+def test_onchip_kernel_residual_replacement(abi, ctx, flags_name):
+    """The exit check of the on-chip kernel (csrc/small.cu): at a bar close to what fp64 reaches
+    the recurrence residual gets there before b - A x does; the kernel then replaces r by
+    b - A x and goes on (status 0, the bar met on the TRUE residual) -- or, below what fp64
+    can do, ends with status 4 instead of running to maxit.  Jacobi and block-Jacobi."""
+    fl = abi.PCG_BLOCK_JACOBI if flags_name == "block_jacobi" else 0
+    A = orc.matrix_read(orc.matrix_path("tj7a_A_18"))
+    Mo = orc.op_upper_mirror(A)
+    b = orc.rhs(Mo.n)
+    M = make(abi, ctx, A, abi.MAT_SYM_UPPER)
+    seen_replacement = False
+    for tol in (1e-11, 4e-12, 2e-12, 1e-12):
+        x, r, rc = M.pcg_host(b, tol=tol, maxit=5000, flags=fl)
+        assert r.path == 1 and r.status in (0, 4), (tol, r.status)
+        seen_replacement |= r.replacements > 0
+        if r.status == 0:
+            assert r.true_relres <= tol and orc.true_relres(Mo, b, x) <= 1.02 * tol, (tol, r.true_relres)
+        assert np.linalg.norm(x - DIRECT["tj7a_A_18"]) / np.linalg.norm(DIRECT["tj7a_A_18"]) <= 1e-8
+        assert r.iters < 1500                      # never to maxit
+    x, r, rc = M.pcg_host(b, tol=3e-14, maxit=5000, flags=fl)
+    assert r.status == 4 and r.iters < 1500 and r.replacements >= 1
+    assert seen_replacement or r.replacements >= 1
+    M.close()
