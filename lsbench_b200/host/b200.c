@@ -623,6 +623,11 @@ int b200_bench(double *x, struct csr *A, const double *r,
   if (cb->verbose > 0) {
     if (sh.last.replacements)
       printf("b200: residual replacements=%d\n", sh.last.replacements);
+    printf("b200: path=%s preconditioner=%s\n", sh.last.path == 1 ? "on-chip kernel" : "streaming kernels",
+           sh.last.block_jacobi   ? (sh.last.block_jacobi == 32 ? "block-Jacobi (32-row blocks)"
+                                                                : "block-Jacobi (16-row blocks)")
+           : sh.last.path == 1 && sh.last.outer_iters > 1 ? "Chebyshev-Jacobi"
+                                                          : "Jacobi");
     printf("b200: rows/rank0=%llu halo=%llu sell_slices=%llu sigma=%llu "
            "vec_rows=%llu long_rows=%llu padded_nnz=%llu device_MB=%.1f\n",
            (unsigned long long)sh.info.n_local,
